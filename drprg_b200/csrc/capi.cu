@@ -1,0 +1,862 @@
+// C ABI of include/drprg_cuda.h: the drop-in for Pandora::genotype_with
+// (/root/reference/src/lib.rs:580-642) plus the staged interface used for multi-GPU read sharding,
+// benches and parity tests.  Owns all device memory of an index (plain cudaMalloc; no torch types).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <stdexcept>
+
+#include "../../include/drprg_cuda.h"
+#include "genotype_host.hpp"
+#include "kernels.cuh"
+#include "prg_graph.hpp"
+
+using namespace drprg;
+
+namespace {
+thread_local std::string g_err;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call); \
+    } while (0)
+
+template <class T>
+struct DBuf {  // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = n + n / 4 + 1024;
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+T* to_device(const std::vector<T>& v) {
+    T* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+int bits_for(uint64_t v) {
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
+    return b;
+}
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+struct drprg_batch {
+    DevReads R{};
+    uint32_t *d_words = nullptr, *d_lens = nullptr;
+    uint64_t* d_off = nullptr;
+    bool owned = false;
+    uint64_t total_bases = 0;
+};
+
+struct drprg_index {
+    HostIndex H;
+    int device = 0, sm_count = 148;
+    // device-resident index
+    DevTable T{};
+    uint2 *d_slots = nullptr, *d_recs = nullptr;
+    uint32_t *d_filter = nullptr, *d_knode_base = nullptr, *d_edge_off = nullptr, *d_edges = nullptr;
+    uint8_t* d_is_terminal = nullptr;
+    uint32_t table_slots = 0, filter_words = 0;
+    uint64_t n_edges = 0, n_ivs = 0;
+    // accumulators: [2*N coverage | P locus reads | 4 scalars]
+    int32_t* d_accum = nullptr;
+    uint64_t n_accum = 0;
+    uint64_t total_bases = 0, n_reads = 0;
+    bool scalars_in_buffer = false;
+    // sample state
+    SampleOpts opts;
+    bool sample_open = false;
+    uint32_t first_read_len = 0;
+    uint32_t* d_thresh = nullptr;
+    // workspace
+    DBuf<unsigned long long> hi, lo, hi2, lo2;
+    DBuf<uint32_t> clist, clist2, cend, keys, keys2;
+    DBuf<uint8_t> calive, kept, temp;
+    unsigned long long* d_counters = nullptr;  // [0] hit count, [1] kept count
+    unsigned long long* h_counters = nullptr;  // pinned
+    uint64_t last_n_hits = 0;
+    cudaEvent_t ev[5]{};
+    float timings[4] = {0, 0, 0, 0};
+    // genotype state
+    std::string refs_path;
+    std::map<std::string, std::string> refs;
+    std::vector<std::vector<uint32_t>> ref_paths;
+    std::vector<std::vector<SiteRecord>> site_cache;
+    std::vector<char> site_cached;
+    FitParams fit;
+    std::vector<std::vector<uint32_t>> mlpaths;
+    std::vector<char> present;
+    std::vector<SiteRecord> records;
+    GenotypeArrays GA;
+    std::vector<std::string> contigs;
+    std::string vcf;
+    bool have_gt = false;
+    DBuf<double> d_prob, d_M;
+    DBuf<uint32_t> d_len, d_prev, d_up, d_path, d_path_len;
+
+    ~drprg_index() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
+                        (void*)d_is_terminal, (void*)d_accum, (void*)d_thresh, (void*)d_counters})
+            if (p) cudaFree(p);
+        if (h_counters) cudaFreeHost(h_counters);
+        hi.release(); lo.release(); hi2.release(); lo2.release();
+        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release();
+        calive.release(); kept.release(); temp.release();
+        d_prob.release(); d_M.release(); d_len.release(); d_prev.release(); d_up.release(); d_path.release(); d_path_len.release();
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+void upload_index(drprg_index* X) {
+    const HostIndex& H = X->H;
+    if (H.k > (uint32_t)K_MAX) throw std::runtime_error("k > 16 is not supported by the device kernels (2k must fit 32 bits)");
+    if (H.w > (uint32_t)W_MAX) throw std::runtime_error("w > 32 is not supported by the device kernels");
+    if (H.loci.size() > 65535) throw std::runtime_error("more than 65535 loci");
+    // ---- hash table + pre-filter
+    std::vector<uint2> recs(H.records.size());
+    size_t distinct = 0;
+    for (size_t i = 0; i < H.records.size(); ++i) {
+        const Record& r = H.records[i];
+        recs[i] = make_uint2(r.knode, (r.prg << 1) | r.strand);
+        if (i == 0 || H.records[i - 1].hash != r.hash) ++distinct;
+    }
+    if (recs.size() >= (1u << 24)) throw std::runtime_error("too many index records");
+    uint32_t sb = 10;
+    while ((1ull << sb) < distinct * 2) ++sb;
+    uint32_t fb = 8;
+    while ((1ull << fb) < (distinct + 1) / 2) ++fb;
+    std::vector<uint2> slots(1ull << sb, make_uint2(0, 0));
+    std::vector<uint32_t> filter(1ull << fb, 0);
+    for (size_t i = 0; i < H.records.size();) {
+        size_t j = i;
+        while (j < H.records.size() && H.records[j].hash == H.records[i].hash) ++j;
+        if (j - i > 255) throw std::runtime_error("a minimizer occurs in more than 255 k-mer nodes");
+        const uint32_t h = (uint32_t)H.records[i].hash;
+        uint32_t s = (h * 0x9E3779B1u) >> (32 - sb);
+        while (slots[s].y != 0) s = (s + 1) & ((1u << sb) - 1);
+        slots[s] = make_uint2(h, (uint32_t)i | ((uint32_t)(j - i) << 24));
+        filter[h & ((1u << fb) - 1)] |= (1u << ((h >> fb) & 31)) | (1u << ((h >> (fb + 5)) & 31));
+        i = j;
+    }
+    X->d_slots = to_device(slots);
+    X->d_recs = to_device(recs);
+    X->d_filter = to_device(filter);
+    X->table_slots = 1u << sb;
+    X->filter_words = 1u << fb;
+    X->T = DevTable{X->d_slots, sb, X->d_recs, X->d_filter, fb};
+    // ---- k-mer graphs
+    const uint32_t N = H.total_knodes();
+    std::vector<uint32_t> edge_off(N + 1, 0), edges;
+    std::vector<uint8_t> term(N, 0);
+    uint64_t n_ivs = 0;
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        const Locus& L = H.loci[l];
+        const uint32_t base = H.knode_base[l];
+        for (uint32_t r = 0; r < L.kpath.size(); ++r) {
+            edge_off[base + r] = (uint32_t)edges.size();
+            for (uint32_t o : L.kout[r]) edges.push_back(o);
+            n_ivs += L.kpath[r].size();
+        }
+        term[base] = 1;
+        term[base + (uint32_t)L.kpath.size() - 1] = 1;
+    }
+    edge_off[N] = (uint32_t)edges.size();
+    X->n_edges = edges.size();
+    X->n_ivs = n_ivs;
+    X->d_knode_base = to_device(H.knode_base);
+    X->d_edge_off = to_device(edge_off);
+    X->d_edges = to_device(edges);
+    X->d_is_terminal = to_device(term);
+    X->n_accum = 2ull * N + H.loci.size() + 4;
+    CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
+    CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
+    CK(cudaMalloc(&X->d_thresh, std::max<size_t>(1, H.loci.size()) * sizeof(uint32_t)));
+    CK(cudaMalloc(&X->d_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&X->h_counters, 2 * sizeof(unsigned long long)));
+    for (auto& e : X->ev) CK(cudaEventCreate(&e));
+    X->ref_paths.resize(H.loci.size());
+    X->site_cache.resize(H.loci.size());
+    X->site_cached.assign(H.loci.size(), 0);
+}
+
+int load_common(const std::string& text, uint32_t w, uint32_t k, int device, drprg_index** out) {
+    std::unique_ptr<drprg_index> X(new drprg_index());
+    X->device = device;
+    if (device == -1) {  // host-only handle: index introspection; every compute entry point refuses it
+        X->H = build_host_index(text, w, k);
+        *out = X.release();
+        return 0;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device visible: drprg-cuda has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::runtime_error("bad device ordinal");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    X->sm_count = prop.multiProcessorCount;
+    X->H = build_host_index(text, w, k);
+    upload_index(X.get());
+    *out = X.release();
+    return 0;
+}
+
+SampleOpts opts_from(const drprg_map_opts* o, uint32_t k) {
+    SampleOpts s;
+    if (o) {
+        s.threads = o->threads ? o->threads : 1;
+        s.min_cluster_size = o->min_cluster_size;
+        s.illumina = o->illumina != 0;
+        if (o->genome_size) s.genome_size = o->genome_size;
+        s.gt_conf = o->gt_conf;
+        if (o->genotyping_error_rate > 0) s.gt_error_rate = o->genotyping_error_rate;
+        if (o->max_diff) s.max_diff = o->max_diff;
+        if (o->error_rate > 0) s.e_rate = o->error_rate;
+    }
+    if (s.illumina) {  // pandora map -I
+        if (s.e_rate == 0.11) s.e_rate = 0.001;
+        if (s.max_diff > 200) s.max_diff = 2 * k + 1;
+    }
+    return s;
+}
+
+void need_device(drprg_index* X) {
+    if (X->device < 0) throw std::runtime_error("host-only index (device = -1): the map path has no CPU fallback");
+}
+
+void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_len) {
+    need_device(X);
+    CK(cudaSetDevice(X->device));
+    X->opts = opts_from(o, X->H.k);
+    X->first_read_len = first_read_len;
+    uint32_t expected = UINT32_MAX;
+    if (X->opts.illumina) expected = first_read_len * 2 / (X->H.w + 1);
+    const double fraction = 0.5 / std::exp(X->opts.e_rate * X->H.k);
+    std::vector<uint32_t> thr(X->H.loci.size());
+    for (size_t l = 0; l < thr.size(); ++l) {
+        uint32_t lbt = (uint32_t)(std::min(X->H.loci[l].min_path_len, expected) * fraction);
+        thr[l] = std::max(lbt, X->opts.min_cluster_size);
+    }
+    if (!thr.empty()) CK(cudaMemcpy(X->d_thresh, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
+    X->total_bases = X->n_reads = 0;
+    X->scalars_in_buffer = false;
+    X->sample_open = true;
+    X->have_gt = false;
+}
+
+void ensure_hit_capacity(drprg_index* X, uint64_t cap) {
+    X->hi.ensure(cap); X->lo.ensure(cap); X->hi2.ensure(cap); X->lo2.ensure(cap);
+    X->clist.ensure(cap); X->clist2.ensure(cap); X->cend.ensure(cap); X->keys.ensure(cap); X->keys2.ensure(cap);
+    X->calive.ensure(cap); X->kept.ensure(cap);
+    X->temp.ensure(std::max(sort_hits_temp_bytes(cap), sort_cov_temp_bytes(cap)));
+}
+
+void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits, uint64_t* n_kept) {
+    if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
+    CK(cudaSetDevice(X->device));
+    const HostIndex& H = X->H;
+    uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 32));
+    ensure_hit_capacity(X, cap);
+    uint64_t nh = 0;
+    CK(cudaEventRecord(X->ev[0], st));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CK(cudaMemsetAsync(X->d_counters, 0, 2 * sizeof(unsigned long long), st));
+        launch_sketch_lookup(B->R, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nh = X->h_counters[0];
+        if (nh <= X->hi.cap) break;
+        if (attempt == 2) throw std::runtime_error("hit buffer overflow");
+        ensure_hit_capacity(X, nh);
+        CK(cudaEventRecord(X->ev[0], st));
+    }
+    CK(cudaEventRecord(X->ev[1], st));
+    uint32_t max_len = 1;  // read_start < longest read: use the batch's word span as a bound
+    {
+        uint64_t max_words = B->R.stride_words ? B->R.stride_words : 0;
+        if (!max_words) max_words = (B->total_bases + 15) / 16 + 1;
+        max_len = (uint32_t)std::min<uint64_t>(UINT32_MAX, max_words * 16);
+    }
+    sort_hits(X->temp.p, X->temp.cap, X->hi.p, X->lo.p, X->hi2.p, X->lo2.p, nh,
+              bits_for((uint64_t)B->R.read_id_base + B->R.n_reads), bits_for(max_len), 32, st);
+    CK(cudaEventRecord(X->ev[2], st));
+    int32_t* d_locus_reads = X->d_accum + 2ull * H.total_knodes();
+    launch_cluster_filter(X->hi.p, X->lo.p, nh, X->opts.max_diff, X->d_thresh, X->clist.p, X->clist2.p, X->cend.p,
+                          X->calive.p, X->kept.p, d_locus_reads, st);
+    CK(cudaEventRecord(X->ev[3], st));
+    launch_coverage(X->hi.p, X->lo.p, X->kept.p, nh, X->d_knode_base, X->keys.p, X->keys2.p, X->temp.p, X->temp.cap, 32,
+                    X->d_accum, X->d_counters + 1, st);
+    CK(cudaEventRecord(X->ev[4], st));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(X->h_counters + 1, X->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&X->timings[i], X->ev[i], X->ev[i + 1]));
+    X->last_n_hits = nh;
+    X->total_bases += B->total_bases;
+    X->n_reads += B->R.n_reads;
+    if (n_hits) *n_hits = nh;
+    if (n_kept) *n_kept = nh ? X->h_counters[1] : 0;
+}
+
+void flush_scalars(drprg_index* X) {
+    if (X->scalars_in_buffer) return;
+    int32_t s[4] = {(int32_t)(X->total_bases & 0xffffff), (int32_t)(X->total_bases >> 24), (int32_t)(X->n_reads & 0xffffff),
+                    (int32_t)(X->n_reads >> 24)};
+    CK(cudaMemcpy(X->d_accum + X->n_accum - 4, s, sizeof s, cudaMemcpyHostToDevice));
+    X->scalars_in_buffer = true;
+}
+
+void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
+    if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
+    CK(cudaSetDevice(X->device));
+    const HostIndex& H = X->H;
+    const uint32_t N = H.total_knodes(), P = (uint32_t)H.loci.size();
+    cudaStream_t st = 0;
+    flush_scalars(X);
+    std::vector<int32_t> acc(X->n_accum);
+    CK(cudaMemcpy(acc.data(), X->d_accum, acc.size() * 4, cudaMemcpyDeviceToHost));
+    const int32_t* cov = acc.data();
+    const int32_t* locus_reads = acc.data() + 2ull * N;
+    const int32_t* sc = acc.data() + X->n_accum - 4;
+    const uint64_t total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
+    // ---- S6 on the host
+    X->fit = fit_parameters(H, cov, locus_reads, total_bases, X->opts);
+    ModelParams MP{};
+    MP.bin = X->fit.bin;
+    MP.nb_p = X->fit.nb_p;
+    MP.nb_r = X->fit.nb_r;
+    MP.bin_p = 1.0 / std::exp(X->fit.e_rate * H.k);
+    MP.exp_depth = X->fit.E;
+    MP.thresh = (double)X->fit.thresh;
+    MP.window = X->opts.window;
+    MP.min_kmer_covg = X->fit.min_kmer_covg;
+    MP.gt_err = X->opts.gt_error_rate;
+    MP.gt_conf = X->opts.gt_conf;
+    // ---- S7 on the device
+    X->d_prob.ensure(N); X->d_M.ensure(N); X->d_len.ensure(N); X->d_prev.ensure(N);
+    X->d_up.ensure((size_t)N * LV_MAX); X->d_path.ensure(N); X->d_path_len.ensure(P);
+    launch_node_prob(X->d_accum, N, X->d_is_terminal, MP, X->d_prob.p, st);
+    launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
+                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, st);
+    CK(cudaGetLastError());
+    std::vector<uint32_t> path(N), plen(P);
+    CK(cudaMemcpy(path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost));
+    // ---- reference paths / site tables (read independent, cached per --vcf-refs file)
+    const std::string rp = vcf_refs ? vcf_refs : "";
+    if (rp != X->refs_path || X->site_cached.empty()) {
+        X->refs = rp.empty() ? std::map<std::string, std::string>() : load_fasta(rp);
+        X->refs_path = rp;
+        std::fill(X->site_cached.begin(), X->site_cached.end(), 0);
+    }
+    X->mlpaths.assign(P, {});
+    X->present.assign(P, 0);
+    X->records.clear();
+    X->contigs.clear();
+    for (uint32_t l = 0; l < P; ++l) {
+        if (plen[l] == 0xffffffffu || plen[l] == 0) continue;
+        const Locus& L = H.loci[l];
+        std::vector<uint32_t> kp(path.begin() + H.knode_base[l], path.begin() + H.knode_base[l] + plen[l]);
+        std::vector<uint32_t> lp = local_path_of(L, kp);
+        if (locus_coverage_outlier(H, l, kp, lp, cov, X->fit.covg)) continue;
+        X->present[l] = 1;
+        X->mlpaths[l] = kp;
+        X->contigs.push_back(L.name);
+        if (!X->site_cached[l]) {
+            std::vector<uint32_t> ref;
+            auto it = X->refs.find(L.name);
+            if (it != X->refs.end()) ref = thread_sequence(L, it->second);
+            if (ref.empty()) ref = top_path(L);
+            X->ref_paths[l] = ref;
+            X->site_cache[l] = enumerate_sites(H, l, ref);
+            X->site_cached[l] = 1;
+        }
+        std::vector<SiteRecord> recs = X->site_cache[l];
+        add_ml_path_records(H, l, X->ref_paths[l], lp, recs);
+        for (auto& r : merge_records(L, X->ref_paths[l], std::move(recs))) X->records.push_back(std::move(r));
+    }
+    std::stable_sort(X->records.begin(), X->records.end(), [&](const SiteRecord& a, const SiteRecord& b) {
+        const std::string &na = H.loci[a.locus].name, &nb = H.loci[b.locus].name;
+        if (na != nb) return na < nb;
+        if (a.pos != b.pos) return a.pos < b.pos;
+        if (a.ref != b.ref) return a.ref < b.ref;
+        return a.alts < b.alts;
+    });
+    std::sort(X->contigs.begin(), X->contigs.end());
+    // ---- S8 on the device
+    GenotypeArrays& G = X->GA;
+    G = GenotypeArrays();
+    G.rec_off.push_back(0);
+    G.allele_off.push_back(0);
+    for (auto& r : X->records) {
+        for (auto& kn : r.allele_kn) {
+            for (uint32_t x : kn) G.allele_kn.push_back(H.knode_base[r.locus] + x);
+            G.allele_off.push_back((uint32_t)G.allele_kn.size());
+        }
+        G.rec_off.push_back((uint32_t)G.allele_off.size() - 1);
+    }
+    const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
+    for (auto* v : {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev}) v->assign(na, 0);
+    G.gaps.assign(na, 0);
+    G.lik.assign(na, 0);
+    G.gt_conf.assign(nr, 0);
+    G.gt.assign(nr, -1);
+    if (nr) {
+        uint32_t *d_rec_off = to_device(G.rec_off), *d_allele_off = to_device(G.allele_off), *d_allele_kn = to_device(G.allele_kn);
+        uint32_t* d_u32 = nullptr;
+        double* d_f64 = nullptr;
+        int32_t* d_gt = nullptr;
+        CK(cudaMalloc(&d_u32, (size_t)na * 6 * 4));
+        CK(cudaMalloc(&d_f64, ((size_t)na * 2 + nr) * 8));
+        CK(cudaMalloc(&d_gt, (size_t)nr * 4));
+        DevGenotype DG{nr, na, d_rec_off, d_allele_off, d_allele_kn, d_u32, d_u32 + na, d_u32 + 2 * (size_t)na,
+                       d_u32 + 3 * (size_t)na, d_u32 + 4 * (size_t)na, d_u32 + 5 * (size_t)na, d_f64, d_f64 + na,
+                       d_f64 + 2 * (size_t)na, d_gt};
+        launch_genotype(X->d_accum, DG, MP, st);
+        CK(cudaGetLastError());
+        std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+        for (int c = 0; c < 6; ++c) CK(cudaMemcpy(cols[c]->data(), d_u32 + (size_t)c * na, (size_t)na * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(G.gaps.data(), d_f64, (size_t)na * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(G.lik.data(), d_f64 + na, (size_t)na * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(G.gt_conf.data(), d_f64 + 2 * (size_t)na, (size_t)nr * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(G.gt.data(), d_gt, (size_t)nr * 4, cudaMemcpyDeviceToHost));
+        for (void* p : {(void*)d_rec_off, (void*)d_allele_off, (void*)d_allele_kn, (void*)d_u32, (void*)d_f64, (void*)d_gt}) cudaFree(p);
+    }
+    X->vcf = format_vcf(H, X->records, G, X->contigs, sample && *sample ? sample : "sample");
+    X->have_gt = true;
+}
+
+void free_batch(drprg_batch* b) {
+    if (!b) return;
+    if (b->owned) {
+        if (b->d_words) cudaFree(b->d_words);
+        if (b->d_lens) cudaFree(b->d_lens);
+        if (b->d_off) cudaFree(b->d_off);
+    }
+    delete b;
+}
+
+drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t* word_off, uint32_t stride, const uint32_t* lens,
+                          uint64_t n, uint64_t total_bases, uint32_t id_base, cudaStream_t st) {
+    need_device(X);
+    CK(cudaSetDevice(X->device));
+    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
+    B->owned = true;
+    const uint64_t nwords = stride ? n * (uint64_t)stride : (n ? word_off[n] : 0);
+    CK(cudaMalloc(&B->d_words, std::max<uint64_t>(1, nwords + 2) * 4));
+    CK(cudaMalloc(&B->d_lens, std::max<uint64_t>(1, n) * 4));
+    if (nwords) CK(cudaMemcpyAsync(B->d_words, words, nwords * 4, cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(B->d_lens, lens, n * 4, cudaMemcpyHostToDevice, st));
+    if (!stride) {
+        CK(cudaMalloc(&B->d_off, (n + 1) * 8));
+        CK(cudaMemcpyAsync(B->d_off, word_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
+    B->total_bases = total_bases;
+    return B.release();
+}
+
+int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir, const drprg_map_opts* o,
+               drprg_map_stats* stats) {
+    need_device(X);
+    const double t0 = now_ms();
+    std::ofstream log(std::string(outdir) + "/pandora.log");
+    PackedReads pr;
+    load_reads_packed(reads_path, o ? o->threads : 1, pr);
+    const double t1 = now_ms();
+    sample_begin(X, o, pr.first_read_len);
+    uint64_t nh = 0, nk = 0;
+    const uint64_t n = pr.lens.size();
+    if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
+    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(
+        upload_batch(X, pr.words.data(), pr.word_off.data(), 0, pr.lens.data(), n, pr.total_bases, 0, 0), free_batch);
+    map_batch(X, B.get(), 0, &nh, &nk);
+    const double t2 = now_ms();
+    genotype(X, vcf_refs, "sample");
+    std::ofstream vcf(std::string(outdir) + "/pandora_genotyped.vcf");
+    if (!vcf) throw std::runtime_error(std::string("cannot write ") + outdir + "/pandora_genotyped.vcf");
+    vcf << X->vcf;
+    const double t3 = now_ms();
+    drprg_map_stats s{};
+    s.n_reads = n;
+    s.n_reads_dropped = pr.n_dropped;
+    s.total_bases = pr.total_bases;
+    s.n_hits = nh;
+    s.n_hits_kept = nk;
+    s.n_loci_present = (uint32_t)X->contigs.size();
+    s.n_records = (uint32_t)X->records.size();
+    s.exp_depth_covg = X->fit.E;
+    s.ms_ingest = t1 - t0;
+    s.ms_map = t2 - t1;
+    s.ms_genotype = t3 - t2;
+    s.ms_total = t3 - t0;
+    if (stats) *stats = s;
+    log << "drprg-cuda map: reads=" << n << " dropped=" << pr.n_dropped << " bases=" << pr.total_bases << " hits=" << nh
+        << " kept=" << nk << " loci=" << s.n_loci_present << " records=" << s.n_records << " E=" << s.exp_depth_covg
+        << "\nkernel ms: sketch_lookup=" << X->timings[0] << " sort=" << X->timings[1] << " cluster=" << X->timings[2]
+        << " coverage=" << X->timings[3] << "\nwall ms: ingest=" << s.ms_ingest << " map=" << s.ms_map
+        << " genotype=" << s.ms_genotype << " total=" << s.ms_total << "\n";
+    return 0;
+}
+}  // namespace
+
+#define API_BEGIN try {
+#define API_END                          \
+    }                                    \
+    catch (const std::exception& e) {    \
+        g_err = e.what();                \
+        return 1;                        \
+    }                                    \
+    catch (...) {                        \
+        g_err = "unknown error";         \
+        return 1;                        \
+    }
+
+extern "C" {
+int drprg_cuda_version(void) { return DRPRG_CUDA_VERSION; }
+const char* drprg_cuda_last_error(void) { return g_err.c_str(); }
+int drprg_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int drprg_cuda_index_load(const char* prg_path, uint32_t w, uint32_t k, int device, drprg_index** out) {
+    API_BEGIN return load_common(read_text_file(prg_path), w, k, device, out);
+    API_END
+}
+int drprg_cuda_index_load_text(const char* prg_text, uint32_t w, uint32_t k, int device, drprg_index** out) {
+    API_BEGIN return load_common(prg_text, w, k, device, out);
+    API_END
+}
+void drprg_cuda_index_free(drprg_index* x) { delete x; }
+
+int drprg_cuda_map_genotype(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir,
+                            const drprg_map_opts* o, drprg_map_stats* stats) {
+    API_BEGIN return run_sample(X, reads_path, vcf_refs, outdir, o, stats);
+    API_END
+}
+int drprg_cuda_map_genotype_batch(drprg_index* X, size_t n, const char* const* reads_paths, const char* vcf_refs,
+                                  const char* const* outdirs, const drprg_map_opts* o, drprg_map_stats* stats) {
+    API_BEGIN for (size_t i = 0; i < n; ++i) run_sample(X, reads_paths[i], vcf_refs, outdirs[i], o, stats ? stats + i : nullptr);
+    return 0;
+    API_END
+}
+
+int64_t drprg_cuda_pack_reads(const uint8_t* ascii, const uint64_t* off, uint64_t n_reads, uint32_t stride_words,
+                              uint32_t* words, uint64_t words_cap, uint64_t* word_off, uint32_t* lens) {
+    int64_t r = pack_ascii(ascii, off, n_reads, stride_words, words, words_cap, word_off, lens);
+    if (r < 0) g_err = (r == -1) ? "read longer than the fixed stride" : "words buffer too small";
+    return r;
+}
+int drprg_cuda_read_fastx(const char* path, uint32_t threads, uint32_t** words, uint64_t** word_off, uint32_t** lens,
+                          uint64_t* n_reads, uint64_t* total_bases, uint32_t* first_read_len) {
+    API_BEGIN PackedReads pr;
+    load_reads_packed(path, threads, pr);
+    *words = (uint32_t*)malloc(std::max<size_t>(1, pr.words.size()) * 4);
+    *word_off = (uint64_t*)malloc(pr.word_off.size() * 8);
+    *lens = (uint32_t*)malloc(std::max<size_t>(1, pr.lens.size()) * 4);
+    memcpy(*words, pr.words.data(), pr.words.size() * 4);
+    memcpy(*word_off, pr.word_off.data(), pr.word_off.size() * 8);
+    memcpy(*lens, pr.lens.data(), pr.lens.size() * 4);
+    *n_reads = pr.lens.size();
+    *total_bases = pr.total_bases;
+    *first_read_len = pr.first_read_len;
+    return 0;
+    API_END
+}
+void drprg_cuda_host_free(void* p) { free(p); }
+
+int drprg_cuda_batch_upload(drprg_index* X, const uint32_t* words, const uint64_t* word_off, uint32_t stride_words,
+                            const uint32_t* lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base, void* stream,
+                            drprg_batch** out) {
+    API_BEGIN if (!stride_words && !word_off) throw std::runtime_error("word_off is required without a fixed stride");
+    *out = upload_batch(X, words, word_off, stride_words, lens, n_reads, total_bases, read_id_base, (cudaStream_t)stream);
+    return 0;
+    API_END
+}
+int drprg_cuda_batch_wrap_device(drprg_index* X, const void* d_words, const void* d_word_off, uint32_t stride_words,
+                                 const void* d_lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base,
+                                 drprg_batch** out) {
+    API_BEGIN(void) X;
+    if (!stride_words && !d_word_off) throw std::runtime_error("word_off is required without a fixed stride");
+    drprg_batch* B = new drprg_batch();
+    B->R = DevReads{(const uint32_t*)d_words, (const uint64_t*)d_word_off, stride_words, (const uint32_t*)d_lens, n_reads, read_id_base};
+    B->total_bases = total_bases;
+    *out = B;
+    return 0;
+    API_END
+}
+void drprg_cuda_batch_free(drprg_batch* b) { free_batch(b); }
+
+int drprg_cuda_sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_len) {
+    API_BEGIN sample_begin(X, o, first_read_len);
+    return 0;
+    API_END
+}
+int drprg_cuda_map_batch(drprg_index* X, drprg_batch* B, void* stream, uint64_t* n_hits, uint64_t* n_kept) {
+    API_BEGIN map_batch(X, B, (cudaStream_t)stream, n_hits, n_kept);
+    return 0;
+    API_END
+}
+int drprg_cuda_accum_device_ptr(drprg_index* X, void** d_ptr, uint64_t* n_int32) {
+    API_BEGIN need_device(X);
+    CK(cudaSetDevice(X->device));
+    flush_scalars(X);
+    *d_ptr = X->d_accum;
+    *n_int32 = X->n_accum;
+    return 0;
+    API_END
+}
+int drprg_cuda_accum_download(drprg_index* X, int32_t* out, uint64_t n) {
+    API_BEGIN need_device(X);
+    if (n != X->n_accum) throw std::runtime_error("accumulator size mismatch");
+    CK(cudaSetDevice(X->device));
+    flush_scalars(X);
+    CK(cudaMemcpy(out, X->d_accum, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+    API_END
+}
+int drprg_cuda_accum_upload(drprg_index* X, const int32_t* in, uint64_t n) {
+    API_BEGIN need_device(X);
+    if (n != X->n_accum) throw std::runtime_error("accumulator size mismatch");
+    CK(cudaSetDevice(X->device));
+    CK(cudaMemcpy(X->d_accum, in, n * 4, cudaMemcpyHostToDevice));
+    X->scalars_in_buffer = true;
+    return 0;
+    API_END
+}
+int drprg_cuda_genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
+    API_BEGIN genotype(X, vcf_refs, sample);
+    return 0;
+    API_END
+}
+int drprg_cuda_write_vcf(drprg_index* X, const char* path) {
+    API_BEGIN if (!X->have_gt) throw std::runtime_error("no genotype results");
+    std::ofstream f(path);
+    if (!f) throw std::runtime_error(std::string("cannot write ") + path);
+    f << X->vcf;
+    return 0;
+    API_END
+}
+const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->vcf.c_str() : ""; }
+
+int drprg_cuda_index_info(drprg_index* X, drprg_index_info* o) {
+    API_BEGIN o->w = X->H.w;
+    o->k = X->H.k;
+    o->n_loci = (uint32_t)X->H.loci.size();
+    o->total_knodes = X->H.total_knodes();
+    o->n_records = X->H.records.size();
+    o->n_edges = X->n_edges;
+    o->n_path_intervals = X->n_ivs;
+    o->table_slots = X->table_slots;
+    o->filter_words = X->filter_words;
+    return 0;
+    API_END
+}
+const char* drprg_cuda_locus_name(drprg_index* X, uint32_t l) { return l < X->H.loci.size() ? X->H.loci[l].name.c_str() : ""; }
+int drprg_cuda_index_knode_base(drprg_index* X, uint32_t* out) {
+    memcpy(out, X->H.knode_base.data(), X->H.knode_base.size() * 4);
+    return 0;
+}
+int drprg_cuda_index_knodes(drprg_index* X, uint64_t* hash, uint8_t* strand, uint32_t* n_out, uint32_t* n_iv) {
+    size_t g = 0;
+    for (auto& L : X->H.loci)
+        for (size_t r = 0; r < L.kpath.size(); ++r, ++g) {
+            hash[g] = L.khash[r];
+            strand[g] = L.kstrand[r];
+            n_out[g] = (uint32_t)L.kout[r].size();
+            n_iv[g] = (uint32_t)L.kpath[r].size();
+        }
+    return 0;
+}
+int drprg_cuda_index_edges(drprg_index* X, uint32_t* edges) {
+    size_t e = 0;
+    for (size_t l = 0; l < X->H.loci.size(); ++l)
+        for (auto& o : X->H.loci[l].kout)
+            for (uint32_t t : o) edges[e++] = X->H.knode_base[l] + t;
+    return 0;
+}
+int drprg_cuda_index_paths(drprg_index* X, uint32_t* iv_start, uint32_t* iv_len) {
+    size_t e = 0;
+    for (auto& L : X->H.loci)
+        for (auto& p : L.kpath)
+            for (auto& sg : p) {
+                iv_start[e] = sg.s;
+                iv_len[e] = sg.e - sg.s;
+                ++e;
+            }
+    return 0;
+}
+int drprg_cuda_index_records(drprg_index* X, uint64_t* hash, uint32_t* prg, uint32_t* knode, uint8_t* strand) {
+    size_t i = 0;
+    for (auto& r : X->H.records) {
+        hash[i] = r.hash;
+        prg[i] = r.prg;
+        knode[i] = r.knode;
+        strand[i] = r.strand;
+        ++i;
+    }
+    return 0;
+}
+int drprg_cuda_index_min_path_length(drprg_index* X, uint32_t* out) {
+    for (size_t l = 0; l < X->H.loci.size(); ++l) out[l] = X->H.loci[l].min_path_len;
+    return 0;
+}
+
+int64_t drprg_cuda_sketch_batch(drprg_index* X, drprg_batch* B, void* stream, uint32_t* read, uint32_t* start, uint64_t* hash,
+                                uint8_t* strand, uint64_t cap) {
+    try {
+        need_device(X);
+        CK(cudaSetDevice(X->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        DBuf<unsigned long long> key, val;
+        key.ensure(cap);
+        val.ensure(cap);
+        CK(cudaMemsetAsync(X->d_counters, 0, 16, st));
+        launch_sketch_only(B->R, X->H.w, X->H.k, key.p, val.p, X->d_counters, cap, X->sm_count, st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t n = X->h_counters[0];
+        if (n > cap) {
+            key.release();
+            val.release();
+            g_err = "sketch output capacity too small";
+            return -(int64_t)n;
+        }
+        std::vector<unsigned long long> hk(n), hv(n);
+        CK(cudaMemcpy(hk.data(), key.p, n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hv.data(), val.p, n * 8, cudaMemcpyDeviceToHost));
+        key.release();
+        val.release();
+        std::vector<uint64_t> ord(n);
+        for (uint64_t i = 0; i < n; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t j = ord[i];
+            read[i] = (uint32_t)(hk[j] >> 32);
+            start[i] = (uint32_t)hk[j];
+            hash[i] = hv[j] >> 1;
+            strand[i] = (uint8_t)(hv[j] & 1);
+        }
+        return (int64_t)n;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return INT64_MIN;
+    }
+}
+int64_t drprg_cuda_last_hits(drprg_index* X, uint32_t* read, uint32_t* start, uint32_t* prg, uint32_t* knode, uint8_t* fwd,
+                             uint8_t* kept, uint64_t cap) {
+    try {
+        need_device(X);
+        CK(cudaSetDevice(X->device));
+        const uint64_t n = X->last_n_hits;
+        if (n > cap) return -(int64_t)n;
+        std::vector<unsigned long long> hi(n), lo(n);
+        if (n) {
+            CK(cudaMemcpy(hi.data(), X->hi.p, n * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(lo.data(), X->lo.p, n * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(kept, X->kept.p, n, cudaMemcpyDeviceToHost));
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            read[i] = (uint32_t)(hi[i] >> 32);
+            prg[i] = (uint32_t)(hi[i] >> 16) & 0xffff;
+            fwd[i] = (uint8_t)((((uint32_t)hi[i] >> 15) & 1) ^ 1);
+            start[i] = (uint32_t)(lo[i] >> 32);
+            knode[i] = (uint32_t)lo[i];
+        }
+        return (int64_t)n;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return INT64_MIN;
+    }
+}
+int drprg_cuda_gt_params(drprg_index* X, double* out) {
+    const FitParams& P = X->fit;
+    out[0] = P.E; out[1] = P.bin; out[2] = P.nb_p; out[3] = P.nb_r; out[4] = P.e_rate; out[5] = P.thresh;
+    out[6] = P.covg; out[7] = P.min_kmer_covg; out[8] = P.mean; out[9] = P.var; out[10] = (double)P.num_reads;
+    return 0;
+}
+int64_t drprg_cuda_gt_mlpath(drprg_index* X, uint32_t locus, uint32_t* out, uint64_t cap) {
+    if (!X->have_gt || locus >= X->present.size() || !X->present[locus]) return -1;
+    const auto& p = X->mlpaths[locus];
+    for (size_t i = 0; i < p.size() && i < cap; ++i) out[i] = p[i];
+    return (int64_t)p.size();
+}
+int drprg_cuda_gt_counts(drprg_index* X, uint32_t* n_records, uint32_t* n_alleles, uint64_t* n_allele_knodes) {
+    *n_records = (uint32_t)X->records.size();
+    *n_alleles = X->GA.allele_off.empty() ? 0 : (uint32_t)X->GA.allele_off.size() - 1;
+    *n_allele_knodes = X->GA.allele_kn.size();
+    return 0;
+}
+int drprg_cuda_gt_records(drprg_index* X, uint32_t* locus, uint32_t* pos, uint32_t* n_alleles, int32_t* gt, double* gt_conf) {
+    for (size_t i = 0; i < X->records.size(); ++i) {
+        locus[i] = X->records[i].locus;
+        pos[i] = X->records[i].pos;
+        n_alleles[i] = X->GA.rec_off[i + 1] - X->GA.rec_off[i];
+        gt[i] = X->GA.gt[i];
+        gt_conf[i] = X->GA.gt_conf[i];
+    }
+    return 0;
+}
+int drprg_cuda_gt_alleles(drprg_index* X, double* lik, double* gaps, uint32_t* mean_fwd, uint32_t* mean_rev, uint32_t* med_fwd,
+                          uint32_t* med_rev, uint32_t* sum_fwd, uint32_t* sum_rev, uint32_t* n_knodes) {
+    const GenotypeArrays& G = X->GA;
+    const size_t na = G.lik.size();
+    memcpy(lik, G.lik.data(), na * 8);
+    memcpy(gaps, G.gaps.data(), na * 8);
+    memcpy(mean_fwd, G.mean_fwd.data(), na * 4);
+    memcpy(mean_rev, G.mean_rev.data(), na * 4);
+    memcpy(med_fwd, G.med_fwd.data(), na * 4);
+    memcpy(med_rev, G.med_rev.data(), na * 4);
+    memcpy(sum_fwd, G.sum_fwd.data(), na * 4);
+    memcpy(sum_rev, G.sum_rev.data(), na * 4);
+    for (size_t a = 0; a < na; ++a) n_knodes[a] = G.allele_off[a + 1] - G.allele_off[a];
+    return 0;
+}
+int drprg_cuda_gt_allele_knodes(drprg_index* X, uint32_t* out) {
+    // ranks within the locus, like the oracle
+    size_t e = 0;
+    for (auto& r : X->records)
+        for (auto& kn : r.allele_kn)
+            for (uint32_t x : kn) out[e++] = x;
+    return 0;
+}
+int drprg_cuda_last_timings(drprg_index* X, float* out4) {
+    memcpy(out4, X->timings, sizeof X->timings);
+    return 0;
+}
+uint64_t drprg_cuda_launch_count(void) { return launch_count(); }
+}

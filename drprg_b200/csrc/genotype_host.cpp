@@ -1,0 +1,635 @@
+// See genotype_host.hpp.  Behaviour follows pandora's estimate_parameters.cpp, LocalPRG::build_vcf /
+// add_sample_gt_to_vcf / add_sample_covgs_to_vcf, VCF::merge_multi_allelic and VCF::save as they
+// run under the argv of /root/reference/src/lib.rs:594-609; the VCF schema is the one
+// /root/reference/src/filter.rs:48-63 and src/lib.rs:935-1181 (VcfExt) consume.
+#include "genotype_host.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+#include <deque>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+
+namespace drprg {
+
+static inline uint32_t sat16(int32_t c) { return c > 65535 ? 65535u : (uint32_t)(c < 0 ? 0 : c); }
+
+// ----------------------------------------------------------------------------- S6 ---
+double host_node_log_prob(const FitParams& P, uint32_t k, uint32_t f, uint32_t r, bool terminal) {
+    if (P.bin) {
+        if (terminal) return 0.0;
+        const double p = 1.0 / std::exp(P.e_rate * k);
+        const uint32_t s = f + r;
+        const double n = (double)std::max(s, P.E);
+        const double lnck2 = std::lgamma(n + 1.0) - std::lgamma(f + 1.0) - std::lgamma(r + 1.0) - std::lgamma(n - f - r + 1.0);
+        if (s > P.E) return lnck2 + s * std::log(p / 2);
+        return lnck2 + s * std::log(p / 2) + (P.E - s) * std::log(1 - p);
+    }
+    const double c = (double)f + (double)r;
+    const double v = std::lgamma(c + P.nb_r) - std::lgamma(P.nb_r) - std::lgamma(c + 1.0) + P.nb_r * std::log(P.nb_p) +
+                     c * std::log(1.0 - P.nb_p);
+    return std::max(v, -(double)FLT_MAX / 1000.0);
+}
+
+FitParams fit_parameters(const HostIndex& H, const int32_t* cov, const int32_t* locus_reads, uint64_t total_bases,
+                         const SampleOpts& o) {
+    FitParams P;
+    P.e_rate = o.e_rate;
+    P.covg = (uint32_t)(total_bases / std::max<uint32_t>(1u, o.genome_size));
+    P.E = P.covg;
+    uint32_t hist[1000] = {0};
+    uint64_t reads = 0, present = 0;
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        if (locus_reads[l] <= 0) continue;
+        ++present;
+        reads += (uint64_t)locus_reads[l];
+        for (uint32_t g = H.knode_base[l] + 1; g + 1 < H.knode_base[l + 1]; ++g) {
+            uint32_t c = sat16(cov[2 * g]) + sat16(cov[2 * g + 1]);
+            if (c < 1000) ++hist[c];
+        }
+    }
+    if (!present) {
+        P.min_kmer_covg = P.E / 10;
+        return P;
+    }
+    P.num_reads = reads / present;
+    auto moments = [&](uint32_t from, double& mean, double& var) {
+        double sum = 0, tot = 0;
+        for (uint32_t i = from; i < 1000; ++i) {
+            sum += (double)hist[i] * i;
+            tot += hist[i];
+        }
+        mean = tot == 0 ? 0 : sum / tot;
+        double acc = 0;
+        for (uint32_t i = from; i < 1000; ++i) acc += ((double)i - mean) * ((double)i - mean) * hist[i];
+        var = tot == 0 ? 0 : acc / tot;
+    };
+    moments(P.covg / 10, P.mean, P.var);
+    if (P.bin && P.num_reads > 30 && P.covg > 30) {
+        // second peak of the coverage histogram
+        bool first_peak = true;
+        uint32_t peak = 0, noise = 0;
+        for (uint32_t i = 1; i < 1000; ++i) {
+            if (hist[i] <= hist[i - 1]) continue;
+            if (first_peak && noise < 3) { ++noise; continue; }
+            if (first_peak) { first_peak = false; peak = i; }
+            else if (hist[i] > hist[peak]) peak = i;
+        }
+        if (first_peak) peak = 0;
+        P.E = peak;
+        if (peak > 0 && peak < P.covg) P.e_rate = -std::log((double)peak / P.covg) / H.k;
+    } else if (!P.bin && P.num_reads > 30 && P.covg > 2 && P.mean < P.var && P.mean > 0) {
+        const double p = P.mean / P.var;
+        const double r = (P.mean * p / (1 - p) + p * P.var / (1 - p)) / 2;
+        P.nb_p = 0.015 + p;  // pandora adds the fit to its defaults (set_negative_binomial_parameters)
+        P.nb_r = 2.0 + r;
+        P.E = (uint32_t)P.mean;
+    } else {
+        double m, v;
+        moments(P.covg / 10, m, v);
+        P.E = std::max<uint32_t>((uint32_t)m, 1u);
+    }
+    if (P.nb_p >= 1.0) P.nb_p = 0.999999;
+    // valley of the log-probability histogram (bins [-200, 0))
+    uint32_t ph[200] = {0};
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        if (locus_reads[l] <= 0) continue;
+        for (uint32_t g = H.knode_base[l] + 1; g + 1 < H.knode_base[l + 1]; ++g) {
+            double p = host_node_log_prob(P, H.k, sat16(cov[2 * g]), sat16(cov[2 * g + 1]), false);
+            if (p >= -200.0 && p < 0.0) {
+                int j = (int)std::floor(p + 200.0);
+                if (j >= 0 && j < 200) ++ph[j];
+            }
+        }
+    }
+    int p1 = (int)(std::max_element(ph, ph + 200) - ph), p2 = -1;
+    for (int i = 0; i < 200; ++i) {
+        if (std::abs(i - p1) <= 10 || ph[i] == 0) continue;
+        if (p2 < 0 || ph[i] > ph[p2]) p2 = i;
+    }
+    if (p2 < 0) {
+        P.thresh = std::max(-200, p1 - 200 - 10);
+    } else {
+        int a = std::min(p1, p2), b = std::max(p1, p2);
+        P.thresh = (int)(std::min_element(ph + a, ph + b + 1) - ph) - 200;
+    }
+    P.min_kmer_covg = P.E / 10;
+    return P;
+}
+
+// ---------------------------------------------------------------- reference path ---
+std::vector<uint32_t> top_path(const Locus& L) {
+    std::vector<uint32_t> p{0};
+    while (!L.nodes[p.back()].out.empty()) p.push_back(L.nodes[p.back()].out[0]);
+    return p;
+}
+
+std::vector<uint32_t> thread_sequence(const Locus& L, const std::string& seq) {
+    auto fits = [&](uint32_t n, size_t off) {
+        uint32_t len = L.node_len(n);
+        if (off + len > seq.size()) return false;
+        for (uint32_t i = 0; i < len; ++i)
+            if (std::toupper((unsigned char)L.text[L.nodes[n].s + i]) != std::toupper((unsigned char)seq[off + i])) return false;
+        return true;
+    };
+    std::vector<uint32_t> path, cursor;
+    std::vector<size_t> offs;
+    if (!fits(0, 0)) return {};
+    path.push_back(0);
+    cursor.push_back(0);
+    offs.push_back(L.node_len(0));
+    while (!path.empty()) {
+        const LNode& nd = L.nodes[path.back()];
+        if (nd.out.empty() && offs.back() == seq.size()) return path;
+        if (cursor.back() >= nd.out.size()) {
+            path.pop_back();
+            cursor.pop_back();
+            offs.pop_back();
+            continue;
+        }
+        uint32_t c = nd.out[cursor.back()++];
+        if (fits(c, offs.back())) {
+            size_t o = offs.back() + L.node_len(c);
+            path.push_back(c);
+            cursor.push_back(0);
+            offs.push_back(o);
+        }
+    }
+    return {};
+}
+
+// ------------------------------------------------------------------- site records ---
+namespace {
+std::string classify(const std::string& ref, const std::string& alt) {
+    if (ref.empty() && alt.empty()) return ".";
+    if (ref.empty() || alt.empty()) return "INDEL";
+    if (ref.size() == 1 && alt.size() == 1) return "SNP";
+    if (ref.size() == alt.size()) return "PH_SNPs";
+    const std::string& shorter = ref.size() < alt.size() ? ref : alt;
+    const std::string& longer = ref.size() < alt.size() ? alt : ref;
+    if (longer.compare(0, shorter.size(), shorter) == 0) return "INDEL";
+    return "COMPLEX";
+}
+
+// k-mer nodes seen as runs of local nodes: a k-mer lies on a node path iff its node run is a
+// contiguous piece of it (every node occurs at most once on a path of the DAG)
+struct KnodeRuns {
+    std::vector<std::vector<uint32_t>> nodes_of;  // per rank, trailing terminus padding removed
+    std::vector<uint32_t> first_off, length;
+    std::vector<std::vector<uint32_t>> starting_in;  // per local node: ranks whose run starts there
+    explicit KnodeRuns(const Locus& L) {
+        const uint32_t N = (uint32_t)L.kpath.size();
+        nodes_of.resize(N);
+        first_off.assign(N, 0);
+        length.assign(N, 0);
+        starting_in.resize(L.nodes.size());
+        for (uint32_t r = 1; r + 1 < N; ++r) {
+            KPath p = L.kpath[r];
+            while (p.size() > 1 && p.back().s == p.back().e) p.pop_back();
+            for (auto& sg : p) {
+                nodes_of[r].push_back(sg.node);
+                length[r] += sg.e - sg.s;
+            }
+            first_off[r] = p[0].s - L.nodes[p[0].node].s;
+            if (length[r]) starting_in[p[0].node].push_back(r);
+        }
+    }
+};
+
+std::vector<uint32_t> kmers_over(const Locus& L, const KnodeRuns& KR, const std::vector<uint32_t>& np, uint32_t A, uint32_t B) {
+    std::vector<uint32_t> res;
+    std::vector<uint32_t> cum(np.size() + 1, 0);
+    for (size_t j = 0; j < np.size(); ++j) cum[j + 1] = cum[j] + L.node_len(np[j]);
+    for (size_t j = 0; j < np.size(); ++j) {
+        if (cum[j] >= std::max(B, A + 1)) break;
+        for (uint32_t r : KR.starting_in[np[j]]) {
+            const uint32_t s = cum[j] + KR.first_off[r], e = s + KR.length[r];
+            const bool over = (A == B) ? (s < A && e > A) : (s < B && e > A);
+            if (!over) continue;
+            const auto& run = KR.nodes_of[r];
+            if (j + run.size() > np.size()) continue;
+            bool same = true;
+            for (size_t t = 1; t < run.size() && same; ++t) same = (np[j + t] == run[t]);
+            if (same) res.push_back(r);
+        }
+    }
+    std::sort(res.begin(), res.end());
+    return res;
+}
+}  // namespace
+
+std::vector<SiteRecord> enumerate_sites(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref) {
+    const Locus& L = H.loci[locus];
+    std::vector<SiteRecord> out;
+    if (ref.size() < 2) return out;
+    KnodeRuns KR(L);
+    std::vector<uint32_t> cum(ref.size() + 1, 0);
+    for (size_t i = 0; i < ref.size(); ++i) cum[i + 1] = cum[i] + L.node_len(ref[i]);
+    std::vector<uint32_t> open;  // indices into ref of nodes that opened a site
+    bool nested = false;
+    std::set<std::tuple<uint32_t, std::string, std::string>> seen;
+    for (uint32_t i = 0; i + 1 < ref.size(); ++i) {
+        const LNode& nd = L.nodes[ref[i]];
+        if (nd.out.size() > 1) {
+            open.push_back(i);
+            if (open.size() > 1) nested = true;
+            continue;
+        }
+        if (open.empty()) continue;
+        const uint32_t o = open.back();
+        open.pop_back();
+        const uint32_t pos = cum[o + 1];
+        std::string ref_seq;
+        for (uint32_t j = o + 1; j <= i; ++j) ref_seq += L.node_seq(ref[j]);
+        const uint32_t join = ref[i + 1];
+        // every alternative route from the opening node to the node where the reference re-joins
+        std::deque<std::vector<uint32_t>> work;
+        for (uint32_t a : L.nodes[ref[o]].out)
+            if (a != ref[o + 1]) work.push_back({a});
+        const std::vector<uint32_t> ref_kn = kmers_over(L, KR, ref, pos, pos + (uint32_t)ref_seq.size());
+        while (!work.empty()) {
+            std::vector<uint32_t> route = std::move(work.front());
+            work.pop_front();
+            const LNode& tail = L.nodes[route.back()];
+            if (tail.out.empty()) continue;
+            if (tail.out[0] != join) {
+                for (uint32_t nx : tail.out) {
+                    work.push_back(route);
+                    work.back().push_back(nx);
+                }
+                continue;
+            }
+            std::string alt_seq;
+            for (uint32_t n : route) alt_seq += L.node_seq(n);
+            if (alt_seq == ref_seq) continue;
+            if (!seen.insert({pos, ref_seq, alt_seq}).second) continue;
+            SiteRecord r;
+            r.locus = locus;
+            r.pos = pos;
+            r.ref = ref_seq;
+            r.alts = {alt_seq};
+            r.vc = classify(ref_seq, alt_seq);
+            r.graphtype = nested ? "NESTED" : "SIMPLE";
+            std::vector<uint32_t> ap(ref.begin(), ref.begin() + o + 1);
+            ap.insert(ap.end(), route.begin(), route.end());
+            ap.insert(ap.end(), ref.begin() + i + 1, ref.end());
+            r.allele_kn.push_back(ref_kn);
+            r.allele_kn.push_back(kmers_over(L, KR, ap, pos, pos + (uint32_t)alt_seq.size()));
+            out.push_back(std::move(r));
+        }
+        if (open.empty()) nested = false;
+    }
+    return out;
+}
+
+std::vector<uint32_t> local_path_of(const Locus& L, const std::vector<uint32_t>& kpath) {
+    std::vector<uint32_t> lp;
+    for (uint32_t r : kpath) {
+        std::vector<uint32_t> nn;
+        for (auto& sg : L.kpath[r]) nn.push_back(sg.node);
+        if (nn.empty()) continue;
+        while (!lp.empty()) {
+            const auto& o = L.nodes[lp.back()].out;
+            if (o.empty() || !(nn[0] > o[0]) || std::find(o.begin(), o.end(), nn[0]) != o.end()) break;
+            lp.push_back(o[0]);
+        }
+        while (!lp.empty() && nn[0] <= lp.back()) lp.pop_back();
+        lp.insert(lp.end(), nn.begin(), nn.end());
+    }
+    if (lp.empty()) return top_path(L);
+    if (lp.front() != 0) {
+        const uint32_t target = lp.front();
+        std::vector<char> reaches(L.nodes.size(), 0);
+        reaches[target] = 1;
+        for (uint32_t i = target; i-- > 0;)
+            for (uint32_t o : L.nodes[i].out)
+                if (o <= target && reaches[o]) reaches[i] = 1;
+        std::vector<uint32_t> head;
+        uint32_t cur = 0;
+        while (cur != target) {
+            head.push_back(cur);
+            uint32_t nx = UINT32_MAX;
+            for (uint32_t o : L.nodes[cur].out)
+                if (o <= target && reaches[o]) {
+                    nx = o;
+                    break;
+                }
+            if (nx == UINT32_MAX) break;
+            cur = nx;
+        }
+        lp.insert(lp.begin(), head.begin(), head.end());
+    }
+    while (!L.nodes[lp.back()].out.empty()) lp.push_back(L.nodes[lp.back()].out[0]);
+    return lp;
+}
+
+void add_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref,
+                         const std::vector<uint32_t>& sp, std::vector<SiteRecord>& recs) {
+    const Locus& L = H.loci[locus];
+    std::vector<uint32_t> cum(ref.size() + 1, 0);
+    for (size_t i = 0; i < ref.size(); ++i) cum[i + 1] = cum[i] + L.node_len(ref[i]);
+    std::unique_ptr<KnodeRuns> KR;
+    size_t ri = 0, si = 0;
+    while (ri < ref.size() && si < sp.size()) {
+        size_t rj = ri + 1, sj = si + 1;
+        while (rj < ref.size() && sj < sp.size() && ref[rj] != sp[sj]) {
+            if (ref[rj] < sp[sj]) ++rj;
+            else ++sj;
+        }
+        if (rj >= ref.size() || sj >= sp.size()) break;
+        if (rj > ri + 1 || sj > si + 1) {
+            std::string rs, as;
+            for (size_t j = ri + 1; j < rj; ++j) rs += L.node_seq(ref[j]);
+            for (size_t j = si + 1; j < sj; ++j) as += L.node_seq(sp[j]);
+            const uint32_t pos = cum[ri + 1];
+            if (!(rs.empty() && as.empty()) && rs != as) {
+                bool found = false;
+                for (auto& r : recs)
+                    if (r.pos == pos && r.ref == rs && r.alts[0] == as) found = true;
+                if (!found) {
+                    if (!KR) KR.reset(new KnodeRuns(L));
+                    SiteRecord r;
+                    r.locus = locus;
+                    r.pos = pos;
+                    r.ref = rs;
+                    r.alts = {as};
+                    r.vc = "COMPLEX";
+                    r.graphtype = "TOO_MANY_ALTS";
+                    std::vector<uint32_t> ap(ref.begin(), ref.begin() + ri + 1);
+                    ap.insert(ap.end(), sp.begin() + si + 1, sp.begin() + sj);
+                    ap.insert(ap.end(), ref.begin() + rj, ref.end());
+                    r.allele_kn.push_back(kmers_over(L, *KR, ref, pos, pos + (uint32_t)rs.size()));
+                    r.allele_kn.push_back(kmers_over(L, *KR, ap, pos, pos + (uint32_t)as.size()));
+                    recs.push_back(std::move(r));
+                }
+            }
+        }
+        ri = rj;
+        si = sj;
+    }
+}
+
+std::vector<SiteRecord> merge_records(const Locus& L, const std::vector<uint32_t>& ref, std::vector<SiteRecord> recs) {
+    std::sort(recs.begin(), recs.end(), [](const SiteRecord& a, const SiteRecord& b) {
+        if (a.pos != b.pos) return a.pos < b.pos;
+        if (a.ref != b.ref) return a.ref < b.ref;
+        return a.alts < b.alts;
+    });
+    std::vector<SiteRecord> merged;
+    for (auto& r : recs) {
+        if (!merged.empty() && merged.back().pos == r.pos && merged.back().ref == r.ref &&
+            merged.back().graphtype != "TOO_MANY_ALTS" && r.graphtype != "TOO_MANY_ALTS") {
+            merged.back().alts.push_back(r.alts[0]);
+            merged.back().allele_kn.push_back(r.allele_kn[1]);
+        } else {
+            merged.push_back(r);
+        }
+    }
+    std::string refseq;
+    for (uint32_t n : ref) refseq += L.node_seq(n);
+    for (auto& r : merged) {
+        bool any_empty = r.ref.empty();
+        for (auto& a : r.alts) any_empty = any_empty || a.empty();
+        if (!any_empty) continue;
+        if (r.pos > 0) {
+            const char anchor = refseq[r.pos - 1];
+            r.pos -= 1;
+            r.ref.insert(r.ref.begin(), anchor);
+            for (auto& a : r.alts) a.insert(a.begin(), anchor);
+        } else if (r.pos + r.ref.size() < refseq.size()) {
+            const char anchor = refseq[r.pos + r.ref.size()];
+            r.ref.push_back(anchor);
+            for (auto& a : r.alts) a.push_back(anchor);
+        }
+    }
+    return merged;
+}
+
+bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& kpath,
+                            const std::vector<uint32_t>& lpath, const int32_t* cov, uint32_t global_covg) {
+    const Locus& L = H.loci[locus];
+    const uint32_t base = H.knode_base[locus];
+    std::vector<int> where(L.nodes.size(), -1);
+    std::vector<std::vector<uint32_t>> per_base(lpath.size());
+    for (size_t i = 0; i < lpath.size(); ++i) {
+        where[lpath[i]] = (int)i;
+        per_base[i].assign(L.node_len(lpath[i]), 0);
+    }
+    for (uint32_t r : kpath) {
+        const uint32_t g = base + r;
+        const uint32_t c = sat16(cov[2 * g]) + sat16(cov[2 * g + 1]);
+        for (auto& sg : L.kpath[r]) {
+            if (sg.s == sg.e || where[sg.node] < 0) continue;
+            auto& v = per_base[where[sg.node]];
+            for (uint32_t x = sg.s - L.nodes[sg.node].s; x < sg.e - L.nodes[sg.node].s; ++x) v[x] = std::max(v[x], c);
+        }
+    }
+    std::vector<uint32_t> flat;
+    for (auto& v : per_base) flat.insert(flat.end(), v.begin(), v.end());
+    if (flat.empty()) return false;
+    std::sort(flat.begin(), flat.end());
+    uint32_t mode = flat[0], best = 0;
+    for (size_t i = 0; i < flat.size();) {
+        size_t j = i;
+        while (j < flat.size() && flat[j] == flat[i]) ++j;
+        if (j - i > best) {
+            best = (uint32_t)(j - i);
+            mode = flat[i];
+        }
+        i = j;
+    }
+    return global_covg > 20 && ((uint64_t)mode * 10 < global_covg || mode > 10ull * global_covg);
+}
+
+// -------------------------------------------------------------------------- VCF ---
+static std::string g6(double v) {
+    char b[64];
+    snprintf(b, sizeof b, "%g", v);
+    return b;
+}
+
+std::string format_vcf(const HostIndex& H, const std::vector<SiteRecord>& recs, const GenotypeArrays& G,
+                       const std::vector<std::string>& contigs, const std::string& sample) {
+    std::string s;
+    s.reserve(4096 + recs.size() * 256);
+    char date[32];
+    time_t t = time(nullptr);
+    strftime(date, sizeof date, "%d/%m/%y", localtime(&t));
+    s += "##fileformat=VCFv4.3\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n##fileDate==";
+    s += date;
+    s += "\n##ALT=<ID=SNP,Description=\"SNP\">\n##ALT=<ID=PH_SNPs,Description=\"Phased SNPs\">\n"
+         "##ALT=<ID=INDEL,Description=\"Insertion-deletion\">\n"
+         "##ALT=<ID=COMPLEX,Description=\"Complex variant, collection of SNPs and indels\">\n"
+         "##INFO=<ID=VC,Number=1,Type=String,Description=\"Type (class) of variant\">\n"
+         "##ALT=<ID=SIMPLE,Description=\"Graph bubble is simple\">\n"
+         "##ALT=<ID=NESTED,Description=\"Variation site was a nested feature in the graph\">\n"
+         "##ALT=<ID=TOO_MANY_ALTS,Description=\"Variation site was a multinested feature with too many alts to include all in the VCF\">\n"
+         "##INFO=<ID=GRAPHTYPE,Number=1,Type=String,Description=\"Type of graph feature\">\n"
+         "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n";
+    static const char* tags[6] = {"MEAN_FWD_COVG", "MEAN_REV_COVG", "MED_FWD_COVG", "MED_REV_COVG", "SUM_FWD_COVG", "SUM_REV_COVG"};
+    static const char* desc[6] = {"Mean forward coverage", "Mean reverse coverage", "Med forward coverage",
+                                  "Med reverse coverage", "Sum forward coverage", "Sum reverse coverage"};
+    for (int i = 0; i < 6; ++i)
+        s += std::string("##FORMAT=<ID=") + tags[i] + ",Number=R,Type=Integer,Description=\"" + desc[i] + "\">\n";
+    s += "##FORMAT=<ID=GAPS,Number=R,Type=Float,Description=\"Number of gap bases\">\n"
+         "##FORMAT=<ID=LIKELIHOOD,Number=R,Type=Float,Description=\"Likelihood\">\n"
+         "##FORMAT=<ID=GT_CONF,Number=1,Type=Float,Description=\"Genotype confidence\">\n";
+    for (auto& c : contigs) s += "##contig=<ID=" + c + ">\n";
+    s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample + "\n";
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const SiteRecord& r = recs[i];
+        const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
+        s += H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
+        for (size_t a = 0; a < r.alts.size(); ++a) s += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
+        s += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
+             "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
+        s += G.gt[i] < 0 ? std::string(".") : std::to_string(G.gt[i]);
+        const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+        for (auto* col : cols) {
+            s += ':';
+            for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + std::to_string((*col)[a]);
+        }
+        s += ':';
+        for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + g6(G.gaps[a]);
+        s += ':';
+        for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + g6(G.lik[a]);
+        s += ':' + g6(G.gt_conf[i]) + '\n';
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------- IO ---
+namespace {
+struct GzLines {
+    gzFile f;
+    std::vector<char> buf;
+    explicit GzLines(const std::string& path) : buf(1 << 20) {
+        f = gzopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open " + path);
+        gzbuffer(f, 1 << 20);
+    }
+    ~GzLines() { gzclose(f); }
+    bool next(std::string& s) {
+        s.clear();
+        while (gzgets(f, buf.data(), (int)buf.size())) {
+            s += buf.data();
+            if (!s.empty() && s.back() == '\n') break;
+        }
+        if (s.empty()) return false;
+        while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back();
+        return true;
+    }
+};
+}  // namespace
+
+std::map<std::string, std::string> load_fasta(const std::string& path) {
+    std::map<std::string, std::string> m;
+    GzLines in(path);
+    std::string line, name;
+    while (in.next(line)) {
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            name = line.substr(1, line.find_first_of(" \t") == std::string::npos ? std::string::npos : line.find_first_of(" \t") - 1);
+            m[name];
+        } else if (!name.empty()) {
+            m[name] += line;
+        }
+    }
+    return m;
+}
+
+static inline uint32_t code4(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+    }
+    return 4;
+}
+
+static void pack_one(const uint8_t* s, uint32_t len, uint32_t* w, uint32_t& out_len) {
+    uint32_t bad = 0;
+    const uint32_t nw = (len + 15) / 16;
+    for (uint32_t j = 0; j < nw; ++j) {
+        uint32_t word = 0;
+        const uint32_t hi = std::min(len, (j + 1) * 16);
+        for (uint32_t i = j * 16; i < hi; ++i) {
+            uint32_t c = code4(s[i]);
+            bad |= c >> 2;
+            word |= (c & 3u) << (30 - 2 * (i & 15));
+        }
+        w[j] = word;
+    }
+    out_len = bad ? 0 : len;
+}
+
+int64_t pack_ascii(const uint8_t* ascii, const uint64_t* off, uint64_t n, uint32_t stride_words, uint32_t* words,
+                   uint64_t words_cap, uint64_t* word_off, uint32_t* lens) {
+    uint64_t cur = 0;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint32_t len = (uint32_t)(off[r + 1] - off[r]);
+        const uint32_t nw = (len + 15) / 16;
+        if (stride_words) {
+            if (nw > stride_words) return -1;
+            cur = r * (uint64_t)stride_words;
+        }
+        if (word_off) word_off[r] = cur;
+        if (cur + std::max(nw, stride_words) > words_cap) return -2;
+        if (stride_words) std::memset(words + cur, 0, (size_t)stride_words * 4);
+        pack_one(ascii + off[r], len, words + cur, lens[r]);
+        cur += stride_words ? stride_words : nw;
+    }
+    if (word_off) word_off[n] = stride_words ? n * (uint64_t)stride_words : cur;
+    return (int64_t)(stride_words ? n * (uint64_t)stride_words : cur);
+}
+
+void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& out) {
+    (void)threads;
+    out = PackedReads();
+    out.word_off.push_back(0);
+    GzLines in(path);
+    std::string line, seq, tmp;
+    bool have = in.next(line);
+    auto emit = [&](const std::string& s) {
+        const uint32_t len = (uint32_t)s.size();
+        const size_t at = out.words.size();
+        out.words.resize(at + (len + 15) / 16);
+        uint32_t l = 0;
+        pack_one((const uint8_t*)s.data(), len, out.words.data() + at, l);
+        if (out.lens.empty()) out.first_read_len = len;
+        if (l == 0 && len > 0) ++out.n_dropped;
+        out.lens.push_back(l);
+        out.word_off.push_back(out.words.size());
+        out.total_bases += len;
+    };
+    while (have) {
+        if (line.empty()) {
+            have = in.next(line);
+            continue;
+        }
+        if (line[0] == '>') {
+            seq.clear();
+            while ((have = in.next(line)) && (line.empty() || line[0] != '>')) seq += line;
+            emit(seq);
+        } else if (line[0] == '@') {
+            in.next(seq);
+            in.next(tmp);
+            in.next(tmp);
+            emit(seq);
+            have = in.next(line);
+        } else {
+            throw std::runtime_error("unrecognised read file format: " + path);
+        }
+    }
+}
+
+}  // namespace drprg

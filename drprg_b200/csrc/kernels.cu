@@ -1,0 +1,666 @@
+// Hand-written sm_100a kernels for the map hot path: read sketching + index lookup (S1+S2), hit
+// clustering (S3/S4), k-mer coverage (S5), ML path (S7) and genotyping (S8).  These replace the
+// per-read and per-locus loops of `pandora map` that drprg launches at
+// /root/reference/src/lib.rs:580-642 (argv :594-609, src/predict.rs:288-294); stage semantics
+// follow pandora's Seq::minimizer_sketch, add_read_hits, define_clusters, filter_clusters(2),
+// add_hits_to_kmergraphs, KmerGraphWithCoverage::find_max_path and SampleInfo.
+#include <cfloat>
+#include <cub/cub.cuh>
+
+#include "kernels.cuh"
+
+namespace drprg {
+
+static uint64_t g_launches = 0;
+uint64_t launch_count() { return g_launches; }
+
+#define FULL 0xffffffffu
+
+// ============================================================================================
+// S1 + S2 : sketch + lookup.  One warp per read; lanes own consecutive k-mer positions.
+//   * bases are 2-bit packed, first base in the top bits, so the forward k-mer at position p is a
+//     funnel shift of two words and the reverse complement is brev + pair swap of its complement;
+//   * k-mers are kept LEFT-ALIGNED in 32 bits (value << (32-2k)): every "& mask" of pandora's
+//     hash64 becomes the natural 2^32 wrap, the three shift-add steps become single IMADs
+//     (x2097151, x265, x21) and hash order is preserved, so the canonical min works in place;
+//   * window minima with all ties (pandora keeps every k-mer attaining a window minimum) are a
+//     sliding min followed by a sliding max of the minima, both by doubling in shared memory:
+//     position i is a minimizer  <=>  h[i] == max over windows s containing i of min(h[s..s+w)).
+// ============================================================================================
+constexpr int WARPS = 8;
+constexpr int EXT_MAX = CHUNK + 2 * (W_MAX - 1);
+constexpr int BUF_N = EXT_MAX + W_MAX + 2;
+constexpr int SW_N = (EXT_MAX + K_MAX + 15) / 16 + 3;
+
+__device__ __forceinline__ uint32_t hash_left_aligned(uint32_t K, uint32_t S, uint32_t hm) {
+    K = K * 2097151u - (1u << S);  // (~key + (key << 21)) & mask
+    K ^= (K >> 24) & hm;           // key ^= key >> 24
+    K *= 265u;                     // (key + (key << 3) + (key << 8)) & mask
+    K ^= (K >> 14) & hm;
+    K *= 21u;                      // (key + (key << 2) + (key << 4)) & mask
+    K ^= (K >> 28) & hm;
+    K += K << 31;                  // (key + (key << 31)) & mask : only bit 31 can change (k = 16)
+    return K;
+}
+
+__device__ __forceinline__ uint32_t table_slot(uint32_t h, uint32_t bits) { return (h * 0x9E3779B1u) >> (32 - bits); }
+
+template <bool LOOKUP>
+__global__ void __launch_bounds__(WARPS * 32) sketch_kernel(DevReads R, DevTable T, uint32_t w, uint32_t k,
+                                                           unsigned long long* __restrict__ out_a,
+                                                           unsigned long long* __restrict__ out_b,
+                                                           unsigned long long* __restrict__ out_count,
+                                                           unsigned long long cap) {
+    __shared__ uint32_t s_words[WARPS][SW_N];
+    __shared__ uint32_t s_h[WARPS][BUF_N];
+    __shared__ uint32_t s_a[WARPS][BUF_N];
+    __shared__ uint32_t s_b[WARPS][BUF_N];
+    __shared__ uint32_t s_strand[WARPS][(EXT_MAX + 31) / 32 + 1];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* sw = s_words[wid];
+    uint32_t* H = s_h[wid];
+    uint32_t* A = s_a[wid];
+    uint32_t* B = s_b[wid];
+    uint32_t* SS = s_strand[wid];
+    const uint32_t S = 32 - 2 * k;
+    const uint32_t hm = (S == 0) ? 0xffffffffu : ~((1u << S) - 1u);
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS;
+
+    for (unsigned long long r = (unsigned long long)blockIdx.x * WARPS + wid; r < R.n_reads; r += nwarps) {
+        const uint32_t len = R.lens[r];
+        if (len + 1 < w + k) continue;  // too short, or flagged 0 (non-ACGT): contributes nothing
+        const uint32_t nk = len - k + 1;
+        const unsigned long long wbase = R.stride_words ? r * R.stride_words : R.word_off[r];
+        const uint32_t nwords_read = (len + 15) >> 4;
+
+        for (uint32_t c0 = 0; c0 < nk; c0 += CHUNK) {
+            const uint32_t ext_lo = (c0 >= w - 1) ? c0 - (w - 1) : 0;
+            const uint32_t ext_hi = min(c0 + CHUNK + (w - 1), nk);
+            const uint32_t n_ext = ext_hi - ext_lo;
+            const uint32_t w0 = ext_lo >> 4;
+            const uint32_t nw = ((ext_hi + k - 2) >> 4) - w0 + 1;
+            __syncwarp();
+            for (uint32_t i = lane; i < nw + 1; i += 32) {
+                uint32_t wi = w0 + i;
+                sw[i] = (wi < nwords_read) ? __ldg(R.words + wbase + wi) : 0u;
+            }
+            __syncwarp();
+            // ---- canonical hashes of positions [ext_lo, ext_hi)
+            for (uint32_t e0 = 0; e0 < n_ext; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                const uint32_t b = 2u * (ext_lo + e - (w0 << 4));
+                const uint32_t wi = min(b >> 5, nw - 1);
+                const uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], b & 31u);
+                const uint32_t F = v & hm;
+                uint32_t y = __brev(~v & hm);
+                y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+                const uint32_t Rc = y << S;
+                const uint32_t hf = hash_left_aligned(F, S, hm), hr = hash_left_aligned(Rc, S, hm);
+                const bool valid = e < n_ext;
+                if (valid) H[e] = min(hf, hr);
+                const uint32_t bal = __ballot_sync(FULL, valid && hf <= hr);
+                if (lane == 0) SS[e0 >> 5] = bal;
+            }
+            __syncwarp();
+            // ---- sliding minimum over w consecutive hashes: wm[e] = min(H[e .. e+w-1])
+            uint32_t span = 1;
+            const uint32_t* src = H;
+            uint32_t* dst = A;
+            while (span * 2 <= w) {
+                const uint32_t cnt = n_ext - (2 * span - 1);
+                for (uint32_t e = lane; e < cnt; e += 32) dst[e] = min(src[e], src[e + span]);
+                __syncwarp();
+                src = dst;
+                dst = (dst == A) ? B : A;
+                span *= 2;
+            }
+            // padded array P[t], t in [0, n_ext + w - 1): windows start at ext_lo - (w-1) + t
+            const uint32_t n_win = n_ext - w + 1;
+            const uint32_t n_pad = n_ext + w - 1;
+            for (uint32_t t = lane; t < n_pad; t += 32) {
+                uint32_t val = 0;
+                if (t >= w - 1 && t - (w - 1) < n_win) {
+                    const uint32_t e = t - (w - 1);
+                    val = min(src[e], src[e + w - span]);
+                }
+                dst[t] = val;
+            }
+            __syncwarp();
+            // ---- sliding maximum of the window minima: X[e] = max(P[e .. e+w-1])
+            src = dst;
+            dst = (dst == A) ? B : A;
+            span = 1;
+            while (span * 2 <= w) {
+                const uint32_t cnt = n_pad - (2 * span - 1);
+                for (uint32_t t = lane; t < cnt; t += 32) dst[t] = max(src[t], src[t + span]);
+                __syncwarp();
+                src = dst;
+                dst = (dst == A) ? B : A;
+                span *= 2;
+            }
+            // ---- minimizers of this chunk
+            const uint32_t chunk_hi = min(c0 + CHUNK, nk);
+            for (uint32_t p0 = c0; p0 < chunk_hi; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const uint32_t e = p - ext_lo;
+                bool is_min = false;
+                uint32_t hv = 0;
+                if (p < chunk_hi) {
+                    const uint32_t x = max(src[e], src[e + w - span]);
+                    hv = H[e];
+                    is_min = (hv == x);
+                    hv >>= S;
+                }
+                const uint32_t read_strand = (SS[e >> 5] >> (e & 31)) & 1u;
+                if (!LOOKUP) {
+                    const uint32_t bal = __ballot_sync(FULL, is_min);
+                    if (bal) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(bal));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (is_min) {
+                            const unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
+                            if (o < cap) {
+                                out_a[o] = ((unsigned long long)(R.read_id_base + (uint32_t)r) << 32) | p;
+                                out_b[o] = ((unsigned long long)hv << 1) | read_strand;
+                            }
+                        }
+                    }
+                } else {
+                    bool pass = false;
+                    if (is_min) {
+                        const uint32_t fw = __ldg(T.filter + (hv & ((1u << T.filter_bits) - 1u)));
+                        const uint32_t m = (1u << ((hv >> T.filter_bits) & 31u)) | (1u << ((hv >> (T.filter_bits + 5)) & 31u));
+                        pass = (fw & m) == m;
+                    }
+                    if (__any_sync(FULL, pass)) {
+                        uint32_t rec_begin = 0, rec_n = 0;
+                        if (pass) {
+                            uint32_t slot = table_slot(hv, T.slot_bits);
+                            const uint32_t smask = (1u << T.slot_bits) - 1u;
+                            while (true) {
+                                const uint2 ent = __ldg(T.slots + slot);
+                                if (ent.y == 0u) break;
+                                if (ent.x == hv) {
+                                    rec_begin = ent.y & 0xffffffu;
+                                    rec_n = ent.y >> 24;
+                                    break;
+                                }
+                                slot = (slot + 1) & smask;
+                            }
+                        }
+                        // warp-aggregated append
+                        uint32_t incl = rec_n;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        const uint32_t total = __shfl_sync(FULL, incl, 31);
+                        if (total) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+                            base = __shfl_sync(FULL, base, 0) + (incl - rec_n);
+                            for (uint32_t j = 0; j < rec_n; ++j) {
+                                const uint2 rc = __ldg(T.recs + rec_begin + j);
+                                const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
+                                if (base + j < cap) {
+                                    out_a[base + j] = ((unsigned long long)(R.read_id_base + (uint32_t)r) << 32) |
+                                                      ((unsigned long long)(rc.y >> 1) << 16) | ((unsigned long long)(fwd ^ 1u) << 15);
+                                    out_b[base + j] = ((unsigned long long)p << 32) | rc.x;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int grid_for(int sm_count, uint64_t n_reads) {
+    // persistent-style grid: a multiple of the SM count, capped by the work available
+    long long want = (long long)((n_reads + WARPS - 1) / WARPS);
+    long long g = (long long)sm_count * 8;
+    if (want < g) g = want;
+    return (int)(g < 1 ? 1 : g);
+}
+
+void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
+                          unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
+                          cudaStream_t st) {
+    if (R.n_reads == 0) return;
+    sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
+    ++g_launches;
+}
+
+void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
+                        unsigned long long* d_count, uint64_t cap, int sm_count, cudaStream_t st) {
+    if (R.n_reads == 0) return;
+    DevTable T{};
+    sketch_kernel<false><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_key, d_val, d_count, cap);
+    ++g_launches;
+}
+
+// ============================================================================================
+// hit ordering: stable LSD radix sort on lo then hi  ==  order by (hi, lo)
+// ============================================================================================
+size_t sort_hits_temp_bytes(uint64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)n, 0, 64);
+    return bytes;
+}
+
+void sort_hits(void* d_temp, size_t temp_bytes, unsigned long long* hi_in, unsigned long long* lo_in,
+               unsigned long long* hi_tmp, unsigned long long* lo_tmp, uint64_t n, int read_bits, int start_bits,
+               int knode_bits, cudaStream_t st) {
+    if (n == 0) return;
+    // pass A: key = lo (start | knode), value = hi.  knode occupies bits [0,knode_bits), start [32,32+start_bits)
+    (void)knode_bits;
+    cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, lo_in, lo_tmp, hi_in, hi_tmp, (int64_t)n, 0, 32 + start_bits, st);
+    // pass B: key = hi (read | prg | strand), value = lo
+    cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, hi_tmp, hi_in, lo_tmp, lo_in, (int64_t)n, 15, 32 + read_bits, st);
+    g_launches += 2;
+}
+
+// ============================================================================================
+// S3 + S4 : clustering.  Hits are sorted (read, prg, fwd-first, read_start, knode), so a read's
+// hits are contiguous; the thread sitting on a read's first hit walks that read: splits clusters
+// (pandora define_clusters), applies the size threshold, then filter_clusters (adjacent pairs in
+// clusterComp order) and filter_clusters2 (by decreasing size, drop clusters whose read span is
+// already covered).  Reads carry tens of hits and a handful of clusters, so per-read work is tiny.
+// ============================================================================================
+__device__ __forceinline__ uint32_t hit_read(unsigned long long hi) { return (uint32_t)(hi >> 32); }
+__device__ __forceinline__ uint32_t hit_prg(unsigned long long hi) { return (uint32_t)(hi >> 16) & 0xffffu; }
+__device__ __forceinline__ uint32_t hit_fwd(unsigned long long hi) { return (((uint32_t)hi >> 15) & 1u) ^ 1u; }
+__device__ __forceinline__ uint32_t hit_start(unsigned long long lo) { return (uint32_t)(lo >> 32); }
+
+__global__ void cluster_filter_kernel(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ lo,
+                                      unsigned long long n, uint32_t max_diff, const uint32_t* __restrict__ thresh,
+                                      uint32_t* __restrict__ clist, uint32_t* __restrict__ clist2,
+                                      uint32_t* __restrict__ cend, uint8_t* __restrict__ calive,
+                                      uint8_t* __restrict__ kept, int32_t* __restrict__ locus_reads) {
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= n) return;
+    const uint32_t read = hit_read(hi[i0]);
+    if (i0 > 0 && hit_read(hi[i0 - 1]) == read) return;  // not the first hit of its read
+    // ---- define_clusters
+    uint32_t ncl = 0;
+    unsigned long long b = i0, i = i0 + 1;
+    while (true) {
+        bool split = true, end_of_read = true;
+        if (i < n && hit_read(hi[i]) == read) {
+            end_of_read = false;
+            const unsigned long long hp = hi[i - 1], hc = hi[i];
+            const long long d = (long long)hit_start(lo[i]) - (long long)hit_start(lo[i - 1]);
+            split = (hit_prg(hp) != hit_prg(hc)) || (hit_fwd(hp) != hit_fwd(hc)) || ((d < 0 ? -d : d) > (long long)max_diff);
+        }
+        if (split) {
+            const uint32_t size = (uint32_t)(i - b);
+            if (size > thresh[hit_prg(hi[b])]) {
+                clist[i0 + ncl] = (uint32_t)(b - i0);
+                cend[b] = (uint32_t)(i - i0);
+                calive[b] = 1;
+                ++ncl;
+            }
+            b = i;
+        }
+        if (end_of_read) break;
+        ++i;
+    }
+    if (ncl == 0) return;
+    auto c_first = [&](uint32_t c) { return hit_start(lo[i0 + c]); };
+    auto c_last = [&](uint32_t c) { return hit_start(lo[i0 + cend[i0 + c] - 1]); };
+    auto c_size = [&](uint32_t c) { return cend[i0 + c] - c; };
+    auto c_prg = [&](uint32_t c) { return hit_prg(hi[i0 + c]); };
+    auto c_fwd = [&](uint32_t c) { return hit_fwd(hi[i0 + c]); };
+    // ---- filter_clusters: order (first start, size desc, prg, fwd asc); adjacent-pair sweep
+    if (ncl > 1) {
+        auto before = [&](uint32_t x, uint32_t y) {
+            if (c_first(x) != c_first(y)) return c_first(x) < c_first(y);
+            if (c_size(x) != c_size(y)) return c_size(x) > c_size(y);
+            if (c_prg(x) != c_prg(y)) return c_prg(x) < c_prg(y);
+            return c_fwd(x) < c_fwd(y);
+        };
+        for (uint32_t a = 1; a < ncl; ++a) {  // insertion sort of clist[i0 .. i0+ncl)
+            const uint32_t v = clist[i0 + a];
+            uint32_t j = a;
+            while (j > 0 && before(v, clist[i0 + j - 1])) {
+                clist[i0 + j] = clist[i0 + j - 1];
+                --j;
+            }
+            clist[i0 + j] = v;
+        }
+        uint32_t prev = clist[i0];
+        for (uint32_t t = 1; t < ncl; ++t) {
+            const uint32_t cur = clist[i0 + t];
+            const bool cond = (c_prg(cur) == c_prg(prev) && c_fwd(cur) != c_fwd(prev)) || (c_last(cur) <= c_last(prev));
+            if (cond) {
+                if (c_size(prev) >= c_size(cur)) {
+                    calive[i0 + cur] = 0;
+                    continue;
+                }
+                calive[i0 + prev] = 0;
+            }
+            prev = cur;
+        }
+        // ---- filter_clusters2
+        uint32_t n2 = 0;
+        for (uint32_t t = 0; t < ncl; ++t)
+            if (calive[i0 + clist[i0 + t]]) clist2[i0 + n2++] = clist[i0 + t];
+        auto before2 = [&](uint32_t x, uint32_t y) {
+            if (c_size(x) != c_size(y)) return c_size(x) > c_size(y);
+            if (c_first(x) != c_first(y)) return c_first(x) < c_first(y);
+            if (c_prg(x) != c_prg(y)) return c_prg(x) < c_prg(y);
+            return c_fwd(x) < c_fwd(y);
+        };
+        for (uint32_t a = 1; a < n2; ++a) {
+            const uint32_t v = clist2[i0 + a];
+            uint32_t j = a;
+            while (j > 0 && before2(v, clist2[i0 + j - 1])) {
+                clist2[i0 + j] = clist2[i0 + j - 1];
+                --j;
+            }
+            clist2[i0 + j] = v;
+        }
+        for (uint32_t t = 1; t < n2; ++t) {
+            const uint32_t c = clist2[i0 + t];
+            const uint32_t z = c_last(c);
+            uint32_t cur = c_first(c);
+            bool contained = true;
+            while (cur < z) {
+                uint32_t best = cur;
+                for (uint32_t u = 0; u < t; ++u) {
+                    const uint32_t pc = clist2[i0 + u];
+                    if (!calive[i0 + pc]) continue;  // erased clusters never marked the read
+                    if (c_first(pc) <= cur && cur < c_last(pc)) best = max(best, c_last(pc));
+                }
+                if (best == cur) {
+                    contained = false;
+                    break;
+                }
+                cur = best;
+            }
+            if (contained) calive[i0 + c] = 0;
+        }
+    }
+    // ---- add_clusters_to_pangraph: mark kept hits, count supporting reads per locus
+    for (uint32_t t = 0; t < ncl; ++t) {
+        const uint32_t c = clist[i0 + t];
+        if (!calive[i0 + c]) continue;
+        const uint32_t e = cend[i0 + c];
+        for (uint32_t j = c; j < e; ++j) kept[i0 + j] = 1;
+        atomicAdd(locus_reads + c_prg(c), 1);
+    }
+}
+
+void launch_cluster_filter(const unsigned long long* hi, const unsigned long long* lo, uint64_t n, uint32_t max_diff,
+                           const uint32_t* d_thresh_per_prg, uint32_t* d_clist, uint32_t* d_clist2, uint32_t* d_cend,
+                           uint8_t* d_calive, uint8_t* d_kept, int32_t* d_locus_reads, cudaStream_t st) {
+    if (n == 0) return;
+    cudaMemsetAsync(d_kept, 0, n, st);
+    cudaMemsetAsync(d_calive, 0, n, st);
+    const int threads = 128;
+    cluster_filter_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(hi, lo, n, max_diff, d_thresh_per_prg,
+                                                                                      d_clist, d_clist2, d_cend, d_calive,
+                                                                                      d_kept, d_locus_reads);
+    ++g_launches;
+}
+
+// ============================================================================================
+// S5 : coverage.  key = 2 * global knode + (reverse ? 1 : 0) for kept hits; sorted keys; the thread
+// on the first element of each run finds the run's end by binary search and adds the run length
+// to that counter (one writer per counter: no atomics).
+// ============================================================================================
+__global__ void cov_keys_kernel(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ lo,
+                                const uint8_t* __restrict__ kept, unsigned long long n,
+                                const uint32_t* __restrict__ knode_base, uint32_t* __restrict__ keys) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = 0xffffffffu;
+    if (kept[i]) {
+        const unsigned long long h = hi[i];
+        const uint32_t g = knode_base[hit_prg(h)] + (uint32_t)lo[i];
+        key = 2u * g + (hit_fwd(h) ^ 1u);
+    }
+    keys[i] = key;
+}
+
+__global__ void cov_runs_kernel(const uint32_t* __restrict__ keys, unsigned long long n, int32_t* __restrict__ cov,
+                                unsigned long long* __restrict__ n_kept) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    if (i > 0 && keys[i - 1] == key) return;
+    if (key == 0xffffffffu) {  // first discarded hit: everything before it was kept
+        *n_kept += i;
+        return;
+    }
+    unsigned long long lo_ = i, hi_ = n;  // first index with keys[idx] > key
+    while (lo_ < hi_) {
+        const unsigned long long mid = (lo_ + hi_) >> 1;
+        if (keys[mid] <= key) lo_ = mid + 1;
+        else hi_ = mid;
+    }
+    cov[key] += (int32_t)(lo_ - i);
+    if (lo_ == n) *n_kept += n;  // no discarded hits at all
+}
+
+size_t sort_cov_temp_bytes(uint64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 32);
+    return bytes;
+}
+
+void launch_coverage(const unsigned long long* hi, const unsigned long long* lo, const uint8_t* kept, uint64_t n,
+                     const uint32_t* d_knode_base, uint32_t* d_keys, uint32_t* d_keys_sorted, void* d_temp,
+                     size_t temp_bytes, int key_bits, int32_t* d_cov, unsigned long long* d_n_kept, cudaStream_t st) {
+    if (n == 0) return;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    cov_keys_kernel<<<blocks, threads, 0, st>>>(hi, lo, kept, n, d_knode_base, d_keys);
+    (void)key_bits;  // discarded hits carry 0xffffffff, so all 32 bits take part
+    cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_keys, d_keys_sorted, (int64_t)n, 0, 32, st);
+    cov_runs_kernel<<<blocks, threads, 0, st>>>(d_keys_sorted, n, d_cov, d_n_kept);
+    g_launches += 3;
+}
+
+// ============================================================================================
+// S7 : node log-probabilities and the max-likelihood path
+// ============================================================================================
+__device__ __forceinline__ uint32_t cov_sat(int32_t c) { return c > 65535 ? 65535u : (uint32_t)c; }  // uint16 upstream
+
+__device__ double node_log_prob(const ModelParams& P, uint32_t f, uint32_t r, bool terminal) {
+    if (P.bin) {
+        if (terminal) return 0.0;
+        const uint32_t s = f + r;
+        const double n = (double)(s > P.exp_depth ? s : P.exp_depth);
+        const double lnck2 = lgamma(n + 1.0) - lgamma((double)f + 1.0) - lgamma((double)r + 1.0) - lgamma(n - (double)f - (double)r + 1.0);
+        if (s > P.exp_depth) return lnck2 + (double)s * log(P.bin_p / 2);
+        return lnck2 + (double)s * log(P.bin_p / 2) + (double)(P.exp_depth - s) * log(1 - P.bin_p);
+    }
+    const double c = (double)f + (double)r;
+    const double v = lgamma(c + P.nb_r) - lgamma(P.nb_r) - lgamma(c + 1.0) + P.nb_r * log(P.nb_p) + c * log(1.0 - P.nb_p);
+    const double FLOOR = -(double)FLT_MAX / 1000.0;
+    return v > FLOOR ? v : FLOOR;
+}
+
+__global__ void node_prob_kernel(const int32_t* __restrict__ cov, uint32_t total, const uint8_t* __restrict__ is_terminal,
+                                 ModelParams P, double* __restrict__ prob) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    prob[g] = node_log_prob(P, cov_sat(cov[2 * g]), cov_sat(cov[2 * g + 1]), is_terminal[g] != 0);
+}
+
+void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t* d_is_terminal, ModelParams P,
+                      double* d_prob, cudaStream_t st) {
+    if (!total_knodes) return;
+    node_prob_kernel<<<(total_knodes + 255) / 256, 256, 0, st>>>(d_cov, total_knodes, d_is_terminal, P, d_prob);
+    ++g_launches;
+}
+
+// One warp per locus.  The recurrence is a chain (node j needs its successors), and the choice
+// among successors is order dependent (1e-6 tolerance, longer path wins ties), so lane 0 walks the
+// nodes in reverse rank order; the windowed mean needs the node `window` steps down the chosen
+// path, found in O(log window) with binary-lifting pointers instead of pandora's linear walk.
+__global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
+                              const uint32_t* __restrict__ edges, const double* __restrict__ prob,
+                              const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ M,
+                              uint32_t* __restrict__ len, uint32_t* __restrict__ prev, uint32_t* __restrict__ up,
+                              uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len) {
+    const uint32_t l = blockIdx.x;
+    if (l >= n_loci || threadIdx.x != 0) return;
+    const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
+    if (locus_reads[l] <= 0 || n < 2) {
+        path_len[l] = 0xffffffffu;
+        return;
+    }
+    int LV = 1;
+    while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
+    const double tol = 0.000001;
+    const uint32_t term = n - 1;
+    M[base + term] = 0.0;
+    len[base + term] = 0;
+    prev[base + term] = term;
+    for (int v = 0; v < LV; ++v) up[(size_t)v * total + base + term] = term;
+    for (uint32_t j = term; j-- > 0;) {
+        double max_mean = -(double)FLT_MAX;
+        uint32_t max_len = 0;
+        double Mj = 0.0;
+        uint32_t lenj = 0, prevj = term;
+        const double pj = prob[base + j];
+        for (uint32_t e = edge_off[base + j]; e < edge_off[base + j + 1]; ++e) {
+            const uint32_t v = edges[e];
+            const bool is_term = (v == term);
+            bool take;
+            const double Mv = M[base + v];
+            const uint32_t lv = len[base + v];
+            if (is_term) {
+                take = P.thresh > max_mean + tol;
+            } else {
+                const double mean_v = Mv / (double)lv;
+                take = (mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len);
+            }
+            if (!take) continue;
+            Mj = pj + Mv;
+            lenj = 1 + lv;
+            prevj = v;
+            if (lenj > P.window) {
+                uint32_t pn = v, steps = P.window - 1;
+                for (int b = 0; steps; ++b, steps >>= 1)
+                    if (steps & 1u) pn = up[(size_t)b * total + base + pn];
+                Mj -= prob[base + pn];
+                lenj -= 1;
+            }
+            if (!is_term) {
+                max_mean = Mv / (double)lv;
+                max_len = lv;
+            } else {
+                max_mean = P.thresh;
+            }
+        }
+        M[base + j] = Mj;
+        len[base + j] = lenj;
+        prev[base + j] = prevj;
+        up[base + j] = prevj;
+        for (int v = 1; v < LV; ++v) {
+            const uint32_t mid = up[(size_t)(v - 1) * total + base + j];
+            up[(size_t)v * total + base + j] = up[(size_t)(v - 1) * total + base + mid];
+        }
+    }
+    uint32_t cnt = 0, p = prev[base];
+    while (p < term && cnt < n) {
+        path[base + cnt++] = p;
+        p = prev[base + p];
+    }
+    path_len[l] = cnt;
+}
+
+void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
+                   const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
+                   uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
+                   cudaStream_t st) {
+    if (!n_loci) return;
+    mlpath_kernel<<<n_loci, 32, 0, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
+                                         d_prev, d_up, total_knodes, d_path, d_path_len);
+    ++g_launches;
+}
+
+// ============================================================================================
+// S8 : per-allele statistics and genotype likelihoods
+// ============================================================================================
+__global__ void allele_stats_kernel(const int32_t* __restrict__ cov, DevGenotype G, uint32_t min_kmer_covg) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= G.n_alleles) return;
+    const uint32_t b = G.allele_off[a], e = G.allele_off[a + 1], n = e - b;
+    uint32_t sf = 0, sr = 0, gaps = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t g = G.allele_kn[i];
+        const uint32_t f = cov_sat(cov[2 * g]), r = cov_sat(cov[2 * g + 1]);
+        sf += f;
+        sr += r;
+        if (f + r < min_kmer_covg) ++gaps;
+    }
+    // integer median by rank selection (n is a handful of k-mers): no scratch memory needed
+    uint32_t med[2] = {0, 0};
+    if (n) {
+        const uint32_t r_hi = n / 2, r_lo = (n % 2) ? n / 2 : n / 2 - 1;
+        for (int s = 0; s < 2; ++s) {
+            uint32_t v_lo = 0, v_hi = 0;
+            for (uint32_t i = b; i < e; ++i) {
+                const uint32_t vi = cov_sat(cov[2 * G.allele_kn[i] + s]);
+                uint32_t less = 0, leq = 0;
+                for (uint32_t j = b; j < e; ++j) {
+                    const uint32_t vj = cov_sat(cov[2 * G.allele_kn[j] + s]);
+                    less += vj < vi;
+                    leq += vj <= vi;
+                }
+                if (less <= r_lo && r_lo < leq) v_lo = vi;
+                if (less <= r_hi && r_hi < leq) v_hi = vi;
+            }
+            med[s] = (n % 2) ? v_hi : (v_lo + v_hi) / 2;
+        }
+    }
+    G.sum_fwd[a] = sf;
+    G.sum_rev[a] = sr;
+    G.mean_fwd[a] = n ? sf / n : 0;
+    G.mean_rev[a] = n ? sr / n : 0;
+    G.med_fwd[a] = med[0];
+    G.med_rev[a] = med[1];
+    G.gaps[a] = n ? (double)gaps / (double)n : 0.0;
+}
+
+__global__ void genotype_kernel(DevGenotype G, ModelParams P) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.n_records) return;
+    const uint32_t b = G.rec_off[r], e = G.rec_off[r + 1];
+    const double E = (double)P.exp_depth;
+    double total = 0.0;
+    for (uint32_t a = b; a < e; ++a) total += (double)G.mean_fwd[a] + (double)G.mean_rev[a];
+    const double lnE = log(E), lnerr = log(P.gt_err), ln1m = log(1.0 - exp(-E));
+    uint32_t best = b;
+    for (uint32_t a = b; a < e; ++a) {
+        const double c = (double)G.mean_fwd[a] + (double)G.mean_rev[a];
+        const double g = G.gaps[a];
+        const double L = -E + c * lnE - lgamma(c + 1.0) + (total - c) * lnerr - E * g + ln1m * (1.0 - g);
+        G.lik[a] = L;
+        if (L > G.lik[best]) best = a;
+    }
+    double second = -INFINITY;
+    for (uint32_t a = b; a < e; ++a)
+        if (a != best && G.lik[a] > second) second = G.lik[a];
+    const double conf = (e - b > 1) ? fabs(G.lik[best] - second) : 0.0;
+    G.gt_conf[r] = conf;
+    G.gt[r] = (conf >= P.gt_conf) ? (int32_t)(best - b) : -1;
+}
+
+void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st) {
+    if (!G.n_records) return;
+    allele_stats_kernel<<<(G.n_alleles + 127) / 128, 128, 0, st>>>(d_cov, G, P.min_kmer_covg);
+    genotype_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, P);
+    g_launches += 2;
+}
+
+}  // namespace drprg

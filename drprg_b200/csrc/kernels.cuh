@@ -1,0 +1,91 @@
+// Device-side interface of the map hot path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace drprg {
+
+constexpr int W_MAX = 32;    // largest minimizer window supported on the device
+constexpr int K_MAX = 16;    // 2k <= 32: k-mers and hashes live in one 32-bit register
+constexpr int CHUNK = 192;   // k-mer positions a warp resolves per pass (a 150 bp read is one pass)
+constexpr int LV_MAX = 12;   // binary-lifting levels of the windowed ML-path score (window <= 4095)
+
+// packed reads resident in HBM
+struct DevReads {
+    const uint32_t* words;     // 2-bit bases, 16 per word, first base in the top bits
+    const uint64_t* word_off;  // n+1 word offsets, or nullptr when stride_words > 0
+    uint32_t stride_words;
+    const uint32_t* lens;      // bases per read; 0 = dropped (non-ACGT)
+    uint64_t n_reads;
+    uint32_t read_id_base;
+};
+
+// minimizer index resident in HBM (small: lives in L2)
+struct DevTable {
+    const uint2* slots;      // {hash, rec_begin | rec_count << 24}; y == 0 => empty
+    uint32_t slot_bits;      // table has 1 << slot_bits slots
+    const uint2* recs;       // {knode rank within locus, prg << 1 | strand}, grouped by hash
+    const uint32_t* filter;  // blocked 2-bit Bloom pre-filter, 1 << filter_bits words
+    uint32_t filter_bits;
+};
+
+struct Hit128 {  // sort key: (hi, lo) ascending == pandora MinimizerHit order
+    unsigned long long hi;  // read_id << 32 | prg << 16 | (!forward) << 15
+    unsigned long long lo;  // read_start << 32 | knode rank
+};
+
+struct ModelParams {  // S6 output, computed on the host
+    int bin;
+    double nb_p, nb_r;
+    double bin_p;          // 1 / exp(e_rate * k)
+    uint32_t exp_depth;    // E (integer)
+    double thresh;
+    uint32_t window;       // max_num_kmers_to_average
+    uint32_t min_kmer_covg;
+    double gt_err, gt_conf;
+};
+
+uint64_t launch_count();
+
+// S1+S2: sketch every read and probe the index; hits appended (unordered) through *hit_count
+void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
+                          unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
+                          cudaStream_t st);
+// S1 only (parity hook): emits key = read << 32 | start, val = hash << 1 | strand
+void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
+                        unsigned long long* d_count, uint64_t cap, int sm_count, cudaStream_t st);
+// 128-bit radix sort of the hits by (hi, lo); temp storage managed by the caller
+size_t sort_hits_temp_bytes(uint64_t n);
+void sort_hits(void* d_temp, size_t temp_bytes, unsigned long long* hi_in, unsigned long long* lo_in,
+               unsigned long long* hi_tmp, unsigned long long* lo_tmp, uint64_t n, int read_bits, int start_bits,
+               int knode_bits, cudaStream_t st);  // result ends in (hi_in, lo_in)
+// S3+S4: clusters per read, size and overlap filters; kept[i] in {0,1}; locus read counts accumulate
+void launch_cluster_filter(const unsigned long long* hi, const unsigned long long* lo, uint64_t n, uint32_t max_diff,
+                           const uint32_t* d_thresh_per_prg, uint32_t* d_clist, uint32_t* d_clist2, uint32_t* d_cend,
+                           uint8_t* d_calive, uint8_t* d_kept, int32_t* d_locus_reads, cudaStream_t st);
+// S5: coverage keys -> sort -> run lengths added to the accumulator (no atomics)
+size_t sort_cov_temp_bytes(uint64_t n);
+void launch_coverage(const unsigned long long* hi, const unsigned long long* lo, const uint8_t* kept, uint64_t n,
+                     const uint32_t* d_knode_base, uint32_t* d_keys, uint32_t* d_keys_sorted, void* d_temp,
+                     size_t temp_bytes, int key_bits, int32_t* d_cov, unsigned long long* d_n_kept, cudaStream_t st);
+// S7: per-node log-probabilities then one warp per locus for the ML-path DP
+void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t* d_is_terminal, ModelParams P,
+                      double* d_prob, cudaStream_t st);
+void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
+                   const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
+                   uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
+                   cudaStream_t st);
+// S8: per-allele coverage statistics, then per-record likelihoods / GT / GT_CONF
+struct DevGenotype {
+    uint32_t n_records, n_alleles;
+    const uint32_t* rec_off;     // n_records+1 -> alleles
+    const uint32_t* allele_off;  // n_alleles+1 -> allele_kn
+    const uint32_t* allele_kn;   // global knode ids
+    uint32_t *mean_fwd, *mean_rev, *med_fwd, *med_rev, *sum_fwd, *sum_rev;
+    double *gaps, *lik, *gt_conf;
+    int32_t* gt;
+};
+void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st);
+
+}  // namespace drprg

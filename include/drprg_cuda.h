@@ -1,0 +1,148 @@
+/* drprg_cuda.h — C ABI of the B200-native replacement for the `pandora map --genotype --local`
+ * step of `drprg predict`.
+ *
+ * Reference interface replaced: Pandora::genotype_with(prg, vcf_ref, reads, outdir, args)
+ *   /root/reference/src/lib.rs:580-642, called from /root/reference/src/predict.rs:296-302 with
+ *   the argv of src/lib.rs:594-609 + src/predict.rs:288-294.  The callee writes
+ *   <outdir>/pandora_genotyped.vcf (src/lib.rs:644-646) and <outdir>/pandora.log (src/lib.rs:592).
+ *   Success <=> return 0 (the reference maps a non-zero exit status to
+ *   DependencyError::ProcessError, src/lib.rs:629-641); drprg_cuda_last_error() carries the text the
+ *   reference would have logged from stderr.
+ *
+ * All pointers are plain host pointers unless a parameter is documented as a device pointer.
+ * No torch types cross this boundary.  Every function is thread-compatible (one index per thread).
+ */
+#ifndef DRPRG_CUDA_H
+#define DRPRG_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRPRG_CUDA_VERSION 100 /* 0.1.0 */
+
+typedef struct drprg_index drprg_index; /* PRG + k-mer graphs + minimizer table, resident in HBM */
+typedef struct drprg_batch drprg_batch; /* 2-bit packed reads, resident in HBM */
+
+/* mirrors the pandora argv drprg builds: -t, -c, -I, -K, -g, --max-covg, --gt-conf (src/lib.rs:594-609,
+ * src/predict.rs:288-294) plus pandora defaults drprg never overrides (0 = pandora default):
+ * -E genotyping error rate 0.01, -m max_diff 250, -e error rate 0.11 (0.001 and 2k+1 under -I). */
+typedef struct {
+    uint32_t threads;          /* -t  (host threads for FASTQ parse/pack) */
+    uint32_t min_cluster_size; /* -c  (drprg default 10, src/predict.rs:194-196) */
+    uint8_t illumina;          /* -I */
+    uint8_t debug;             /* -K */
+    uint32_t genome_size;      /* -g  (drprg passes 4411532, src/lib.rs:36) */
+    uint32_t max_covg;         /* --max-covg (drprg passes u32::MAX = never subsample) */
+    double gt_conf;            /* --gt-conf (drprg passes 0) */
+    double genotyping_error_rate;
+    uint32_t max_diff;
+    double error_rate;
+} drprg_map_opts;
+
+typedef struct {
+    uint64_t n_reads, n_reads_dropped, total_bases;
+    uint64_t n_hits, n_hits_kept;
+    uint32_t n_loci_present, n_records;
+    uint32_t exp_depth_covg;
+    double ms_ingest, ms_map, ms_genotype, ms_total;
+} drprg_map_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int drprg_cuda_version(void);
+const char* drprg_cuda_last_error(void); /* thread-local, valid until the next call */
+int drprg_cuda_device_count(void);
+
+/* Parse the PRG text (pandora format, e.g. /root/reference/tests/cases/expected/dr.prg), sketch it with
+ * (w,k), build k-mer graphs + minimizer hash table and upload them to `device`.  Replaces what
+ * `pandora index` (src/lib.rs:479-510) writes and `pandora map` re-loads (dr.prg.kK.wW.idx, kmer_prgs/).
+ * device = -1 builds a host-only handle for index introspection (no GPU needed); every compute entry point
+ * refuses such a handle — there is no CPU fallback for the map path. */
+int drprg_cuda_index_load(const char* prg_path, uint32_t w, uint32_t k, int device, drprg_index** out);
+int drprg_cuda_index_load_text(const char* prg_text, uint32_t w, uint32_t k, int device, drprg_index** out);
+void drprg_cuda_index_free(drprg_index*);
+
+/* ---- the drop-in call: one sample, files in, pandora_genotyped.vcf out -------------------------- */
+int drprg_cuda_map_genotype(drprg_index*, const char* reads_path, const char* vcf_refs_fasta, const char* outdir,
+                            const drprg_map_opts*, drprg_map_stats* out_stats /* may be NULL */);
+/* config 5: independent samples, one after another on this index's GPU (sample-sharding across GPUs is
+ * one process per GPU, each calling this on its share) */
+int drprg_cuda_map_genotype_batch(drprg_index*, size_t n, const char* const* reads_paths, const char* vcf_refs_fasta,
+                                  const char* const* outdirs, const drprg_map_opts*, drprg_map_stats* out_stats /* n or NULL */);
+
+/* ---- staged interface (multi-GPU read sharding, benches, parity tests) -------------------------- */
+/* host 2-bit packer: ASCII reads (concatenated, off[n+1]) -> words/word_off/lens.  Base i of a read sits in
+ * bits [30-2(i%16), 31-2(i%16)] of word i/16 (A0 C1 G2 T3).  A read with a non-ACGT base gets lens=0
+ * (pandora drops such reads).  stride_words>0 => fixed stride (word_off may be NULL).  Returns words used. */
+int64_t drprg_cuda_pack_reads(const uint8_t* ascii, const uint64_t* off, uint64_t n_reads, uint32_t stride_words,
+                              uint32_t* words, uint64_t words_cap, uint64_t* word_off, uint32_t* lens);
+/* read a fasta/fastq(.gz) file and pack it (host); caller frees with drprg_cuda_host_free */
+int drprg_cuda_read_fastx(const char* path, uint32_t threads, uint32_t** words, uint64_t** word_off, uint32_t** lens,
+                          uint64_t* n_reads, uint64_t* total_bases, uint32_t* first_read_len);
+void drprg_cuda_host_free(void*);
+
+/* H2D copy of a packed batch (pinned staging inside).  read_id_base = global id of the batch's first read. */
+int drprg_cuda_batch_upload(drprg_index*, const uint32_t* words, const uint64_t* word_off /* NULL if stride */,
+                            uint32_t stride_words, const uint32_t* lens, uint64_t n_reads, uint64_t total_bases,
+                            uint32_t read_id_base, void* stream, drprg_batch** out);
+/* adopt device-resident arrays (no copy; caller keeps ownership) */
+int drprg_cuda_batch_wrap_device(drprg_index*, const void* d_words, const void* d_word_off, uint32_t stride_words,
+                                 const void* d_lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base,
+                                 drprg_batch** out);
+void drprg_cuda_batch_free(drprg_batch*);
+
+/* start a sample: zero the coverage accumulators, fix the options (thresholds depend on -c/-I and on the
+ * length of the sample's first read, pandora's expected_number_kmers_in_short_read_sketch) */
+int drprg_cuda_sample_begin(drprg_index*, const drprg_map_opts*, uint32_t first_read_len);
+/* S1-S5 for one batch on `stream`: sketch -> lookup -> sort -> cluster/filter -> coverage (+=) */
+int drprg_cuda_map_batch(drprg_index*, drprg_batch*, void* stream, uint64_t* n_hits, uint64_t* n_kept);
+/* packed int32 accumulator [2*total_knodes coverage (fwd,rev interleaved) | n_loci locus read counts |
+ * total_bases lo24,hi | n_reads lo24,hi]: device pointer + element count, for an in-place allreduce(sum)
+ * across ranks (NCCL via torch.distributed) before genotyping.  Scalars are flushed by this call. */
+int drprg_cuda_accum_device_ptr(drprg_index*, void** d_ptr, uint64_t* n_int32);
+int drprg_cuda_accum_download(drprg_index*, int32_t* out, uint64_t n_int32);
+int drprg_cuda_accum_upload(drprg_index*, const int32_t* in, uint64_t n_int32);
+/* S6-S8 from the accumulators: parameters (host), ML path + genotype kernels; keeps results for the getters */
+int drprg_cuda_genotype(drprg_index*, const char* vcf_refs_fasta /* NULL = top path */, const char* sample_name);
+int drprg_cuda_write_vcf(drprg_index*, const char* path);
+const char* drprg_cuda_vcf_text(drprg_index*);
+
+/* ---- introspection / parity hooks (same .so, used by tests and bench) --------------------------- */
+typedef struct {
+    uint32_t w, k, n_loci, total_knodes;
+    uint64_t n_records, n_edges, n_path_intervals;
+    uint32_t table_slots, filter_words;
+} drprg_index_info;
+int drprg_cuda_index_info(drprg_index*, drprg_index_info*);
+const char* drprg_cuda_locus_name(drprg_index*, uint32_t locus);
+int drprg_cuda_index_knode_base(drprg_index*, uint32_t* out /* n_loci+1 */);
+int drprg_cuda_index_knodes(drprg_index*, uint64_t* hash, uint8_t* strand, uint32_t* n_out, uint32_t* n_iv);
+int drprg_cuda_index_edges(drprg_index*, uint32_t* edges /* global ids */);
+int drprg_cuda_index_paths(drprg_index*, uint32_t* iv_start, uint32_t* iv_len);
+int drprg_cuda_index_records(drprg_index*, uint64_t* hash, uint32_t* prg, uint32_t* knode, uint8_t* strand);
+int drprg_cuda_index_min_path_length(drprg_index*, uint32_t* out /* n_loci */);
+/* S1 only: all (w,k)-minimizers of the batch, ordered (read, start); returns count (or <0) */
+int64_t drprg_cuda_sketch_batch(drprg_index*, drprg_batch*, void* stream, uint32_t* read, uint32_t* start,
+                                uint64_t* hash, uint8_t* strand, uint64_t cap);
+/* hits of the last drprg_cuda_map_batch, sorted (read, prg, fwd first, start, knode) */
+int64_t drprg_cuda_last_hits(drprg_index*, uint32_t* read, uint32_t* start, uint32_t* prg, uint32_t* knode,
+                             uint8_t* fwd, uint8_t* kept, uint64_t cap);
+/* genotype results: out[11] = E, bin, nb_p, nb_r, e_rate, thresh, covg, min_kmer_covg, mean, var, num_reads */
+int drprg_cuda_gt_params(drprg_index*, double* out);
+int64_t drprg_cuda_gt_mlpath(drprg_index*, uint32_t locus, uint32_t* out, uint64_t cap); /* -1: locus absent */
+int drprg_cuda_gt_counts(drprg_index*, uint32_t* n_records, uint32_t* n_alleles, uint64_t* n_allele_knodes);
+int drprg_cuda_gt_records(drprg_index*, uint32_t* locus, uint32_t* pos, uint32_t* n_alleles, int32_t* gt, double* gt_conf);
+int drprg_cuda_gt_alleles(drprg_index*, double* lik, double* gaps, uint32_t* mean_fwd, uint32_t* mean_rev,
+                          uint32_t* med_fwd, uint32_t* med_rev, uint32_t* sum_fwd, uint32_t* sum_rev, uint32_t* n_knodes);
+int drprg_cuda_gt_allele_knodes(drprg_index*, uint32_t* out);
+/* kernel timing of the last map_batch in ms (CUDA events on its stream): [sketch_lookup, sort, cluster, coverage] */
+int drprg_cuda_last_timings(drprg_index*, float* out4);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t drprg_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

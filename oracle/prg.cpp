@@ -4,6 +4,8 @@
 // (walk), kmergraph.cpp.  Reference call sites: /root/reference/src/lib.rs:479-510 (pandora index),
 // :580-642 (pandora map).  PRG grammar pinned by /root/reference/tests/cases/expected/dr.prg.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cassert>
 #include <deque>
 #include <fstream>
@@ -234,28 +236,30 @@ void KmerGraph::finalize() {
 }
 
 // pandora KmerGraph::remove_shortcut_edges: drop a->c when a->b->c exists and b lies on the
-// PRG path spanned by a and c (b.path is a subpath of union(a.path, c.path)).
+// PRG path spanned by a and c (b.path is a subpath of union(a.path, c.path)).  All removals are
+// decided against the original edge set (order-free), then applied together.
 void KmerGraph::remove_shortcut_edges() {
+    std::vector<std::pair<uint32_t, uint32_t>> kill;
     for (auto& n : nodes) {
-        bool again = true;
-        while (again) {
-            again = false;
+        for (uint32_t c : n.out) {
+            bool shortcut = false;
             for (uint32_t b : n.out) {
-                for (uint32_t c : nodes[b].out) {
-                    auto it = std::find(n.out.begin(), n.out.end(), c);
-                    if (it == n.out.end()) continue;
-                    if (!path_less(n.path, nodes[c].path)) continue;
-                    Path u = path_union(n.path, nodes[c].path);
-                    if (u.empty() || !path_is_subpath(nodes[b].path, u)) continue;
-                    n.out.erase(it);
-                    auto& in = nodes[c].in;
-                    in.erase(std::find(in.begin(), in.end(), n.id));
-                    again = true;
-                    break;
-                }
-                if (again) break;
+                if (b == c) continue;
+                if (std::find(nodes[b].out.begin(), nodes[b].out.end(), c) == nodes[b].out.end()) continue;
+                if (!path_less(n.path, nodes[c].path)) continue;
+                Path u = path_union(n.path, nodes[c].path);
+                if (u.empty() || !path_is_subpath(nodes[b].path, u)) continue;
+                shortcut = true;
+                break;
             }
+            if (shortcut) kill.push_back({n.id, c});
         }
+    }
+    for (auto& e : kill) {
+        auto& o = nodes[e.first].out;
+        o.erase(std::find(o.begin(), o.end(), e.second));
+        auto& in = nodes[e.second].in;
+        in.erase(std::find(in.begin(), in.end(), e.first));
     }
 }
 

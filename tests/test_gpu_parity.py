@@ -1,0 +1,223 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs.  Integer stages are compared bit-exactly; log-likelihoods at 1e-9 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from drprg_b200 import lib, sim
+from helpers import TOY_PRG, TOY_REFS, long_reads_sample, panel_sample, reads_from_strings, small_panel
+
+pytestmark = pytest.mark.gpu
+
+
+def both_indexes(prg, w, k):
+    return lib.Index(prg, w, k, device=0), O.Index(prg, w, k)
+
+
+def gpu_sketch(gx, data, off, stride_words=0):
+    words, woff, lens = lib.pack_reads(data, off, stride_words)
+    b = gx.upload(words, woff, lens, stride_words=stride_words)
+    return gx.sketch(b, cap=max(4096, len(data)))
+
+
+def oracle_sketch_all(data, off, w, k):
+    rd, st, hs, sd = [], [], [], []
+    for i in range(len(off) - 1):
+        h, s, d = O.sketch(data[int(off[i]):int(off[i + 1])].tobytes(), w, k)
+        rd += [i] * len(h); st += s.tolist(); hs += h.tolist(); sd += d.tolist()
+    return dict(read=np.array(rd, np.uint32), start=np.array(st, np.uint32), hash=np.array(hs, np.uint64), strand=np.array(sd, np.uint8))
+
+
+def assert_sketch_equal(a, b):
+    for k in ("read", "start", "hash", "strand"):
+        assert len(a[k]) == len(b[k]), (k, len(a[k]), len(b[k]))
+        assert (a[k] == b[k]).all(), k
+
+
+@pytest.mark.parametrize("w,k", [(11, 15), (14, 15), (1, 15), (32, 16), (5, 7), (19, 11), (11, 16), (8, 3)])
+def test_sketch_parity_edge_cases(w, k):
+    gx = lib.Index(TOY_PRG, w, k, device=0)
+    rng = np.random.default_rng(w * 100 + k)
+    strs = []
+    for L in [0, 1, k - 1, k, w + k - 2, w + k - 1, w + k, 100, 150, 151, 191 + k, 192 + k, 193 + k, 400, 1000, 5000]:
+        strs.append("".join("ACGT"[i] for i in rng.integers(0, 4, size=L)))
+    strs.append("A" * 300)                                  # homopolymer: every k-mer ties
+    strs.append("ACGT" * 100)                               # short tandem repeat
+    strs.append(strs[9][:70] + "N" + strs[9][71:])          # non-ACGT base drops the read
+    strs.append(strs[9].lower())                            # soft-masked bases hash like upper case
+    strs.append("AC" * 80 + "GATTACA" * 30)
+    data, off = reads_from_strings(strs)
+    assert_sketch_equal(gpu_sketch(gx, data, off), oracle_sketch_all(data, off, w, k))
+
+
+def test_sketch_parity_fixed_stride_and_ragged():
+    w, k = 11, 15
+    gx = lib.Index(TOY_PRG, w, k, device=0)
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=20, decoys=3, seed=5)
+    want = oracle_sketch_all(d, o, w, k)
+    assert_sketch_equal(gpu_sketch(gx, d, o, stride_words=10), want)
+    assert_sketch_equal(gpu_sketch(gx, d, o, stride_words=0), want)
+    rng = np.random.default_rng(3)
+    strs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(L))) for L in rng.integers(0, 700, size=300)]
+    data, off = reads_from_strings(strs)
+    assert_sketch_equal(gpu_sketch(gx, data, off), oracle_sketch_all(data, off, w, k))
+
+
+def test_empty_batch():
+    gx = lib.Index(TOY_PRG, 11, 15, device=0)
+    data, off = reads_from_strings([])
+    words, woff, lens = lib.pack_reads(data, off)
+    gx.sample_begin(lib.make_opts(illumina=True), 150)
+    b = gx.upload(words, woff, lens)
+    assert gx.map_batch(b) == (0, 0)
+    gx.genotype(TOY_REFS)
+    assert [l for l in gx.vcf().splitlines() if not l.startswith("#")] == []
+
+
+def run_both(prg, refs, data, off, w=11, k=15, illumina=True, genome_size=4411532, stride_words=0, n_batches=1, c=10):
+    gx, ox = both_indexes(prg, w, k)
+    oo = O.make_opts(illumina=illumina, genome_size=genome_size, min_cluster_size=c)
+    go = lib.make_opts(illumina=illumina, genome_size=genome_size, min_cluster_size=c)
+    first_len = int(off[1] - off[0]) if len(off) > 1 else 0
+    mr = O.MapRun(ox, data, off, oo)
+    gx.sample_begin(go, first_len)
+    n = len(off) - 1
+    hits = []
+    bounds = np.linspace(0, n, n_batches + 1).astype(int)
+    for bi in range(n_batches):
+        lo, hi = int(bounds[bi]), int(bounds[bi + 1])
+        sub_off = off[lo:hi + 1] - off[lo]
+        sub = data[int(off[lo]):int(off[hi])]
+        words, woff, lens = lib.pack_reads(sub, sub_off, stride_words)
+        b = gx.upload(words, woff, lens, total_bases=int(sub_off[-1]), stride_words=stride_words, read_id_base=lo)
+        nh, nk = gx.map_batch(b)
+        h = gx.last_hits(nh)
+        assert int(h["kept"].sum()) == nk
+        hits.append(h)
+    gh = {key: np.concatenate([h[key] for h in hits]) for key in hits[0]}
+    return gx, ox, mr, gh, oo
+
+
+def assert_map_equal(gx, mr, gh):
+    oh = mr.hits()
+    for key in ("read", "prg", "fwd", "start", "knode", "kept"):
+        assert len(gh[key]) == len(oh[key]), (key, len(gh[key]), len(oh[key]))
+        assert (gh[key] == oh[key]).all(), key
+    cov = gx.coverage()
+    f, r = mr.coverage()
+    assert (cov["fwd"] == f).all() and (cov["rev"] == r).all()
+    assert (cov["locus_reads"] == mr.locus_reads()).all()
+    sc = mr.scalars()
+    assert cov["total_bases"] == sc["total_bases"] and cov["n_reads"] == sc["n_reads"]
+
+
+def assert_genotype_equal(gx, ox, mr, oo, refs):
+    og = O.Genotype(ox, mr, oo, refs)
+    gx.genotype(refs)
+    gp, op = gx.params(), og.params()
+    for key in op:
+        assert gp[key] == op[key], (key, gp[key], op[key])
+    for l in range(ox.n_loci):
+        a, b = gx.mlpath(l), og.mlpath(l)
+        assert (a is None) == (b is None), l
+        if a is not None:
+            assert len(a) == len(b) and (a == b).all(), ("ml path", l)
+    gr, orr = gx.gt_records(), og.records()
+    for key in ("locus", "pos", "n_alleles", "gt", "mean_fwd", "mean_rev", "med_fwd", "med_rev", "sum_fwd", "sum_rev",
+                "n_knodes", "allele_knodes", "gaps"):
+        assert len(gr[key]) == len(orr[key]), key
+        assert (gr[key] == orr[key]).all(), key
+    # log-likelihoods: fp64 on both sides, 1e-9 relative (BASELINE.json north_star)
+    np.testing.assert_allclose(gr["lik"], orr["lik"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(gr["gt_conf"], orr["gt_conf"], rtol=1e-9, atol=1e-9)
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    assert strip(gx.vcf()) == strip(og.vcf())
+    return og
+
+
+def test_toy_config1_full_pipeline():
+    """BASELINE config 1: the reference's toy PRG (gid, pncA), simulated Illumina reads + decoys."""
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=60, decoys=5, seed=1)
+    for w in (11, 14):
+        gx, ox, mr, gh, oo = run_both(TOY_PRG, TOY_REFS, d, o, w=w, genome_size=2000, stride_words=10)
+        assert len(gh["read"]) > 1000
+        assert_map_equal(gx, mr, gh)
+        og = assert_genotype_equal(gx, ox, mr, oo, TOY_REFS)
+        assert len(og.records()["pos"]) == 23
+
+
+def test_synthetic_panel_illumina_multibatch():
+    p, prg, refs = small_panel()
+    d, o, g, pl = panel_sample(p, 60000)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10, n_batches=3)
+    assert gh["kept"].sum() > 10000
+    assert_map_equal(gx, mr, gh)
+    og = assert_genotype_equal(gx, ox, mr, oo, refs)
+    r = og.records()
+    assert (r["gt"] > 0).sum() > 10  # the sample carries alt alleles and they are called
+
+
+def test_synthetic_panel_nanopore_long_reads():
+    """config 4 shape: long noisy reads, no -I (max_diff 250, e_rate 0.11), ragged lengths, multi-chunk sketch."""
+    p, prg, refs = small_panel()
+    d, o, g, pl = long_reads_sample(p, 600)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, illumina=False, genome_size=len(g))
+    assert gh["kept"].sum() > 1000
+    assert_map_equal(gx, mr, gh)
+    assert_genotype_equal(gx, ox, mr, oo, refs)
+
+
+def test_low_min_cluster_size_many_clusters():
+    """-c 2 lets short spurious clusters through so the overlap filters (filter_clusters/2) do real work."""
+    p, prg, refs = small_panel()
+    d, o, g, pl = long_reads_sample(p, 300, seed=33, mean_len=6000)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, illumina=False, genome_size=len(g), c=2)
+    assert_map_equal(gx, mr, gh)
+    assert_genotype_equal(gx, ox, mr, oo, refs)
+
+
+def test_coverage_is_additive_over_shards():
+    """read sharding (BASELINE config 3): per-shard accumulators summed == single run (the allreduce identity)."""
+    p, prg, refs = small_panel()
+    d, o, g, pl = panel_sample(p, 30000, seed=41)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10)
+    whole = gx.accum_download()
+    go = lib.make_opts(illumina=True, genome_size=len(g))
+    n = len(o) - 1
+    parts = []
+    for s in range(4):
+        lo, hi = n * s // 4, n * (s + 1) // 4
+        sub_off = o[lo:hi + 1] - o[lo]
+        words, woff, lens = lib.pack_reads(d[int(o[lo]):int(o[hi])], sub_off, 10)
+        gx.sample_begin(go, 150)
+        gx.map_batch(gx.upload(words, woff, lens, total_bases=int(sub_off[-1]), stride_words=10, read_id_base=lo))
+        parts.append(gx.accum_download().astype(np.int64))
+    tot = sum(parts)
+    # scalars are split lo24/hi: recombine before comparing
+    def scal(a):
+        return (int(a[-4]) + (int(a[-3]) << 24), int(a[-2]) + (int(a[-1]) << 24))
+    assert (tot[:-4] == whole[:-4]).all()
+    assert scal(tot) == scal(whole.astype(np.int64))
+    gx.sample_begin(go, 150)
+    gx.accum_upload(tot.astype(np.int32))
+    assert_genotype_equal(gx, ox, mr, oo, refs)
+
+
+def test_drop_in_call_writes_pandora_vcf(tmp_path):
+    """drprg_cuda_map_genotype == Pandora::genotype_with: files in, outdir/pandora_genotyped.vcf out."""
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=40, decoys=2, seed=9)
+    fq = tmp_path / "reads.fq.gz"
+    sim.write_fastq(str(fq), d, o, gz=True)
+    gx, ox = both_indexes(TOY_PRG, 11, 15)
+    st = gx.map_genotype(fq, TOY_REFS, tmp_path, lib.make_opts(illumina=True, genome_size=2000))
+    assert st["n_reads"] == len(o) - 1 and st["n_records"] == 23
+    assert (tmp_path / "pandora.log").exists()
+    got = (tmp_path / "pandora_genotyped.vcf").read_text()
+    oo = O.make_opts(illumina=True, genome_size=2000)
+    og = O.Genotype(ox, O.MapRun(ox, d, o, oo), oo, TOY_REFS)
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    assert strip(got) == strip(og.vcf())
+    with pytest.raises(lib.DrprgCudaError):
+        gx.map_genotype(tmp_path / "missing.fq", TOY_REFS, tmp_path)

@@ -1,0 +1,96 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, the host index builder agrees with the oracle, the packer round-trips, and compute
+entry points refuse to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from drprg_b200 import lib, sim
+from helpers import TOY_PRG, TOY_REFS, small_panel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "drprg_cuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(drprg_cuda_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(lib.SYMBOLS)
+    L = lib.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.drprg_cuda_version() == 100
+
+
+@pytest.mark.parametrize("w,k", [(11, 15), (14, 15), (5, 7), (20, 11), (1, 15), (11, 16)])
+def test_host_index_builder_matches_oracle_toy(w, k):
+    gx = lib.Index(TOY_PRG, w, k, device=-1)
+    ox = O.Index(TOY_PRG, w, k)
+    assert gx.names == ox.names and gx.total_knodes == ox.total_knodes
+    assert (gx.knode_base == ox.knode_base).all()
+    a, b = gx.knodes(), ox.knodes()
+    for key in ("n_out", "n_iv", "edges", "iv_start", "iv_len"):
+        assert (a[key] == b[key]).all(), key
+    inner = b["hash"] != np.uint64(2 ** 64 - 1)
+    assert (a["hash"][inner] == b["hash"][inner]).all() and (a["strand"][inner] == b["strand"][inner]).all()
+    ra, rb = gx.records(), ox.records()
+    for key in ra:
+        assert (ra[key] == rb[key]).all(), key
+    assert gx.min_path_lengths().tolist() == [ox.min_path_length(i) for i in range(ox.n_loci)]
+
+
+def test_host_index_builder_matches_oracle_panel():
+    p, prg, refs = small_panel()
+    gx = lib.Index(prg, 11, 15, device=-1)
+    ox = O.Index(prg, 11, 15)
+    a, b = gx.knodes(), ox.knodes()
+    for key in ("n_out", "n_iv", "edges", "iv_start", "iv_len"):
+        assert (a[key] == b[key]).all(), key
+    ra, rb = gx.records(), ox.records()
+    for key in ra:
+        assert (ra[key] == rb[key]).all(), key
+
+
+def test_every_linear_minimizer_of_a_prg_path_is_indexed():
+    """SURVEY A.4 property: sketching any full path of the PRG as a linear sequence only yields
+    k-mers the graph sketch indexed (so reads from any haplotype of the panel find their k-mer nodes)."""
+    p, prg, refs = small_panel()
+    ox = O.Index(prg, 11, 15)
+    rec = ox.records()
+    for li, locus in enumerate(p.loci):
+        have = set(rec["hash"][rec["prg"] == li].tolist())
+        rng = np.random.default_rng(li)
+        for trial in range(6):
+            seq = locus.spell(lambda site: int(rng.integers(0, len(site.alleles))))
+            h, s, d = O.sketch(seq, 11, 15)
+            missing = [int(x) for x in h if int(x) not in have]
+            assert not missing, (locus.name, trial, len(missing))
+
+
+def test_packer_layout_and_flags():
+    strs = ["ACGT" * 5, "T" * 33, "ACGNACGT", "", "acgtACGT"]
+    data = np.frombuffer("".join(strs).encode(), np.uint8).copy()
+    off = np.zeros(len(strs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in strs])
+    words, woff, lens = lib.pack_reads(data, off)
+    w2, o2, l2 = sim.pack_reads(data, off)
+    assert (words == w2).all() and (woff == o2).all() and (lens == l2).all()
+    assert lens.tolist() == [20, 33, 0, 0, 8]
+    assert words[0] == int("00011011" * 4, 2)        # ACGT ACGT ACGT ACGT, first base in the top bits
+    assert words[int(woff[1])] == 0xFFFFFFFF         # 16 T
+    words, woff, lens = lib.pack_reads(data, off, stride_words=3)
+    assert len(words) == 15 and words[3] == 0xFFFFFFFF and words[5] == 0xC0000000
+    with pytest.raises(lib.DrprgCudaError):
+        lib.pack_reads(data, off, stride_words=2)     # 33 bases need 3 words
+
+
+def test_compute_refuses_without_gpu():
+    gx = lib.Index(TOY_PRG, 11, 15, device=-1)
+    with pytest.raises(lib.DrprgCudaError, match="no CPU fallback"):
+        gx.sample_begin(lib.make_opts(), 150)
+    with pytest.raises(lib.DrprgCudaError):
+        gx.map_genotype("x.fq", TOY_REFS, ".")
+    with pytest.raises(lib.DrprgCudaError, match="k > 16|no CUDA device"):
+        lib.Index(TOY_PRG, 11, 17, device=0)
