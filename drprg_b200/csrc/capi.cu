@@ -8,6 +8,7 @@
 #include <cmath>
 #include <map>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <memory>
 #include <stdexcept>
@@ -56,6 +57,33 @@ T* to_device(const std::vector<T>& v) {
     return d;
 }
 
+// freed batch buffers are parked here and reused by the next upload: cudaFree synchronises the device and
+// cudaMalloc costs ~0.1-1 ms, both of which would sit inside every end-to-end step
+struct DevPool {
+    struct Slot { void* p; size_t bytes; int device; };
+    std::vector<Slot> free_;
+    void* get(size_t bytes, int device) {
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); ++i)
+            if (free_[i].device == device && free_[i].bytes >= bytes && (best == free_.size() || free_[i].bytes < free_[best].bytes)) best = i;
+        if (best != free_.size() && free_[best].bytes <= bytes * 2 + (1 << 20)) {
+            void* p = free_[best].p;
+            free_.erase(free_.begin() + best);
+            return p;
+        }
+        void* p = nullptr;
+        CK(cudaMalloc(&p, bytes));
+        return p;
+    }
+    void put(void* p, size_t bytes, int device) {
+        if (free_.size() >= 16) {
+            cudaFree(free_.front().p);
+            free_.erase(free_.begin());
+        }
+        free_.push_back({p, bytes, device});
+    }
+} g_pool;
+
 int bits_for(uint64_t v) {
     int b = 1;
     while (b < 64 && (v >> b)) ++b;
@@ -71,7 +99,10 @@ struct drprg_batch {
     uint32_t *d_words = nullptr, *d_lens = nullptr;
     uint64_t* d_off = nullptr;
     bool owned = false;
+    size_t b_words = 0, b_lens = 0, b_off = 0;
+    int device = 0;
     uint64_t total_bases = 0;
+    uint32_t max_len = UINT32_MAX;  // longest read (bound); selects the short-read kernel
 };
 
 struct drprg_index {
@@ -106,14 +137,26 @@ struct drprg_index {
     // genotype state
     std::string refs_path;
     std::map<std::string, std::string> refs;
-    std::vector<std::vector<uint32_t>> ref_paths;
-    std::vector<std::vector<SiteRecord>> site_cache;
-    std::vector<char> site_cached;
+    struct LocusSites {  // read-independent site tables of one locus for the current --vcf-refs
+        bool ready = false;
+        std::vector<uint32_t> ref_path;
+        std::vector<SiteRecord> biallelic, merged;
+        SiteKeySet known;
+    };
+    std::vector<LocusSites> sites;
+    std::vector<uint32_t> loci_by_name;
     FitParams fit;
     std::vector<std::vector<uint32_t>> mlpaths;
     std::vector<char> present;
-    std::vector<SiteRecord> records;
+    std::vector<const SiteRecord*> records, csr_records;  // csr_records: what the device CSR was built for
+    std::deque<std::vector<SiteRecord>> sample_records;    // per-sample merged lists (ML path added records)
     GenotypeArrays GA;
+    uint32_t *d_rec_off = nullptr, *d_allele_off = nullptr, *d_allele_kn = nullptr, *d_knode_locus = nullptr, *d_hist = nullptr;
+    DBuf<uint32_t> d_gt_u32;
+    DBuf<double> d_gt_f64;
+    DBuf<int32_t> d_gt_i32;
+    uint32_t max_locus_knodes = 0;
+    double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::string> contigs;
     std::string vcf;
     bool have_gt = false;
@@ -124,12 +167,14 @@ struct drprg_index {
         if (device < 0) return;
         cudaSetDevice(device);
         for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
-                        (void*)d_is_terminal, (void*)d_accum, (void*)d_thresh, (void*)d_counters})
+                        (void*)d_is_terminal, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
+                        (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist})
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
         hi.release(); lo.release(); hi2.release(); lo2.release();
         clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release();
         calive.release(); kept.release(); temp.release();
+        d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
         d_prob.release(); d_M.release(); d_len.release(); d_prev.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
@@ -204,9 +249,18 @@ void upload_index(drprg_index* X) {
     CK(cudaMalloc(&X->d_counters, 2 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&X->h_counters, 2 * sizeof(unsigned long long)));
     for (auto& e : X->ev) CK(cudaEventCreate(&e));
-    X->ref_paths.resize(H.loci.size());
-    X->site_cache.resize(H.loci.size());
-    X->site_cached.assign(H.loci.size(), 0);
+    std::vector<uint32_t> knode_locus(N);
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        for (uint32_t g = H.knode_base[l]; g < H.knode_base[l + 1]; ++g) knode_locus[g] = (uint32_t)l;
+        X->max_locus_knodes = std::max(X->max_locus_knodes, H.knode_base[l + 1] - H.knode_base[l]);
+    }
+    X->d_knode_locus = to_device(knode_locus);
+    CK(cudaMalloc(&X->d_hist, 200 * sizeof(uint32_t)));
+    X->sites.assign(H.loci.size(), drprg_index::LocusSites());
+    X->loci_by_name.resize(H.loci.size());
+    for (uint32_t l = 0; l < H.loci.size(); ++l) X->loci_by_name[l] = l;
+    std::sort(X->loci_by_name.begin(), X->loci_by_name.end(),
+              [&](uint32_t a, uint32_t b) { return H.loci[a].name < H.loci[b].name; });
 }
 
 int load_common(const std::string& text, uint32_t w, uint32_t k, int device, drprg_index** out) {
@@ -292,7 +346,7 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     CK(cudaEventRecord(X->ev[0], st));
     for (int attempt = 0; attempt < 3; ++attempt) {
         CK(cudaMemsetAsync(X->d_counters, 0, 2 * sizeof(unsigned long long), st));
-        launch_sketch_lookup(B->R, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, st);
+        launch_sketch_lookup(B->R, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(X->h_counters, X->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -303,12 +357,7 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
         CK(cudaEventRecord(X->ev[0], st));
     }
     CK(cudaEventRecord(X->ev[1], st));
-    uint32_t max_len = 1;  // read_start < longest read: use the batch's word span as a bound
-    {
-        uint64_t max_words = B->R.stride_words ? B->R.stride_words : 0;
-        if (!max_words) max_words = (B->total_bases + 15) / 16 + 1;
-        max_len = (uint32_t)std::min<uint64_t>(UINT32_MAX, max_words * 16);
-    }
+    const uint32_t max_len = B->max_len;  // read_start < longest read
     sort_hits(X->temp.p, X->temp.cap, X->hi.p, X->lo.p, X->hi2.p, X->lo2.p, nh,
               bits_for((uint64_t)B->R.read_id_base + B->R.n_reads), bits_for(max_len), 32, st);
     CK(cudaEventRecord(X->ev[2], st));
@@ -340,10 +389,17 @@ void flush_scalars(drprg_index* X) {
 
 void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
+    need_device(X);
     CK(cudaSetDevice(X->device));
     const HostIndex& H = X->H;
     const uint32_t N = H.total_knodes(), P = (uint32_t)H.loci.size();
     cudaStream_t st = 0;
+    double t0 = now_ms();
+    auto lap = [&](int i) {
+        const double t = now_ms();
+        X->gt_ms[i] = t - t0;
+        t0 = t;
+    };
     flush_scalars(X);
     std::vector<int32_t> acc(X->n_accum);
     CK(cudaMemcpy(acc.data(), X->d_accum, acc.size() * 4, cudaMemcpyDeviceToHost));
@@ -351,7 +407,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     const int32_t* locus_reads = acc.data() + 2ull * N;
     const int32_t* sc = acc.data() + X->n_accum - 4;
     const uint64_t total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
-    // ---- S6 on the host
+    lap(0);
+    // ---- S6: moments / model choice on the host, log-prob histogram on the device
     X->fit = fit_parameters(H, cov, locus_reads, total_bases, X->opts);
     ModelParams MP{};
     MP.bin = X->fit.bin;
@@ -359,111 +416,132 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     MP.nb_r = X->fit.nb_r;
     MP.bin_p = 1.0 / std::exp(X->fit.e_rate * H.k);
     MP.exp_depth = X->fit.E;
-    MP.thresh = (double)X->fit.thresh;
     MP.window = X->opts.window;
     MP.min_kmer_covg = X->fit.min_kmer_covg;
     MP.gt_err = X->opts.gt_error_rate;
     MP.gt_conf = X->opts.gt_conf;
-    // ---- S7 on the device
     X->d_prob.ensure(N); X->d_M.ensure(N); X->d_len.ensure(N); X->d_prev.ensure(N);
     X->d_up.ensure((size_t)N * LV_MAX); X->d_path.ensure(N); X->d_path_len.ensure(P);
     launch_node_prob(X->d_accum, N, X->d_is_terminal, MP, X->d_prob.p, st);
+    launch_prob_hist(X->d_prob.p, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist, st);
+    uint32_t hist[200];
+    CK(cudaMemcpy(hist, X->d_hist, sizeof hist, cudaMemcpyDeviceToHost));
+    bool any_present = false;
+    for (uint32_t l = 0; l < P; ++l) any_present = any_present || locus_reads[l] > 0;
+    if (any_present) X->fit.thresh = prob_threshold(hist);
+    MP.thresh = (double)X->fit.thresh;
+    lap(1);
+    // ---- S7 on the device
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
-                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, st);
+                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, st);
     CK(cudaGetLastError());
     std::vector<uint32_t> path(N), plen(P);
     CK(cudaMemcpy(path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost));
+    lap(2);
     // ---- reference paths / site tables (read independent, cached per --vcf-refs file)
     const std::string rp = vcf_refs ? vcf_refs : "";
-    if (rp != X->refs_path || X->site_cached.empty()) {
+    if (rp != X->refs_path) {
         X->refs = rp.empty() ? std::map<std::string, std::string>() : load_fasta(rp);
         X->refs_path = rp;
-        std::fill(X->site_cached.begin(), X->site_cached.end(), 0);
+        for (auto& s : X->sites) s = drprg_index::LocusSites();
+        X->csr_records.clear();
     }
     X->mlpaths.assign(P, {});
     X->present.assign(P, 0);
     X->records.clear();
+    X->sample_records.clear();
     X->contigs.clear();
-    for (uint32_t l = 0; l < P; ++l) {
+    for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
         if (plen[l] == 0xffffffffu || plen[l] == 0) continue;
         const Locus& L = H.loci[l];
         std::vector<uint32_t> kp(path.begin() + H.knode_base[l], path.begin() + H.knode_base[l] + plen[l]);
         std::vector<uint32_t> lp = local_path_of(L, kp);
         if (locus_coverage_outlier(H, l, kp, lp, cov, X->fit.covg)) continue;
         X->present[l] = 1;
-        X->mlpaths[l] = kp;
+        X->mlpaths[l] = std::move(kp);
         X->contigs.push_back(L.name);
-        if (!X->site_cached[l]) {
-            std::vector<uint32_t> ref;
+        auto& S = X->sites[l];
+        if (!S.ready) {
             auto it = X->refs.find(L.name);
-            if (it != X->refs.end()) ref = thread_sequence(L, it->second);
-            if (ref.empty()) ref = top_path(L);
-            X->ref_paths[l] = ref;
-            X->site_cache[l] = enumerate_sites(H, l, ref);
-            X->site_cached[l] = 1;
+            if (it != X->refs.end()) S.ref_path = thread_sequence(L, it->second);
+            if (S.ref_path.empty()) S.ref_path = top_path(L);
+            S.biallelic = enumerate_sites(H, l, S.ref_path);
+            for (auto& r : S.biallelic) S.known.insert(std::make_tuple(r.pos, r.ref, r.alts[0]));
+            S.merged = merge_records(L, S.ref_path, S.biallelic);
+            S.ready = true;
         }
-        std::vector<SiteRecord> recs = X->site_cache[l];
-        add_ml_path_records(H, l, X->ref_paths[l], lp, recs);
-        for (auto& r : merge_records(L, X->ref_paths[l], std::move(recs))) X->records.push_back(std::move(r));
+        std::vector<SiteRecord> extra;
+        find_ml_path_records(H, l, S.ref_path, lp, S.known, extra);
+        if (extra.empty()) {
+            for (auto& r : S.merged) X->records.push_back(&r);
+        } else {  // the ML path spells alleles the site table lacks: merge them in for this sample only
+            std::vector<SiteRecord> all = S.biallelic;
+            for (auto& r : extra) all.push_back(std::move(r));
+            X->sample_records.push_back(merge_records(L, S.ref_path, std::move(all)));
+            for (auto& r : X->sample_records.back()) X->records.push_back(&r);
+        }
     }
-    std::stable_sort(X->records.begin(), X->records.end(), [&](const SiteRecord& a, const SiteRecord& b) {
-        const std::string &na = H.loci[a.locus].name, &nb = H.loci[b.locus].name;
-        if (na != nb) return na < nb;
-        if (a.pos != b.pos) return a.pos < b.pos;
-        if (a.ref != b.ref) return a.ref < b.ref;
-        return a.alts < b.alts;
-    });
-    std::sort(X->contigs.begin(), X->contigs.end());
-    // ---- S8 on the device
+    lap(3);
+    // ---- S8 on the device (CSR re-used while the record set is unchanged)
     GenotypeArrays& G = X->GA;
-    G = GenotypeArrays();
-    G.rec_off.push_back(0);
-    G.allele_off.push_back(0);
-    for (auto& r : X->records) {
-        for (auto& kn : r.allele_kn) {
-            for (uint32_t x : kn) G.allele_kn.push_back(H.knode_base[r.locus] + x);
-            G.allele_off.push_back((uint32_t)G.allele_kn.size());
+    if (X->records != X->csr_records || G.rec_off.empty() || !X->sample_records.empty()) {
+        G.rec_off.assign(1, 0);
+        G.allele_off.assign(1, 0);
+        G.allele_kn.clear();
+        for (const SiteRecord* r : X->records) {
+            for (auto& kn : r->allele_kn) {
+                for (uint32_t x : kn) G.allele_kn.push_back(H.knode_base[r->locus] + x);
+                G.allele_off.push_back((uint32_t)G.allele_kn.size());
+            }
+            G.rec_off.push_back((uint32_t)G.allele_off.size() - 1);
         }
-        G.rec_off.push_back((uint32_t)G.allele_off.size() - 1);
+        for (void* p : {(void*)X->d_rec_off, (void*)X->d_allele_off, (void*)X->d_allele_kn})
+            if (p) cudaFree(p);
+        X->d_rec_off = to_device(G.rec_off);
+        X->d_allele_off = to_device(G.allele_off);
+        X->d_allele_kn = to_device(G.allele_kn);
+        X->csr_records = X->sample_records.empty() ? X->records : std::vector<const SiteRecord*>();
     }
     const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
-    for (auto* v : {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev}) v->assign(na, 0);
-    G.gaps.assign(na, 0);
-    G.lik.assign(na, 0);
-    G.gt_conf.assign(nr, 0);
-    G.gt.assign(nr, -1);
+    std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+    for (auto* v : cols) v->resize(na);
+    G.gaps.resize(na);
+    G.lik.resize(na);
+    G.gt_conf.resize(nr);
+    G.gt.resize(nr);
     if (nr) {
-        uint32_t *d_rec_off = to_device(G.rec_off), *d_allele_off = to_device(G.allele_off), *d_allele_kn = to_device(G.allele_kn);
-        uint32_t* d_u32 = nullptr;
-        double* d_f64 = nullptr;
-        int32_t* d_gt = nullptr;
-        CK(cudaMalloc(&d_u32, (size_t)na * 6 * 4));
-        CK(cudaMalloc(&d_f64, ((size_t)na * 2 + nr) * 8));
-        CK(cudaMalloc(&d_gt, (size_t)nr * 4));
-        DevGenotype DG{nr, na, d_rec_off, d_allele_off, d_allele_kn, d_u32, d_u32 + na, d_u32 + 2 * (size_t)na,
-                       d_u32 + 3 * (size_t)na, d_u32 + 4 * (size_t)na, d_u32 + 5 * (size_t)na, d_f64, d_f64 + na,
-                       d_f64 + 2 * (size_t)na, d_gt};
+        X->d_gt_u32.ensure((size_t)na * 6);
+        X->d_gt_f64.ensure((size_t)na * 2 + nr);
+        X->d_gt_i32.ensure(nr);
+        uint32_t* u = X->d_gt_u32.p;
+        double* f = X->d_gt_f64.p;
+        DevGenotype DG{nr, na, X->d_rec_off, X->d_allele_off, X->d_allele_kn, u, u + na, u + 2 * (size_t)na, u + 3 * (size_t)na,
+                       u + 4 * (size_t)na, u + 5 * (size_t)na, f, f + na, f + 2 * (size_t)na, X->d_gt_i32.p};
         launch_genotype(X->d_accum, DG, MP, st);
         CK(cudaGetLastError());
-        std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
-        for (int c = 0; c < 6; ++c) CK(cudaMemcpy(cols[c]->data(), d_u32 + (size_t)c * na, (size_t)na * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(G.gaps.data(), d_f64, (size_t)na * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(G.lik.data(), d_f64 + na, (size_t)na * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(G.gt_conf.data(), d_f64 + 2 * (size_t)na, (size_t)nr * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(G.gt.data(), d_gt, (size_t)nr * 4, cudaMemcpyDeviceToHost));
-        for (void* p : {(void*)d_rec_off, (void*)d_allele_off, (void*)d_allele_kn, (void*)d_u32, (void*)d_f64, (void*)d_gt}) cudaFree(p);
+        std::vector<uint32_t> hu((size_t)na * 6);
+        std::vector<double> hf((size_t)na * 2 + nr);
+        CK(cudaMemcpy(hu.data(), u, hu.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hf.data(), f, hf.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(G.gt.data(), X->d_gt_i32.p, (size_t)nr * 4, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < 6; ++c) std::copy(hu.begin() + (size_t)c * na, hu.begin() + (size_t)(c + 1) * na, cols[c]->begin());
+        std::copy(hf.begin(), hf.begin() + na, G.gaps.begin());
+        std::copy(hf.begin() + na, hf.begin() + 2 * (size_t)na, G.lik.begin());
+        std::copy(hf.begin() + 2 * (size_t)na, hf.end(), G.gt_conf.begin());
     }
+    lap(4);
     X->vcf = format_vcf(H, X->records, G, X->contigs, sample && *sample ? sample : "sample");
+    lap(5);
     X->have_gt = true;
 }
 
 void free_batch(drprg_batch* b) {
     if (!b) return;
     if (b->owned) {
-        if (b->d_words) cudaFree(b->d_words);
-        if (b->d_lens) cudaFree(b->d_lens);
-        if (b->d_off) cudaFree(b->d_off);
+        if (b->d_words) g_pool.put(b->d_words, b->b_words, b->device);
+        if (b->d_lens) g_pool.put(b->d_lens, b->b_lens, b->device);
+        if (b->d_off) g_pool.put(b->d_off, b->b_off, b->device);
     }
     delete b;
 }
@@ -475,16 +553,23 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
     std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
     B->owned = true;
     const uint64_t nwords = stride ? n * (uint64_t)stride : (n ? word_off[n] : 0);
-    CK(cudaMalloc(&B->d_words, std::max<uint64_t>(1, nwords + 2) * 4));
-    CK(cudaMalloc(&B->d_lens, std::max<uint64_t>(1, n) * 4));
+    B->device = X->device;
+    B->b_words = std::max<uint64_t>(1, nwords + 2) * 4;
+    B->b_lens = std::max<uint64_t>(1, n) * 4;
+    B->d_words = (uint32_t*)g_pool.get(B->b_words, X->device);
+    B->d_lens = (uint32_t*)g_pool.get(B->b_lens, X->device);
     if (nwords) CK(cudaMemcpyAsync(B->d_words, words, nwords * 4, cudaMemcpyHostToDevice, st));
     if (n) CK(cudaMemcpyAsync(B->d_lens, lens, n * 4, cudaMemcpyHostToDevice, st));
     if (!stride) {
-        CK(cudaMalloc(&B->d_off, (n + 1) * 8));
+        B->b_off = (n + 1) * 8;
+        B->d_off = (uint64_t*)g_pool.get(B->b_off, X->device);
         CK(cudaMemcpyAsync(B->d_off, word_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     }
     B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
     B->total_bases = total_bases;
+    uint32_t ml = 0;
+    for (uint64_t i = 0; i < n; ++i) ml = std::max(ml, lens[i]);
+    B->max_len = ml;
     return B.release();
 }
 
@@ -614,6 +699,7 @@ int drprg_cuda_batch_wrap_device(drprg_index* X, const void* d_words, const void
     drprg_batch* B = new drprg_batch();
     B->R = DevReads{(const uint32_t*)d_words, (const uint64_t*)d_word_off, stride_words, (const uint32_t*)d_lens, n_reads, read_id_base};
     B->total_bases = total_bases;
+    B->max_len = stride_words ? stride_words * 16u : UINT32_MAX;
     *out = B;
     return 0;
     API_END
@@ -745,7 +831,7 @@ int64_t drprg_cuda_sketch_batch(drprg_index* X, drprg_batch* B, void* stream, ui
         key.ensure(cap);
         val.ensure(cap);
         CK(cudaMemsetAsync(X->d_counters, 0, 16, st));
-        launch_sketch_only(B->R, X->H.w, X->H.k, key.p, val.p, X->d_counters, cap, X->sm_count, st);
+        launch_sketch_only(B->R, X->H.w, X->H.k, key.p, val.p, X->d_counters, cap, X->sm_count, B->max_len, st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -823,8 +909,8 @@ int drprg_cuda_gt_counts(drprg_index* X, uint32_t* n_records, uint32_t* n_allele
 }
 int drprg_cuda_gt_records(drprg_index* X, uint32_t* locus, uint32_t* pos, uint32_t* n_alleles, int32_t* gt, double* gt_conf) {
     for (size_t i = 0; i < X->records.size(); ++i) {
-        locus[i] = X->records[i].locus;
-        pos[i] = X->records[i].pos;
+        locus[i] = X->records[i]->locus;
+        pos[i] = X->records[i]->pos;
         n_alleles[i] = X->GA.rec_off[i + 1] - X->GA.rec_off[i];
         gt[i] = X->GA.gt[i];
         gt_conf[i] = X->GA.gt_conf[i];
@@ -849,13 +935,17 @@ int drprg_cuda_gt_alleles(drprg_index* X, double* lik, double* gaps, uint32_t* m
 int drprg_cuda_gt_allele_knodes(drprg_index* X, uint32_t* out) {
     // ranks within the locus, like the oracle
     size_t e = 0;
-    for (auto& r : X->records)
-        for (auto& kn : r.allele_kn)
+    for (const SiteRecord* r : X->records)
+        for (auto& kn : r->allele_kn)
             for (uint32_t x : kn) out[e++] = x;
     return 0;
 }
 int drprg_cuda_last_timings(drprg_index* X, float* out4) {
     memcpy(out4, X->timings, sizeof X->timings);
+    return 0;
+}
+int drprg_cuda_last_genotype_timings(drprg_index* X, double* out6) {
+    memcpy(out6, X->gt_ms, 6 * sizeof(double));
     return 0;
 }
 uint64_t drprg_cuda_launch_count(void) { return launch_count(); }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <charconv>
 #include <cmath>
 #include <cstring>
 #include <ctime>
@@ -98,31 +99,21 @@ FitParams fit_parameters(const HostIndex& H, const int32_t* cov, const int32_t* 
         P.E = std::max<uint32_t>((uint32_t)m, 1u);
     }
     if (P.nb_p >= 1.0) P.nb_p = 0.999999;
-    // valley of the log-probability histogram (bins [-200, 0))
-    uint32_t ph[200] = {0};
-    for (size_t l = 0; l < H.loci.size(); ++l) {
-        if (locus_reads[l] <= 0) continue;
-        for (uint32_t g = H.knode_base[l] + 1; g + 1 < H.knode_base[l + 1]; ++g) {
-            double p = host_node_log_prob(P, H.k, sat16(cov[2 * g]), sat16(cov[2 * g + 1]), false);
-            if (p >= -200.0 && p < 0.0) {
-                int j = (int)std::floor(p + 200.0);
-                if (j >= 0 && j < 200) ++ph[j];
-            }
-        }
-    }
+    P.min_kmer_covg = P.E / 10;
+    return P;
+}
+
+// valley between the error peak and the signal peak of the log-probability histogram (bins [-200, 0));
+// the histogram itself is built on the device (prob_hist_kernel)
+int prob_threshold(const uint32_t* ph) {
     int p1 = (int)(std::max_element(ph, ph + 200) - ph), p2 = -1;
     for (int i = 0; i < 200; ++i) {
         if (std::abs(i - p1) <= 10 || ph[i] == 0) continue;
         if (p2 < 0 || ph[i] > ph[p2]) p2 = i;
     }
-    if (p2 < 0) {
-        P.thresh = std::max(-200, p1 - 200 - 10);
-    } else {
-        int a = std::min(p1, p2), b = std::max(p1, p2);
-        P.thresh = (int)(std::min_element(ph + a, ph + b + 1) - ph) - 200;
-    }
-    P.min_kmer_covg = P.E / 10;
-    return P;
+    if (p2 < 0) return std::max(-200, p1 - 200 - 10);
+    int a = std::min(p1, p2), b = std::max(p1, p2);
+    return (int)(std::min_element(ph + a, ph + b + 1) - ph) - 200;
 }
 
 // ---------------------------------------------------------------- reference path ---
@@ -331,11 +322,10 @@ std::vector<uint32_t> local_path_of(const Locus& L, const std::vector<uint32_t>&
     return lp;
 }
 
-void add_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref,
-                         const std::vector<uint32_t>& sp, std::vector<SiteRecord>& recs) {
+void find_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref,
+                          const std::vector<uint32_t>& sp, const SiteKeySet& known, std::vector<SiteRecord>& extra) {
     const Locus& L = H.loci[locus];
-    std::vector<uint32_t> cum(ref.size() + 1, 0);
-    for (size_t i = 0; i < ref.size(); ++i) cum[i + 1] = cum[i] + L.node_len(ref[i]);
+    std::vector<uint32_t> cum;
     std::unique_ptr<KnodeRuns> KR;
     size_t ri = 0, si = 0;
     while (ri < ref.size() && si < sp.size()) {
@@ -349,12 +339,15 @@ void add_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<u
             std::string rs, as;
             for (size_t j = ri + 1; j < rj; ++j) rs += L.node_seq(ref[j]);
             for (size_t j = si + 1; j < sj; ++j) as += L.node_seq(sp[j]);
+            if (cum.empty()) {
+                cum.assign(ref.size() + 1, 0);
+                for (size_t i = 0; i < ref.size(); ++i) cum[i + 1] = cum[i] + L.node_len(ref[i]);
+            }
             const uint32_t pos = cum[ri + 1];
-            if (!(rs.empty() && as.empty()) && rs != as) {
-                bool found = false;
-                for (auto& r : recs)
-                    if (r.pos == pos && r.ref == rs && r.alts[0] == as) found = true;
-                if (!found) {
+            if (!(rs.empty() && as.empty()) && rs != as && !known.count(std::make_tuple(pos, rs, as))) {
+                bool dup = false;
+                for (auto& r : extra) dup = dup || (r.pos == pos && r.ref == rs && r.alts[0] == as);
+                if (!dup) {
                     if (!KR) KR.reset(new KnodeRuns(L));
                     SiteRecord r;
                     r.locus = locus;
@@ -368,7 +361,7 @@ void add_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<u
                     ap.insert(ap.end(), ref.begin() + rj, ref.end());
                     r.allele_kn.push_back(kmers_over(L, *KR, ref, pos, pos + (uint32_t)rs.size()));
                     r.allele_kn.push_back(kmers_over(L, *KR, ap, pos, pos + (uint32_t)as.size()));
-                    recs.push_back(std::move(r));
+                    extra.push_back(std::move(r));
                 }
             }
         }
@@ -450,13 +443,20 @@ bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vecto
 }
 
 // -------------------------------------------------------------------------- VCF ---
-static std::string g6(double v) {
+// "%g" (6 significant digits) like pandora's ostream output; std::to_chars(general, 6) is specified to
+// give the printf result and is several times faster
+static inline void put_g6(std::string& s, double v) {
     char b[64];
-    snprintf(b, sizeof b, "%g", v);
-    return b;
+    auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6);
+    s.append(b, r.ptr);
+}
+static inline void put_u(std::string& s, uint32_t v) {
+    char b[16];
+    auto r = std::to_chars(b, b + sizeof b, v);
+    s.append(b, r.ptr);
 }
 
-std::string format_vcf(const HostIndex& H, const std::vector<SiteRecord>& recs, const GenotypeArrays& G,
+std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
                        const std::vector<std::string>& contigs, const std::string& sample) {
     std::string s;
     s.reserve(4096 + recs.size() * 256);
@@ -485,23 +485,39 @@ std::string format_vcf(const HostIndex& H, const std::vector<SiteRecord>& recs, 
     for (auto& c : contigs) s += "##contig=<ID=" + c + ">\n";
     s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample + "\n";
     for (size_t i = 0; i < recs.size(); ++i) {
-        const SiteRecord& r = recs[i];
+        const SiteRecord& r = *recs[i];
         const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
-        s += H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
-        for (size_t a = 0; a < r.alts.size(); ++a) s += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
-        s += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
-             "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
-        s += G.gt[i] < 0 ? std::string(".") : std::to_string(G.gt[i]);
+        if (r.text_prefix.empty()) {  // CHROM .. FORMAT columns never change for a site: format once
+            std::string& t = r.text_prefix;
+            t = H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
+            for (size_t a = 0; a < r.alts.size(); ++a) t += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
+            t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
+                 "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
+        }
+        s += r.text_prefix;
+        if (G.gt[i] < 0) s += '.';
+        else put_u(s, (uint32_t)G.gt[i]);
         const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
         for (auto* col : cols) {
             s += ':';
-            for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + std::to_string((*col)[a]);
+            for (uint32_t a = b; a < e; ++a) {
+                if (a > b) s += ',';
+                put_u(s, (*col)[a]);
+            }
         }
         s += ':';
-        for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + g6(G.gaps[a]);
+        for (uint32_t a = b; a < e; ++a) {
+            if (a > b) s += ',';
+            put_g6(s, G.gaps[a]);
+        }
         s += ':';
-        for (uint32_t a = b; a < e; ++a) s += (a > b ? "," : "") + g6(G.lik[a]);
-        s += ':' + g6(G.gt_conf[i]) + '\n';
+        for (uint32_t a = b; a < e; ++a) {
+            if (a > b) s += ',';
+            put_g6(s, G.lik[a]);
+        }
+        s += ':';
+        put_g6(s, G.gt_conf[i]);
+        s += '\n';
     }
     return s;
 }

@@ -4,6 +4,8 @@
 // (/root/reference/src/lib.rs:644-646; schema /root/reference/tests/cases/predict/*.vcf).
 #pragma once
 #include <map>
+#include <set>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -35,8 +37,10 @@ struct FitParams {
 };
 
 // cov: interleaved (fwd, rev) per global knode, already summed over ranks; saturates at 65535
+// everything of estimate_parameters except the probability threshold (set from the device histogram)
 FitParams fit_parameters(const HostIndex& H, const int32_t* cov, const int32_t* locus_reads, uint64_t total_bases,
                          const SampleOpts& o);
+int prob_threshold(const uint32_t* hist200);
 double host_node_log_prob(const FitParams& P, uint32_t k, uint32_t f, uint32_t r, bool terminal);
 
 struct SiteRecord {
@@ -45,6 +49,7 @@ struct SiteRecord {
     std::vector<std::string> alts;
     std::string vc, graphtype;
     std::vector<std::vector<uint32_t>> allele_kn;  // ranks within the locus, ref allele first
+    mutable std::string text_prefix;               // cached VCF columns CHROM..FORMAT
 };
 
 // node path threading `seq` from node 0 to the sink (empty if none); top_path = first out-edges
@@ -55,8 +60,9 @@ std::vector<SiteRecord> enumerate_sites(const HostIndex& H, uint32_t locus, cons
 // local node path under an ML k-mer path (ranks)
 std::vector<uint32_t> local_path_of(const Locus& L, const std::vector<uint32_t>& kpath);
 // records the ML path spells but enumerate_sites did not (pandora add_sample_gt_to_vcf)
-void add_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref,
-                         const std::vector<uint32_t>& lpath, std::vector<SiteRecord>& recs);
+using SiteKeySet = std::set<std::tuple<uint32_t, std::string, std::string>>;  // (pos, ref, alt) of the biallelic records
+void find_ml_path_records(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& ref,
+                          const std::vector<uint32_t>& lpath, const SiteKeySet& known, std::vector<SiteRecord>& extra);
 // sort + merge records sharing (pos, ref); anchor empty alleles
 std::vector<SiteRecord> merge_records(const Locus& L, const std::vector<uint32_t>& ref, std::vector<SiteRecord> recs);
 // coverage sanity filter of pandora add_consensus_path_to_fastaq: true = drop the locus
@@ -69,7 +75,7 @@ struct GenotypeArrays {  // flattened over records / alleles, device results cop
     std::vector<double> gaps, lik, gt_conf;
     std::vector<int32_t> gt;
 };
-std::string format_vcf(const HostIndex& H, const std::vector<SiteRecord>& recs, const GenotypeArrays& G,
+std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
                        const std::vector<std::string>& contigs, const std::string& sample);
 
 std::map<std::string, std::string> load_fasta(const std::string& path);

@@ -4,6 +4,7 @@
 // /root/reference/src/lib.rs:580-642 (argv :594-609, src/predict.rs:288-294); stage semantics
 // follow pandora's Seq::minimizer_sketch, add_read_hits, define_clusters, filter_clusters(2),
 // add_hits_to_kmergraphs, KmerGraphWithCoverage::find_max_path and SampleInfo.
+#include <algorithm>
 #include <cfloat>
 #include <cub/cub.cuh>
 
@@ -219,6 +220,189 @@ __global__ void __launch_bounds__(WARPS * 32) sketch_kernel(DevReads R, DevTable
     }
 }
 
+// ============================================================================================
+// S1 + S2, short reads (Illumina): ONE THREAD PER READ, W and K compile-time.
+// The warp-per-read kernel above spends ~90 % of its issue slots on the shared-memory min/max passes
+// and partial rounds (ncu: 1236 warp instructions per 150 bp read, hashing only 8 % of them).  Here all
+// 32 lanes of a warp walk 32 different reads in lockstep, everything lives in registers and the
+// per-position cost is ~50 instructions:
+//   * rolling k-mers: forward by one funnel shift taking the next base from the top of the current
+//     word, reverse complement by one funnel shift taking the complemented base from a rotating copy;
+//   * window minima with ties by the van Herk / Gil-Werman block decomposition with block = W and the
+//     loop unrolled by W so every array index is static: prefix/suffix minima give the minimum of each
+//     window, prefix/suffix maxima of those give, per position, the largest window minimum among the
+//     windows containing it; position i is a minimizer iff h[i] equals that value;
+//   * positions past the read end (and windows before its start) carry hash 0 == "-infinity": a window
+//     touching them has minimum 0 and so can never certify a real minimizer (a real hash of 0 is the
+//     minimum of its valid windows anyway), which removes every boundary branch;
+//   * the block's hashes are parked in shared memory ([slot][thread], conflict free) only so that the
+//     rare flagged positions can be fetched with a dynamic index when they probe the index.
+// ============================================================================================
+constexpr int SHORT_THREADS = 128;
+
+template <int W, int K, bool LOOKUP>
+__global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R, DevTable T,
+                                                                     unsigned long long* __restrict__ out_a,
+                                                                     unsigned long long* __restrict__ out_b,
+                                                                     unsigned long long* __restrict__ out_count,
+                                                                     unsigned long long cap) {
+    static_assert(K >= 2 && K <= 15, "left-aligned hash with a spare low bit range needs k <= 15");
+    constexpr uint32_t S = 32 - 2 * K;
+    constexpr uint32_t HM = ~((1u << S) - 1u);
+    __shared__ uint32_t s_h[2][W][SHORT_THREADS];
+    const int tid = threadIdx.x;
+    const unsigned long long r = (unsigned long long)blockIdx.x * SHORT_THREADS + tid;
+    const bool have = r < R.n_reads;
+    uint32_t len = have ? __ldg(R.lens + r) : 0u;
+    if (len + 1 < (uint32_t)(W + K)) len = 0;  // too short or dropped: no k-mer position is valid
+    const uint32_t nk = len ? len - K + 1 : 0;
+    const uint32_t nk_max = __reduce_max_sync(FULL, nk);
+    if (nk_max == 0) return;
+    const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull);
+    const uint32_t nwords = (len + 15) >> 4;
+
+    uint32_t cur = 0, ncur = 0, F = 0, Rc = 0, widx = 0;
+    auto next_base = [&](uint32_t base_index) {
+        if ((base_index & 15u) == 0u) {  // warp-uniform: every lane is at the same base index
+            cur = (widx < nwords) ? __ldg(wp + widx) : 0u;
+            ncur = ~cur;
+            ++widx;
+        }
+        F = __funnelshift_l(cur, F, 2);      // F = F << 2 | next base (garbage above bit 2K is shifted out later)
+        cur <<= 2;
+        ncur = __funnelshift_l(ncur, ncur, 2);  // rotate: complemented base now in the low two bits
+        Rc = __funnelshift_r(Rc, ncur, 2);   // Rc = comp(base) << 30 | Rc >> 2 : rc of the last 16 bases
+    };
+#pragma unroll 1
+    for (uint32_t i = 0; i < (uint32_t)(K - 1); ++i) next_base(i);
+
+    uint32_t hp[W], Sp[W], SXo[W + 1];
+#pragma unroll
+    for (int j = 0; j < W; ++j) hp[j] = Sp[j] = SXo[j] = 0u;
+    SXo[W] = 0u;
+    uint32_t strand_prev = 0;
+    const uint32_t n_blocks = (nk_max + W - 1) / W + 1;  // one extra all-padding block resolves the last real one
+#pragma unroll 1
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        uint32_t h[W];
+        uint32_t strand_cur = 0;
+        const uint32_t p0 = b * W;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            next_base(p0 + j + K - 1);
+            const uint32_t hf = hash_left_aligned(F << S, S, HM), hr = hash_left_aligned(Rc & HM, S, HM);
+            uint32_t hv = min(hf, hr);
+            strand_cur |= (hf <= hr ? 1u : 0u) << j;
+            hv = (p0 + j < nk) ? hv : 0u;
+            h[j] = hv;
+            s_h[b & 1][j][tid] = hv;
+        }
+        // windows starting in the previous block: offset t covers prev[t..W-1] + cur[0..t-1]
+        uint32_t wm[W];
+        wm[0] = Sp[0];
+        {
+            uint32_t pmin = h[0];
+#pragma unroll
+            for (int t = 1; t < W; ++t) {
+                wm[t] = min(Sp[t], pmin);
+                pmin = min(pmin, h[t]);
+            }
+        }
+        // previous block's positions: best window minimum among the windows containing them
+        uint32_t flags = 0;
+        {
+            uint32_t pmax = 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                pmax = max(pmax, wm[j]);
+                const uint32_t best = max(pmax, SXo[j + 1]);
+                flags |= (hp[j] == best ? 1u : 0u) << j;
+            }
+        }
+        if (b > 0) {
+            const uint32_t prev0 = p0 - W;
+            const uint32_t valid = nk > prev0 ? min(nk - prev0, (uint32_t)W) : 0u;
+            uint32_t fm = flags & ((1u << valid) - 1u);
+            while (fm) {
+                const int j = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const uint32_t hv = s_h[(b - 1) & 1][j][tid] >> S;
+                const uint32_t pos = prev0 + j;
+                const uint32_t read_strand = (strand_prev >> j) & 1u;
+                if (!LOOKUP) {
+                    const unsigned long long o = atomicAdd(out_count, 1ull);
+                    if (o < cap) {
+                        out_a[o] = ((unsigned long long)(R.read_id_base + (uint32_t)r) << 32) | pos;
+                        out_b[o] = ((unsigned long long)hv << 1) | read_strand;
+                    }
+                } else {
+                    const uint32_t fw = __ldg(T.filter + (hv & ((1u << T.filter_bits) - 1u)));
+                    const uint32_t m = (1u << ((hv >> T.filter_bits) & 31u)) | (1u << ((hv >> (T.filter_bits + 5)) & 31u));
+                    if ((fw & m) != m) continue;
+                    uint32_t slot = table_slot(hv, T.slot_bits);
+                    const uint32_t smask = (1u << T.slot_bits) - 1u;
+                    uint32_t rec_begin = 0, rec_n = 0;
+                    while (true) {
+                        const uint2 ent = __ldg(T.slots + slot);
+                        if (ent.y == 0u) break;
+                        if (ent.x == hv) {
+                            rec_begin = ent.y & 0xffffffu;
+                            rec_n = ent.y >> 24;
+                            break;
+                        }
+                        slot = (slot + 1) & smask;
+                    }
+                    if (rec_n) {
+                        const unsigned long long base = atomicAdd(out_count, (unsigned long long)rec_n);
+                        for (uint32_t q = 0; q < rec_n; ++q) {
+                            const uint2 rc = __ldg(T.recs + rec_begin + q);
+                            const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
+                            if (base + q < cap) {
+                                out_a[base + q] = ((unsigned long long)(R.read_id_base + (uint32_t)r) << 32) |
+                                                  ((unsigned long long)(rc.y >> 1) << 16) | ((unsigned long long)(fwd ^ 1u) << 15);
+                                out_b[base + q] = ((unsigned long long)pos << 32) | rc.x;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // roll the block state
+        {
+            uint32_t smax = 0;
+#pragma unroll
+            for (int j = W - 1; j >= 0; --j) {
+                smax = max(smax, wm[j]);
+                SXo[j] = smax;
+            }
+            uint32_t smin = 0xffffffffu;
+#pragma unroll
+            for (int j = W - 1; j >= 0; --j) {
+                smin = min(smin, h[j]);
+                Sp[j] = smin;
+                hp[j] = h[j];
+            }
+        }
+        strand_prev = strand_cur;
+    }
+}
+
+template <bool LOOKUP>
+static bool launch_short(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* a,
+                         unsigned long long* b, unsigned long long* cnt, uint64_t cap, cudaStream_t st) {
+    const unsigned grid = (unsigned)((R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS);
+#define DRPRG_SHORT(WW, KK)                                                                          \
+    if (w == WW && k == KK) {                                                                        \
+        sketch_short_kernel<WW, KK, LOOKUP><<<grid, SHORT_THREADS, 0, st>>>(R, T, a, b, cnt, cap); \
+        ++g_launches;                                                                                \
+        return true;                                                                                 \
+    }
+    DRPRG_SHORT(11, 15)  // drprg defaults (src/builder.rs:40-41)
+    DRPRG_SHORT(14, 15)  // pandora's default w, used by the reference's build tests (src/builder.rs:1181)
+#undef DRPRG_SHORT
+    return false;
+}
+
 static int grid_for(int sm_count, uint64_t n_reads) {
     // persistent-style grid: a multiple of the SM count, capped by the work available
     long long want = (long long)((n_reads + WARPS - 1) / WARPS);
@@ -229,16 +413,18 @@ static int grid_for(int sm_count, uint64_t n_reads) {
 
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
-                          cudaStream_t st) {
+                          uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
+    if (max_len <= SHORT_READ_MAX && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, st)) return;
     sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
     ++g_launches;
 }
 
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
-                        unsigned long long* d_count, uint64_t cap, int sm_count, cudaStream_t st) {
+                        unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
     DevTable T{};
+    if (max_len <= SHORT_READ_MAX && launch_short<false>(R, T, w, k, d_key, d_val, d_count, cap, st)) return;
     sketch_kernel<false><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_key, d_val, d_count, cap);
     ++g_launches;
 }
@@ -501,28 +687,71 @@ void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t
     ++g_launches;
 }
 
+// histogram of floor(log-prob + 200) over the inner k-mer nodes of the loci present in the sample: the
+// data-parallel half of pandora's estimate_parameters (the valley search itself is a 200-bin host scan)
+__global__ void prob_hist_kernel(const double* __restrict__ prob, uint32_t total, const uint8_t* __restrict__ is_terminal,
+                                 const uint32_t* __restrict__ knode_locus, const int32_t* __restrict__ locus_reads,
+                                 uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[200];
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < total && !is_terminal[g] && locus_reads[knode_locus[g]] > 0) {
+        const double p = prob[g];
+        if (p >= -200.0 && p < 0.0) {
+            const int j = (int)floor(p + 200.0);
+            if (j >= 0 && j < 200) atomicAdd(&sh[j], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 200; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
+                      const int32_t* d_locus_reads, uint32_t* d_hist, cudaStream_t st) {
+    cudaMemsetAsync(d_hist, 0, 200 * sizeof(uint32_t), st);
+    if (!total) return;
+    prob_hist_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_prob, total, d_is_terminal, d_knode_locus, d_locus_reads, d_hist);
+    ++g_launches;
+}
+
 // One warp per locus.  The recurrence is a chain (node j needs its successors), and the choice
 // among successors is order dependent (1e-6 tolerance, longer path wins ties), so lane 0 walks the
 // nodes in reverse rank order; the windowed mean needs the node `window` steps down the chosen
 // path, found in O(log window) with binary-lifting pointers instead of pandora's linear walk.
 __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
                               const uint32_t* __restrict__ edges, const double* __restrict__ prob,
-                              const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ M,
-                              uint32_t* __restrict__ len, uint32_t* __restrict__ prev, uint32_t* __restrict__ up,
-                              uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len) {
+                              const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ gM,
+                              uint32_t* __restrict__ glen, uint32_t* __restrict__ prev, uint32_t* __restrict__ up,
+                              uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
+                              uint32_t smem_nodes) {
+    extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
-    if (l >= n_loci || threadIdx.x != 0) return;
+    if (l >= n_loci) return;
     const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
     if (locus_reads[l] <= 0 || n < 2) {
-        path_len[l] = 0xffffffffu;
+        if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
         return;
     }
+    // the chain's working set (running sums, lengths, node scores) lives in shared memory when the
+    // locus fits: the serial dependency then costs an LDS (~30 cycles), not an L2 round trip
+    const bool in_smem = n <= smem_nodes;
+    double* M = in_smem ? s_dyn : gM + base;
+    double* pr = in_smem ? s_dyn + smem_nodes : nullptr;
+    uint32_t* len = in_smem ? (uint32_t*)(s_dyn + 2 * (size_t)smem_nodes) : glen + base;
+    if (in_smem) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pr[i] = prob[base + i];
+        __syncwarp();
+    }
+    if (threadIdx.x != 0) return;
+    const double* prb = in_smem ? pr : prob + base;
     int LV = 1;
     while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
     const double tol = 0.000001;
     const uint32_t term = n - 1;
-    M[base + term] = 0.0;
-    len[base + term] = 0;
+    M[term] = 0.0;
+    len[term] = 0;
     prev[base + term] = term;
     for (int v = 0; v < LV; ++v) up[(size_t)v * total + base + term] = term;
     for (uint32_t j = term; j-- > 0;) {
@@ -530,13 +759,14 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         uint32_t max_len = 0;
         double Mj = 0.0;
         uint32_t lenj = 0, prevj = term;
-        const double pj = prob[base + j];
-        for (uint32_t e = edge_off[base + j]; e < edge_off[base + j + 1]; ++e) {
+        const double pj = prb[j];
+        const uint32_t e1 = edge_off[base + j + 1];
+        for (uint32_t e = edge_off[base + j]; e < e1; ++e) {
             const uint32_t v = edges[e];
             const bool is_term = (v == term);
             bool take;
-            const double Mv = M[base + v];
-            const uint32_t lv = len[base + v];
+            const double Mv = M[v];
+            const uint32_t lv = len[v];
             if (is_term) {
                 take = P.thresh > max_mean + tol;
             } else {
@@ -551,7 +781,7 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
                 uint32_t pn = v, steps = P.window - 1;
                 for (int b = 0; steps; ++b, steps >>= 1)
                     if (steps & 1u) pn = up[(size_t)b * total + base + pn];
-                Mj -= prob[base + pn];
+                Mj -= prb[pn];
                 lenj -= 1;
             }
             if (!is_term) {
@@ -561,8 +791,8 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
                 max_mean = P.thresh;
             }
         }
-        M[base + j] = Mj;
-        len[base + j] = lenj;
+        M[j] = Mj;
+        len[j] = lenj;
         prev[base + j] = prevj;
         up[base + j] = prevj;
         for (int v = 1; v < LV; ++v) {
@@ -581,10 +811,19 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
-                   cudaStream_t st) {
+                   uint32_t max_locus_knodes, cudaStream_t st) {
     if (!n_loci) return;
-    mlpath_kernel<<<n_loci, 32, 0, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
-                                         d_prev, d_up, total_knodes, d_path, d_path_len);
+    // 20 B of shared memory per k-mer node (sum f64, score f64, length u32), up to the 227 KB a CTA may own
+    uint32_t smem_nodes = std::min<uint32_t>(max_locus_knodes, 11000u);
+    smem_nodes = (smem_nodes + 1) & ~1u;
+    const size_t smem = (size_t)smem_nodes * 20;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(mlpath_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    mlpath_kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
+                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes);
     ++g_launches;
 }
 

@@ -9,6 +9,7 @@ namespace drprg {
 constexpr int W_MAX = 32;    // largest minimizer window supported on the device
 constexpr int K_MAX = 16;    // 2k <= 32: k-mers and hashes live in one 32-bit register
 constexpr int CHUNK = 192;   // k-mer positions a warp resolves per pass (a 150 bp read is one pass)
+constexpr uint32_t SHORT_READ_MAX = 640;  // batches whose reads are all this short take the thread-per-read kernel
 constexpr int LV_MAX = 12;   // binary-lifting levels of the windowed ML-path score (window <= 4095)
 
 // packed reads resident in HBM
@@ -51,10 +52,10 @@ uint64_t launch_count();
 // S1+S2: sketch every read and probe the index; hits appended (unordered) through *hit_count
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
-                          cudaStream_t st);
+                          uint32_t max_len, cudaStream_t st);
 // S1 only (parity hook): emits key = read << 32 | start, val = hash << 1 | strand
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
-                        unsigned long long* d_count, uint64_t cap, int sm_count, cudaStream_t st);
+                        unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st);
 // 128-bit radix sort of the hits by (hi, lo); temp storage managed by the caller
 size_t sort_hits_temp_bytes(uint64_t n);
 void sort_hits(void* d_temp, size_t temp_bytes, unsigned long long* hi_in, unsigned long long* lo_in,
@@ -75,7 +76,9 @@ void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
-                   cudaStream_t st);
+                   uint32_t max_locus_knodes, cudaStream_t st);
+void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
+                      const int32_t* d_locus_reads, uint32_t* d_hist, cudaStream_t st);
 // S8: per-allele coverage statistics, then per-record likelihoods / GT / GT_CONF
 struct DevGenotype {
     uint32_t n_records, n_alleles;

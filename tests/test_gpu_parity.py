@@ -65,6 +65,24 @@ def test_sketch_parity_fixed_stride_and_ragged():
     assert_sketch_equal(gpu_sketch(gx, data, off), oracle_sketch_all(data, off, w, k))
 
 
+@pytest.mark.parametrize("w,k", [(11, 15), (14, 15)])
+def test_sketch_parity_short_read_kernel(w, k):
+    """the thread-per-read kernel (reads <= 640 bp, compile-time w,k): ragged lengths, ties, drops, padding lanes"""
+    gx = lib.Index(TOY_PRG, w, k, device=0)
+    rng = np.random.default_rng(w)
+    strs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(L))) for L in rng.integers(0, 600, size=700)]
+    strs += ["A" * 300, "ACGT" * 100, "AC" * 80 + "GATTACA" * 30, "T" * (w + k - 1), "G" * (w + k - 2), "",
+             strs[5][:40] + "N" + strs[5][41:], "C" * 640, "ACG" * 213]
+    for L in (w + k - 1, w + k, 2 * w + k - 1, 2 * w + k, 150, 151, 160, 161):
+        strs.append("".join("ACGT"[i] for i in rng.integers(0, 4, size=L)))
+    data, off = reads_from_strings(strs)
+    want = oracle_sketch_all(data, off, w, k)
+    assert_sketch_equal(gpu_sketch(gx, data, off), want)                      # ragged offsets
+    assert_sketch_equal(gpu_sketch(gx, data, off, stride_words=40), want)     # fixed stride
+    # a batch that is not a multiple of the CTA size, and a single read
+    assert_sketch_equal(gpu_sketch(gx, *reads_from_strings(strs[:1])), oracle_sketch_all(*reads_from_strings(strs[:1]), w, k))
+
+
 def test_empty_batch():
     gx = lib.Index(TOY_PRG, 11, 15, device=0)
     data, off = reads_from_strings([])
