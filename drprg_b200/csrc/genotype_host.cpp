@@ -425,20 +425,21 @@ bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vecto
             for (uint32_t x = sg.s - L.nodes[sg.node].s; x < sg.e - L.nodes[sg.node].s; ++x) v[x] = std::max(v[x], c);
         }
     }
-    std::vector<uint32_t> flat;
-    for (auto& v : per_base) flat.insert(flat.end(), v.begin(), v.end());
-    if (flat.empty()) return false;
-    std::sort(flat.begin(), flat.end());
-    uint32_t mode = flat[0], best = 0;
-    for (size_t i = 0; i < flat.size();) {
-        size_t j = i;
-        while (j < flat.size() && flat[j] == flat[i]) ++j;
-        if (j - i > best) {
-            best = (uint32_t)(j - i);
-            mode = flat[i];
+    // mode of the per-base coverages (smallest value among ties), by counting
+    uint32_t top = 0;
+    size_t nbases = 0;
+    for (auto& v : per_base)
+        for (uint32_t x : v) {
+            top = std::max(top, x);
+            ++nbases;
         }
-        i = j;
-    }
+    if (!nbases) return false;
+    std::vector<uint32_t> count(top + 1, 0);
+    for (auto& v : per_base)
+        for (uint32_t x : v) ++count[x];
+    uint32_t mode = 0;
+    for (uint32_t x = 0; x <= top; ++x)
+        if (count[x] > count[mode]) mode = x;
     return global_covg > 20 && ((uint64_t)mode * 10 < global_covg || mode > 10ull * global_covg);
 }
 
@@ -484,40 +485,56 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
          "##FORMAT=<ID=GT_CONF,Number=1,Type=Float,Description=\"Genotype confidence\">\n";
     for (auto& c : contigs) s += "##contig=<ID=" + c + ">\n";
     s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample + "\n";
-    for (size_t i = 0; i < recs.size(); ++i) {
-        const SiteRecord& r = *recs[i];
-        const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
-        if (r.text_prefix.empty()) {  // CHROM .. FORMAT columns never change for a site: format once
-            std::string& t = r.text_prefix;
-            t = H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
-            for (size_t a = 0; a < r.alts.size(); ++a) t += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
-            t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
-                 "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
-        }
-        s += r.text_prefix;
-        if (G.gt[i] < 0) s += '.';
-        else put_u(s, (uint32_t)G.gt[i]);
-        const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
-        for (auto* col : cols) {
+    auto format_range = [&](size_t lo, size_t hi, std::string& s) {
+        for (size_t i = lo; i < hi; ++i) {
+            const SiteRecord& r = *recs[i];
+            const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
+            if (r.text_prefix.empty()) {  // CHROM .. FORMAT columns never change for a site: format once
+                std::string& t = r.text_prefix;
+                t = H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
+                for (size_t a = 0; a < r.alts.size(); ++a) t += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
+                t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
+                     "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
+            }
+            s += r.text_prefix;
+            if (G.gt[i] < 0) s += '.';
+            else put_u(s, (uint32_t)G.gt[i]);
+            const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+            for (auto* col : cols) {
+                s += ':';
+                for (uint32_t a = b; a < e; ++a) {
+                    if (a > b) s += ',';
+                    put_u(s, (*col)[a]);
+                }
+            }
             s += ':';
             for (uint32_t a = b; a < e; ++a) {
                 if (a > b) s += ',';
-                put_u(s, (*col)[a]);
+                put_g6(s, G.gaps[a]);
             }
+            s += ':';
+            for (uint32_t a = b; a < e; ++a) {
+                if (a > b) s += ',';
+                put_g6(s, G.lik[a]);
+            }
+            s += ':';
+            put_g6(s, G.gt_conf[i]);
+            s += '\n';
         }
-        s += ':';
-        for (uint32_t a = b; a < e; ++a) {
-            if (a > b) s += ',';
-            put_g6(s, G.gaps[a]);
-        }
-        s += ':';
-        for (uint32_t a = b; a < e; ++a) {
-            if (a > b) s += ',';
-            put_g6(s, G.lik[a]);
-        }
-        s += ':';
-        put_g6(s, G.gt_conf[i]);
-        s += '\n';
+    };
+    const size_t nthreads = recs.size() >= 1024 ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nthreads <= 1) {
+        format_range(0, recs.size(), s);
+    } else {  // records are independent lines: format contiguous ranges in parallel, then concatenate
+        std::vector<std::string> parts(nthreads);
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nthreads; ++t)
+            pool.emplace_back([&, t] {
+                parts[t].reserve((recs.size() / nthreads + 1) * 200);
+                format_range(recs.size() * t / nthreads, recs.size() * (t + 1) / nthreads, parts[t]);
+            });
+        for (auto& th : pool) th.join();
+        for (auto& part : parts) s += part;
     }
     return s;
 }

@@ -261,20 +261,35 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
     const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull);
     const uint32_t nwords = (len + 15) >> 4;
 
-    uint32_t cur = 0, ncur = 0, F = 0, Rc = 0, widx = 0;
-    auto next_base = [&](uint32_t base_index) {
-        if ((base_index & 15u) == 0u) {  // warp-uniform: every lane is at the same base index
-            cur = (widx < nwords) ? __ldg(wp + widx) : 0u;
-            ncur = ~cur;
+    // Bases are served from a 64-bit shift register (hi:lo) holding `avail` bases, top aligned; it is
+    // topped up with the next 16-base word once per block of W positions (W <= 16 bases are consumed per
+    // block), so the refill test is per block, not per base, and warp-uniform: all lanes are in lockstep.
+    static_assert(W <= 16, "one refill per block must cover the block");
+    uint32_t hi = 0, lo = 0, avail = 0, widx = 0, F = 0, Rc = 0;
+    auto refill = [&]() {
+        if (avail <= 16u) {
+            const uint32_t word = (widx < nwords) ? __ldg(wp + widx) : 0u;
             ++widx;
+            const uint32_t t = 2u * avail;  // 0..32 bits already occupied at the top of hi; lo is empty
+            hi |= __funnelshift_rc(word, 0u, t);
+            lo = __funnelshift_rc(0u, word, t);
+            avail += 16u;
         }
-        F = __funnelshift_l(cur, F, 2);      // F = F << 2 | next base (garbage above bit 2K is shifted out later)
-        cur <<= 2;
-        ncur = __funnelshift_l(ncur, ncur, 2);  // rotate: complemented base now in the low two bits
-        Rc = __funnelshift_r(Rc, ncur, 2);   // Rc = comp(base) << 30 | Rc >> 2 : rc of the last 16 bases
     };
+    auto next_base = [&]() {
+        const uint32_t c = hi >> 30;
+        F = F * 4u + c;                                     // garbage above bit 2K is shifted out by << S
+        Rc = __funnelshift_r(Rc, c, 2) ^ 0xC0000000u;       // complemented base enters at the top: rc of the last 16
+        hi = __funnelshift_l(lo, hi, 2);
+        lo <<= 2;
+    };
+    {
+        // prime the first K-1 bases (K-1 <= 14 < 16: one word)
+        refill();
 #pragma unroll 1
-    for (uint32_t i = 0; i < (uint32_t)(K - 1); ++i) next_base(i);
+        for (uint32_t i = 0; i < (uint32_t)(K - 1); ++i) next_base();
+        avail -= (uint32_t)(K - 1);
+    }
 
     uint32_t hp[W], Sp[W], SXo[W + 1];
 #pragma unroll
@@ -285,18 +300,25 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
 #pragma unroll 1
     for (uint32_t b = 0; b < n_blocks; ++b) {
         uint32_t h[W];
-        uint32_t strand_cur = 0;
+        uint32_t not_strand = 0;  // bit (W-1-j) = !(hf <= hr) of position j, shifted in through the carry flag
         const uint32_t p0 = b * W;
+        uint32_t* sh = &s_h[b & 1][0][tid];
+        refill();
+        avail -= (uint32_t)W;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            next_base(p0 + j + K - 1);
+            next_base();
             const uint32_t hf = hash_left_aligned(F << S, S, HM), hr = hash_left_aligned(Rc & HM, S, HM);
             uint32_t hv = min(hf, hr);
-            strand_cur |= (hf <= hr ? 1u : 0u) << j;
+            {
+                uint32_t tmp;
+                asm("sub.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;" : "+r"(not_strand), "=r"(tmp) : "r"(hr), "r"(hf));
+            }
             hv = (p0 + j < nk) ? hv : 0u;
             h[j] = hv;
-            s_h[b & 1][j][tid] = hv;
+            sh[j * SHORT_THREADS] = hv;
         }
+        const uint32_t strand_cur = ~not_strand;
         // windows starting in the previous block: offset t covers prev[t..W-1] + cur[0..t-1]
         uint32_t wm[W];
         wm[0] = Sp[0];
@@ -328,7 +350,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                 fm &= fm - 1;
                 const uint32_t hv = s_h[(b - 1) & 1][j][tid] >> S;
                 const uint32_t pos = prev0 + j;
-                const uint32_t read_strand = (strand_prev >> j) & 1u;
+                const uint32_t read_strand = (strand_prev >> (W - 1 - j)) & 1u;
                 if (!LOOKUP) {
                     const unsigned long long o = atomicAdd(out_count, 1ull);
                     if (o < cap) {
@@ -723,9 +745,9 @@ void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_
 __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
                               const uint32_t* __restrict__ edges, const double* __restrict__ prob,
                               const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ gM,
-                              uint32_t* __restrict__ glen, uint32_t* __restrict__ prev, uint32_t* __restrict__ up,
+                              uint32_t* __restrict__ glen, uint32_t* __restrict__ prev, uint32_t* __restrict__ gup,
                               uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
-                              uint32_t smem_nodes) {
+                              uint32_t smem_nodes, int LV) {
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
@@ -734,26 +756,30 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
         return;
     }
-    // the chain's working set (running sums, lengths, node scores) lives in shared memory when the
-    // locus fits: the serial dependency then costs an LDS (~30 cycles), not an L2 round trip
+    // The chain's working set lives in shared memory when the locus fits: running sum, cached mean
+    // (sum / length: one fp64 division per node instead of one per edge visit), node score, length and
+    // the binary-lifting pointers.  Every step of the serial dependency is then an LDS (~30 cycles)
+    // instead of an L2 round trip (the first version spent 2.6 ms here, mostly on the lifting pointers).
     const bool in_smem = n <= smem_nodes;
     double* M = in_smem ? s_dyn : gM + base;
-    double* pr = in_smem ? s_dyn + smem_nodes : nullptr;
-    uint32_t* len = in_smem ? (uint32_t*)(s_dyn + 2 * (size_t)smem_nodes) : glen + base;
+    double* mean = in_smem ? s_dyn + smem_nodes : nullptr;
+    double* pr = in_smem ? s_dyn + 2 * (size_t)smem_nodes : nullptr;
+    uint32_t* len = in_smem ? (uint32_t*)(s_dyn + 3 * (size_t)smem_nodes) : glen + base;
+    uint32_t* up = in_smem ? len + smem_nodes : gup + base;
+    const size_t up_stride = in_smem ? smem_nodes : total;
     if (in_smem) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pr[i] = prob[base + i];
         __syncwarp();
     }
     if (threadIdx.x != 0) return;
     const double* prb = in_smem ? pr : prob + base;
-    int LV = 1;
-    while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
     const double tol = 0.000001;
     const uint32_t term = n - 1;
     M[term] = 0.0;
     len[term] = 0;
+    if (in_smem) mean[term] = 0.0 / 0.0;  // pandora divides 0 by 0 for the terminus; never compared
     prev[base + term] = term;
-    for (int v = 0; v < LV; ++v) up[(size_t)v * total + base + term] = term;
+    for (int v = 0; v < LV; ++v) up[(size_t)v * up_stride + term] = term;
     for (uint32_t j = term; j-- > 0;) {
         double max_mean = -(double)FLT_MAX;
         uint32_t max_len = 0;
@@ -764,40 +790,33 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         for (uint32_t e = edge_off[base + j]; e < e1; ++e) {
             const uint32_t v = edges[e];
             const bool is_term = (v == term);
-            bool take;
-            const double Mv = M[v];
             const uint32_t lv = len[v];
-            if (is_term) {
-                take = P.thresh > max_mean + tol;
-            } else {
-                const double mean_v = Mv / (double)lv;
-                take = (mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len);
-            }
+            const double mean_v = in_smem ? mean[v] : M[v] / (double)lv;
+            const bool take = is_term ? (P.thresh > max_mean + tol)
+                                      : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
             if (!take) continue;
-            Mj = pj + Mv;
+            Mj = pj + M[v];
             lenj = 1 + lv;
             prevj = v;
             if (lenj > P.window) {
                 uint32_t pn = v, steps = P.window - 1;
                 for (int b = 0; steps; ++b, steps >>= 1)
-                    if (steps & 1u) pn = up[(size_t)b * total + base + pn];
+                    if (steps & 1u) pn = up[(size_t)b * up_stride + pn];
                 Mj -= prb[pn];
                 lenj -= 1;
             }
-            if (!is_term) {
-                max_mean = Mv / (double)lv;
-                max_len = lv;
-            } else {
-                max_mean = P.thresh;
-            }
+            max_mean = is_term ? P.thresh : mean_v;
+            if (!is_term) max_len = lv;
         }
         M[j] = Mj;
         len[j] = lenj;
+        if (in_smem) mean[j] = Mj / (double)lenj;
         prev[base + j] = prevj;
-        up[base + j] = prevj;
+        up[j] = prevj;
+        uint32_t a = prevj;
         for (int v = 1; v < LV; ++v) {
-            const uint32_t mid = up[(size_t)(v - 1) * total + base + j];
-            up[(size_t)v * total + base + j] = up[(size_t)(v - 1) * total + base + mid];
+            a = up[(size_t)(v - 1) * up_stride + a];
+            up[(size_t)v * up_stride + j] = a;
         }
     }
     uint32_t cnt = 0, p = prev[base];
@@ -813,17 +832,21 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
                    uint32_t max_locus_knodes, cudaStream_t st) {
     if (!n_loci) return;
-    // 20 B of shared memory per k-mer node (sum f64, score f64, length u32), up to the 227 KB a CTA may own
-    uint32_t smem_nodes = std::min<uint32_t>(max_locus_knodes, 11000u);
+    // shared memory per k-mer node: sum, mean, score (f64), length (u32) and LV lifting pointers (u32),
+    // up to the 227 KB a CTA may own; larger loci fall back to global memory
+    int LV = 1;
+    while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
+    const size_t per_node = 24 + 4 + 4 * (size_t)LV;
+    uint32_t smem_nodes = std::min<uint32_t>(max_locus_knodes, (uint32_t)((220u * 1024u) / per_node));
     smem_nodes = (smem_nodes + 1) & ~1u;
-    const size_t smem = (size_t)smem_nodes * 20;
+    const size_t smem = (size_t)smem_nodes * per_node;
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(mlpath_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     mlpath_kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
-                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes);
+                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes, LV);
     ++g_launches;
 }
 
