@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <map>
@@ -12,6 +13,7 @@
 #include <fstream>
 #include <memory>
 #include <stdexcept>
+#include <thread>
 
 #include "../../include/drprg_cuda.h"
 #include "genotype_host.hpp"
@@ -155,7 +157,7 @@ struct drprg_index {
     DBuf<uint32_t> d_gt_u32;
     DBuf<double> d_gt_f64;
     DBuf<int32_t> d_gt_i32;
-    uint32_t max_locus_knodes = 0;
+    uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::string> contigs;
     std::string vcf;
@@ -199,7 +201,7 @@ void upload_index(drprg_index* X) {
     uint32_t sb = 10;
     while ((1ull << sb) < distinct * 2) ++sb;
     uint32_t fb = 8;
-    while ((1ull << fb) < (distinct + 1) / 2) ++fb;
+    while ((1ull << fb) < (distinct + 3) / 4) ++fb;  // ~4 keys per 32-bit word: 2 % false positives, 64 KB for a 60 k-key panel
     std::vector<uint2> slots(1ull << sb, make_uint2(0, 0));
     std::vector<uint32_t> filter(1ull << fb, 0);
     for (size_t i = 0; i < H.records.size();) {
@@ -253,6 +255,7 @@ void upload_index(drprg_index* X) {
     for (size_t l = 0; l < H.loci.size(); ++l) {
         for (uint32_t g = H.knode_base[l]; g < H.knode_base[l + 1]; ++g) knode_locus[g] = (uint32_t)l;
         X->max_locus_knodes = std::max(X->max_locus_knodes, H.knode_base[l + 1] - H.knode_base[l]);
+        X->max_locus_edges = std::max(X->max_locus_edges, edge_off[H.knode_base[l + 1]] - edge_off[H.knode_base[l]]);
     }
     X->d_knode_locus = to_device(knode_locus);
     CK(cudaMalloc(&X->d_hist, 200 * sizeof(uint32_t)));
@@ -433,7 +436,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     lap(1);
     // ---- S7 on the device
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
-                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, st);
+                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges, st);
     CK(cudaGetLastError());
     std::vector<uint32_t> path(N), plen(P);
     CK(cudaMemcpy(path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
@@ -452,15 +455,22 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     X->records.clear();
     X->sample_records.clear();
     X->contigs.clear();
-    for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
-        if (plen[l] == 0xffffffffu || plen[l] == 0) continue;
+    // per-locus host work is independent: spread the loci over a few host threads
+    struct LocusOut {
+        bool present = false;
+        std::vector<uint32_t> kp;
+        std::vector<SiteRecord> sample_merged;  // only when the ML path adds records
+        bool use_cached = true;
+    };
+    std::vector<LocusOut> lout(P);
+    auto do_locus = [&](uint32_t l) {
+        if (plen[l] == 0xffffffffu || plen[l] == 0) return;
         const Locus& L = H.loci[l];
-        std::vector<uint32_t> kp(path.begin() + H.knode_base[l], path.begin() + H.knode_base[l] + plen[l]);
-        std::vector<uint32_t> lp = local_path_of(L, kp);
-        if (locus_coverage_outlier(H, l, kp, lp, cov, X->fit.covg)) continue;
-        X->present[l] = 1;
-        X->mlpaths[l] = std::move(kp);
-        X->contigs.push_back(L.name);
+        LocusOut& O = lout[l];
+        O.kp.assign(path.begin() + H.knode_base[l], path.begin() + H.knode_base[l] + plen[l]);
+        std::vector<uint32_t> lp = local_path_of(L, O.kp);
+        if (locus_coverage_outlier(H, l, O.kp, lp, cov, X->fit.covg)) return;
+        O.present = true;
         auto& S = X->sites[l];
         if (!S.ready) {
             auto it = X->refs.find(L.name);
@@ -473,12 +483,45 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         }
         std::vector<SiteRecord> extra;
         find_ml_path_records(H, l, S.ref_path, lp, S.known, extra);
-        if (extra.empty()) {
-            for (auto& r : S.merged) X->records.push_back(&r);
-        } else {  // the ML path spells alleles the site table lacks: merge them in for this sample only
+        if (!extra.empty()) {  // the ML path spells alleles the site table lacks: merge them in for this sample only
             std::vector<SiteRecord> all = S.biallelic;
             for (auto& r : extra) all.push_back(std::move(r));
-            X->sample_records.push_back(merge_records(L, S.ref_path, std::move(all)));
+            O.sample_merged = merge_records(L, S.ref_path, std::move(all));
+            O.use_cached = false;
+        }
+    };
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned T = std::min<unsigned>({8u, hw, std::max<uint32_t>(1u, P)});
+        if (T <= 1) {
+            for (uint32_t l = 0; l < P; ++l) do_locus(l);
+        } else {
+            std::atomic<uint32_t> next{0};
+            std::vector<std::thread> pool;
+            std::vector<std::string> errs(T);
+            for (unsigned t = 0; t < T; ++t)
+                pool.emplace_back([&, t] {
+                    try {
+                        for (uint32_t l = next++; l < P; l = next++) do_locus(l);
+                    } catch (const std::exception& e) {
+                        errs[t] = e.what();
+                    }
+                });
+            for (auto& th : pool) th.join();
+            for (auto& e : errs)
+                if (!e.empty()) throw std::runtime_error(e);
+        }
+    }
+    for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
+        LocusOut& O = lout[l];
+        if (!O.present) continue;
+        X->present[l] = 1;
+        X->mlpaths[l] = std::move(O.kp);
+        X->contigs.push_back(H.loci[l].name);
+        if (O.use_cached) {
+            for (auto& r : X->sites[l].merged) X->records.push_back(&r);
+        } else {
+            X->sample_records.push_back(std::move(O.sample_merged));
             for (auto& r : X->sample_records.back()) X->records.push_back(&r);
         }
     }

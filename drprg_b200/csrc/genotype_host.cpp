@@ -283,17 +283,18 @@ std::vector<SiteRecord> enumerate_sites(const HostIndex& H, uint32_t locus, cons
 
 std::vector<uint32_t> local_path_of(const Locus& L, const std::vector<uint32_t>& kpath) {
     std::vector<uint32_t> lp;
+    lp.reserve(L.nodes.size());
     for (uint32_t r : kpath) {
-        std::vector<uint32_t> nn;
-        for (auto& sg : L.kpath[r]) nn.push_back(sg.node);
-        if (nn.empty()) continue;
+        const KPath& kp = L.kpath[r];
+        if (kp.empty()) continue;
+        const uint32_t first = kp[0].node;
         while (!lp.empty()) {
             const auto& o = L.nodes[lp.back()].out;
-            if (o.empty() || !(nn[0] > o[0]) || std::find(o.begin(), o.end(), nn[0]) != o.end()) break;
+            if (o.empty() || !(first > o[0]) || std::find(o.begin(), o.end(), first) != o.end()) break;
             lp.push_back(o[0]);
         }
-        while (!lp.empty() && nn[0] <= lp.back()) lp.pop_back();
-        lp.insert(lp.end(), nn.begin(), nn.end());
+        while (!lp.empty() && first <= lp.back()) lp.pop_back();
+        for (auto& sg : kp) lp.push_back(sg.node);
     }
     if (lp.empty()) return top_path(L);
     if (lp.front() != 0) {
@@ -408,35 +409,32 @@ std::vector<SiteRecord> merge_records(const Locus& L, const std::vector<uint32_t
 
 bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& kpath,
                             const std::vector<uint32_t>& lpath, const int32_t* cov, uint32_t global_covg) {
+    if (global_covg <= 20) return false;  // pandora only applies the filter above 20x
     const Locus& L = H.loci[locus];
     const uint32_t base = H.knode_base[locus];
-    std::vector<int> where(L.nodes.size(), -1);
-    std::vector<std::vector<uint32_t>> per_base(lpath.size());
-    for (size_t i = 0; i < lpath.size(); ++i) {
-        where[lpath[i]] = (int)i;
-        per_base[i].assign(L.node_len(lpath[i]), 0);
+    // per-base coverage along the local path = max over the ML k-mers covering the base (one flat array)
+    std::vector<int64_t> node_off(L.nodes.size(), -1);
+    size_t nbases = 0;
+    for (uint32_t n : lpath) {
+        node_off[n] = (int64_t)nbases;
+        nbases += L.node_len(n);
     }
+    if (!nbases) return false;
+    std::vector<uint32_t> per_base(nbases, 0);
+    uint32_t top = 0;
     for (uint32_t r : kpath) {
         const uint32_t g = base + r;
         const uint32_t c = sat16(cov[2 * g]) + sat16(cov[2 * g + 1]);
+        top = std::max(top, c);
         for (auto& sg : L.kpath[r]) {
-            if (sg.s == sg.e || where[sg.node] < 0) continue;
-            auto& v = per_base[where[sg.node]];
+            if (sg.s == sg.e || node_off[sg.node] < 0) continue;
+            uint32_t* v = per_base.data() + node_off[sg.node];
             for (uint32_t x = sg.s - L.nodes[sg.node].s; x < sg.e - L.nodes[sg.node].s; ++x) v[x] = std::max(v[x], c);
         }
     }
-    // mode of the per-base coverages (smallest value among ties), by counting
-    uint32_t top = 0;
-    size_t nbases = 0;
-    for (auto& v : per_base)
-        for (uint32_t x : v) {
-            top = std::max(top, x);
-            ++nbases;
-        }
-    if (!nbases) return false;
+    // mode (smallest value among ties), by counting
     std::vector<uint32_t> count(top + 1, 0);
-    for (auto& v : per_base)
-        for (uint32_t x : v) ++count[x];
+    for (uint32_t x : per_base) ++count[x];
     uint32_t mode = 0;
     for (uint32_t x = 0; x <= top; ++x)
         if (count[x] > count[mode]) mode = x;

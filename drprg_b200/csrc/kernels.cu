@@ -6,6 +6,7 @@
 // add_hits_to_kmergraphs, KmerGraphWithCoverage::find_max_path and SampleInfo.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -238,26 +239,41 @@ __global__ void __launch_bounds__(WARPS * 32) sketch_kernel(DevReads R, DevTable
 //   * the block's hashes are parked in shared memory ([slot][thread], conflict free) only so that the
 //     rare flagged positions can be fetched with a dynamic index when they probe the index.
 // ============================================================================================
-constexpr int SHORT_THREADS = 128;
+constexpr int SHORT_THREADS = 512;
+constexpr uint32_t SMEM_FILTER_BITS = 14;  // a pre-filter of <= 2^14 words (64 KB) is copied into shared memory
+#ifndef DRPRG_DEFAULT_VARIANT
+#define DRPRG_DEFAULT_VARIANT 0
+#endif
 
-template <int W, int K, bool LOOKUP>
+template <int W, int K, bool LOOKUP, int VARIANT, bool SMEM_FILTER>
 __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R, DevTable T,
                                                                      unsigned long long* __restrict__ out_a,
                                                                      unsigned long long* __restrict__ out_b,
                                                                      unsigned long long* __restrict__ out_count,
-                                                                     unsigned long long cap) {
+                                                                     unsigned long long cap, uint32_t four) {
     static_assert(K >= 2 && K <= 15, "left-aligned hash with a spare low bit range needs k <= 15");
     constexpr uint32_t S = 32 - 2 * K;
     constexpr uint32_t HM = ~((1u << S) - 1u);
-    __shared__ uint32_t s_h[2][W][SHORT_THREADS];
+    extern __shared__ uint32_t s_short[];
+    uint32_t(*s_h)[W][SHORT_THREADS] = reinterpret_cast<uint32_t(*)[W][SHORT_THREADS]>(s_short);
+    const uint32_t* s_filter = s_short + 2 * W * SHORT_THREADS;
     const int tid = threadIdx.x;
-    const unsigned long long r = (unsigned long long)blockIdx.x * SHORT_THREADS + tid;
+    if (LOOKUP && SMEM_FILTER) {  // "hot buckets in shared memory": the whole negative filter, once per persistent CTA
+        uint32_t* f = s_short + 2 * W * SHORT_THREADS;
+        const uint32_t nwf = 1u << T.filter_bits;
+        for (uint32_t i = tid * 4; i < nwf; i += SHORT_THREADS * 4)
+            *reinterpret_cast<uint4*>(f + i) = __ldg(reinterpret_cast<const uint4*>(T.filter + i));
+        __syncthreads();
+    }
+    const unsigned long long n_tiles = (R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long r = tile * SHORT_THREADS + tid;
     const bool have = r < R.n_reads;
     uint32_t len = have ? __ldg(R.lens + r) : 0u;
     if (len + 1 < (uint32_t)(W + K)) len = 0;  // too short or dropped: no k-mer position is valid
     const uint32_t nk = len ? len - K + 1 : 0;
     const uint32_t nk_max = __reduce_max_sync(FULL, nk);
-    if (nk_max == 0) return;
+    if (nk_max == 0) continue;
     const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull);
     const uint32_t nwords = (len + 15) >> 4;
 
@@ -266,10 +282,12 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
     // block), so the refill test is per block, not per base, and warp-uniform: all lanes are in lockstep.
     static_assert(W <= 16, "one refill per block must cover the block");
     uint32_t hi = 0, lo = 0, avail = 0, widx = 0, F = 0, Rc = 0;
+    uint32_t wnext = nwords ? __ldg(wp) : 0u;  // always one word ahead: the load has a whole block to land
     auto refill = [&]() {
         if (avail <= 16u) {
-            const uint32_t word = (widx < nwords) ? __ldg(wp + widx) : 0u;
+            const uint32_t word = wnext;
             ++widx;
+            wnext = (widx < nwords) ? __ldg(wp + widx) : 0u;
             const uint32_t t = 2u * avail;  // 0..32 bits already occupied at the top of hi; lo is empty
             hi |= __funnelshift_rc(word, 0u, t);
             lo = __funnelshift_rc(0u, word, t);
@@ -277,11 +295,23 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         }
     };
     auto next_base = [&]() {
-        const uint32_t c = hi >> 30;
+        uint32_t c;
+        if (VARIANT & 1) {
+            // (hi:lo) <<= 2 on the multiplier pipe: the high half of hi * 4 is exactly the base leaving the top
+            // `four` is a kernel argument so that the compiler keeps these as IMAD.WIDE instead of
+            // strength-reducing them back into ALU-pipe shifts
+            const unsigned long long t1 = (unsigned long long)lo * four;
+            const unsigned long long t2 = (unsigned long long)hi * four + (t1 >> 32);
+            lo = (uint32_t)t1;
+            hi = (uint32_t)t2;
+            c = (uint32_t)(t2 >> 32);
+        } else {
+            c = hi >> 30;
+            hi = __funnelshift_l(lo, hi, 2);
+            lo <<= 2;
+        }
         F = F * 4u + c;                                     // garbage above bit 2K is shifted out by << S
         Rc = __funnelshift_r(Rc, c, 2) ^ 0xC0000000u;       // complemented base enters at the top: rc of the last 16
-        hi = __funnelshift_l(lo, hi, 2);
-        lo <<= 2;
     };
     {
         // prime the first K-1 bases (K-1 <= 14 < 16: one word)
@@ -300,7 +330,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
 #pragma unroll 1
     for (uint32_t b = 0; b < n_blocks; ++b) {
         uint32_t h[W];
-        uint32_t not_strand = 0;  // bit (W-1-j) = !(hf <= hr) of position j, shifted in through the carry flag
+        uint32_t not_strand = 0;  // bit (W-1-j) = !(hf <= hr) of position j
         const uint32_t p0 = b * W;
         uint32_t* sh = &s_h[b & 1][0][tid];
         refill();
@@ -310,10 +340,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             next_base();
             const uint32_t hf = hash_left_aligned(F << S, S, HM), hr = hash_left_aligned(Rc & HM, S, HM);
             uint32_t hv = min(hf, hr);
-            {
-                uint32_t tmp;
-                asm("sub.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;" : "+r"(not_strand), "=r"(tmp) : "r"(hr), "r"(hf));
-            }
+            if (hf > hr) not_strand |= 1u << (W - 1 - j);
             hv = (p0 + j < nk) ? hv : 0u;
             h[j] = hv;
             sh[j * SHORT_THREADS] = hv;
@@ -358,7 +385,8 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                         out_b[o] = ((unsigned long long)hv << 1) | read_strand;
                     }
                 } else {
-                    const uint32_t fw = __ldg(T.filter + (hv & ((1u << T.filter_bits) - 1u)));
+                    const uint32_t fidx = hv & ((1u << T.filter_bits) - 1u);
+                    const uint32_t fw = SMEM_FILTER ? s_filter[fidx] : __ldg(T.filter + fidx);
                     const uint32_t m = (1u << ((hv >> T.filter_bits) & 31u)) | (1u << ((hv >> (T.filter_bits + 5)) & 31u));
                     if ((fw & m) != m) continue;
                     uint32_t slot = table_slot(hv, T.slot_bits);
@@ -407,17 +435,43 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         }
         strand_prev = strand_cur;
     }
+    }  // persistent tile loop
+}
+
+template <int W, int K, bool LOOKUP, int V, bool SF>
+static void launch_short_one(const DevReads& R, const DevTable& T, unsigned long long* a, unsigned long long* b,
+                             unsigned long long* cnt, uint64_t cap, int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)2 * W * SHORT_THREADS * 4 + (SF ? (size_t)4 << T.filter_bits : 0);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sketch_short_kernel<W, K, LOOKUP, V, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * W * SHORT_THREADS * 4 + (SF ? (4u << SMEM_FILTER_BITS) : 0)));
+        configured = true;
+    }
+    // persistent CTAs: two per SM (register file: 2 x 512 threads x 62 registers), each loops over read tiles
+    const unsigned long long n_tiles = (R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, 2ull * (unsigned)sm_count);
+    sketch_short_kernel<W, K, LOOKUP, V, SF><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap, 4u);
+    ++g_launches;
 }
 
 template <bool LOOKUP>
 static bool launch_short(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* a,
-                         unsigned long long* b, unsigned long long* cnt, uint64_t cap, cudaStream_t st) {
-    const unsigned grid = (unsigned)((R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS);
-#define DRPRG_SHORT(WW, KK)                                                                          \
-    if (w == WW && k == KK) {                                                                        \
-        sketch_short_kernel<WW, KK, LOOKUP><<<grid, SHORT_THREADS, 0, st>>>(R, T, a, b, cnt, cap); \
-        ++g_launches;                                                                                \
-        return true;                                                                                 \
+                         unsigned long long* b, unsigned long long* cnt, uint64_t cap, int sm_count, cudaStream_t st) {
+    static const int variant = [] {
+        const char* e = getenv("DRPRG_SKETCH_VARIANT");  // tuning switch: bit0 = wide-multiply base feed, bit1 = global-memory filter
+        return e ? atoi(e) & 3 : DRPRG_DEFAULT_VARIANT;
+    }();
+    const bool sf = LOOKUP && T.filter_bits <= SMEM_FILTER_BITS && !(variant & 2);
+#define DRPRG_SHORT(WW, KK)                                                                                       \
+    if (w == WW && k == KK) {                                                                                     \
+        if (variant & 1) {                                                                                        \
+            if (sf) launch_short_one<WW, KK, LOOKUP, 1, true>(R, T, a, b, cnt, cap, sm_count, st);                \
+            else launch_short_one<WW, KK, LOOKUP, 1, false>(R, T, a, b, cnt, cap, sm_count, st);                  \
+        } else {                                                                                                  \
+            if (sf) launch_short_one<WW, KK, LOOKUP, 0, true>(R, T, a, b, cnt, cap, sm_count, st);                \
+            else launch_short_one<WW, KK, LOOKUP, 0, false>(R, T, a, b, cnt, cap, sm_count, st);                  \
+        }                                                                                                         \
+        return true;                                                                                              \
     }
     DRPRG_SHORT(11, 15)  // drprg defaults (src/builder.rs:40-41)
     DRPRG_SHORT(14, 15)  // pandora's default w, used by the reference's build tests (src/builder.rs:1181)
@@ -437,7 +491,7 @@ void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
                           uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
-    if (max_len <= SHORT_READ_MAX && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, st)) return;
+    if (max_len <= SHORT_READ_MAX && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, sm_count, st)) return;
     sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
     ++g_launches;
 }
@@ -446,7 +500,7 @@ void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
     DevTable T{};
-    if (max_len <= SHORT_READ_MAX && launch_short<false>(R, T, w, k, d_key, d_val, d_count, cap, st)) return;
+    if (max_len <= SHORT_READ_MAX && launch_short<false>(R, T, w, k, d_key, d_val, d_count, cap, sm_count, st)) return;
     sketch_kernel<false><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_key, d_val, d_count, cap);
     ++g_launches;
 }
@@ -745,9 +799,9 @@ void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_
 __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
                               const uint32_t* __restrict__ edges, const double* __restrict__ prob,
                               const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ gM,
-                              uint32_t* __restrict__ glen, uint32_t* __restrict__ prev, uint32_t* __restrict__ gup,
+                              uint32_t* __restrict__ glen, uint32_t* __restrict__ gprev, uint32_t* __restrict__ gup,
                               uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
-                              uint32_t smem_nodes, int LV) {
+                              uint32_t smem_nodes, uint32_t smem_edges, int LV) {
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
@@ -756,29 +810,35 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
         return;
     }
-    // The chain's working set lives in shared memory when the locus fits: running sum, cached mean
-    // (sum / length: one fp64 division per node instead of one per edge visit), node score, length and
-    // the binary-lifting pointers.  Every step of the serial dependency is then an LDS (~30 cycles)
-    // instead of an L2 round trip (the first version spent 2.6 ms here, mostly on the lifting pointers).
-    const bool in_smem = n <= smem_nodes;
+    // The chain's whole working set lives in shared memory when the locus fits: running sum, cached mean
+    // (sum / length: one fp64 division per node instead of one per edge visit), node score, length, the
+    // binary-lifting pointers and the locus's CSR edges.  Every step of the serial dependency is then an
+    // LDS (~30 cycles) instead of an L2 round trip (the first version spent 2.6 ms in this kernel).
+    const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
+    const bool in_smem = n <= smem_nodes && n_edges <= smem_edges;
     double* M = in_smem ? s_dyn : gM + base;
     double* mean = in_smem ? s_dyn + smem_nodes : nullptr;
     double* pr = in_smem ? s_dyn + 2 * (size_t)smem_nodes : nullptr;
     uint32_t* len = in_smem ? (uint32_t*)(s_dyn + 3 * (size_t)smem_nodes) : glen + base;
     uint32_t* up = in_smem ? len + smem_nodes : gup + base;
+    uint32_t* s_eoff = up + (size_t)LV * smem_nodes;      // smem only
+    uint32_t* s_edges = s_eoff + smem_nodes + 2;         // smem only
     const size_t up_stride = in_smem ? smem_nodes : total;
     if (in_smem) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pr[i] = prob[base + i];
+        for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) s_eoff[i] = edge_off[base + i] - e_base;
+        for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[e_base + i];
         __syncwarp();
     }
     if (threadIdx.x != 0) return;
     const double* prb = in_smem ? pr : prob + base;
+    const uint32_t* eo = in_smem ? s_eoff : edge_off + base;
+    const uint32_t* ed = in_smem ? s_edges : edges;  // global CSR offsets are absolute
     const double tol = 0.000001;
     const uint32_t term = n - 1;
     M[term] = 0.0;
     len[term] = 0;
-    if (in_smem) mean[term] = 0.0 / 0.0;  // pandora divides 0 by 0 for the terminus; never compared
-    prev[base + term] = term;
+    if (in_smem) mean[term] = 0.0;  // never read: the terminus competes with the threshold instead
     for (int v = 0; v < LV; ++v) up[(size_t)v * up_stride + term] = term;
     for (uint32_t j = term; j-- > 0;) {
         double max_mean = -(double)FLT_MAX;
@@ -786,12 +846,13 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         double Mj = 0.0;
         uint32_t lenj = 0, prevj = term;
         const double pj = prb[j];
-        const uint32_t e1 = edge_off[base + j + 1];
-        for (uint32_t e = edge_off[base + j]; e < e1; ++e) {
-            const uint32_t v = edges[e];
+        const uint32_t e1 = eo[j + 1];
+        for (uint32_t e = eo[j]; e < e1; ++e) {
+            const uint32_t v = ed[e];
             const bool is_term = (v == term);
             const uint32_t lv = len[v];
-            const double mean_v = in_smem ? mean[v] : M[v] / (double)lv;
+            double mean_v = 0.0;
+            if (!is_term) mean_v = in_smem ? mean[v] : M[v] / (double)lv;
             const bool take = is_term ? (P.thresh > max_mean + tol)
                                       : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
             if (!take) continue;
@@ -810,8 +871,7 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         }
         M[j] = Mj;
         len[j] = lenj;
-        if (in_smem) mean[j] = Mj / (double)lenj;
-        prev[base + j] = prevj;
+        if (in_smem) mean[j] = Mj / (double)lenj;  // 0/0 = NaN for a dead end: never chosen, like pandora
         up[j] = prevj;
         uint32_t a = prevj;
         for (int v = 1; v < LV; ++v) {
@@ -819,10 +879,10 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
             up[(size_t)v * up_stride + j] = a;
         }
     }
-    uint32_t cnt = 0, p = prev[base];
+    uint32_t cnt = 0, p = up[0];
     while (p < term && cnt < n) {
         path[base + cnt++] = p;
-        p = prev[base + p];
+        p = up[p];
     }
     path_len[l] = cnt;
 }
@@ -830,23 +890,27 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
-                   uint32_t max_locus_knodes, cudaStream_t st) {
+                   uint32_t max_locus_knodes, uint32_t max_locus_edges, cudaStream_t st) {
     if (!n_loci) return;
-    // shared memory per k-mer node: sum, mean, score (f64), length (u32) and LV lifting pointers (u32),
-    // up to the 227 KB a CTA may own; larger loci fall back to global memory
+    // shared memory: per k-mer node sum, mean, score (f64), length, LV lifting pointers, edge offset (u32);
+    // per edge one u32.  Up to the 227 KB a CTA may own; larger loci fall back to global memory.
     int LV = 1;
     while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
-    const size_t per_node = 24 + 4 + 4 * (size_t)LV;
-    uint32_t smem_nodes = std::min<uint32_t>(max_locus_knodes, (uint32_t)((220u * 1024u) / per_node));
-    smem_nodes = (smem_nodes + 1) & ~1u;
-    const size_t smem = (size_t)smem_nodes * per_node;
+    const size_t per_node = 24 + 4 + 4 * (size_t)LV + 4;
+    const size_t budget = 220u * 1024u;
+    uint32_t smem_nodes = (max_locus_knodes + 3) & ~1u, smem_edges = max_locus_edges + 2;
+    if ((size_t)smem_nodes * per_node + 16 + 4 * (size_t)smem_edges > budget) {  // biggest locus does not fit: size for the rest
+        smem_nodes = (uint32_t)((budget / 2) / per_node) & ~1u;
+        smem_edges = (uint32_t)((budget / 2) / 4);
+    }
+    const size_t smem = (size_t)smem_nodes * per_node + 16 + 4 * (size_t)smem_edges;
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(mlpath_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     mlpath_kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
-                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes, LV);
+                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes, smem_edges, LV);
     ++g_launches;
 }
 
