@@ -490,28 +490,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             O.use_cached = false;
         }
     };
-    {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned T = std::min<unsigned>({8u, hw, std::max<uint32_t>(1u, P)});
-        if (T <= 1) {
-            for (uint32_t l = 0; l < P; ++l) do_locus(l);
-        } else {
-            std::atomic<uint32_t> next{0};
-            std::vector<std::thread> pool;
-            std::vector<std::string> errs(T);
-            for (unsigned t = 0; t < T; ++t)
-                pool.emplace_back([&, t] {
-                    try {
-                        for (uint32_t l = next++; l < P; l = next++) do_locus(l);
-                    } catch (const std::exception& e) {
-                        errs[t] = e.what();
-                    }
-                });
-            for (auto& th : pool) th.join();
-            for (auto& e : errs)
-                if (!e.empty()) throw std::runtime_error(e);
-        }
-    }
+    parallel_for(P, [&](size_t l) { do_locus((uint32_t)l); });
     for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
         LocusOut& O = lout[l];
         if (!O.present) continue;

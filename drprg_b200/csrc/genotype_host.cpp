@@ -7,19 +7,102 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <charconv>
 #include <cmath>
 #include <cstring>
 #include <ctime>
 #include <deque>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
 
 namespace drprg {
+
+namespace {
+class WorkerPool {
+  public:
+    static WorkerPool& get() {
+        static WorkerPool* p = new WorkerPool();  // leaked on purpose: workers may outlive static destructors
+        return *p;
+    }
+    void run(size_t n, const std::function<void(size_t)>& fn, size_t max_threads) {
+        if (n == 0) return;
+        const size_t helpers = std::min({workers_.size(), max_threads > 0 ? max_threads - 1 : 0, n - 1});
+        if (helpers == 0) {
+            for (size_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        std::unique_lock<std::mutex> run_lock(run_mutex_);  // one parallel_for at a time
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            pending_ = helpers;
+            wanted_ = helpers;
+            error_.clear();
+            ++generation_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+        if (!error_.empty()) throw std::runtime_error(error_);
+    }
+
+  private:
+    WorkerPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n = std::min(15u, hw > 1 ? hw - 1 : 0);
+        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+        for (auto& w : workers_) w.detach();
+    }
+    void work() {
+        try {
+            for (size_t i = next_++; i < n_; i = next_++) (*fn_)(i);
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> g(m_);
+            if (error_.empty()) error_ = e.what();
+            next_.store(n_);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen && wanted_ > 0; });
+                seen = generation_;
+                --wanted_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, run_mutex_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t n_ = 0, pending_ = 0, wanted_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t generation_ = 0;
+    std::string error_;
+};
+}  // namespace
+
+void parallel_for(size_t n, const std::function<void(size_t)>& fn, size_t max_threads) {
+    WorkerPool::get().run(n, fn, max_threads);
+}
 
 static inline uint32_t sat16(int32_t c) { return c > 65535 ? 65535u : (uint32_t)(c < 0 ? 0 : c); }
 
@@ -520,18 +603,18 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
             s += '\n';
         }
     };
-    const size_t nthreads = recs.size() >= 1024 ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (nthreads <= 1) {
+    const size_t parts_n = recs.size() >= 1024 ? 16 : 1;
+    if (parts_n <= 1) {
         format_range(0, recs.size(), s);
     } else {  // records are independent lines: format contiguous ranges in parallel, then concatenate
-        std::vector<std::string> parts(nthreads);
-        std::vector<std::thread> pool;
-        for (size_t t = 0; t < nthreads; ++t)
-            pool.emplace_back([&, t] {
-                parts[t].reserve((recs.size() / nthreads + 1) * 200);
-                format_range(recs.size() * t / nthreads, recs.size() * (t + 1) / nthreads, parts[t]);
-            });
-        for (auto& th : pool) th.join();
+        std::vector<std::string> parts(parts_n);
+        parallel_for(parts_n, [&](size_t t) {
+            parts[t].reserve((recs.size() / parts_n + 1) * 224);
+            format_range(recs.size() * t / parts_n, recs.size() * (t + 1) / parts_n, parts[t]);
+        });
+        size_t total = s.size();
+        for (auto& part : parts) total += part.size();
+        s.reserve(total);
         for (auto& part : parts) s += part;
     }
     return s;

@@ -3,6 +3,7 @@
 // allele -> k-mer-node CSR the genotype kernel consumes, and the pandora_genotyped.vcf writer
 // (/root/reference/src/lib.rs:644-646; schema /root/reference/tests/cases/predict/*.vcf).
 #pragma once
+#include <functional>
 #include <map>
 #include <set>
 #include <tuple>
@@ -13,6 +14,10 @@
 #include "prg_graph.hpp"
 
 namespace drprg {
+
+// Small persistent host thread pool (creating threads per call cost more than the work they did).
+// parallel_for(n, fn) runs fn(0..n-1) on the pool plus the calling thread and rethrows the first error.
+void parallel_for(size_t n, const std::function<void(size_t)>& fn, size_t max_threads = 8);
 
 struct SampleOpts {
     uint32_t min_cluster_size = 10;

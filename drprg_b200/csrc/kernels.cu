@@ -796,50 +796,20 @@ void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_
 // among successors is order dependent (1e-6 tolerance, longer path wins ties), so lane 0 walks the
 // nodes in reverse rank order; the windowed mean needs the node `window` steps down the chosen
 // path, found in O(log window) with binary-lifting pointers instead of pandora's linear walk.
-__global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
-                              const uint32_t* __restrict__ edges, const double* __restrict__ prob,
-                              const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ gM,
-                              uint32_t* __restrict__ glen, uint32_t* __restrict__ gprev, uint32_t* __restrict__ gup,
-                              uint32_t total, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
-                              uint32_t smem_nodes, uint32_t smem_edges, int LV) {
-    extern __shared__ double s_dyn[];
-    const uint32_t l = blockIdx.x;
-    if (l >= n_loci) return;
-    const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
-    if (locus_reads[l] <= 0 || n < 2) {
-        if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
-        return;
-    }
-    // The chain's whole working set lives in shared memory when the locus fits: running sum, cached mean
-    // (sum / length: one fp64 division per node instead of one per edge visit), node score, length, the
-    // binary-lifting pointers and the locus's CSR edges.  Every step of the serial dependency is then an
-    // LDS (~30 cycles) instead of an L2 round trip (the first version spent 2.6 ms in this kernel).
-    const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
-    const bool in_smem = n <= smem_nodes && n_edges <= smem_edges;
-    double* M = in_smem ? s_dyn : gM + base;
-    double* mean = in_smem ? s_dyn + smem_nodes : nullptr;
-    double* pr = in_smem ? s_dyn + 2 * (size_t)smem_nodes : nullptr;
-    uint32_t* len = in_smem ? (uint32_t*)(s_dyn + 3 * (size_t)smem_nodes) : glen + base;
-    uint32_t* up = in_smem ? len + smem_nodes : gup + base;
-    uint32_t* s_eoff = up + (size_t)LV * smem_nodes;      // smem only
-    uint32_t* s_edges = s_eoff + smem_nodes + 2;         // smem only
-    const size_t up_stride = in_smem ? smem_nodes : total;
-    if (in_smem) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pr[i] = prob[base + i];
-        for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) s_eoff[i] = edge_off[base + i] - e_base;
-        for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[e_base + i];
-        __syncwarp();
-    }
-    if (threadIdx.x != 0) return;
-    const double* prb = in_smem ? pr : prob + base;
-    const uint32_t* eo = in_smem ? s_eoff : edge_off + base;
-    const uint32_t* ed = in_smem ? s_edges : edges;  // global CSR offsets are absolute
+template <bool IN_SMEM, int LVT>
+__device__ __forceinline__ void mlpath_chain(uint32_t n, double* __restrict__ M, double* __restrict__ mean,
+                                             const double* __restrict__ prb, uint32_t* __restrict__ len,
+                                             uint32_t* __restrict__ up, uint32_t up_stride,
+                                             const uint32_t* __restrict__ eo, const uint32_t* __restrict__ ed,
+                                             const ModelParams& P) {
     const double tol = 0.000001;
     const uint32_t term = n - 1;
+    const uint32_t steps = P.window - 1;  // the node `window` steps down the chosen path = window-1 steps after v
     M[term] = 0.0;
     len[term] = 0;
-    if (in_smem) mean[term] = 0.0;  // never read: the terminus competes with the threshold instead
-    for (int v = 0; v < LV; ++v) up[(size_t)v * up_stride + term] = term;
+    if (IN_SMEM) mean[term] = 0.0;  // never read: the terminus competes with the threshold instead
+#pragma unroll
+    for (int v = 0; v < LVT; ++v) up[v * up_stride + term] = term;
     for (uint32_t j = term; j-- > 0;) {
         double max_mean = -(double)FLT_MAX;
         uint32_t max_len = 0;
@@ -852,7 +822,7 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
             const bool is_term = (v == term);
             const uint32_t lv = len[v];
             double mean_v = 0.0;
-            if (!is_term) mean_v = in_smem ? mean[v] : M[v] / (double)lv;
+            if (!is_term) mean_v = IN_SMEM ? mean[v] : M[v] / (double)lv;
             const bool take = is_term ? (P.thresh > max_mean + tol)
                                       : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
             if (!take) continue;
@@ -860,9 +830,10 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
             lenj = 1 + lv;
             prevj = v;
             if (lenj > P.window) {
-                uint32_t pn = v, steps = P.window - 1;
-                for (int b = 0; steps; ++b, steps >>= 1)
-                    if (steps & 1u) pn = up[(size_t)b * up_stride + pn];
+                uint32_t pn = v;
+#pragma unroll
+                for (int b = 0; b < LVT; ++b)
+                    if ((steps >> b) & 1u) pn = up[b * up_stride + pn];
                 Mj -= prb[pn];
                 lenj -= 1;
             }
@@ -871,18 +842,68 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
         }
         M[j] = Mj;
         len[j] = lenj;
-        if (in_smem) mean[j] = Mj / (double)lenj;  // 0/0 = NaN for a dead end: never chosen, like pandora
+        if (IN_SMEM) mean[j] = Mj / (double)lenj;  // 0/0 = NaN for a dead end: never chosen, like pandora
         up[j] = prevj;
         uint32_t a = prevj;
-        for (int v = 1; v < LV; ++v) {
-            a = up[(size_t)(v - 1) * up_stride + a];
-            up[(size_t)v * up_stride + j] = a;
+#pragma unroll
+        for (int v = 1; v < LVT; ++v) {
+            a = up[(v - 1) * up_stride + a];
+            up[v * up_stride + j] = a;
         }
     }
-    uint32_t cnt = 0, p = up[0];
-    while (p < term && cnt < n) {
-        path[base + cnt++] = p;
-        p = up[p];
+}
+
+template <int LVT>
+__global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
+                              const uint32_t* __restrict__ edges, const double* __restrict__ prob,
+                              const int32_t* __restrict__ locus_reads, ModelParams P, double* __restrict__ gM,
+                              uint32_t* __restrict__ glen, uint32_t* __restrict__ gup, uint32_t total,
+                              uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t smem_nodes,
+                              uint32_t smem_edges) {
+    extern __shared__ double s_dyn[];
+    const uint32_t l = blockIdx.x;
+    if (l >= n_loci) return;
+    const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
+    if (locus_reads[l] <= 0 || n < 2) {
+        if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
+        return;
+    }
+    // The chain's whole working set lives in shared memory when the locus fits: running sum, cached mean
+    // (sum / length: one fp64 division per node instead of one per edge visit), node score, length, the
+    // binary-lifting pointers and the locus's CSR edges.  Every step of the serial dependency is then an
+    // LDS with 32-bit addressing instead of an L2 round trip.
+    const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
+    const bool in_smem = n <= smem_nodes && n_edges <= smem_edges;
+    const uint32_t term = n - 1;
+    uint32_t cnt = 0;
+    if (in_smem) {
+        double* M = s_dyn;
+        double* mean = s_dyn + smem_nodes;
+        double* pr = s_dyn + 2 * (size_t)smem_nodes;
+        uint32_t* len = (uint32_t*)(s_dyn + 3 * (size_t)smem_nodes);
+        uint32_t* up = len + smem_nodes;
+        uint32_t* s_eoff = up + (size_t)LVT * smem_nodes;
+        uint32_t* s_edges = s_eoff + smem_nodes + 2;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) pr[i] = prob[base + i];
+        for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) s_eoff[i] = edge_off[base + i] - e_base;
+        for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[e_base + i];
+        __syncwarp();
+        if (threadIdx.x != 0) return;
+        mlpath_chain<true, LVT>(n, M, mean, pr, len, up, smem_nodes, s_eoff, s_edges, P);
+        uint32_t p = up[0];
+        while (p < term && cnt < n) {
+            path[base + cnt++] = p;
+            p = up[p];
+        }
+    } else {
+        if (threadIdx.x != 0) return;
+        uint32_t* up = gup + base;
+        mlpath_chain<false, LVT>(n, gM + base, nullptr, prob + base, glen + base, up, total, edge_off + base, edges, P);
+        uint32_t p = up[0];
+        while (p < term && cnt < n) {
+            path[base + cnt++] = p;
+            p = up[p];
+        }
     }
     path_len[l] = cnt;
 }
@@ -896,6 +917,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
     // per edge one u32.  Up to the 227 KB a CTA may own; larger loci fall back to global memory.
     int LV = 1;
     while ((1u << LV) <= P.window && LV < LV_MAX) ++LV;
+    LV = LV <= 7 ? 7 : LV_MAX;  // the two instantiated level counts
     const size_t per_node = 24 + 4 + 4 * (size_t)LV + 4;
     const size_t budget = 220u * 1024u;
     uint32_t smem_nodes = (max_locus_knodes + 3) & ~1u, smem_edges = max_locus_edges + 2;
@@ -904,13 +926,17 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
         smem_edges = (uint32_t)((budget / 2) / 4);
     }
     const size_t smem = (size_t)smem_nodes * per_node + 16 + 4 * (size_t)smem_edges;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(mlpath_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    auto go = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len, d_up,
+                                         total_knodes, d_path, d_path_len, smem_nodes, smem_edges);
+    };
+    (void)d_prev;
+    switch (LV) {  // levels needed for the window (pandora's default 100 -> 7)
+        case 7: go(mlpath_kernel<7>); break;
+        case 1: case 2: case 3: case 4: case 5: case 6: go(mlpath_kernel<7>); break;
+        default: go(mlpath_kernel<LV_MAX>); break;
     }
-    mlpath_kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len,
-                                            d_prev, d_up, total_knodes, d_path, d_path_len, smem_nodes, smem_edges, LV);
     ++g_launches;
 }
 
