@@ -181,7 +181,7 @@ def main():
             sharded.allreduce_accum(ix)
             torch.cuda.current_stream().synchronize()
         ix.genotype(wl.refs_path)
-        return ix.vcf()
+        return ix.vcf_bytes()
 
     def step_resident():
         return hot_path(resident)
@@ -236,7 +236,7 @@ def main():
     alg_bytes = n * (workload.STRIDE_WORDS * 4 + 4) + 16.0 * hits
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith("#"))
+    n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
     h2d = int(h_words.numel() * 4 + h_lens.numel() * 4)
     d2h = int(ix.n_accum * 4 + n_records * 64 + 8)
 
@@ -250,7 +250,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "sketch_kernel<LOOKUP> (S1+S2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "sketch_short_kernel<11,15,LOOKUP> (S1+S2: sketch + index lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "integer-issue bound (~5k INT32 ops per read vs 44 B), see DESIGN.md"},

@@ -52,6 +52,30 @@ struct DBuf {  // grow-only device buffer
 };
 
 template <class T>
+struct PinnedBuf {  // grow-only pinned host buffer: async D2H into pageable memory would block the host
+    T* p = nullptr;
+    size_t cap = 0, n = 0;
+    void resize(size_t want) {
+        if (want > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = want + want / 4 + 256;
+            CK(cudaMallocHost(&p, cap * sizeof(T)));
+        }
+        n = want;
+    }
+    T* data() { return p; }
+    size_t size() const { return n; }
+    T* begin() { return p; }
+    T* end() { return p + n; }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = n = 0;
+    }
+};
+
+template <class T>
 T* to_device(const std::vector<T>& v) {
     T* d = nullptr;
     CK(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T)));
@@ -158,6 +182,10 @@ struct drprg_index {
     DBuf<double> d_gt_f64;
     DBuf<int32_t> d_gt_i32;
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
+    cudaStream_t st_ml = nullptr, st_gt = nullptr;  // ML-path kernel / genotype kernels run concurrently
+    PinnedBuf<uint32_t> h_path, h_plen, h_u32;
+    PinnedBuf<double> h_f64;
+    PinnedBuf<int32_t> h_gt;
     double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::string> contigs;
     std::string vcf;
@@ -180,6 +208,9 @@ struct drprg_index {
         d_prob.release(); d_M.release(); d_len.release(); d_prev.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release();
+        if (st_ml) cudaStreamDestroy(st_ml);
+        if (st_gt) cudaStreamDestroy(st_gt);
     }
 };
 
@@ -434,14 +465,23 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     if (any_present) X->fit.thresh = prob_threshold(hist);
     MP.thresh = (double)X->fit.thresh;
     lap(1);
-    // ---- S7 on the device
+    // ---- S7 on the device: the ML-path kernel is a serial chain per locus (~1 ms).  It only decides which loci
+    // are reported and whether the path spells alleles the site tables lack (rare), so it runs on its own stream
+    // while S8 (per-allele statistics + likelihoods) and the VCF text are produced SPECULATIVELY for the common
+    // outcome "every locus with reads is present, no extra records"; the outcome is verified afterwards and
+    // anything that deviates is redone on the slow path.
+    if (!X->st_ml) {
+        CK(cudaStreamCreateWithFlags(&X->st_ml, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&X->st_gt, cudaStreamNonBlocking));
+    }
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
-                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges, st);
+                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
+                  X->st_ml);
     CK(cudaGetLastError());
-    std::vector<uint32_t> path(N), plen(P);
-    CK(cudaMemcpy(path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost));
-    lap(2);
+    X->h_path.resize(N);
+    X->h_plen.resize(P);
+    CK(cudaMemcpyAsync(X->h_path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost, X->st_ml));
+    CK(cudaMemcpyAsync(X->h_plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost, X->st_ml));
     // ---- reference paths / site tables (read independent, cached per --vcf-refs file)
     const std::string rp = vcf_refs ? vcf_refs : "";
     if (rp != X->refs_path) {
@@ -450,12 +490,98 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         for (auto& s : X->sites) s = drprg_index::LocusSites();
         X->csr_records.clear();
     }
-    X->mlpaths.assign(P, {});
-    X->present.assign(P, 0);
+    auto ensure_sites = [&](uint32_t l) {
+        auto& S = X->sites[l];
+        if (S.ready) return;
+        const Locus& L = H.loci[l];
+        auto it = X->refs.find(L.name);
+        if (it != X->refs.end()) S.ref_path = thread_sequence(L, it->second);
+        if (S.ref_path.empty()) S.ref_path = top_path(L);
+        S.biallelic = enumerate_sites(H, l, S.ref_path);
+        for (auto& r : S.biallelic) S.known.insert(std::make_tuple(r.pos, r.ref, r.alts[0]));
+        S.merged = merge_records(L, S.ref_path, S.biallelic);
+        S.ready = true;
+    };
+    const std::string sample_name = sample && *sample ? sample : "sample";
+    GenotypeArrays& G = X->GA;
+    // S8 + text for a given record list (uses the cached device CSR while the list is the cached one)
+    auto run_s8_and_format = [&](cudaStream_t s8) {
+        if (X->records != X->csr_records || G.rec_off.empty() || !X->sample_records.empty()) {
+            G.rec_off.assign(1, 0);
+            G.allele_off.assign(1, 0);
+            G.allele_kn.clear();
+            for (const SiteRecord* r : X->records) {
+                for (auto& kn : r->allele_kn) {
+                    for (uint32_t x : kn) G.allele_kn.push_back(H.knode_base[r->locus] + x);
+                    G.allele_off.push_back((uint32_t)G.allele_kn.size());
+                }
+                G.rec_off.push_back((uint32_t)G.allele_off.size() - 1);
+            }
+            CK(cudaStreamSynchronize(s8));
+            for (void* p : {(void*)X->d_rec_off, (void*)X->d_allele_off, (void*)X->d_allele_kn})
+                if (p) cudaFree(p);
+            X->d_rec_off = to_device(G.rec_off);
+            X->d_allele_off = to_device(G.allele_off);
+            X->d_allele_kn = to_device(G.allele_kn);
+            X->csr_records = X->sample_records.empty() ? X->records : std::vector<const SiteRecord*>();
+        }
+        const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
+        std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+        for (auto* v : cols) v->resize(na);
+        G.gaps.resize(na);
+        G.lik.resize(na);
+        G.gt_conf.resize(nr);
+        G.gt.resize(nr);
+        if (nr) {
+            X->d_gt_u32.ensure((size_t)na * 6);
+            X->d_gt_f64.ensure((size_t)na * 2 + nr);
+            X->d_gt_i32.ensure(nr);
+            uint32_t* u = X->d_gt_u32.p;
+            double* f = X->d_gt_f64.p;
+            DevGenotype DG{nr, na, X->d_rec_off, X->d_allele_off, X->d_allele_kn, u, u + na, u + 2 * (size_t)na, u + 3 * (size_t)na,
+                           u + 4 * (size_t)na, u + 5 * (size_t)na, f, f + na, f + 2 * (size_t)na, X->d_gt_i32.p};
+            launch_genotype(X->d_accum, DG, MP, s8);
+            CK(cudaGetLastError());
+            X->h_u32.resize((size_t)na * 6);
+            X->h_f64.resize((size_t)na * 2 + nr);
+            CK(cudaMemcpyAsync(X->h_u32.data(), u, X->h_u32.size() * 4, cudaMemcpyDeviceToHost, s8));
+            CK(cudaMemcpyAsync(X->h_f64.data(), f, X->h_f64.size() * 8, cudaMemcpyDeviceToHost, s8));
+            X->h_gt.resize(nr);
+            CK(cudaMemcpyAsync(X->h_gt.data(), X->d_gt_i32.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s8));
+            CK(cudaStreamSynchronize(s8));
+            std::copy(X->h_gt.begin(), X->h_gt.end(), G.gt.begin());
+            for (int c = 0; c < 6; ++c)
+                std::copy(X->h_u32.begin() + (size_t)c * na, X->h_u32.begin() + (size_t)(c + 1) * na, cols[c]->begin());
+            std::copy(X->h_f64.begin(), X->h_f64.begin() + na, G.gaps.begin());
+            std::copy(X->h_f64.begin() + na, X->h_f64.begin() + 2 * (size_t)na, G.lik.begin());
+            std::copy(X->h_f64.begin() + 2 * (size_t)na, X->h_f64.end(), G.gt_conf.begin());
+        }
+        X->vcf = format_vcf(H, X->records, G, X->contigs, sample_name);
+    };
+    // ---- speculative pass: every locus with reads present, cached merged site tables
+    {
+        std::vector<uint32_t> todo;
+        for (uint32_t l = 0; l < P; ++l)
+            if (locus_reads[l] > 0 && !X->sites[l].ready) todo.push_back(l);
+        parallel_for(todo.size(), [&](size_t i) { ensure_sites(todo[i]); });
+    }
     X->records.clear();
     X->sample_records.clear();
     X->contigs.clear();
-    // per-locus host work is independent: spread the loci over a few host threads
+    for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
+        if (locus_reads[l] <= 0) continue;
+        X->contigs.push_back(H.loci[l].name);
+        for (auto& r : X->sites[l].merged) X->records.push_back(&r);
+    }
+    lap(2);
+    run_s8_and_format(X->st_gt);
+    lap(3);
+    // ---- verify the speculation against the ML paths
+    CK(cudaStreamSynchronize(X->st_ml));
+    const uint32_t* path = X->h_path.data();
+    const uint32_t* plen = X->h_plen.data();
+    X->mlpaths.assign(P, {});
+    X->present.assign(P, 0);
     struct LocusOut {
         bool present = false;
         std::vector<uint32_t> kp;
@@ -463,24 +589,16 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         bool use_cached = true;
     };
     std::vector<LocusOut> lout(P);
-    auto do_locus = [&](uint32_t l) {
-        if (plen[l] == 0xffffffffu || plen[l] == 0) return;
+    parallel_for(P, [&](size_t li) {
+        const uint32_t l = (uint32_t)li;
+        if (locus_reads[l] <= 0 || plen[l] == 0xffffffffu || plen[l] == 0) return;
         const Locus& L = H.loci[l];
         LocusOut& O = lout[l];
-        O.kp.assign(path.begin() + H.knode_base[l], path.begin() + H.knode_base[l] + plen[l]);
+        O.kp.assign(path + H.knode_base[l], path + H.knode_base[l] + plen[l]);
         std::vector<uint32_t> lp = local_path_of(L, O.kp);
         if (locus_coverage_outlier(H, l, O.kp, lp, cov, X->fit.covg)) return;
         O.present = true;
         auto& S = X->sites[l];
-        if (!S.ready) {
-            auto it = X->refs.find(L.name);
-            if (it != X->refs.end()) S.ref_path = thread_sequence(L, it->second);
-            if (S.ref_path.empty()) S.ref_path = top_path(L);
-            S.biallelic = enumerate_sites(H, l, S.ref_path);
-            for (auto& r : S.biallelic) S.known.insert(std::make_tuple(r.pos, r.ref, r.alts[0]));
-            S.merged = merge_records(L, S.ref_path, S.biallelic);
-            S.ready = true;
-        }
         std::vector<SiteRecord> extra;
         find_ml_path_records(H, l, S.ref_path, lp, S.known, extra);
         if (!extra.empty()) {  // the ML path spells alleles the site table lacks: merge them in for this sample only
@@ -489,71 +607,32 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             O.sample_merged = merge_records(L, S.ref_path, std::move(all));
             O.use_cached = false;
         }
-    };
-    parallel_for(P, [&](size_t l) { do_locus((uint32_t)l); });
-    for (uint32_t l : X->loci_by_name) {  // name order == VCF record order
-        LocusOut& O = lout[l];
-        if (!O.present) continue;
-        X->present[l] = 1;
-        X->mlpaths[l] = std::move(O.kp);
-        X->contigs.push_back(H.loci[l].name);
-        if (O.use_cached) {
-            for (auto& r : X->sites[l].merged) X->records.push_back(&r);
-        } else {
-            X->sample_records.push_back(std::move(O.sample_merged));
-            for (auto& r : X->sample_records.back()) X->records.push_back(&r);
+    });
+    bool speculation_ok = true;
+    for (uint32_t l = 0; l < P; ++l) {
+        if (lout[l].present) {
+            X->present[l] = 1;
+            X->mlpaths[l] = std::move(lout[l].kp);
         }
-    }
-    lap(3);
-    // ---- S8 on the device (CSR re-used while the record set is unchanged)
-    GenotypeArrays& G = X->GA;
-    if (X->records != X->csr_records || G.rec_off.empty() || !X->sample_records.empty()) {
-        G.rec_off.assign(1, 0);
-        G.allele_off.assign(1, 0);
-        G.allele_kn.clear();
-        for (const SiteRecord* r : X->records) {
-            for (auto& kn : r->allele_kn) {
-                for (uint32_t x : kn) G.allele_kn.push_back(H.knode_base[r->locus] + x);
-                G.allele_off.push_back((uint32_t)G.allele_kn.size());
-            }
-            G.rec_off.push_back((uint32_t)G.allele_off.size() - 1);
-        }
-        for (void* p : {(void*)X->d_rec_off, (void*)X->d_allele_off, (void*)X->d_allele_kn})
-            if (p) cudaFree(p);
-        X->d_rec_off = to_device(G.rec_off);
-        X->d_allele_off = to_device(G.allele_off);
-        X->d_allele_kn = to_device(G.allele_kn);
-        X->csr_records = X->sample_records.empty() ? X->records : std::vector<const SiteRecord*>();
-    }
-    const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
-    std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
-    for (auto* v : cols) v->resize(na);
-    G.gaps.resize(na);
-    G.lik.resize(na);
-    G.gt_conf.resize(nr);
-    G.gt.resize(nr);
-    if (nr) {
-        X->d_gt_u32.ensure((size_t)na * 6);
-        X->d_gt_f64.ensure((size_t)na * 2 + nr);
-        X->d_gt_i32.ensure(nr);
-        uint32_t* u = X->d_gt_u32.p;
-        double* f = X->d_gt_f64.p;
-        DevGenotype DG{nr, na, X->d_rec_off, X->d_allele_off, X->d_allele_kn, u, u + na, u + 2 * (size_t)na, u + 3 * (size_t)na,
-                       u + 4 * (size_t)na, u + 5 * (size_t)na, f, f + na, f + 2 * (size_t)na, X->d_gt_i32.p};
-        launch_genotype(X->d_accum, DG, MP, st);
-        CK(cudaGetLastError());
-        std::vector<uint32_t> hu((size_t)na * 6);
-        std::vector<double> hf((size_t)na * 2 + nr);
-        CK(cudaMemcpy(hu.data(), u, hu.size() * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hf.data(), f, hf.size() * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(G.gt.data(), X->d_gt_i32.p, (size_t)nr * 4, cudaMemcpyDeviceToHost));
-        for (int c = 0; c < 6; ++c) std::copy(hu.begin() + (size_t)c * na, hu.begin() + (size_t)(c + 1) * na, cols[c]->begin());
-        std::copy(hf.begin(), hf.begin() + na, G.gaps.begin());
-        std::copy(hf.begin() + na, hf.begin() + 2 * (size_t)na, G.lik.begin());
-        std::copy(hf.begin() + 2 * (size_t)na, hf.end(), G.gt_conf.begin());
+        if ((locus_reads[l] > 0) != lout[l].present || !lout[l].use_cached) speculation_ok = false;
     }
     lap(4);
-    X->vcf = format_vcf(H, X->records, G, X->contigs, sample && *sample ? sample : "sample");
+    if (!speculation_ok) {  // slow path: rebuild the record list exactly and redo S8 + text
+        X->records.clear();
+        X->contigs.clear();
+        for (uint32_t l : X->loci_by_name) {
+            LocusOut& O = lout[l];
+            if (!O.present) continue;
+            X->contigs.push_back(H.loci[l].name);
+            if (O.use_cached) {
+                for (auto& r : X->sites[l].merged) X->records.push_back(&r);
+            } else {
+                X->sample_records.push_back(std::move(O.sample_merged));
+                for (auto& r : X->sample_records.back()) X->records.push_back(&r);
+            }
+        }
+        run_s8_and_format(X->st_gt);
+    }
     lap(5);
     X->have_gt = true;
 }

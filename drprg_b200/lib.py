@@ -263,6 +263,10 @@ class Index:
     def vcf(self):
         return lib().drprg_cuda_vcf_text(self.h).decode()
 
+    def vcf_bytes(self):
+        """the VCF text as bytes (no UTF-8 decode: the text is ~1 MB per sample)"""
+        return lib().drprg_cuda_vcf_text(self.h)
+
     def write_vcf(self, path):
         _check(lib().drprg_cuda_write_vcf(self.h, str(path).encode()), "write_vcf")
 
@@ -304,7 +308,7 @@ class Index:
     def last_genotype_timings(self):
         o = np.zeros(6, np.float64)
         lib().drprg_cuda_last_genotype_timings(self.h, _p(o))
-        return dict(zip(("download", "fit", "mlpath", "sites", "genotype", "vcf_text"), o.tolist()))
+        return dict(zip(("download", "fit", "launch_ml+records", "s8+vcf_text", "ml_wait+verify", "redo"), o.tolist()))
 
     # ---- the drop-in call ----
     def map_genotype(self, reads_path, vcf_refs, outdir, opts=None):

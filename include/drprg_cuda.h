@@ -140,7 +140,8 @@ int drprg_cuda_gt_allele_knodes(drprg_index*, uint32_t* out);
 /* kernel timing of the last map_batch in ms (CUDA events on its stream): [sketch_lookup, sort, cluster, coverage] */
 int drprg_cuda_last_timings(drprg_index*, float* out4);
 /* host wall time of the last drprg_cuda_genotype in ms: [accumulator download, parameter fit + log-prob histogram,
- * ML-path kernel + download, site tables / ML-path records, genotype kernels + download, VCF text] */
+ * ML-path launch + speculative record list, genotype kernels + VCF text (overlapping the ML-path kernel),
+ * wait for the ML paths + verification, slow-path redo (0 when the speculation held)] */
 int drprg_cuda_last_genotype_timings(drprg_index*, double* out6);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t drprg_cuda_launch_count(void);
