@@ -1049,5 +1049,10 @@ int drprg_cuda_last_genotype_timings(drprg_index* X, double* out6) {
     memcpy(out6, X->gt_ms, 6 * sizeof(double));
     return 0;
 }
+int drprg_cuda_format_g6(double v, char* out) {
+    size_t n = format_g6(v, out);
+    out[n] = 0;
+    return (int)n;
+}
 uint64_t drprg_cuda_launch_count(void) { return launch_count(); }
 }

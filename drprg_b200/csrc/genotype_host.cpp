@@ -525,12 +525,62 @@ bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vecto
 }
 
 // -------------------------------------------------------------------------- VCF ---
-// "%g" (6 significant digits) like pandora's ostream output; std::to_chars(general, 6) is specified to
-// give the printf result and is several times faster
+// "%g" (6 significant digits) like pandora's ostream output.  Fast path: scale to a 6-digit integer and print
+// it in fixed notation; whenever the decimal rounding could be affected by the one floating-point rounding of the
+// scaling (within 1e-6 of a tie), or the value needs exponent notation, fall back to std::to_chars(general, 6),
+// which is specified to give the printf result.
+size_t format_g6(double v, char* out) {
+    auto slow = [&]() -> size_t {
+        auto r = std::to_chars(out, out + 40, v, std::chars_format::general, 6);
+        return (size_t)(r.ptr - out);
+    };
+    if (v == 0.0) {
+        if (std::signbit(v)) return slow();
+        out[0] = '0';
+        return 1;
+    }
+    const double a = std::fabs(v);
+    if (!(a >= 1e-4 && a < 999999.0)) return slow();  // exponent notation, inf, nan
+    static const double P10[11] = {1e-4, 1e-3, 1e-2, 1e-1, 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6};
+    int e10 = -4;
+    while (a >= P10[e10 + 5]) ++e10;  // a in [10^e10, 10^(e10+1))
+    static const double SC[10] = {1e9, 1e8, 1e7, 1e6, 1e5, 1e4, 1e3, 1e2, 1e1, 1e0};  // 10^(5-e10)
+    const double x = a * SC[e10 + 4];
+    const double fl = std::floor(x);
+    const double frac = x - fl;
+    if (std::fabs(frac - 0.5) < 1e-6) return slow();
+    uint32_t n = (uint32_t)fl + (frac > 0.5 ? 1u : 0u);
+    if (n >= 1000000u) {
+        n = 100000u;
+        ++e10;
+        if (e10 > 5) return slow();
+    }
+    char d[6];
+    for (int i = 5; i >= 0; --i) {
+        d[i] = (char)('0' + n % 10);
+        n /= 10;
+    }
+    int last = 5;
+    while (last > 0 && d[last] == '0') --last;  // significant digits d[0..last]
+    char* o = out;
+    if (v < 0) *o++ = '-';
+    if (e10 >= 0) {
+        for (int i = 0; i <= e10; ++i) *o++ = d[i];  // integer part (zeros included)
+        if (last > e10) {
+            *o++ = '.';
+            for (int i = e10 + 1; i <= last; ++i) *o++ = d[i];
+        }
+    } else {
+        *o++ = '0';
+        *o++ = '.';
+        for (int i = 0; i < -e10 - 1; ++i) *o++ = '0';
+        for (int i = 0; i <= last; ++i) *o++ = d[i];
+    }
+    return (size_t)(o - out);
+}
 static inline void put_g6(std::string& s, double v) {
-    char b[64];
-    auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6);
-    s.append(b, r.ptr);
+    char b[48];
+    s.append(b, format_g6(v, b));
 }
 static inline void put_u(std::string& s, uint32_t v) {
     char b[16];

@@ -83,6 +83,7 @@ struct GenotypeArrays {  // flattened over records / alleles, device results cop
 std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
                        const std::vector<std::string>& contigs, const std::string& sample);
 
+size_t format_g6(double v, char* out);  // printf("%g") text of v, out has room for 40 chars
 std::map<std::string, std::string> load_fasta(const std::string& path);
 
 // fasta/fastq (plain or gzip) -> 2-bit packed reads

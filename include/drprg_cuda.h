@@ -143,6 +143,8 @@ int drprg_cuda_last_timings(drprg_index*, float* out4);
  * ML-path launch + speculative record list, genotype kernels + VCF text (overlapping the ML-path kernel),
  * wait for the ML paths + verification, slow-path redo (0 when the speculation held)] */
 int drprg_cuda_last_genotype_timings(drprg_index*, double* out6);
+/* the VCF writer's float formatting (printf "%g"); out needs 48 bytes.  Exposed so tests can pin it against printf. */
+int drprg_cuda_format_g6(double v, char* out);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t drprg_cuda_launch_count(void);
 

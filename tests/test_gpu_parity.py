@@ -239,3 +239,50 @@ def test_drop_in_call_writes_pandora_vcf(tmp_path):
     assert strip(got) == strip(og.vcf())
     with pytest.raises(lib.DrprgCudaError):
         gx.map_genotype(tmp_path / "missing.fq", TOY_REFS, tmp_path)
+
+
+def test_batch_of_samples_config5(tmp_path):
+    """BASELINE config 5 shape: several samples through drprg_cuda_map_genotype_batch on one resident index;
+    every sample's VCF equals the oracle's."""
+    import ctypes as C
+    p, prg, refs = small_panel()
+    gx, ox = both_indexes(prg, 11, 15)
+    n_samples = 3
+    reads, outs, datas = [], [], []
+    for s in range(n_samples):
+        d, o, g, pl = panel_sample(p, 20000, seed=100 + 7 * s)
+        fq = tmp_path / f"s{s}.fq"
+        sim.write_fastq(str(fq), d, o)
+        od = tmp_path / f"out{s}"
+        od.mkdir()
+        reads.append(str(fq).encode()); outs.append(str(od).encode()); datas.append((d, o, len(g)))
+    L = lib.lib()
+    arr_r = (C.c_char_p * n_samples)(*reads)
+    arr_o = (C.c_char_p * n_samples)(*outs)
+    stats = (lib.MapStats * n_samples)()
+    go = lib.make_opts(illumina=True, genome_size=200_000)
+    rc = L.drprg_cuda_map_genotype_batch(gx.h, C.c_size_t(n_samples), arr_r, refs.encode(), arr_o, C.byref(go), stats)
+    assert rc == 0, L.drprg_cuda_last_error()
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    for s in range(n_samples):
+        d, o, gl = datas[s]
+        oo = O.make_opts(illumina=True, genome_size=200_000)
+        og = O.Genotype(ox, O.MapRun(ox, d, o, oo), oo, refs)
+        got = open(os.path.join(outs[s].decode(), "pandora_genotyped.vcf")).read()
+        assert strip(got) == strip(og.vcf()), s
+        assert stats[s].n_reads == len(o) - 1
+
+
+def test_pandora_mirror_interface(tmp_path):
+    """drprg_b200.pandora.Pandora mirrors Pandora::genotype_with / vcf_filename (src/lib.rs:580-646)."""
+    from drprg_b200.pandora import DependencyError, Pandora
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=30, decoys=1, seed=4)
+    fq = tmp_path / "r.fq"
+    sim.write_fastq(str(fq), d, o)
+    pan = Pandora.from_path()
+    st = pan.genotype_with(TOY_PRG, TOY_REFS, fq, tmp_path, ["-t", "2", "-w", "11", "-k", "15", "-c", "10", "-I"])
+    assert (tmp_path / Pandora.vcf_filename()).exists() and st["n_records"] == 23
+    with pytest.raises(DependencyError):
+        pan.genotype_with(TOY_PRG, TOY_REFS, tmp_path / "nope.fq", tmp_path, ["-w", "11", "-k", "15"])
+    with pytest.raises(DependencyError):
+        pan.genotype_with(TOY_PRG, TOY_REFS, fq, tmp_path, ["--bogus"])

@@ -94,3 +94,21 @@ def test_compute_refuses_without_gpu():
         gx.map_genotype("x.fq", TOY_REFS, ".")
     with pytest.raises(lib.DrprgCudaError, match="k > 16|no CUDA device"):
         lib.Index(TOY_PRG, 11, 17, device=0)
+
+
+def test_vcf_float_formatting_matches_printf_g():
+    """the VCF writer's fast "%g" must be byte-identical to printf (pandora prints floats with ostream defaults)"""
+    import ctypes as C
+    L = lib.lib()
+    L.drprg_cuda_format_g6.argtypes = [C.c_double, C.c_char_p]
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(0)
+    vals = [0.0, 1.0, -1.0, 0.5, 0.25, 0.125, 0.2, 1 / 3, 2 / 3, 0.666667, 1e-4, 9.99999e-5, 123456.5, 999999.4, 999999.5,
+            999999.6, 1e6, -144.0, -0.0001, 100000.0, 99999.95, 0.000123456789, 5e-324, 1e300, float("inf"), 0.1 + 0.2,
+            1234565.0, 12.34565, 0.3333335, 2.5e-5, 1.0000005, 1.00000049999, 322.1215, -716.9895]
+    vals += list(-np.exp(rng.uniform(-12, 14, 60000)))               # likelihood-like magnitudes
+    vals += list(rng.uniform(0, 1000, 30000)) + list(rng.integers(0, 40, 5000) / rng.integers(1, 40, 5000))
+    vals += [round(float(x), 5) + 5e-7 for x in rng.uniform(0, 100, 5000)]   # near decimal ties
+    for v in vals:
+        n = L.drprg_cuda_format_g6(float(v), buf)
+        assert buf.value[:n].decode() == "%g" % float(v), (v, buf.value, "%g" % float(v))
