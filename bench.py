@@ -181,6 +181,8 @@ def main():
             sharded.allreduce_accum(ix)
             torch.cuda.current_stream().synchronize()
         ix.genotype(wl.refs_path)
+        for k_, v_ in ix.last_genotype_timings().items():
+            stats.setdefault("gt_" + k_, []).append(v_)
         return ix.vcf_bytes()
 
     def step_resident():
@@ -253,7 +255,11 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "sketch_short_kernel<11,15,LOOKUP> (S1+S2: sketch + index lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "integer-issue bound (~5k INT32 ops per read vs 44 B), see DESIGN.md"},
+                     "note": "this kernel carries all of the step's HBM traffic and ~98% of its instructions; it is bound by INT32 issue "
+                             "(ncu: ALU pipe 80% active, 302 warp-instr per read vs 49.7 B), not by HBM. The only kernel with a longer "
+                             "duration at this batch size is mlpath_kernel (30 warps, a serial dependency chain per locus, see "
+                             "stage_ms.gt_mlpath_kernel); it runs concurrently with the genotype kernels and the host VCF formatting. "
+                             "See DESIGN.md section 4 and profiles/."},
         "stage_ms": {k_: float(np.mean(v_)) for k_, v_ in st.items() if k_ != "hits"},
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -908,6 +908,105 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
     path_len[l] = cnt;
 }
 
+// ---- fast variant: 64-byte node records addressed by their shared-memory address ---------------------------
+// The generic kernel above spends ~160 instructions and ~1000 cycles per node, two thirds of it address
+// arithmetic and dependent-issue waits (ncu: stall_wait 2.4, stall_short_scoreboard 2.6 per issued instruction).
+// Here every pointer the chain follows (successor, lifting pointers, edge targets) is stored as the 32-bit
+// shared-memory ADDRESS of the target's 64-byte record, so one hop is a single LDS with an immediate offset.
+constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF = 28, R_UP = 32;  // up[0..7] at 32..63
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+
+__global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
+                                  const uint32_t* __restrict__ edges, const double* __restrict__ prob,
+                                  const int32_t* __restrict__ locus_reads, ModelParams P, uint32_t* __restrict__ path,
+                                  uint32_t* __restrict__ path_len, uint32_t max_nodes) {
+    extern __shared__ double s_dyn[];
+    const uint32_t l = blockIdx.x;
+    if (l >= n_loci) return;
+    const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
+    if (locus_reads[l] <= 0 || n < 2) {
+        if (threadIdx.x == 0) path_len[l] = 0xffffffffu;
+        return;
+    }
+    const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
+    const uint32_t recs = (uint32_t)__cvta_generic_to_shared(s_dyn);  // n + 1 records (the extra one carries the edge end)
+    const uint32_t edg = recs + (max_nodes + 1) * REC;                // successor record addresses
+    for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) {
+        const uint32_t a = recs + i * REC;
+        if (i < n) sts64(a + R_PR, prob[base + i]);
+        sts32(a + R_EOFF, edg + (edge_off[base + i] - e_base) * 4u);
+    }
+    for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const double tol = 0.000001;
+    const uint32_t term = recs + (n - 1) * REC;
+    const uint32_t steps = P.window - 1;
+    sts64(term + R_M, 0.0);
+    sts32(term + R_LEN, 0u);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);
+    for (uint32_t a = term - REC; a + REC > recs; a -= REC) {  // nodes n-2 .. 0
+        double max_mean = -(double)FLT_MAX;
+        uint32_t max_len = 0;
+        double Mj = 0.0;
+        uint32_t lenj = 0, prevj = term;
+        const double pj = lds64(a + R_PR);
+        const uint32_t e1 = lds32(a + REC + R_EOFF);
+        for (uint32_t e = lds32(a + R_EOFF); e < e1; e += 4u) {
+            const uint32_t v = lds32(e);
+            const bool is_term = (v == term);
+            const uint32_t lv = lds32(v + R_LEN);
+            const double mean_v = lds64(v + R_MEAN);
+            const double Mv = lds64(v + R_M);
+            const bool take = is_term ? (P.thresh > max_mean + tol)
+                                      : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
+            if (!take) continue;
+            Mj = pj + Mv;
+            lenj = 1 + lv;
+            prevj = v;
+            if (lenj > P.window) {
+                uint32_t pn = v;
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    if ((steps >> b) & 1u) pn = lds32(pn + R_UP + 4 * b);
+                Mj -= lds64(pn + R_PR);
+                lenj -= 1;
+            }
+            max_mean = is_term ? P.thresh : mean_v;
+            if (!is_term) max_len = lv;
+        }
+        sts64(a + R_M, Mj);
+        sts32(a + R_LEN, lenj);
+        sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
+        sts32(a + R_UP, prevj);
+        uint32_t x = prevj;
+#pragma unroll
+        for (int v = 1; v < 8; ++v) {
+            x = lds32(x + R_UP + 4 * (v - 1));
+            sts32(a + R_UP + 4 * v, x);
+        }
+    }
+    uint32_t cnt = 0, p = lds32(recs + R_UP);
+    while (p != term && cnt < n) {
+        path[base + cnt++] = (p - recs) / REC;
+        p = lds32(p + R_UP);
+    }
+    path_len[l] = cnt;
+}
+
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
@@ -926,6 +1025,21 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
         smem_edges = (uint32_t)((budget / 2) / 4);
     }
     const size_t smem = (size_t)smem_nodes * per_node + 16 + 4 * (size_t)smem_edges;
+    {
+        const size_t rec_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4;
+        static const bool force_generic = getenv("DRPRG_MLPATH_GENERIC") != nullptr;
+        if (P.window <= 256 && rec_smem <= budget && !force_generic) {
+            static size_t configured = 0;
+            if (rec_smem > configured) {
+                cudaFuncSetAttribute(mlpath_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
+                configured = rec_smem;
+            }
+            mlpath_rec_kernel<<<n_loci, 32, rec_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P,
+                                                           d_path, d_path_len, max_locus_knodes);
+            ++g_launches;
+            return;
+        }
+    }
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len, d_up,

@@ -306,9 +306,9 @@ class Index:
         return dict(zip(("sketch_lookup", "sort", "cluster", "coverage"), o.tolist()))
 
     def last_genotype_timings(self):
-        o = np.zeros(6, np.float64)
+        o = np.zeros(7, np.float64)
         lib().drprg_cuda_last_genotype_timings(self.h, _p(o))
-        return dict(zip(("download", "fit", "launch_ml+records", "s8+vcf_text", "ml_wait+verify", "redo"), o.tolist()))
+        return dict(zip(("download", "fit", "launch_ml+records", "s8+vcf_text", "ml_wait+verify", "redo", "mlpath_kernel"), o.tolist()))
 
     # ---- the drop-in call ----
     def map_genotype(self, reads_path, vcf_refs, outdir, opts=None):

@@ -141,8 +141,9 @@ int drprg_cuda_gt_allele_knodes(drprg_index*, uint32_t* out);
 int drprg_cuda_last_timings(drprg_index*, float* out4);
 /* host wall time of the last drprg_cuda_genotype in ms: [accumulator download, parameter fit + log-prob histogram,
  * ML-path launch + speculative record list, genotype kernels + VCF text (overlapping the ML-path kernel),
- * wait for the ML paths + verification, slow-path redo (0 when the speculation held)] */
-int drprg_cuda_last_genotype_timings(drprg_index*, double* out6);
+ * wait for the ML paths + verification, slow-path redo (0 when the speculation held),
+ * device time of the ML-path kernel (CUDA events on its stream)] — 7 doubles */
+int drprg_cuda_last_genotype_timings(drprg_index*, double* out7);
 /* the VCF writer's float formatting (printf "%g"); out needs 48 bytes.  Exposed so tests can pin it against printf. */
 int drprg_cuda_format_g6(double v, char* out);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
