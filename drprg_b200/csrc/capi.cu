@@ -138,7 +138,7 @@ struct drprg_index {
     DevTable T{};
     uint2 *d_slots = nullptr, *d_recs = nullptr;
     uint32_t *d_filter = nullptr, *d_knode_base = nullptr, *d_edge_off = nullptr, *d_edges = nullptr;
-    uint8_t* d_is_terminal = nullptr;
+    uint8_t *d_is_terminal = nullptr, *d_needs_mean = nullptr;
     uint32_t table_slots = 0, filter_words = 0;
     uint64_t n_edges = 0, n_ivs = 0;
     // accumulators: [2*N coverage | P locus reads | 4 scalars]
@@ -198,7 +198,7 @@ struct drprg_index {
         if (device < 0) return;
         cudaSetDevice(device);
         for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
-                        (void*)d_is_terminal, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
+                        (void*)d_is_terminal, (void*)d_needs_mean, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
                         (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist})
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
@@ -278,6 +278,17 @@ void upload_index(drprg_index* X) {
     X->d_edge_off = to_device(edge_off);
     X->d_edges = to_device(edges);
     X->d_is_terminal = to_device(term);
+    {   // a node's mean log-prob is only ever compared when one of its predecessors has more than one out-edge
+        std::vector<uint8_t> needs(N, 0);
+        for (size_t l = 0; l < H.loci.size(); ++l) {
+            const Locus& L = H.loci[l];
+            const uint32_t base = H.knode_base[l];
+            for (uint32_t r = 0; r < L.kpath.size(); ++r)
+                if (L.kout[r].size() > 1)
+                    for (uint32_t o : L.kout[r]) needs[base + o] = 1;
+        }
+        X->d_needs_mean = to_device(needs);
+    }
     X->n_accum = 2ull * N + H.loci.size() + 4;
     CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
@@ -484,7 +495,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
                   X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
-                  X->st_ml);
+                  X->d_needs_mean, X->st_ml);
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());
     X->h_path.resize(N);

@@ -930,8 +930,9 @@ __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.s
 
 __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
                                   const uint32_t* __restrict__ edges, const double* __restrict__ prob,
-                                  const int32_t* __restrict__ locus_reads, ModelParams P, uint32_t* __restrict__ path,
-                                  uint32_t* __restrict__ path_len, uint32_t max_nodes) {
+                                  const int32_t* __restrict__ locus_reads, const uint8_t* __restrict__ needs_mean,
+                                  ModelParams P, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
+                                  uint32_t max_nodes) {
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
@@ -946,7 +947,8 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
     for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) {
         const uint32_t a = recs + i * REC;
         if (i < n) sts64(a + R_PR, prob[base + i]);
-        sts32(a + R_EOFF, edg + (edge_off[base + i] - e_base) * 4u);
+        // edge list address (4-byte aligned) | bit0: some predecessor has a choice, so this node's mean is compared
+        sts32(a + R_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
     }
     for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
     __syncwarp();
@@ -964,8 +966,29 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
         double Mj = 0.0;
         uint32_t lenj = 0, prevj = term;
         const double pj = lds64(a + R_PR);
-        const uint32_t e1 = lds32(a + REC + R_EOFF);
-        for (uint32_t e = lds32(a + R_EOFF); e < e1; e += 4u) {
+        const uint32_t e1 = lds32(a + REC + R_EOFF) & ~3u;
+        const uint32_t e0w = lds32(a + R_EOFF);
+        const uint32_t e0 = e0w & ~3u;
+        if (e1 - e0 == 4u) {
+            // single successor (most nodes): no choice to make.  pandora's comparison against the initial
+            // -FLT_MAX accepts any successor with a real mean, i.e. any successor that is not a dead end.
+            const uint32_t v = lds32(e0);
+            const uint32_t lv = lds32(v + R_LEN);
+            if (v == term || lv > 0u) {
+                Mj = pj + lds64(v + R_M);
+                lenj = 1 + lv;
+                prevj = v;
+                if (lenj > P.window) {
+                    uint32_t pn = v;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b)
+                        if ((steps >> b) & 1u) pn = lds32(pn + R_UP + 4 * b);
+                    Mj -= lds64(pn + R_PR);
+                    lenj -= 1;
+                }
+            }
+        } else
+        for (uint32_t e = e0; e < e1; e += 4u) {
             const uint32_t v = lds32(e);
             const bool is_term = (v == term);
             const uint32_t lv = lds32(v + R_LEN);
@@ -990,7 +1013,7 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
         }
         sts64(a + R_M, Mj);
         sts32(a + R_LEN, lenj);
-        sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
+        if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
         sts32(a + R_UP, prevj);
         uint32_t x = prevj;
 #pragma unroll
@@ -1010,7 +1033,7 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
-                   uint32_t max_locus_knodes, uint32_t max_locus_edges, cudaStream_t st) {
+                   uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean, cudaStream_t st) {
     if (!n_loci) return;
     // shared memory: per k-mer node sum, mean, score (f64), length, LV lifting pointers, edge offset (u32);
     // per edge one u32.  Up to the 227 KB a CTA may own; larger loci fall back to global memory.
@@ -1028,14 +1051,14 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
     {
         const size_t rec_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4;
         static const bool force_generic = getenv("DRPRG_MLPATH_GENERIC") != nullptr;
-        if (P.window <= 256 && rec_smem <= budget && !force_generic) {
+        if (P.window <= 256 && rec_smem <= budget && !force_generic && d_needs_mean) {
             static size_t configured = 0;
             if (rec_smem > configured) {
                 cudaFuncSetAttribute(mlpath_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
                 configured = rec_smem;
             }
-            mlpath_rec_kernel<<<n_loci, 32, rec_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P,
-                                                           d_path, d_path_len, max_locus_knodes);
+            mlpath_rec_kernel<<<n_loci, 32, rec_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads,
+                                                           d_needs_mean, P, d_path, d_path_len, max_locus_knodes);
             ++g_launches;
             return;
         }
