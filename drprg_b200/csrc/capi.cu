@@ -129,6 +129,11 @@ struct drprg_batch {
     int device = 0;
     uint64_t total_bases = 0;
     uint32_t max_len = UINT32_MAX;  // longest read (bound); selects the short-read kernel
+    // host uploads are split into chunks copied on a separate stream; the sketch kernel of chunk c starts as soon
+    // as its bytes have landed, so the H2D copy overlaps the sketch of the previous chunks
+    int n_chunks = 1;
+    uint64_t chunk_lo[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct drprg_index {
@@ -183,7 +188,7 @@ struct drprg_index {
     DBuf<int32_t> d_gt_i32;
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     cudaEvent_t ev_ml[2] = {nullptr, nullptr};
-    cudaStream_t st_ml = nullptr, st_gt = nullptr;  // ML-path kernel / genotype kernels run concurrently
+    cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr;  // ML-path kernel / genotype kernels run concurrently
     PinnedBuf<uint32_t> h_path, h_plen, h_u32;
     PinnedBuf<double> h_f64;
     PinnedBuf<int32_t> h_gt;
@@ -212,6 +217,7 @@ struct drprg_index {
         h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release();
         for (auto& e : ev_ml)
             if (e) cudaEventDestroy(e);
+        if (st_copy) cudaStreamDestroy(st_copy);
         if (st_ml) cudaStreamDestroy(st_ml);
         if (st_gt) cudaStreamDestroy(st_gt);
     }
@@ -394,7 +400,19 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     CK(cudaEventRecord(X->ev[0], st));
     for (int attempt = 0; attempt < 3; ++attempt) {
         CK(cudaMemsetAsync(X->d_counters, 0, 2 * sizeof(unsigned long long), st));
-        launch_sketch_lookup(B->R, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st);
+        for (int c = 0; c < B->n_chunks; ++c) {
+            DevReads Rc = B->R;
+            if (B->n_chunks > 1) {
+                const uint64_t lo = B->chunk_lo[c], hi = B->chunk_lo[c + 1];
+                if (B->ev[c]) CK(cudaStreamWaitEvent(st, B->ev[c], 0));
+                Rc.words = B->R.stride_words ? B->R.words + lo * B->R.stride_words : B->R.words;
+                Rc.word_off = B->R.word_off ? B->R.word_off + lo : nullptr;
+                Rc.lens = B->R.lens + lo;
+                Rc.n_reads = hi - lo;
+                Rc.read_id_base = B->R.read_id_base + (uint32_t)lo;
+            }
+            launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st);
+        }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(X->h_counters, X->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -664,6 +682,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
 
 void free_batch(drprg_batch* b) {
     if (!b) return;
+    for (auto& e : b->ev)
+        if (e) cudaEventDestroy(e);
     if (b->owned) {
         if (b->d_words) g_pool.put(b->d_words, b->b_words, b->device);
         if (b->d_lens) g_pool.put(b->d_lens, b->b_lens, b->device);
@@ -684,17 +704,34 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
     B->b_lens = std::max<uint64_t>(1, n) * 4;
     B->d_words = (uint32_t*)g_pool.get(B->b_words, X->device);
     B->d_lens = (uint32_t*)g_pool.get(B->b_lens, X->device);
-    if (nwords) CK(cudaMemcpyAsync(B->d_words, words, nwords * 4, cudaMemcpyHostToDevice, st));
-    if (n) CK(cudaMemcpyAsync(B->d_lens, lens, n * 4, cudaMemcpyHostToDevice, st));
     if (!stride) {
         B->b_off = (n + 1) * 8;
         B->d_off = (uint64_t*)g_pool.get(B->b_off, X->device);
-        CK(cudaMemcpyAsync(B->d_off, word_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    const bool chunked = (st == nullptr) && nwords * 4 >= (8u << 20);
+    cudaStream_t cs = st;
+    if (chunked) {
+        if (!X->st_copy) CK(cudaStreamCreateWithFlags(&X->st_copy, cudaStreamNonBlocking));
+        cs = X->st_copy;
+        B->n_chunks = 4;
+    }
+    if (!stride) CK(cudaMemcpyAsync(B->d_off, word_off, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    uint32_t ml = 0;
+    for (int c = 0; c < B->n_chunks; ++c) {
+        const uint64_t lo = n * (uint64_t)c / B->n_chunks, hi = n * (uint64_t)(c + 1) / B->n_chunks;
+        B->chunk_lo[c] = lo;
+        B->chunk_lo[c + 1] = hi;
+        const uint64_t w0 = stride ? lo * stride : word_off[lo], w1 = stride ? hi * stride : word_off[hi];
+        if (w1 > w0) CK(cudaMemcpyAsync(B->d_words + w0, words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, cs));
+        if (hi > lo) CK(cudaMemcpyAsync(B->d_lens + lo, lens + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, cs));
+        if (chunked) {
+            CK(cudaEventCreateWithFlags(&B->ev[c], cudaEventDisableTiming));
+            CK(cudaEventRecord(B->ev[c], cs));
+        }
+        for (uint64_t i = lo; i < hi; ++i) ml = std::max(ml, lens[i]);  // overlaps the copy just enqueued
     }
     B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
     B->total_bases = total_bases;
-    uint32_t ml = 0;
-    for (uint64_t i = 0; i < n; ++i) ml = std::max(ml, lens[i]);
     B->max_len = ml;
     return B.release();
 }
@@ -957,6 +994,8 @@ int64_t drprg_cuda_sketch_batch(drprg_index* X, drprg_batch* B, void* stream, ui
         key.ensure(cap);
         val.ensure(cap);
         CK(cudaMemsetAsync(X->d_counters, 0, 16, st));
+        for (auto& e : B->ev)
+            if (e) CK(cudaStreamWaitEvent(st, e, 0));
         launch_sketch_only(B->R, X->H.w, X->H.k, key.p, val.p, X->d_counters, cap, X->sm_count, B->max_len, st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 8, cudaMemcpyDeviceToHost, st));
