@@ -728,8 +728,11 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
             CK(cudaEventCreateWithFlags(&B->ev[c], cudaEventDisableTiming));
             CK(cudaEventRecord(B->ev[c], cs));
         }
-        for (uint64_t i = lo; i < hi; ++i) ml = std::max(ml, lens[i]);  // overlaps the copy just enqueued
+        // the longest read only selects the kernel: a fixed stride that already bounds it needs no scan
+        if (!(stride && stride * 16u <= SHORT_READ_MAX))
+            for (uint64_t i = lo; i < hi; ++i) ml = std::max(ml, lens[i]);  // overlaps the copy just enqueued
     }
+    if (stride && stride * 16u <= SHORT_READ_MAX) ml = stride * 16u;
     B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
     B->total_bases = total_bases;
     B->max_len = ml;
