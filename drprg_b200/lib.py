@@ -116,7 +116,10 @@ class Batch:
 
     def free(self):
         if self.h:
-            lib().drprg_cuda_batch_free(self.h)
+            try:
+                lib().drprg_cuda_batch_free(self.h)
+            except Exception:
+                pass
             self.h = None
 
     def __del__(self):
@@ -148,7 +151,10 @@ class Index:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().drprg_cuda_index_free(self.h)
+            try:
+                lib().drprg_cuda_index_free(self.h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self.h = None
 
     def __del__(self):

@@ -1,5 +1,5 @@
 import sys, os, subprocess, json
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 if len(sys.argv) > 1:
     from drprg_b200 import lib, workload
     import numpy as np
