@@ -756,44 +756,197 @@ int64_t pack_ascii(const uint8_t* ascii, const uint64_t* off, uint64_t n, uint32
     return (int64_t)(stride_words ? n * (uint64_t)stride_words : cur);
 }
 
-void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& out) {
-    (void)threads;
-    out = PackedReads();
-    out.word_off.push_back(0);
-    GzLines in(path);
-    std::string line, seq, tmp;
-    bool have = in.next(line);
-    auto emit = [&](const std::string& s) {
-        const uint32_t len = (uint32_t)s.size();
+// Ingest: the whole file is brought into memory (gzip inflated on one thread — a gzip stream is serial), split
+// at record boundaries into one piece per worker, parsed + 2-bit packed in parallel, then stitched together.
+// Inputs: fasta/fastq, plain or gzip (/root/reference/src/predict.rs:166-170).
+namespace {
+struct RawText {  // whole input file in memory, no zero-initialisation, no growth copies for plain files
+    char* p = nullptr;
+    size_t n = 0;
+    ~RawText() { free(p); }
+    size_t size() const { return n; }
+    const char* data() const { return p; }
+    char operator[](size_t i) const { return p[i]; }
+};
+
+void slurp(const std::string& path, RawText& buf) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) throw std::runtime_error("cannot open " + path);
+    unsigned char magic[2] = {0, 0};
+    size_t got = fread(magic, 1, 2, fp);
+    fseek(fp, 0, SEEK_END);
+    const size_t fsize = (size_t)ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz) {
+        buf.p = (char*)malloc(fsize + 1);
+        if (!buf.p) { fclose(fp); throw std::runtime_error("out of memory reading " + path); }
+        buf.n = fread(buf.p, 1, fsize, fp);
+        fclose(fp);
+        return;
+    }
+    fclose(fp);
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    gzbuffer(f, 1 << 20);
+    size_t cap = std::max<size_t>(fsize * 5, 1 << 20);
+    buf.p = (char*)malloc(cap);
+    size_t n = 0;
+    while (buf.p) {
+        if (n == cap) {
+            cap *= 2;
+            char* q = (char*)realloc(buf.p, cap);
+            if (!q) break;
+            buf.p = q;
+        }
+        int r = gzread(f, buf.p + n, (unsigned)std::min<size_t>(cap - n, 1u << 30));
+        if (r < 0) {
+            gzclose(f);
+            throw std::runtime_error("read error in " + path);
+        }
+        if (r == 0) break;
+        n += (size_t)r;
+    }
+    gzclose(f);
+    if (!buf.p) throw std::runtime_error("out of memory reading " + path);
+    buf.n = n;
+}
+
+struct Piece {
+    std::vector<uint32_t> words, lens;
+    std::vector<uint32_t> nwords;  // per read
+    uint64_t total_bases = 0, n_dropped = 0;
+};
+
+inline size_t line_end(const RawText& b, size_t p) {
+    const void* q = memchr(b.data() + p, '\n', b.size() - p);
+    return q ? (size_t)((const char*)q - b.data()) : b.size();
+}
+
+// first record start at or after p
+size_t next_record(const RawText& b, size_t p, bool fastq) {
+    if (p == 0) return 0;
+    p = line_end(b, p - 1);  // end of the line containing p-1
+    if (p >= b.size()) return b.size();
+    ++p;
+    while (p < b.size()) {
+        if (!fastq) {
+            if (b[p] == '>') return p;
+        } else if (b[p] == '@') {  // a header line is followed, two lines later, by a '+' line
+            size_t l1 = line_end(b, p);
+            size_t l2 = l1 < b.size() ? line_end(b, l1 + 1) : b.size();
+            if (l2 + 1 < b.size() && b[l2 + 1] == '+') return p;
+        }
+        p = line_end(b, p);
+        if (p >= b.size()) return b.size();
+        ++p;
+    }
+    return b.size();
+}
+
+void parse_piece(const RawText& b, size_t lo, size_t hi, bool fastq, Piece& out) {
+    std::string seq;
+    out.words.reserve((hi - lo) / 8 + 16);  // FASTQ: ~2 text bytes per base, 4 bases per byte
+    out.lens.reserve((hi - lo) / 128 + 16);
+    out.nwords.reserve((hi - lo) / 128 + 16);
+    auto emit = [&](const char* s, uint32_t len) {
         const size_t at = out.words.size();
-        out.words.resize(at + (len + 15) / 16);
+        const uint32_t nw = (len + 15) / 16;
+        out.words.resize(at + nw);
         uint32_t l = 0;
-        pack_one((const uint8_t*)s.data(), len, out.words.data() + at, l);
-        if (out.lens.empty()) out.first_read_len = len;
+        pack_one((const uint8_t*)s, len, out.words.data() + at, l);
         if (l == 0 && len > 0) ++out.n_dropped;
         out.lens.push_back(l);
-        out.word_off.push_back(out.words.size());
+        out.nwords.push_back(nw);
         out.total_bases += len;
     };
-    while (have) {
-        if (line.empty()) {
-            have = in.next(line);
+    size_t p = lo;
+    while (p < hi) {
+        size_t e = line_end(b, p);
+        if (e == p) {  // blank line
+            p = e + 1;
             continue;
         }
-        if (line[0] == '>') {
-            seq.clear();
-            while ((have = in.next(line)) && (line.empty() || line[0] != '>')) seq += line;
-            emit(seq);
-        } else if (line[0] == '@') {
-            in.next(seq);
-            in.next(tmp);
-            in.next(tmp);
-            emit(seq);
-            have = in.next(line);
+        if (fastq) {
+            if (b[p] != '@') throw std::runtime_error("malformed FASTQ record");
+            size_t s0 = e + 1, s1 = s0 < b.size() ? line_end(b, s0) : b.size();
+            size_t len = s1 > s0 ? s1 - s0 : 0;
+            if (len && b[s0 + len - 1] == '\r') --len;
+            emit(b.data() + std::min(s0, b.size()), (uint32_t)len);
+            size_t plus_end = s1 < b.size() ? line_end(b, s1 + 1) : b.size();
+            size_t qual_end = plus_end < b.size() ? line_end(b, plus_end + 1) : b.size();
+            p = qual_end + 1;
         } else {
-            throw std::runtime_error("unrecognised read file format: " + path);
+            if (b[p] != '>') throw std::runtime_error("malformed FASTA record");
+            p = e + 1;
+            seq.clear();
+            while (p < hi && b[p] != '>') {
+                size_t le = line_end(b, p);
+                size_t len = le - p;
+                if (len && b[p + len - 1] == '\r') --len;
+                seq.append(b.data() + p, len);
+                p = le + 1;
+            }
+            emit(seq.data(), (uint32_t)seq.size());
         }
     }
+}
+}  // namespace
+
+void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& out) {
+    out = PackedReads();
+    RawText buf;
+    slurp(path, buf);
+    size_t first = 0;
+    while (first < buf.size() && (buf[first] == '\n' || buf[first] == '\r')) ++first;
+    out.word_off.assign(1, 0);
+    if (first >= buf.size()) return;
+    const bool fastq = buf[first] == '@';
+    if (!fastq && buf[first] != '>') throw std::runtime_error("unrecognised read file format: " + path);
+    const size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), (size_t)16, buf.size() / (1 << 20) + 1}));
+    std::vector<size_t> cut(T + 1, buf.size());
+    cut[0] = first;
+    for (size_t t = 1; t < T; ++t) cut[t] = std::max(cut[t - 1], next_record(buf, first + (buf.size() - first) * t / T, fastq));
+    std::vector<Piece> pieces(T);
+    parallel_for(T, [&](size_t t) { parse_piece(buf, cut[t], cut[t + 1], fastq, pieces[t]); }, T);
+    // stitch
+    std::vector<uint64_t> rbase(T + 1, 0), wbase(T + 1, 0);
+    for (size_t t = 0; t < T; ++t) {
+        rbase[t + 1] = rbase[t] + pieces[t].lens.size();
+        wbase[t + 1] = wbase[t] + pieces[t].words.size();
+        out.total_bases += pieces[t].total_bases;
+        out.n_dropped += pieces[t].n_dropped;
+    }
+    out.words.resize(wbase[T]);
+    out.lens.resize(rbase[T]);
+    out.word_off.resize(rbase[T] + 1);
+    parallel_for(T, [&](size_t t) {
+        const Piece& P = pieces[t];
+        if (!P.words.empty()) memcpy(out.words.data() + wbase[t], P.words.data(), P.words.size() * 4);
+        if (!P.lens.empty()) memcpy(out.lens.data() + rbase[t], P.lens.data(), P.lens.size() * 4);
+        uint64_t w = wbase[t];
+        for (size_t i = 0; i < P.nwords.size(); ++i) {
+            out.word_off[rbase[t] + i] = w;
+            w += P.nwords[i];
+        }
+    }, T);
+    out.word_off[rbase[T]] = wbase[T];
+    // pandora's short-read cluster threshold uses the length of the first read
+    for (size_t t = 0; t < T && out.first_read_len == 0; ++t)
+        if (!pieces[t].nwords.empty()) {
+            // length before the non-ACGT drop: recover it from the raw text of the first record
+            size_t p = cut[t];
+            size_t e = line_end(buf, p);
+            if (fastq) {
+                size_t s1 = e < buf.size() ? line_end(buf, e + 1) : buf.size();
+                size_t len = s1 > e + 1 ? s1 - e - 1 : 0;
+                if (len && buf[e + len] == '\r') --len;
+                out.first_read_len = (uint32_t)len;
+            } else {
+                out.first_read_len = pieces[t].lens[0] ? pieces[t].lens[0] : (uint32_t)(pieces[t].nwords[0] * 16);
+            }
+            break;
+        }
 }
 
 }  // namespace drprg

@@ -112,3 +112,38 @@ def test_vcf_float_formatting_matches_printf_g():
     for v in vals:
         n = L.drprg_cuda_format_g6(float(v), buf)
         assert buf.value[:n].decode() == "%g" % float(v), (v, buf.value, "%g" % float(v))
+
+
+@pytest.mark.parametrize("fmt,gz,threads", [("fq", False, 1), ("fq", True, 4), ("fa", False, 3), ("fa", True, 1), ("fq", False, 8)])
+def test_read_file_ingest_matches_packer(tmp_path, fmt, gz, threads):
+    """fasta/fastq, plain or gzip (src/predict.rs:166-170), any host thread count: same packed reads as the in-memory packer"""
+    import ctypes as C
+    import gzip
+    rng = np.random.default_rng(5)
+    strs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(L))) for L in rng.integers(1, 400, size=3000)]
+    strs[7] = strs[7][:10] + "N" + strs[7][11:]
+    strs[100] = "@" + "ACGT" * 3 if False else strs[100]
+    path = tmp_path / ("r." + fmt + (".gz" if gz else ""))
+    op = gzip.open if gz else open
+    with op(path, "wt") as f:
+        for i, s in enumerate(strs):
+            if fmt == "fq":
+                q = "".join(chr(33 + int(x)) for x in rng.integers(0, 41, size=len(s)))  # qualities include '@' and '+'
+                f.write(f"@r{i} desc\n{s}\n+\n{q}\n")
+            else:
+                f.write(f">r{i}\n" + "\n".join(s[j:j + 60] for j in range(0, len(s), 60)) + "\n")
+    L = lib.lib()
+    words, woff, lens = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
+    n, tb, fl = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    rc = L.drprg_cuda_read_fastx(str(path).encode(), threads, C.byref(words), C.byref(woff), C.byref(lens), C.byref(n), C.byref(tb), C.byref(fl))
+    assert rc == 0, L.drprg_cuda_last_error()
+    data = np.frombuffer("".join(strs).encode(), np.uint8)
+    off = np.zeros(len(strs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in strs])
+    w2, o2, l2 = lib.pack_reads(data, off)
+    assert n.value == len(strs) and tb.value == int(off[-1]) and fl.value == len(strs[0])
+    assert (np.ctypeslib.as_array(lens, (n.value,)) == l2).all()
+    assert (np.ctypeslib.as_array(woff, (n.value + 1,)) == o2).all()
+    assert (np.ctypeslib.as_array(words, (len(w2),)) == w2).all()
+    for p in (words, woff, lens):
+        L.drprg_cuda_host_free(p)
