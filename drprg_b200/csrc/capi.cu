@@ -122,10 +122,10 @@ double now_ms() {
 
 struct drprg_batch {
     DevReads R{};
-    uint32_t *d_words = nullptr, *d_lens = nullptr;
+    uint32_t *d_words = nullptr, *d_lens = nullptr, *d_seg_read = nullptr, *d_seg_start = nullptr;
     uint64_t* d_off = nullptr;
     bool owned = false;
-    size_t b_words = 0, b_lens = 0, b_off = 0;
+    size_t b_words = 0, b_lens = 0, b_off = 0, b_seg = 0;
     int device = 0;
     uint64_t total_bases = 0;
     uint32_t max_len = UINT32_MAX;  // longest read (bound); selects the short-read kernel
@@ -688,6 +688,8 @@ void free_batch(drprg_batch* b) {
         if (b->d_words) g_pool.put(b->d_words, b->b_words, b->device);
         if (b->d_lens) g_pool.put(b->d_lens, b->b_lens, b->device);
         if (b->d_off) g_pool.put(b->d_off, b->b_off, b->device);
+        if (b->d_seg_read) g_pool.put(b->d_seg_read, b->b_seg, b->device);
+        if (b->d_seg_start) g_pool.put(b->d_seg_start, b->b_seg, b->device);
     }
     delete b;
 }
@@ -708,7 +710,7 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
         B->b_off = (n + 1) * 8;
         B->d_off = (uint64_t*)g_pool.get(B->b_off, X->device);
     }
-    const bool chunked = (st == nullptr) && nwords * 4 >= (8u << 20);
+    const bool chunked = (st == nullptr) && nwords * 4 >= (8u << 20) && stride && stride * 16u <= SHORT_READ_MAX;
     cudaStream_t cs = st;
     if (chunked) {
         if (!X->st_copy) CK(cudaStreamCreateWithFlags(&X->st_copy, cudaStreamNonBlocking));
@@ -736,6 +738,35 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
     B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
     B->total_bases = total_bases;
     B->max_len = ml;
+    if (ml > SHORT_READ_MAX) {
+        // long reads: cut every read into segments of 40*w k-mer positions so that the thread-per-item sketch kernel
+        // gets evenly sized work (a 10 kb read becomes ~23 items instead of one warp-long loop)
+        const uint32_t w = X->H.w, k = X->H.k, seg_len = 40 * w;
+        std::vector<uint32_t> sr, ss;
+        sr.reserve(total_bases / seg_len + n);
+        ss.reserve(total_bases / seg_len + n);
+        for (uint64_t r = 0; r < n; ++r) {
+            const uint32_t len = lens[r];
+            if (len + 1 < w + k) continue;
+            const uint32_t nk = len - k + 1;
+            for (uint32_t s0 = 0; s0 < nk; s0 += seg_len) {
+                sr.push_back((uint32_t)r);
+                ss.push_back(s0);
+            }
+        }
+        if (!sr.empty()) {
+            B->b_seg = sr.size() * 4;
+            B->d_seg_read = (uint32_t*)g_pool.get(B->b_seg, X->device);
+            B->d_seg_start = (uint32_t*)g_pool.get(B->b_seg, X->device);
+            CK(cudaMemcpyAsync(B->d_seg_read, sr.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(B->d_seg_start, ss.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
+            CK(cudaStreamSynchronize(cs));  // the staging vectors die with this scope
+            B->R.seg_read = B->d_seg_read;
+            B->R.seg_start = B->d_seg_start;
+            B->R.n_segs = sr.size();
+            B->R.seg_len = seg_len;
+        }
+    }
     return B.release();
 }
 

@@ -265,17 +265,27 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             *reinterpret_cast<uint4*>(f + i) = __ldg(reinterpret_cast<const uint4*>(T.filter + i));
         __syncthreads();
     }
-    const unsigned long long n_tiles = (R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS;
+    // A work item is a whole read, or — for long reads — a SEGMENT of one (R.seg_read != nullptr): seg_len k-mer
+    // positions whose minimizer status only depends on the w-1 positions either side, so a thread streams
+    // [seg_start-(w-1), seg_end+(w-1)) and reports [seg_start, seg_end).  Padding with hash 0 outside the streamed
+    // range is exact at the true read ends and harmless inside the read (it only affects the halo).
+    const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
+    const unsigned long long n_tiles = (n_items + SHORT_THREADS - 1) / SHORT_THREADS;
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long r = tile * SHORT_THREADS + tid;
-    const bool have = r < R.n_reads;
+    const unsigned long long item = tile * SHORT_THREADS + tid;
+    const bool have = item < n_items;
+    const unsigned long long r = have ? (R.seg_read ? (unsigned long long)__ldg(R.seg_read + item) : item) : 0ull;
     uint32_t len = have ? __ldg(R.lens + r) : 0u;
     if (len + 1 < (uint32_t)(W + K)) len = 0;  // too short or dropped: no k-mer position is valid
-    const uint32_t nk = len ? len - K + 1 : 0;
+    const uint32_t nk_read = len ? len - K + 1 : 0;
+    const uint32_t seg_s = (have && R.seg_read) ? __ldg(R.seg_start + item) : 0u;
+    const uint32_t seg_e = R.seg_read ? min(seg_s + R.seg_len, nk_read) : nk_read;   // report [seg_s, seg_e)
+    const uint32_t str_lo = seg_s >= (uint32_t)(W - 1) ? seg_s - (W - 1) : 0u;        // stream [str_lo, str_lo + nk)
+    const uint32_t nk = nk_read ? min(nk_read, seg_e + (W - 1)) - str_lo : 0u;
     const uint32_t nk_max = __reduce_max_sync(FULL, nk);
     if (nk_max == 0) continue;
-    const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull);
-    const uint32_t nwords = (len + 15) >> 4;
+    const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull) + (str_lo >> 4);
+    const uint32_t nwords = ((len + 15) >> 4) - (nk_read ? (str_lo >> 4) : 0u);
 
     // Bases are served from a 64-bit shift register (hi:lo) holding `avail` bases, top aligned; it is
     // topped up with the next 16-base word once per block of W positions (W <= 16 bases are consumed per
@@ -314,11 +324,14 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         Rc = __funnelshift_r(Rc, c, 2) ^ 0xC0000000u;       // complemented base enters at the top: rc of the last 16
     };
     {
-        // prime the first K-1 bases (K-1 <= 14 < 16: one word)
-        refill();
+        // skip to the first streamed base inside its word, then prime the first K-1 bases
+        const uint32_t prime = (str_lo & 15u) + (uint32_t)(K - 1);
 #pragma unroll 1
-        for (uint32_t i = 0; i < (uint32_t)(K - 1); ++i) next_base();
-        avail -= (uint32_t)(K - 1);
+        for (uint32_t i = 0; i < prime; ++i) {
+            refill();
+            next_base();
+            --avail;
+        }
     }
 
     uint32_t hp[W], Sp[W], SXo[W + 1];
@@ -369,9 +382,11 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             }
         }
         if (b > 0) {
-            const uint32_t prev0 = p0 - W;
-            const uint32_t valid = nk > prev0 ? min(nk - prev0, (uint32_t)W) : 0u;
-            uint32_t fm = flags & ((1u << valid) - 1u);
+            const uint32_t prev0 = str_lo + p0 - W;  // read coordinate of the previous block's first position
+            // positions to report: prev0 + j in [seg_s, seg_e)
+            const uint32_t first = seg_s > prev0 ? min(seg_s - prev0, (uint32_t)W) : 0u;
+            const uint32_t last = seg_e > prev0 ? min(seg_e - prev0, (uint32_t)W) : 0u;
+            uint32_t fm = flags & ((1u << last) - 1u) & ~((1u << first) - 1u);
             while (fm) {
                 const int j = __ffs(fm) - 1;
                 fm &= fm - 1;
@@ -448,7 +463,8 @@ static void launch_short_one(const DevReads& R, const DevTable& T, unsigned long
         configured = true;
     }
     // persistent CTAs: two per SM (register file: 2 x 512 threads x 62 registers), each loops over read tiles
-    const unsigned long long n_tiles = (R.n_reads + SHORT_THREADS - 1) / SHORT_THREADS;
+    const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
+    const unsigned long long n_tiles = (n_items + SHORT_THREADS - 1) / SHORT_THREADS;
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, 2ull * (unsigned)sm_count);
     sketch_short_kernel<W, K, LOOKUP, V, SF><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap, 4u);
     ++g_launches;
@@ -491,7 +507,7 @@ void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
                           uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
-    if (max_len <= SHORT_READ_MAX && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, sm_count, st)) return;
+    if ((max_len <= SHORT_READ_MAX || R.seg_read) && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, sm_count, st)) return;
     sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
     ++g_launches;
 }
@@ -500,7 +516,7 @@ void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;
     DevTable T{};
-    if (max_len <= SHORT_READ_MAX && launch_short<false>(R, T, w, k, d_key, d_val, d_count, cap, sm_count, st)) return;
+    if ((max_len <= SHORT_READ_MAX || R.seg_read) && launch_short<false>(R, T, w, k, d_key, d_val, d_count, cap, sm_count, st)) return;
     sketch_kernel<false><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_key, d_val, d_count, cap);
     ++g_launches;
 }

@@ -20,6 +20,12 @@ struct DevReads {
     const uint32_t* lens;      // bases per read; 0 = dropped (non-ACGT)
     uint64_t n_reads;
     uint32_t read_id_base;
+    // optional segment table for long reads (thread-per-segment sketching): segment i covers k-mer positions
+    // [seg_start[i], seg_start[i] + seg_len) of read seg_read[i]
+    const uint32_t* seg_read = nullptr;
+    const uint32_t* seg_start = nullptr;
+    uint64_t n_segs = 0;
+    uint32_t seg_len = 0;
 };
 
 // minimizer index resident in HBM (small: lives in L2)

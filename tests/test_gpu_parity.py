@@ -83,6 +83,18 @@ def test_sketch_parity_short_read_kernel(w, k):
     assert_sketch_equal(gpu_sketch(gx, *reads_from_strings(strs[:1])), oracle_sketch_all(*reads_from_strings(strs[:1]), w, k))
 
 
+@pytest.mark.parametrize("w,k", [(11, 15), (14, 15)])
+def test_sketch_parity_long_reads_segmented(w, k):
+    """long reads are cut into segments for the thread-per-item kernel: every segment boundary must be seamless"""
+    gx = lib.Index(TOY_PRG, w, k, device=0)
+    rng = np.random.default_rng(k * 7 + w)
+    lens = [641, 40 * w + k - 1, 40 * w + k, 40 * w + k + 1, 80 * w + k - 1, 80 * w + k + w, 3000, 12345, 50000, 7, 0, 700]
+    strs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=L)) for L in lens]
+    strs += ["A" * 2000, "ACGT" * 800, "AC" * 500 + "GATTACA" * 300, strs[6][:1500] + "N" + strs[6][1501:]]
+    data, off = reads_from_strings(strs)
+    assert_sketch_equal(gpu_sketch(gx, data, off), oracle_sketch_all(data, off, w, k))
+
+
 def test_empty_batch():
     gx = lib.Index(TOY_PRG, 11, 15, device=0)
     data, off = reads_from_strings([])
