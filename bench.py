@@ -239,6 +239,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
+    kept_cluster_reads = int(ix.coverage()["locus_reads"].sum())  # reads (clusters) that support a panel locus, all ranks
     h2d = int(h_words.numel() * 4 + h_lens.numel() * 4)
     d2h = int(ix.n_accum * 4 + n_records * 64 + 8)
 
@@ -248,7 +249,8 @@ def main():
         "dtype": "u32 (hash/cluster/coverage), f64 (likelihoods)", "data": "synthetic",
         "config": {"workload": wl.name, "reads_per_gpu_per_step": n, "read_len": workload.READ_LEN,
                    "l2": "flushed with a 512 MiB memset between timed iterations", "sharding": f"reads x{world}, index replicated",
-                   "vcf_records": n_records},
+                   "vcf_records": n_records, "reads_with_kept_cluster_per_step": kept_cluster_reads,
+                   "kept_cluster_reads_per_s": kept_cluster_reads / (ms_step * 1e-3)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
