@@ -45,6 +45,20 @@ __device__ __forceinline__ uint32_t hash_left_aligned(uint32_t K, uint32_t S, ui
     return K;
 }
 
+// hash of the k-mer held RIGHT-aligned (possibly with garbage above bit 2k): the left alignment (<< S) is folded
+// into the first multiply
+template <uint32_t S>
+__device__ __forceinline__ uint32_t hash_right_aligned(uint32_t F) {
+    constexpr uint32_t hm = ~((1u << S) - 1u);
+    uint32_t K = F * (2097151u << S) - (1u << S);
+    K ^= (K >> 24) & hm;
+    K *= 265u;
+    K ^= (K >> 14) & hm;
+    K *= 21u;
+    K ^= (K >> 28) & hm;
+    return K;  // S >= 1: the final (key + (key << 31)) & mask step cannot change a kept bit
+}
+
 __device__ __forceinline__ uint32_t table_slot(uint32_t h, uint32_t bits) { return (h * 0x9E3779B1u) >> (32 - bits); }
 
 template <bool LOOKUP>
@@ -284,6 +298,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
     const uint32_t nk = nk_read ? min(nk_read, seg_e + (W - 1)) - str_lo : 0u;
     const uint32_t nk_max = __reduce_max_sync(FULL, nk);
     if (nk_max == 0) continue;
+    const uint32_t nk_min = __reduce_min_sync(FULL, nk);
     const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull) + (str_lo >> 4);
     const uint32_t nwords = ((len + 15) >> 4) - (nk_read ? (str_lo >> 4) : 0u);
 
@@ -320,8 +335,8 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             hi = __funnelshift_l(lo, hi, 2);
             lo <<= 2;
         }
-        F = F * 4u + c;                                     // garbage above bit 2K is shifted out by << S
-        Rc = __funnelshift_r(Rc, c, 2) ^ 0xC0000000u;       // complemented base enters at the top: rc of the last 16
+        F = F * 4u + c;                                     // garbage above bit 2K wraps away in the first hash multiply
+        Rc = (__funnelshift_r(Rc, c, 2) & HM) ^ 0xC0000000u;  // complemented base enters at the top; bases older than K fall off
     };
     {
         // skip to the first streamed base inside its word, then prime the first K-1 bases
@@ -348,15 +363,28 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         uint32_t* sh = &s_h[b & 1][0][tid];
         refill();
         avail -= (uint32_t)W;
+        // blocks that lie inside every lane's read (all but the last one or two) skip the per-position padding select
+        if (p0 + W <= nk_min) {
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            next_base();
-            const uint32_t hf = hash_left_aligned(F << S, S, HM), hr = hash_left_aligned(Rc & HM, S, HM);
-            uint32_t hv = min(hf, hr);
-            if (hf > hr) not_strand |= 1u << (W - 1 - j);
-            hv = (p0 + j < nk) ? hv : 0u;
-            h[j] = hv;
-            sh[j * SHORT_THREADS] = hv;
+            for (int j = 0; j < W; ++j) {
+                next_base();
+                const uint32_t hf = hash_right_aligned<S>(F), hr = hash_left_aligned(Rc, S, HM);
+                const uint32_t hv = min(hf, hr);
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(not_strand) : "r"(hf), "r"(hr), "r"(1u << (W - 1 - j)));
+                h[j] = hv;
+                sh[j * SHORT_THREADS] = hv;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                next_base();
+                const uint32_t hf = hash_right_aligned<S>(F), hr = hash_left_aligned(Rc, S, HM);
+                uint32_t hv = min(hf, hr);
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(not_strand) : "r"(hf), "r"(hr), "r"(1u << (W - 1 - j)));
+                hv = (p0 + j < nk) ? hv : 0u;
+                h[j] = hv;
+                sh[j * SHORT_THREADS] = hv;
+            }
         }
         const uint32_t strand_cur = ~not_strand;
         // windows starting in the previous block: offset t covers prev[t..W-1] + cur[0..t-1]
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             for (int j = 0; j < W; ++j) {
                 pmax = max(pmax, wm[j]);
                 const uint32_t best = max(pmax, SXo[j + 1]);
-                flags |= (hp[j] == best ? 1u : 0u) << j;
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(flags) : "r"(hp[j]), "r"(best), "r"(1u << j));
             }
         }
         if (b > 0) {
@@ -402,8 +430,9 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                 } else {
                     const uint32_t fidx = hv & ((1u << T.filter_bits) - 1u);
                     const uint32_t fw = SMEM_FILTER ? s_filter[fidx] : __ldg(T.filter + fidx);
-                    const uint32_t m = (1u << ((hv >> T.filter_bits) & 31u)) | (1u << ((hv >> (T.filter_bits + 5)) & 31u));
-                    if ((fw & m) != m) continue;
+                    // both filter bits set?  (funnel shifts take the shift amount modulo 32)
+                    const uint32_t hb = hv >> T.filter_bits;
+                    if (!(__funnelshift_r(fw, 0u, hb) & __funnelshift_r(fw, 0u, hb >> 5) & 1u)) continue;
                     uint32_t slot = table_slot(hv, T.slot_bits);
                     const uint32_t smask = (1u << T.slot_bits) - 1u;
                     uint32_t rec_begin = 0, rec_n = 0;
