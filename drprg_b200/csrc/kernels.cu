@@ -320,21 +320,10 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         }
     };
     auto next_base = [&]() {
-        uint32_t c;
-        if (VARIANT & 1) {
-            // (hi:lo) <<= 2 on the multiplier pipe: the high half of hi * 4 is exactly the base leaving the top
-            // `four` is a kernel argument so that the compiler keeps these as IMAD.WIDE instead of
-            // strength-reducing them back into ALU-pipe shifts
-            const unsigned long long t1 = (unsigned long long)lo * four;
-            const unsigned long long t2 = (unsigned long long)hi * four + (t1 >> 32);
-            lo = (uint32_t)t1;
-            hi = (uint32_t)t2;
-            c = (uint32_t)(t2 >> 32);
-        } else {
-            c = hi >> 30;
-            hi = __funnelshift_l(lo, hi, 2);
-            lo <<= 2;
-        }
+        const uint32_t c = hi >> 30;
+        hi = __funnelshift_l(lo, hi, 2);
+        lo <<= 2;
+        (void)four;
         F = F * 4u + c;                                     // garbage above bit 2K wraps away in the first hash multiply
         Rc = (__funnelshift_r(Rc, c, 2) & HM) ^ 0xC0000000u;  // complemented base enters at the top; bases older than K fall off
     };
@@ -363,14 +352,20 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         uint32_t* sh = &s_h[b & 1][0][tid];
         refill();
         avail -= (uint32_t)W;
-        // blocks that lie inside every lane's read (all but the last one or two) skip the per-position padding select
-        if (p0 + W <= nk_min) {
+        // blocks that lie inside every lane's read (all but the last one or two) may skip the per-position padding select
+        auto strand_bit = [&](uint32_t hf, uint32_t hr, int j) {
+            if (VARIANT & 1)
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(not_strand) : "r"(hf), "r"(hr), "r"(1u << (W - 1 - j)));
+            else
+                not_strand |= (hf > hr ? 1u : 0u) << (W - 1 - j);
+        };
+        if ((VARIANT & 2) && p0 + W <= nk_min) {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 next_base();
                 const uint32_t hf = hash_right_aligned<S>(F), hr = hash_left_aligned(Rc, S, HM);
                 const uint32_t hv = min(hf, hr);
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(not_strand) : "r"(hf), "r"(hr), "r"(1u << (W - 1 - j)));
+                strand_bit(hf, hr, j);
                 h[j] = hv;
                 sh[j * SHORT_THREADS] = hv;
             }
@@ -380,7 +375,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                 next_base();
                 const uint32_t hf = hash_right_aligned<S>(F), hr = hash_left_aligned(Rc, S, HM);
                 uint32_t hv = min(hf, hr);
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(not_strand) : "r"(hf), "r"(hr), "r"(1u << (W - 1 - j)));
+                strand_bit(hf, hr, j);
                 hv = (p0 + j < nk) ? hv : 0u;
                 h[j] = hv;
                 sh[j * SHORT_THREADS] = hv;
@@ -406,7 +401,10 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
             for (int j = 0; j < W; ++j) {
                 pmax = max(pmax, wm[j]);
                 const uint32_t best = max(pmax, SXo[j + 1]);
-                asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(flags) : "r"(hp[j]), "r"(best), "r"(1u << j));
+                if (VARIANT & 1)
+                    asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(flags) : "r"(hp[j]), "r"(best), "r"(1u << j));
+                else
+                    flags |= (hp[j] == best ? 1u : 0u) << j;
             }
         }
         if (b > 0) {
@@ -503,24 +501,27 @@ template <bool LOOKUP>
 static bool launch_short(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* a,
                          unsigned long long* b, unsigned long long* cnt, uint64_t cap, int sm_count, cudaStream_t st) {
     static const int variant = [] {
-        const char* e = getenv("DRPRG_SKETCH_VARIANT");  // tuning switch: bit0 = wide-multiply base feed, bit1 = global-memory filter
+        const char* e = getenv("DRPRG_SKETCH_VARIANT");  // tuning switch: bit0 = predicated-OR flag accumulation, bit1 = padding-free fast path
         return e ? atoi(e) & 3 : DRPRG_DEFAULT_VARIANT;
     }();
-    const bool sf = LOOKUP && T.filter_bits <= SMEM_FILTER_BITS && !(variant & 2);
-#define DRPRG_SHORT(WW, KK)                                                                                       \
-    if (w == WW && k == KK) {                                                                                     \
-        if (variant & 1) {                                                                                        \
-            if (sf) launch_short_one<WW, KK, LOOKUP, 1, true>(R, T, a, b, cnt, cap, sm_count, st);                \
-            else launch_short_one<WW, KK, LOOKUP, 1, false>(R, T, a, b, cnt, cap, sm_count, st);                  \
-        } else {                                                                                                  \
-            if (sf) launch_short_one<WW, KK, LOOKUP, 0, true>(R, T, a, b, cnt, cap, sm_count, st);                \
-            else launch_short_one<WW, KK, LOOKUP, 0, false>(R, T, a, b, cnt, cap, sm_count, st);                  \
-        }                                                                                                         \
-        return true;                                                                                              \
+    const bool sf = LOOKUP && T.filter_bits <= SMEM_FILTER_BITS;
+#define DRPRG_SHORT_V(WW, KK, VV)                                                                 \
+    if (variant == VV) {                                                                          \
+        if (sf) launch_short_one<WW, KK, LOOKUP, VV, true>(R, T, a, b, cnt, cap, sm_count, st);   \
+        else launch_short_one<WW, KK, LOOKUP, VV, false>(R, T, a, b, cnt, cap, sm_count, st);     \
+        return true;                                                                              \
+    }
+#define DRPRG_SHORT(WW, KK)      \
+    if (w == WW && k == KK) {    \
+        DRPRG_SHORT_V(WW, KK, 0) \
+        DRPRG_SHORT_V(WW, KK, 1) \
+        DRPRG_SHORT_V(WW, KK, 2) \
+        DRPRG_SHORT_V(WW, KK, 3) \
     }
     DRPRG_SHORT(11, 15)  // drprg defaults (src/builder.rs:40-41)
     DRPRG_SHORT(14, 15)  // pandora's default w, used by the reference's build tests (src/builder.rs:1181)
 #undef DRPRG_SHORT
+#undef DRPRG_SHORT_V
     return false;
 }
 
