@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(WARPS * 32) sketch_kernel(DevReads R, DevTable
 constexpr int SHORT_THREADS = 512;
 constexpr uint32_t SMEM_FILTER_BITS = 14;  // a pre-filter of <= 2^14 words (64 KB) is copied into shared memory
 #ifndef DRPRG_DEFAULT_VARIANT
-#define DRPRG_DEFAULT_VARIANT 0
+#define DRPRG_DEFAULT_VARIANT 3
 #endif
 
 template <int W, int K, bool LOOKUP, int VARIANT, bool SMEM_FILTER>

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdrprg_cuda.so")
+SO_PATH = os.environ.get("DRPRG_CUDA_LIB") or os.path.join(_HERE, "libdrprg_cuda.so")  # env override: A/B builds
 _LIB = None
 
 
