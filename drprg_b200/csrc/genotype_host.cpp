@@ -616,7 +616,35 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
          "##FORMAT=<ID=GT_CONF,Number=1,Type=Float,Description=\"Genotype confidence\">\n";
     for (auto& c : contigs) s += "##contig=<ID=" + c + ">\n";
     s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample + "\n";
-    auto format_range = [&](size_t lo, size_t hi, std::string& s) {
+    // Records are independent lines.  Each worker formats a contiguous range with raw pointer writes into its own
+    // buffer (an upper bound on the line length is known: prefix + 12 bytes per integer + 26 per float), then the
+    // ranges are copied into place in parallel.
+    auto put_uint = [](char* o, uint32_t v) -> char* {
+        char tmp[10];
+        int n = 0;
+        do {
+            tmp[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (n) *o++ = tmp[--n];
+        return o;
+    };
+    auto line_bound = [&](size_t i) -> size_t {
+        const SiteRecord& r = *recs[i];
+        const size_t na = G.rec_off[i + 1] - G.rec_off[i];
+        size_t prefix = r.text_prefix.size();
+        if (!prefix) {
+            prefix = H.loci[r.locus].name.size() + r.ref.size() + 160;
+            for (auto& a : r.alts) prefix += a.size() + 1;
+        }
+        return prefix + 16 + na * (6 * 12 + 2 * 28) + 40;
+    };
+    auto format_range = [&](size_t lo, size_t hi, std::vector<char>& buf) -> size_t {
+        size_t bound = 0;
+        for (size_t i = lo; i < hi; ++i) bound += line_bound(i);
+        buf.resize(bound);
+        char* o = buf.data();
+        const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
         for (size_t i = lo; i < hi; ++i) {
             const SiteRecord& r = *recs[i];
             const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
@@ -627,46 +655,45 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
                 t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
                      "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
             }
-            s += r.text_prefix;
-            if (G.gt[i] < 0) s += '.';
-            else put_u(s, (uint32_t)G.gt[i]);
-            const std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+            memcpy(o, r.text_prefix.data(), r.text_prefix.size());
+            o += r.text_prefix.size();
+            if (G.gt[i] < 0) *o++ = '.';
+            else o = put_uint(o, (uint32_t)G.gt[i]);
             for (auto* col : cols) {
-                s += ':';
+                *o++ = ':';
                 for (uint32_t a = b; a < e; ++a) {
-                    if (a > b) s += ',';
-                    put_u(s, (*col)[a]);
+                    if (a > b) *o++ = ',';
+                    o = put_uint(o, (*col)[a]);
                 }
             }
-            s += ':';
+            *o++ = ':';
             for (uint32_t a = b; a < e; ++a) {
-                if (a > b) s += ',';
-                put_g6(s, G.gaps[a]);
+                if (a > b) *o++ = ',';
+                o += format_g6(G.gaps[a], o);
             }
-            s += ':';
+            *o++ = ':';
             for (uint32_t a = b; a < e; ++a) {
-                if (a > b) s += ',';
-                put_g6(s, G.lik[a]);
+                if (a > b) *o++ = ',';
+                o += format_g6(G.lik[a], o);
             }
-            s += ':';
-            put_g6(s, G.gt_conf[i]);
-            s += '\n';
+            *o++ = ':';
+            o += format_g6(G.gt_conf[i], o);
+            *o++ = '\n';
         }
+        return (size_t)(o - buf.data());
     };
-    const size_t parts_n = recs.size() >= 1024 ? 16 : 1;
-    if (parts_n <= 1) {
-        format_range(0, recs.size(), s);
-    } else {  // records are independent lines: format contiguous ranges in parallel, then concatenate
-        std::vector<std::string> parts(parts_n);
-        parallel_for(parts_n, [&](size_t t) {
-            parts[t].reserve((recs.size() / parts_n + 1) * 224);
-            format_range(recs.size() * t / parts_n, recs.size() * (t + 1) / parts_n, parts[t]);
-        });
-        size_t total = s.size();
-        for (auto& part : parts) total += part.size();
-        s.reserve(total);
-        for (auto& part : parts) s += part;
-    }
+    const size_t parts_n = recs.size() >= 512 ? 16 : 1;
+    std::vector<std::vector<char>> parts(parts_n);
+    std::vector<size_t> used(parts_n, 0);
+    parallel_for(parts_n, [&](size_t t) {
+        used[t] = format_range(recs.size() * t / parts_n, recs.size() * (t + 1) / parts_n, parts[t]);
+    });
+    std::vector<size_t> at(parts_n + 1, s.size());
+    for (size_t t = 0; t < parts_n; ++t) at[t + 1] = at[t] + used[t];
+    s.resize(at[parts_n]);
+    parallel_for(parts_n, [&](size_t t) {
+        if (used[t]) memcpy(&s[at[t]], parts[t].data(), used[t]);
+    });
     return s;
 }
 

@@ -959,7 +959,9 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
 // arithmetic and dependent-issue waits (ncu: stall_wait 2.4, stall_short_scoreboard 2.6 per issued instruction).
 // Here every pointer the chain follows (successor, lifting pointers, edge targets) is stored as the 32-bit
 // shared-memory ADDRESS of the target's 64-byte record, so one hop is a single LDS with an immediate offset.
-constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF = 28, R_UP = 32;  // up[0..7] at 32..63
+constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF = 28, R_UP = 32, R_T = 60;
+// record: sum f64 | mean f64 | score f64 | len u32 | edge-list address u32 | lifting pointers up[0..6] | T
+// T = the node window-1 steps down the chosen path (what a predecessor subtracts when its window is full)
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
@@ -973,6 +975,26 @@ __device__ __forceinline__ double lds64(uint32_t a) {
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+
+// After the successor v of node a is known, two pointer chases remain, both through tables of OLDER nodes only and
+// therefore independent of each other and of the fp chain: the lifting pointers of a (level l of a = level l-1 of
+// the node 2^(l-1) steps down) and T(a) = succ^(window-2)(v).  Their loads are issued interleaved so the two chains
+// overlap instead of adding up (volatile asm keeps this order).
+__device__ __forceinline__ void mlpath_link(uint32_t a, uint32_t v, uint32_t steps2) {
+    sts32(a + R_UP, v);
+    uint32_t x = v, t = v;
+#pragma unroll
+    for (int l = 0; l < 7; ++l) {
+        const uint32_t xn = (l < 6) ? lds32(x + R_UP + 4 * l) : 0u;          // level l+1 of a
+        const uint32_t tn = ((steps2 >> l) & 1u) ? lds32(t + R_UP + 4 * l) : t;  // walk window-2 steps from v
+        if (l < 6) {
+            sts32(a + R_UP + 4 * (l + 1), xn);
+            x = xn;
+        }
+        t = tn;
+    }
+    sts32(a + R_T, t);
+}
 
 __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
                                   const uint32_t* __restrict__ edges, const double* __restrict__ prob,
@@ -1001,14 +1023,12 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
     if (threadIdx.x != 0) return;
     const double tol = 0.000001;
     const uint32_t term = recs + (n - 1) * REC;
-    const uint32_t steps = P.window - 1;
+    const uint32_t steps2 = P.window - 2;  // T(a) = succ^(window-1)(a) = succ^(window-2)(chosen successor)
     sts64(term + R_M, 0.0);
     sts32(term + R_LEN, 0u);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);
+    for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // includes R_T
     for (uint32_t a = term - REC; a + REC > recs; a -= REC) {  // nodes n-2 .. 0
-        double max_mean = -(double)FLT_MAX;
-        uint32_t max_len = 0;
         double Mj = 0.0;
         uint32_t lenj = 0, prevj = term;
         const double pj = lds64(a + R_PR);
@@ -1020,53 +1040,50 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
             // -FLT_MAX accepts any successor with a real mean, i.e. any successor that is not a dead end.
             const uint32_t v = lds32(e0);
             const uint32_t lv = lds32(v + R_LEN);
+            const uint32_t tv = lds32(v + R_T);
+            const double Mv = lds64(v + R_M);
             if (v == term || lv > 0u) {
-                Mj = pj + lds64(v + R_M);
-                lenj = 1 + lv;
+                mlpath_link(a, v, steps2);  // independent of the sums below: overlaps them
                 prevj = v;
+                lenj = 1 + lv;
+                Mj = pj + Mv;
                 if (lenj > P.window) {
-                    uint32_t pn = v;
-#pragma unroll
-                    for (int b = 0; b < 8; ++b)
-                        if ((steps >> b) & 1u) pn = lds32(pn + R_UP + 4 * b);
-                    Mj -= lds64(pn + R_PR);
+                    Mj -= lds64(tv + R_PR);
                     lenj -= 1;
                 }
             }
-        } else
-        for (uint32_t e = e0; e < e1; e += 4u) {
-            const uint32_t v = lds32(e);
-            const bool is_term = (v == term);
-            const uint32_t lv = lds32(v + R_LEN);
-            const double mean_v = lds64(v + R_MEAN);
-            const double Mv = lds64(v + R_M);
-            const bool take = is_term ? (P.thresh > max_mean + tol)
-                                      : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
-            if (!take) continue;
-            Mj = pj + Mv;
-            lenj = 1 + lv;
-            prevj = v;
-            if (lenj > P.window) {
-                uint32_t pn = v;
-#pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if ((steps >> b) & 1u) pn = lds32(pn + R_UP + 4 * b);
-                Mj -= lds64(pn + R_PR);
-                lenj -= 1;
+        } else {
+            double max_mean = -(double)FLT_MAX;
+            uint32_t max_len = 0;
+            for (uint32_t e = e0; e < e1; e += 4u) {
+                const uint32_t v = lds32(e);
+                const bool is_term = (v == term);
+                const uint32_t lv = lds32(v + R_LEN);
+                const uint32_t tv = lds32(v + R_T);
+                const double mean_v = lds64(v + R_MEAN);
+                const double Mv = lds64(v + R_M);
+                const bool take = is_term ? (P.thresh > max_mean + tol)
+                                          : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
+                if (!take) continue;
+                Mj = pj + Mv;
+                lenj = 1 + lv;
+                prevj = v;
+                if (lenj > P.window) {
+                    Mj -= lds64(tv + R_PR);
+                    lenj -= 1;
+                }
+                max_mean = is_term ? P.thresh : mean_v;
+                if (!is_term) max_len = lv;
             }
-            max_mean = is_term ? P.thresh : mean_v;
-            if (!is_term) max_len = lv;
+            if (lenj) mlpath_link(a, prevj, steps2);
+        }
+        if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
+#pragma unroll
+            for (int v = 0; v < 8; ++v) sts32(a + R_UP + 4 * v, term);
         }
         sts64(a + R_M, Mj);
         sts32(a + R_LEN, lenj);
         if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
-        sts32(a + R_UP, prevj);
-        uint32_t x = prevj;
-#pragma unroll
-        for (int v = 1; v < 8; ++v) {
-            x = lds32(x + R_UP + 4 * (v - 1));
-            sts32(a + R_UP + 4 * v, x);
-        }
     }
     uint32_t cnt = 0, p = lds32(recs + R_UP);
     while (p != term && cnt < n) {
@@ -1097,7 +1114,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
     {
         const size_t rec_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4;
         static const bool force_generic = getenv("DRPRG_MLPATH_GENERIC") != nullptr;
-        if (P.window <= 256 && rec_smem <= budget && !force_generic && d_needs_mean) {
+        if (P.window >= 2 && P.window <= 128 && rec_smem <= budget && !force_generic && d_needs_mean) {
             static size_t configured = 0;
             if (rec_smem > configured) {
                 cudaFuncSetAttribute(mlpath_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
