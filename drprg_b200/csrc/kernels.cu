@@ -959,13 +959,9 @@ __global__ void mlpath_kernel(uint32_t n_loci, const uint32_t* __restrict__ knod
 // arithmetic and dependent-issue waits (ncu: stall_wait 2.4, stall_short_scoreboard 2.6 per issued instruction).
 // Here every pointer the chain follows (successor, lifting pointers, edge targets) is stored as the 32-bit
 // shared-memory ADDRESS of the target's 64-byte record, so one hop is a single LDS with an immediate offset.
-constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF = 28, R_UP = 32, R_T = 56;
-constexpr int NLV = 6;  // jump pointers of 1, 3, 7, 15, 31 and 63 steps
-// record: sum f64 | mean f64 | score f64 | len u32 | edge-list address u32 | jump pointers up[0..5] | T | pad
-// T = the node window-1 steps down the chosen path (what a predecessor subtracts when its window is full).
-// Jump strides are 2^l - 1, not 2^l: succ^(2c+1)(a) = succ^c(succ^c(v)) for the successor v of a, so EVERY level of
-// a is two loads through tables of older nodes and all levels are independent of each other — a dependency depth
-// of 2 instead of the log2(window) of classic binary lifting, which is what a single-lane chain pays for.
+constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF = 28, R_UP = 32, R_T = 60;
+// record: sum f64 | mean f64 | score f64 | len u32 | edge-list address u32 | lifting pointers up[0..6] | T
+// T = the node window-1 steps down the chosen path (what a predecessor subtracts when its window is full)
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
@@ -980,23 +976,23 @@ __device__ __forceinline__ double lds64(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 
-// After the successor v of node a is known: (1) the jump pointers of a, two independent-per-level loads through v's
-// tables; (2) T(a) = succ^(window-2)(v), a greedy walk over the strides (98 = 63 + 31 + 3 + 1).  All loads are issued
-// interleaved so the chains overlap (volatile asm keeps this order); `hops` packs the walk, 4 bits per hop.
-__device__ __forceinline__ void mlpath_link(uint32_t a, uint32_t v, unsigned long long hops, int n_hops) {
+// After the successor v of node a is known, two pointer chases remain, both through tables of OLDER nodes only and
+// therefore independent of each other and of the fp chain: the lifting pointers of a (level l of a = level l-1 of
+// the node 2^(l-1) steps down) and T(a) = succ^(window-2)(v).  Their loads are issued interleaved so the two chains
+// overlap instead of adding up (volatile asm keeps this order).
+__device__ __forceinline__ void mlpath_link(uint32_t a, uint32_t v, uint32_t steps2) {
     sts32(a + R_UP, v);
-    uint32_t y[NLV];
+    uint32_t x = v, t = v;
 #pragma unroll
-    for (int l = 1; l < NLV; ++l) y[l] = lds32(v + R_UP + 4 * (l - 1));        // succ^c(v), c = 2^(l-1) - 1... of v
-    uint32_t t = v;
-    if (n_hops > 0) t = lds32(t + R_UP + 4 * (uint32_t)(hops & 15u));
-#pragma unroll
-    for (int l = 1; l < NLV; ++l) y[l] = lds32(y[l] + R_UP + 4 * (l - 1));     // succ^c(succ^c(v)) = succ^(2c+1)(a)
-#pragma unroll
-    for (int h = 1; h < 12; ++h)
-        if (h < n_hops) t = lds32(t + R_UP + 4 * (uint32_t)((hops >> (4 * h)) & 15u));
-#pragma unroll
-    for (int l = 1; l < NLV; ++l) sts32(a + R_UP + 4 * l, y[l]);
+    for (int l = 0; l < 7; ++l) {
+        const uint32_t xn = (l < 6) ? lds32(x + R_UP + 4 * l) : 0u;          // level l+1 of a
+        const uint32_t tn = ((steps2 >> l) & 1u) ? lds32(t + R_UP + 4 * l) : t;  // walk window-2 steps from v
+        if (l < 6) {
+            sts32(a + R_UP + 4 * (l + 1), xn);
+            x = xn;
+        }
+        t = tn;
+    }
     sts32(a + R_T, t);
 }
 
@@ -1027,22 +1023,11 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
     if (threadIdx.x != 0) return;
     const double tol = 0.000001;
     const uint32_t term = recs + (n - 1) * REC;
-    // T(a) = succ^(window-1)(a) = succ^(window-2)(chosen successor): greedy decomposition over strides 63,31,..,1
-    unsigned long long hops = 0;
-    int n_hops = 0;
-    for (uint32_t rest = P.window - 2, lvl = NLV - 1; rest;) {
-        const uint32_t stride = (2u << lvl) - 1u;
-        if (stride <= rest) {
-            hops |= (unsigned long long)lvl << (4 * n_hops++);
-            rest -= stride;
-        } else {
-            --lvl;
-        }
-    }
+    const uint32_t steps2 = P.window - 2;  // T(a) = succ^(window-1)(a) = succ^(window-2)(chosen successor)
     sts64(term + R_M, 0.0);
     sts32(term + R_LEN, 0u);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // jump pointers, T and the pad word
+    for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // includes R_T
     for (uint32_t a = term - REC; a + REC > recs; a -= REC) {  // nodes n-2 .. 0
         double Mj = 0.0;
         uint32_t lenj = 0, prevj = term;
@@ -1058,7 +1043,7 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
             const uint32_t tv = lds32(v + R_T);
             const double Mv = lds64(v + R_M);
             if (v == term || lv > 0u) {
-                mlpath_link(a, v, hops, n_hops);  // independent of the sums below: overlaps them
+                mlpath_link(a, v, steps2);  // independent of the sums below: overlaps them
                 prevj = v;
                 lenj = 1 + lv;
                 Mj = pj + Mv;
@@ -1090,7 +1075,7 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
                 max_mean = is_term ? P.thresh : mean_v;
                 if (!is_term) max_len = lv;
             }
-            if (lenj) mlpath_link(a, prevj, hops, n_hops);
+            if (lenj) mlpath_link(a, prevj, steps2);
         }
         if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
 #pragma unroll
@@ -1129,7 +1114,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
     {
         const size_t rec_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4;
         static const bool force_generic = getenv("DRPRG_MLPATH_GENERIC") != nullptr;
-        if (P.window >= 2 && P.window <= 256 && rec_smem <= budget && !force_generic && d_needs_mean) {
+        if (P.window >= 2 && P.window <= 128 && rec_smem <= budget && !force_generic && d_needs_mean) {
             static size_t configured = 0;
             if (rec_smem > configured) {
                 cudaFuncSetAttribute(mlpath_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
