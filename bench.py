@@ -150,6 +150,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
     wl = workload.Config2()
@@ -178,8 +179,7 @@ def main():
             stats.setdefault(k_, []).append(v_)
         stats.setdefault("hits", []).append(nh)
         if world > 1:
-            sharded.allreduce_accum(ix)
-            torch.cuda.current_stream().synchronize()
+            sharded.allreduce_accum(ix)  # the genotype step's first device->host copy is ordered after it on the same stream
         ix.genotype(wl.refs_path)
         for k_, v_ in ix.last_genotype_timings().items():
             stats.setdefault("gt_" + k_, []).append(v_)
