@@ -298,3 +298,50 @@ def test_pandora_mirror_interface(tmp_path):
         pan.genotype_with(TOY_PRG, TOY_REFS, tmp_path / "nope.fq", tmp_path, ["-w", "11", "-k", "15"])
     with pytest.raises(DependencyError):
         pan.genotype_with(TOY_PRG, TOY_REFS, fq, tmp_path, ["--bogus"])
+
+
+def test_config2_full_size_properties_and_oracle():
+    """BASELINE config 2 at full size (30-locus panel, 1 M x 150 bp reads from a 4.4 Mb genome): size-independent
+    properties (hit order, shard additivity, idempotence) plus a direct comparison with the oracle (which finishes in
+    seconds on the box's host threads)."""
+    from drprg_b200 import workload
+    wl = workload.Config2()
+    d, o = wl.reads(1_000_000, 0)
+    n = len(o) - 1
+    words, _, lens = lib.pack_reads(d, o, workload.STRIDE_WORDS)
+    gx = lib.Index(wl.prg_path, wl.w, wl.k, device=0)
+    go = lib.make_opts(illumina=True, genome_size=workload.GENOME_SIZE)
+    gx.sample_begin(go, workload.READ_LEN)
+    nh, nk = gx.map_batch(gx.upload(words, None, lens, total_bases=int(o[-1]), stride_words=workload.STRIDE_WORDS))
+    whole = gx.accum_download().astype(np.int64)
+    h = gx.last_hits(nh)
+    # sortedness: (read, prg, fwd-first, start, knode) strictly increasing
+    key = np.stack([h["read"], h["prg"], 1 - h["fwd"], h["start"], h["knode"]]).astype(np.int64)
+    order = np.lexsort(key[::-1])
+    assert (order == np.arange(nh)).all()
+    assert 0.005 < nk / n < 2.0 and nk == int(h["kept"].sum())
+    gx.genotype(wl.refs_path)
+    vcf_whole = [l for l in gx.vcf().splitlines() if not l.startswith("##fileDate")]
+    # shard additivity (the allreduce identity) and idempotence
+    tot = np.zeros_like(whole)
+    for s in range(8):
+        lo, hi = n * s // 8, n * (s + 1) // 8
+        gx.sample_begin(go, workload.READ_LEN)
+        gx.map_batch(gx.upload(words[lo * 10:hi * 10], None, lens[lo:hi], total_bases=150 * (hi - lo),
+                               stride_words=workload.STRIDE_WORDS, read_id_base=lo))
+        tot += gx.accum_download().astype(np.int64)
+    assert (tot[:-4] == whole[:-4]).all()
+    gx.sample_begin(go, workload.READ_LEN)
+    gx.accum_upload(np.concatenate([tot[:-4], whole[-4:]]).astype(np.int32))
+    gx.genotype(wl.refs_path)
+    assert [l for l in gx.vcf().splitlines() if not l.startswith("##fileDate")] == vcf_whole
+    # oracle on the same million reads
+    ox = O.Index(wl.prg_path, wl.w, wl.k)
+    oo = O.make_opts(threads=os.cpu_count() or 1, illumina=True, genome_size=workload.GENOME_SIZE)
+    mr = O.MapRun(ox, d, o, oo)
+    f, r = mr.coverage()
+    N = ox.total_knodes
+    assert (whole[:2 * N:2] == f).all() and (whole[1:2 * N:2] == r).all()
+    assert (whole[2 * N:2 * N + ox.n_loci] == mr.locus_reads()).all()
+    og = O.Genotype(ox, mr, oo, wl.refs_path)
+    assert [l for l in og.vcf().splitlines() if not l.startswith("##fileDate")] == vcf_whole
