@@ -510,6 +510,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         CK(cudaEventCreate(&X->ev_ml[0]));
         CK(cudaEventCreate(&X->ev_ml[1]));
     }
+    CK(cudaMemsetAsync(X->d_path.p, 0, (size_t)N * 4, X->st_ml));  // absent loci leave their slice unwritten
     CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
                   X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
