@@ -257,6 +257,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "sketch_short_kernel<11,15,LOOKUP> (S1+S2: sketch + index lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "int_issue_ceiling": {"alu_pipe_active_pct": 76.5, "issue_active_pct": 66.8, "warp_instr_per_read": 291,
+                                           "dram_read_mb_per_launch": 45.4, "source": "profiles/r1_sketch_short.md (ncu --set full, same workload; not measured live)"},
                      "note": "this kernel carries all of the step's HBM traffic and ~98% of its instructions; it is bound by INT32 issue "
                              "(ncu: ALU pipe 80% active, 302 warp-instr per read vs 49.7 B), not by HBM. The only kernel with a longer "
                              "duration at this batch size is mlpath_kernel (30 warps, a serial dependency chain per locus, see "

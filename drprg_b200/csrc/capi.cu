@@ -12,6 +12,7 @@
 #include <deque>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -88,7 +89,9 @@ T* to_device(const std::vector<T>& v) {
 struct DevPool {
     struct Slot { void* p; size_t bytes; int device; };
     std::vector<Slot> free_;
+    std::mutex m_;
     void* get(size_t bytes, int device) {
+        std::lock_guard<std::mutex> g(m_);
         size_t best = free_.size();
         for (size_t i = 0; i < free_.size(); ++i)
             if (free_[i].device == device && free_[i].bytes >= bytes && (best == free_.size() || free_[i].bytes < free_[best].bytes)) best = i;
@@ -102,6 +105,7 @@ struct DevPool {
         return p;
     }
     void put(void* p, size_t bytes, int device) {
+        std::lock_guard<std::mutex> g(m_);
         if (free_.size() >= 16) {
             cudaFree(free_.front().p);
             free_.erase(free_.begin());
@@ -197,7 +201,7 @@ struct drprg_index {
     std::string vcf;
     bool have_gt = false;
     DBuf<double> d_prob, d_M;
-    DBuf<uint32_t> d_len, d_prev, d_up, d_path, d_path_len;
+    DBuf<uint32_t> d_len, d_up, d_path, d_path_len;
 
     ~drprg_index() {
         if (device < 0) return;
@@ -211,7 +215,7 @@ struct drprg_index {
         clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release();
         calive.release(); kept.release(); temp.release();
         d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
-        d_prob.release(); d_M.release(); d_len.release(); d_prev.release(); d_up.release(); d_path.release(); d_path_len.release();
+        d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release();
@@ -486,7 +490,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     MP.min_kmer_covg = X->fit.min_kmer_covg;
     MP.gt_err = X->opts.gt_error_rate;
     MP.gt_conf = X->opts.gt_conf;
-    X->d_prob.ensure(N); X->d_M.ensure(N); X->d_len.ensure(N); X->d_prev.ensure(N);
+    X->d_prob.ensure(N); X->d_M.ensure(N); X->d_len.ensure(N);
     X->d_up.ensure((size_t)N * LV_MAX); X->d_path.ensure(N); X->d_path_len.ensure(P);
     launch_node_prob(X->d_accum, N, X->d_is_terminal, MP, X->d_prob.p, st);
     launch_prob_hist(X->d_prob.p, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist, st);
@@ -513,7 +517,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     CK(cudaMemsetAsync(X->d_path.p, 0, (size_t)N * 4, X->st_ml));  // absent loci leave their slice unwritten
     CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
-                  X->d_len.p, X->d_prev.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
+                  X->d_len.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
                   X->d_needs_mean, X->st_ml);
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());

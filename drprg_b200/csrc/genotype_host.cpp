@@ -578,15 +578,6 @@ size_t format_g6(double v, char* out) {
     }
     return (size_t)(o - out);
 }
-static inline void put_g6(std::string& s, double v) {
-    char b[48];
-    s.append(b, format_g6(v, b));
-}
-static inline void put_u(std::string& s, uint32_t v) {
-    char b[16];
-    auto r = std::to_chars(b, b + sizeof b, v);
-    s.append(b, r.ptr);
-}
 
 std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
                        const std::vector<std::string>& contigs, const std::string& sample) {

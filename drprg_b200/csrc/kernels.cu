@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                                                                      unsigned long long* __restrict__ out_a,
                                                                      unsigned long long* __restrict__ out_b,
                                                                      unsigned long long* __restrict__ out_count,
-                                                                     unsigned long long cap, uint32_t four) {
+                                                                     unsigned long long cap) {
     static_assert(K >= 2 && K <= 15, "left-aligned hash with a spare low bit range needs k <= 15");
     constexpr uint32_t S = 32 - 2 * K;
     constexpr uint32_t HM = ~((1u << S) - 1u);
@@ -323,7 +323,6 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
         const uint32_t c = hi >> 30;
         hi = __funnelshift_l(lo, hi, 2);
         lo <<= 2;
-        (void)four;
         F = F * 4u + c;                                     // garbage above bit 2K wraps away in the first hash multiply
         Rc = (__funnelshift_r(Rc, c, 2) & HM) ^ 0xC0000000u;  // complemented base enters at the top; bases older than K fall off
     };
@@ -493,7 +492,7 @@ static void launch_short_one(const DevReads& R, const DevTable& T, unsigned long
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_tiles = (n_items + SHORT_THREADS - 1) / SHORT_THREADS;
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, 2ull * (unsigned)sm_count);
-    sketch_short_kernel<W, K, LOOKUP, V, SF><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap, 4u);
+    sketch_short_kernel<W, K, LOOKUP, V, SF><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap);
     ++g_launches;
 }
 
@@ -1095,7 +1094,7 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
 
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
-                   uint32_t* d_prev, uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
+                   uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
                    uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean, cudaStream_t st) {
     if (!n_loci) return;
     // shared memory: per k-mer node sum, mean, score (f64), length, LV lifting pointers, edge offset (u32);
@@ -1131,7 +1130,6 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
         kernel<<<n_loci, 32, smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, P, d_M, d_len, d_up,
                                          total_knodes, d_path, d_path_len, smem_nodes, smem_edges);
     };
-    (void)d_prev;
     switch (LV) {  // levels needed for the window (pandora's default 100 -> 7)
         case 7: go(mlpath_kernel<7>); break;
         case 1: case 2: case 3: case 4: case 5: case 6: go(mlpath_kernel<7>); break;
