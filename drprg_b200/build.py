@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdrprg_cuda.so")
 SOURCES = ["kernels.cu", "capi.cu", "prg_graph.cpp", "genotype_host.cpp"]
+EXTRA = ["pandora_cuda_main.cpp"]
 HEADERS = ["kernels.cuh", "prg_graph.hpp", "genotype_host.hpp", "../../include/drprg_cuda.h"]
 
 
@@ -22,7 +23,7 @@ def stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS + EXTRA)
 
 
 def build(force=False, verbose=False):
@@ -36,6 +37,10 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # pandora-argv-compatible front end (drprg -p/--pandora can point at it)
+    exe = os.path.join(HERE, "pandora_cuda")
+    subprocess.check_call([host_cxx, "-std=c++17", "-O2", "-o", exe, os.path.join(CSRC, "pandora_cuda_main.cpp"),
+                           "-L" + HERE, "-ldrprg_cuda", "-Wl,-rpath,$ORIGIN"])
     return SO
 
 

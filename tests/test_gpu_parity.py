@@ -345,3 +345,25 @@ def test_config2_full_size_properties_and_oracle():
     assert (whole[2 * N:2 * N + ox.n_loci] == mr.locus_reads()).all()
     og = O.Genotype(ox, mr, oo, wl.refs_path)
     assert [l for l in og.vcf().splitlines() if not l.startswith("##fileDate")] == vcf_whole
+
+
+def test_pandora_cuda_cli_drop_in(tmp_path):
+    """drprg_b200/pandora_cuda takes the exact argv drprg builds for `pandora map` (src/lib.rs:594-617,
+    src/predict.rs:288-294), so `drprg predict -p pandora_cuda` needs no Rust change."""
+    import subprocess
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=40, decoys=2, seed=12)
+    fq = tmp_path / "reads.fq"
+    sim.write_fastq(str(fq), d, o)
+    exe = os.path.join(os.path.dirname(lib.SO_PATH), "pandora_cuda")
+    out = tmp_path / "out"
+    argv = [exe, "map", "--genotype", "--local", "--gt-conf", "0", "-v", "-o", str(out), "-g", "2000", "--max-covg", "4294967295",
+            "--vcf-refs", TOY_REFS, "-t", "2", "-w", "11", "-k", "15", "-c", "10", "-I", TOY_PRG, str(fq)]
+    r = subprocess.run(argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ox = O.Index(TOY_PRG, 11, 15)
+    oo = O.make_opts(illumina=True, genome_size=2000)
+    og = O.Genotype(ox, O.MapRun(ox, d, o, oo), oo, TOY_REFS)
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    assert strip((out / "pandora_genotyped.vcf").read_text()) == strip(og.vcf())
+    bad = subprocess.run([exe, "map", "-w", "11", "-k", "15", str(tmp_path / "missing.prg"), str(fq)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "cannot open" in bad.stderr
