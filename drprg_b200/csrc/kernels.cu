@@ -1092,11 +1092,206 @@ __global__ void mlpath_rec_kernel(uint32_t n_loci, const uint32_t* __restrict__ 
     path_len[l] = cnt;
 }
 
+// ---- run-parallel variant ---------------------------------------------------------------------------------
+// Most k-mer nodes have a single successor, so which node follows them is known from the graph alone; only the
+// running sums are sequential.  The host cuts every locus into UNITS in processing order: a node with a choice (or
+// none), or a RUN of up to 32 single-successor nodes j_1 <- j_2 <- ... hanging off an already finished node b.  For
+// a run every pointer a node needs (lifting pointers, window tail T, the node whose score leaves the window) is
+// succ^m(j_i) = j_(i-m) inside the run or a walk of m-i steps from b through finished tables: all 32 lanes resolve
+// their node's pointers at once (independent loads, no stores in between), then lane 0 adds up the sums in pandora's
+// order from staged operands (two dependent DADDs per node instead of ~10 dependent shared-memory hops).
+struct MlUnitsDev {
+    const uint32_t* locus_unit_off;  // n_loci + 1
+    const uint32_t* unit_start;      // n_units + 1 -> unit_nodes
+    const uint32_t* unit_nodes;      // ranks within the locus, chain order (highest rank first)
+};
+
+__device__ __forceinline__ uint32_t ldsx32(uint32_t a, uint32_t token) {  // reorderable load, tied to the unit by `token`
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a), "r"(token));
+    return v;
+}
+__device__ __forceinline__ double ldsx64(uint32_t a, uint32_t token) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a), "r"(token));
+    return v;
+}
+__device__ __forceinline__ uint32_t ml_walk(uint32_t x, uint32_t steps, uint32_t token) {
+#pragma unroll
+    for (int l = 0; l < 7; ++l)
+        if ((steps >> l) & 1u) x = ldsx32(x + R_UP + 4 * l, token);
+    return x;
+}
+
+__global__ void mlpath_unit_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
+                                   const uint32_t* __restrict__ edges, const double* __restrict__ prob,
+                                   const int32_t* __restrict__ locus_reads, const uint8_t* __restrict__ needs_mean,
+                                   MlUnitsDev U, ModelParams P, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
+                                   uint32_t max_nodes, uint32_t max_edges) {
+    extern __shared__ double s_dyn[];
+    const uint32_t l = blockIdx.x;
+    if (l >= n_loci) return;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
+    if (locus_reads[l] <= 0 || n < 2) {
+        if (lane == 0) path_len[l] = 0xffffffffu;
+        return;
+    }
+    const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
+    const uint32_t recs = (uint32_t)__cvta_generic_to_shared(s_dyn);
+    const uint32_t edg = recs + (max_nodes + 1) * REC;
+    const uint32_t scr = (edg + (max_edges + 1) * 4u + 7u) & ~7u;  // staging: 32 x {p f64, q f64, node u32}
+    const uint32_t s_p = scr, s_q = scr + 256, s_n = scr + 512;
+    for (uint32_t i = lane; i <= n; i += 32) {
+        const uint32_t a = recs + i * REC;
+        if (i < n) sts64(a + R_PR, prob[base + i]);
+        sts32(a + R_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
+    }
+    for (uint32_t i = lane; i < n_edges; i += 32) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
+    const double tol = 0.000001;
+    const uint32_t term = recs + (n - 1) * REC;
+    const uint32_t W = P.window;
+    if (lane == 0) {
+        sts64(term + R_M, 0.0);
+        sts32(term + R_LEN, 0u);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // includes R_T
+    }
+    __syncwarp();
+    const uint32_t u0 = U.locus_unit_off[l], u1 = U.locus_unit_off[l + 1];
+    for (uint32_t u = u0; u < u1; ++u) {
+        const uint32_t s0 = U.unit_start[u], k = U.unit_start[u + 1] - s0;
+        const uint32_t a1 = recs + U.unit_nodes[s0] * REC;
+        const uint32_t e0w = lds32(a1 + R_EOFF);
+        const uint32_t e0 = e0w & ~3u, e1 = lds32(a1 + REC + R_EOFF) & ~3u;
+        if (e1 - e0 != 4u) {
+            // ---- a node with a choice (or a dead end): pandora's sequential comparison, one lane
+            if (lane == 0) {
+                const uint32_t a = a1;
+                double Mj = 0.0, max_mean = -(double)FLT_MAX;
+                uint32_t lenj = 0, prevj = term, max_len = 0;
+                const double pj = lds64(a + R_PR);
+                for (uint32_t e = e0; e < e1; e += 4u) {
+                    const uint32_t v = lds32(e);
+                    const bool is_term = (v == term);
+                    const uint32_t lv = lds32(v + R_LEN);
+                    const uint32_t tv = lds32(v + R_T);
+                    const double mean_v = lds64(v + R_MEAN);
+                    const double Mv = lds64(v + R_M);
+                    const bool take = is_term ? (P.thresh > max_mean + tol)
+                                              : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
+                    if (!take) continue;
+                    Mj = pj + Mv;
+                    lenj = 1 + lv;
+                    prevj = v;
+                    if (lenj > W) {
+                        Mj -= lds64(tv + R_PR);
+                        lenj -= 1;
+                    }
+                    max_mean = is_term ? P.thresh : mean_v;
+                    if (!is_term) max_len = lv;
+                }
+                if (lenj) {
+                    mlpath_link(a, prevj, W - 2);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) sts32(a + R_UP + 4 * v, term);
+                }
+                sts64(a + R_M, Mj);
+                sts32(a + R_LEN, lenj);
+                if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- a run of k single-successor nodes hanging off b
+        const uint32_t b = lds32(e0);
+        const uint32_t lb = lds32(b + R_LEN);
+        const double Mb = lds64(b + R_M);
+        const bool active = lane < k;
+        const uint32_t me = active ? recs + U.unit_nodes[s0 + lane] * REC : term;
+        if (b != term && lb == 0u) {  // hanging off a dead end: the whole run is dead (pandora never takes a NaN mean)
+            if (active) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) sts32(me + R_UP + 4 * v, term);
+                sts64(me + R_M, 0.0);
+                sts32(me + R_LEN, 0u);
+                if (lds32(me + R_EOFF) & 1u) sts64(me + R_MEAN, 0.0 / 0.0);
+            }
+            __syncwarp();
+            continue;
+        }
+        if (active) {
+            const uint32_t i = lane + 1;  // j_i
+            auto succ = [&](uint32_t m) -> uint32_t {  // succ^m(j_i), m >= 1
+                return (m < i) ? recs + U.unit_nodes[s0 + lane - m] * REC : ml_walk(b, m - i, u);
+            };
+            uint32_t up[7];
+#pragma unroll
+            for (int lv = 0; lv < 7; ++lv) up[lv] = succ(1u << lv);
+            const uint32_t T = succ(W - 1);
+            const uint32_t qn = succ(W);  // = T(successor of j_i): its score leaves the window when j_i joins a full one
+            const double p = ldsx64(me + R_PR, u), q = ldsx64(qn + R_PR, u);
+#pragma unroll
+            for (int lv = 0; lv < 7; ++lv) sts32(me + R_UP + 4 * lv, up[lv]);
+            sts32(me + R_T, T);
+            sts64(s_p + 8 * lane, p);
+            sts64(s_q + 8 * lane, q);
+            sts32(s_n + 4 * lane, me);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double M = Mb;
+            uint32_t len = lb;
+            for (uint32_t i = 0; i < k; ++i) {
+                const uint32_t node = lds32(s_n + 4 * i);
+                M = lds64(s_p + 8 * i) + M;
+                len += 1;
+                if (len > W) {
+                    M -= lds64(s_q + 8 * i);
+                    len = W;
+                }
+                sts64(node + R_M, M);
+                sts32(node + R_LEN, len);
+            }
+        }
+        __syncwarp();
+        if (active && (lds32(me + R_EOFF) & 1u)) sts64(me + R_MEAN, lds64(me + R_M) / (double)lds32(me + R_LEN));
+        __syncwarp();
+    }
+    if (lane == 0) {
+        uint32_t cnt = 0, p = lds32(recs + R_UP);
+        while (p != term && cnt < n) {
+            path[base + cnt++] = (p - recs) / REC;
+            p = lds32(p + R_UP);
+        }
+        path_len[l] = cnt;
+    }
+}
+
 void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
-                   uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean, cudaStream_t st) {
+                   uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean,
+                   const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes, cudaStream_t st) {
     if (!n_loci) return;
+    {
+        const size_t unit_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4 + 8 + 32 * 20;
+        static const bool no_units = getenv("DRPRG_MLPATH_NO_UNITS") != nullptr || getenv("DRPRG_MLPATH_GENERIC") != nullptr;
+        if (P.window >= 2 && P.window <= 127 && unit_smem <= 220u * 1024u && !no_units && d_needs_mean && d_unit_nodes) {
+            static size_t configured = 0;
+            if (unit_smem > configured) {
+                cudaFuncSetAttribute(mlpath_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem);
+                configured = unit_smem;
+            }
+            MlUnitsDev U{d_locus_unit_off, d_unit_start, d_unit_nodes};
+            mlpath_unit_kernel<<<n_loci, 32, unit_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads,
+                                                             d_needs_mean, U, P, d_path, d_path_len, max_locus_knodes,
+                                                             max_locus_edges);
+            ++g_launches;
+            return;
+        }
+    }
     // shared memory: per k-mer node sum, mean, score (f64), length, LV lifting pointers, edge offset (u32);
     // per edge one u32.  Up to the 227 KB a CTA may own; larger loci fall back to global memory.
     int LV = 1;
