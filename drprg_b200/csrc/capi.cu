@@ -149,6 +149,7 @@ struct drprg_index {
     uint32_t *d_filter = nullptr, *d_knode_base = nullptr, *d_edge_off = nullptr, *d_edges = nullptr;
     uint8_t *d_is_terminal = nullptr, *d_needs_mean = nullptr;
     uint32_t *d_locus_unit_off = nullptr, *d_unit_start = nullptr, *d_unit_nodes = nullptr;
+    float mean_run_len = 0.f;
     uint32_t table_slots = 0, filter_words = 0;
     uint64_t n_edges = 0, n_ivs = 0;
     // accumulators: [2*N coverage | P locus reads | 4 scalars]
@@ -329,6 +330,16 @@ void upload_index(drprg_index* X) {
                 unit_start.push_back((uint32_t)unit_nodes.size());
             }
             locus_unit_off.push_back((uint32_t)unit_start.size() - 1);
+        }
+        {
+            uint64_t runs = 0, run_nodes = 0;
+            for (size_t l = 0; l < H.loci.size(); ++l)
+                for (uint32_t uu = locus_unit_off[l]; uu < locus_unit_off[l + 1]; ++uu)
+                    if (H.loci[l].kout[unit_nodes[unit_start[uu]]].size() == 1) {
+                        ++runs;
+                        run_nodes += unit_start[uu + 1] - unit_start[uu];
+                    }
+            X->mean_run_len = runs ? (float)run_nodes / (float)runs : 0.f;
         }
         X->d_locus_unit_off = to_device(locus_unit_off);
         X->d_unit_start = to_device(unit_start);
@@ -553,7 +564,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
                   X->d_len.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
-                  X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start, X->d_unit_nodes, X->st_ml);
+                  X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start, X->d_unit_nodes, X->mean_run_len, X->st_ml);
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());
     X->h_path.resize(N);

@@ -1273,11 +1273,17 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
                    uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean,
-                   const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes, cudaStream_t st) {
+                   const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes,
+                   float mean_run_len, cudaStream_t st) {
     if (!n_loci) return;
-    {
+    // The run-parallel kernel pays ~1.5k cycles of per-unit overhead (warp syncs, ~50 loads per lane): it wins when
+    // runs of single-successor nodes are long (sparse panels) and loses on bubble-dense graphs (the benchmark panel:
+    // 32 % of the nodes have a choice, mean run 2.6 nodes: 1.23 ms vs 0.78 ms), so it is chosen by run length.
+    static const char* force_units = getenv("DRPRG_MLPATH_UNITS");
+    const bool want_units = force_units ? atoi(force_units) != 0 : mean_run_len >= 8.0f;
+    if (want_units) {
         const size_t unit_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4 + 8 + 32 * 20;
-        static const bool no_units = getenv("DRPRG_MLPATH_NO_UNITS") != nullptr || getenv("DRPRG_MLPATH_GENERIC") != nullptr;
+        static const bool no_units = getenv("DRPRG_MLPATH_GENERIC") != nullptr;
         if (P.window >= 2 && P.window <= 127 && unit_smem <= 220u * 1024u && !no_units && d_needs_mean && d_unit_nodes) {
             static size_t configured = 0;
             if (unit_smem > configured) {

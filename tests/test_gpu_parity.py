@@ -367,3 +367,15 @@ def test_pandora_cuda_cli_drop_in(tmp_path):
     assert strip((out / "pandora_genotyped.vcf").read_text()) == strip(og.vcf())
     bad = subprocess.run([exe, "map", "-w", "11", "-k", "15", str(tmp_path / "missing.prg"), str(fq)], capture_output=True, text=True)
     assert bad.returncode != 0 and "cannot open" in bad.stderr
+
+
+@pytest.mark.parametrize("env", [{"DRPRG_MLPATH_UNITS": "1"}, {"DRPRG_MLPATH_UNITS": "0"}, {"DRPRG_MLPATH_GENERIC": "1", "DRPRG_MLPATH_UNITS": "0"},
+                                 {"DRPRG_SKETCH_VARIANT": "0"}])
+def test_alternative_kernel_variants_keep_parity(env):
+    """the ML-path kernel has three implementations (run-parallel units, record-addressed chain, generic lifting) and the
+    sketch kernel a switchable variant; each must give the oracle's results.  The switches are read once per process."""
+    import subprocess, sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "toy_config1 or nanopore or low_min_cluster or short_read_kernel"], env=e, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
