@@ -444,7 +444,8 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
     CK(cudaSetDevice(X->device));
     const HostIndex& H = X->H;
-    uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 32));
+    // whole-genome reads give ~0.35 hits per 150 bp read; a targeted run overflows once, regrows to the exact count and re-sketches
+    uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 256));
     ensure_hit_capacity(X, cap);
     uint64_t nh = 0;
     CK(cudaEventRecord(X->ev[0], st));
