@@ -379,3 +379,16 @@ def test_alternative_kernel_variants_keep_parity(env):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                         "toy_config1 or nanopore or low_min_cluster or short_read_kernel"], env=e, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_hit_buffer_regrows_on_targeted_reads():
+    """every read on the panel (targeted sequencing): ~20 hits per read overflow the initial hit buffer, which must
+    regrow to the exact count and re-run the sketch without changing the result"""
+    p, prg, refs = small_panel()
+    hap = sim.sample_haplotype(p, 5, 0.1)
+    g, placements = sim.make_genome(p, [h[0] for h in hap], size=60_000, seed=6, min_sep=3000)
+    regions = [(s, ln) for s, ln, st in placements]
+    d, o = sim.simulate_reads(g, 120_000, 150, seed=8, sub_rate=0.002, regions=regions)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10)
+    assert len(gh["read"]) > (1 << 20)
+    assert_map_equal(gx, mr, gh)
