@@ -146,6 +146,7 @@ struct drprg_index {
     // device-resident index
     DevTable T{};
     uint2 *d_slots = nullptr, *d_recs = nullptr;
+    uint32_t* d_kfilter = nullptr;
     uint32_t *d_filter = nullptr, *d_knode_base = nullptr, *d_edge_off = nullptr, *d_edges = nullptr;
     uint8_t *d_is_terminal = nullptr, *d_needs_mean = nullptr;
     uint32_t *d_locus_unit_off = nullptr, *d_unit_start = nullptr, *d_unit_nodes = nullptr;
@@ -165,6 +166,7 @@ struct drprg_index {
     // workspace
     DBuf<unsigned long long> hi, lo, hi2, lo2;
     DBuf<uint32_t> clist, clist2, cend, keys, keys2;
+    DBuf<unsigned long long> queue;  // k-mer screen: flagged (read, position) pairs
     DBuf<uint8_t> calive, kept, temp;
     unsigned long long* d_counters = nullptr;  // [0] hit count, [1] kept count
     unsigned long long* h_counters = nullptr;  // pinned
@@ -210,11 +212,11 @@ struct drprg_index {
         cudaSetDevice(device);
         for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
                         (void*)d_is_terminal, (void*)d_needs_mean, (void*)d_locus_unit_off, (void*)d_unit_start, (void*)d_unit_nodes, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
-                        (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist})
+                        (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist, (void*)d_kfilter})
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
         hi.release(); lo.release(); hi2.release(); lo2.release();
-        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release();
+        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release(); queue.release();
         calive.release(); kept.release(); temp.release();
         d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
@@ -267,6 +269,34 @@ void upload_index(drprg_index* X) {
     X->table_slots = 1u << sb;
     X->filter_words = 1u << fb;
     X->T = DevTable{X->d_slots, sb, X->d_recs, X->d_filter, fb};
+    // ---- k-mer screen: the k-mers behind the indexed hashes, both orientations (hash64 is invertible)
+    if (H.k >= 8 && H.k <= 15 && distinct > 0) {
+        const uint64_t mask = (1ull << (2 * H.k)) - 1;
+        std::vector<uint32_t> kmers;
+        kmers.reserve(distinct * 2);
+        for (size_t i = 0; i < H.records.size(); ++i) {
+            if (i && H.records[i - 1].hash == H.records[i].hash) continue;
+            const uint64_t y = hash64_inverse_host(H.records[i].hash, mask);
+            if (hash64_host(y, mask) != H.records[i].hash) throw std::runtime_error("hash64 inversion failed");
+            uint64_t rc = 0, t = y;
+            for (uint32_t b = 0; b < H.k; ++b) {
+                rc = (rc << 2) | (3 - (t & 3));
+                t >>= 2;
+            }
+            kmers.push_back((uint32_t)y);
+            kmers.push_back((uint32_t)rc);
+        }
+        std::sort(kmers.begin(), kmers.end());
+        kmers.erase(std::unique(kmers.begin(), kmers.end()), kmers.end());
+        // ~24 filter bits per k-mer, capped by the shared memory of one SM
+        uint32_t nw = (uint32_t)std::min<uint64_t>(SCREEN_MAX_FILTER_WORDS, std::max<uint64_t>(1024, (kmers.size() * 24 + 31) / 32));
+        nw = (nw + 3) & ~3u;
+        std::vector<uint32_t> kfilter(nw, 0);
+        for (uint32_t x : kmers) screen_filter_insert(kfilter.data(), nw, x, H.k);
+        X->d_kfilter = to_device(kfilter);
+        X->T.kfilter = X->d_kfilter;
+        X->T.kfilter_words = nw;
+    }
     // ---- k-mer graphs
     const uint32_t N = H.total_knodes();
     std::vector<uint32_t> edge_off(N + 1, 0), edges;
@@ -349,8 +379,8 @@ void upload_index(drprg_index* X) {
     CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
     CK(cudaMalloc(&X->d_thresh, std::max<size_t>(1, H.loci.size()) * sizeof(uint32_t)));
-    CK(cudaMalloc(&X->d_counters, 2 * sizeof(unsigned long long)));
-    CK(cudaMallocHost(&X->h_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&X->d_counters, 8 * sizeof(unsigned long long)));  // [0] hits, [1] kept hits, [2] screen queue length, [3] screen ticket, [4] largest queue length wanted
+    CK(cudaMallocHost(&X->h_counters, 8 * sizeof(unsigned long long)));
     for (auto& e : X->ev) CK(cudaEventCreate(&e));
     std::vector<uint32_t> knode_locus(N);
     for (size_t l = 0; l < H.loci.size(); ++l) {
@@ -447,10 +477,11 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     // whole-genome reads give ~0.35 hits per 150 bp read; a targeted run overflows once, regrows to the exact count and re-sketches
     uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 256));
     ensure_hit_capacity(X, cap);
+    if (X->T.kfilter) X->queue.ensure(std::max<uint64_t>(X->queue.cap, B->total_bases / 32 + (1u << 20)));  // ~1.6 flagged positions per 150 bp read
     uint64_t nh = 0;
     CK(cudaEventRecord(X->ev[0], st));
     for (int attempt = 0; attempt < 3; ++attempt) {
-        CK(cudaMemsetAsync(X->d_counters, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(X->d_counters, 0, 5 * sizeof(unsigned long long), st));
         for (int c = 0; c < B->n_chunks; ++c) {
             DevReads Rc = B->R;
             if (B->n_chunks > 1) {
@@ -462,15 +493,18 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
                 Rc.n_reads = hi - lo;
                 Rc.read_id_base = B->R.read_id_base + (uint32_t)lo;
             }
-            launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st);
+            launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st,
+                                 X->queue.p, X->queue.cap, X->d_counters + 2);
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         nh = X->h_counters[0];
-        if (nh <= X->hi.cap) break;
+        const uint64_t nq = X->h_counters[4];  // largest screen queue any chunk wanted
+        if (nh <= X->hi.cap && nq <= X->queue.cap) break;
         if (attempt == 2) throw std::runtime_error("hit buffer overflow");
-        ensure_hit_capacity(X, nh);
+        if (nh > X->hi.cap) ensure_hit_capacity(X, nh);
+        if (nq > X->queue.cap) X->queue.ensure(nq);
         CK(cudaEventRecord(X->ev[0], st));
     }
     CK(cudaEventRecord(X->ev[1], st));

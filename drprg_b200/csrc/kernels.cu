@@ -259,8 +259,8 @@ constexpr uint32_t SMEM_FILTER_BITS = 14;  // a pre-filter of <= 2^14 words (64 
 #define DRPRG_DEFAULT_VARIANT 3
 #endif
 
-template <int W, int K, bool LOOKUP, int VARIANT, bool SMEM_FILTER>
-__global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R, DevTable T,
+template <int W, int K, bool LOOKUP, int VARIANT, bool SMEM_FILTER, int THREADS>
+__global__ void __launch_bounds__(THREADS) sketch_short_kernel(DevReads R, DevTable T,
                                                                      unsigned long long* __restrict__ out_a,
                                                                      unsigned long long* __restrict__ out_b,
                                                                      unsigned long long* __restrict__ out_count,
@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
     constexpr uint32_t S = 32 - 2 * K;
     constexpr uint32_t HM = ~((1u << S) - 1u);
     extern __shared__ uint32_t s_short[];
-    uint32_t(*s_h)[W][SHORT_THREADS] = reinterpret_cast<uint32_t(*)[W][SHORT_THREADS]>(s_short);
-    const uint32_t* s_filter = s_short + 2 * W * SHORT_THREADS;
+    uint32_t(*s_h)[W][THREADS] = reinterpret_cast<uint32_t(*)[W][THREADS]>(s_short);
+    const uint32_t* s_filter = s_short + 2 * W * THREADS;
     const int tid = threadIdx.x;
     if (LOOKUP && SMEM_FILTER) {  // "hot buckets in shared memory": the whole negative filter, once per persistent CTA
-        uint32_t* f = s_short + 2 * W * SHORT_THREADS;
+        uint32_t* f = s_short + 2 * W * THREADS;
         const uint32_t nwf = 1u << T.filter_bits;
-        for (uint32_t i = tid * 4; i < nwf; i += SHORT_THREADS * 4)
+        for (uint32_t i = tid * 4; i < nwf; i += THREADS * 4)
             *reinterpret_cast<uint4*>(f + i) = __ldg(reinterpret_cast<const uint4*>(T.filter + i));
         __syncthreads();
     }
@@ -284,9 +284,9 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
     // [seg_start-(w-1), seg_end+(w-1)) and reports [seg_start, seg_end).  Padding with hash 0 outside the streamed
     // range is exact at the true read ends and harmless inside the read (it only affects the halo).
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
-    const unsigned long long n_tiles = (n_items + SHORT_THREADS - 1) / SHORT_THREADS;
+    const unsigned long long n_tiles = (n_items + THREADS - 1) / THREADS;
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long item = tile * SHORT_THREADS + tid;
+    const unsigned long long item = tile * THREADS + tid;
     const bool have = item < n_items;
     const unsigned long long r = have ? (R.seg_read ? (unsigned long long)__ldg(R.seg_read + item) : item) : 0ull;
     uint32_t len = have ? __ldg(R.lens + r) : 0u;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                 const uint32_t hv = min(hf, hr);
                 strand_bit(hf, hr, j);
                 h[j] = hv;
-                sh[j * SHORT_THREADS] = hv;
+                sh[j * THREADS] = hv;
             }
         } else {
 #pragma unroll
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) sketch_short_kernel(DevReads R,
                 strand_bit(hf, hr, j);
                 hv = (p0 + j < nk) ? hv : 0u;
                 h[j] = hv;
-                sh[j * SHORT_THREADS] = hv;
+                sh[j * THREADS] = hv;
             }
         }
         const uint32_t strand_cur = ~not_strand;
@@ -485,14 +485,14 @@ static void launch_short_one(const DevReads& R, const DevTable& T, unsigned long
     const size_t smem = (size_t)2 * W * SHORT_THREADS * 4 + (SF ? (size_t)4 << T.filter_bits : 0);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(sketch_short_kernel<W, K, LOOKUP, V, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * W * SHORT_THREADS * 4 + (SF ? (4u << SMEM_FILTER_BITS) : 0)));
+        cudaFuncSetAttribute(sketch_short_kernel<W, K, LOOKUP, V, SF, SHORT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * W * SHORT_THREADS * 4 + (SF ? (4u << SMEM_FILTER_BITS) : 0)));
         configured = true;
     }
     // persistent CTAs: two per SM (register file: 2 x 512 threads x 62 registers), each loops over read tiles
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_tiles = (n_items + SHORT_THREADS - 1) / SHORT_THREADS;
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, 2ull * (unsigned)sm_count);
-    sketch_short_kernel<W, K, LOOKUP, V, SF><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap);
+    sketch_short_kernel<W, K, LOOKUP, V, SF, SHORT_THREADS><<<grid, SHORT_THREADS, smem, st>>>(R, T, a, b, cnt, cap);
     ++g_launches;
 }
 
@@ -524,6 +524,343 @@ static bool launch_short(const DevReads& R, const DevTable& T, uint32_t w, uint3
     return false;
 }
 
+// ============================================================================================
+// K-mer screen.  ~99 % of whole-genome reads share no k-mer with the panel, yet the sketch above spends
+// ~70 instructions per k-mer position on them (two hashes + window minima).  pandora's hash64 is a
+// bijection on 2k-bit values, so "this minimizer is in the index" implies "this FORWARD k-mer of the read is
+// one of the indexed k-mers or their reverse complements" — a set-membership test on the raw 2-bit k-mer
+// that needs no hash and no window logic.
+//   screen_kernel   streams every read once (a warp takes 32 reads at a time from a global ticket counter,
+//                   words in registers) and tests each k-mer against a blocked 2-bit Bloom filter held in
+//                   shared memory: one multiply, one LDS, two shifts, ~10 instructions per position.  The
+//                   flagged positions (~1 % false positives + the real ones) are appended to a queue.
+//   resolve_kernel  one thread per queued (read, position): canonical hash of that k-mer, index probe (exact,
+//                   drops the false positives), then the minimizer test restricted to that position — it is a
+//                   (w,k)-minimizer with pandora's "all ties kept" rule iff the run of neighbours whose hash
+//                   is >= its own covers a whole window — and the hit records.
+// The hits are the same set the full sketch + lookup kernels emit; only ~2 % of the positions ever get hashed.
+// ============================================================================================
+constexpr int SCREEN_THREADS = 1024;
+constexpr uint32_t SCREEN_MUL = 0x9E3779B1u;
+
+void screen_filter_insert(uint32_t* filter, uint32_t n_words, uint32_t kmer, uint32_t k) {
+    const uint32_t p = kmer * (SCREEN_MUL << (32u - 2u * k));  // bits above 2k wrap away
+    const uint32_t idx = (uint32_t)(((unsigned long long)p * n_words) >> 32);
+    filter[idx] |= (1u << (kmer & 31u)) | (1u << ((p >> 11) & 31u));
+}
+
+// V: pipe-balance variants (the ALU pipe — SHF/LOP3/LEA — binds first, the multiplier pipe has room):
+//   bit 0: shared-memory address by IMAD with a run-time 4 instead of LEA;  bit 1: the second bit index by
+//   multiply-high with a run-time 2^21 instead of a shift.
+struct ScreenConsts { uint32_t four, two21; };
+template <int K, int CW, int V>
+__global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, DevTable T, uint32_t wk, ScreenConsts SC,
+                                                                   unsigned long long* __restrict__ queue,
+                                                                   unsigned long long* __restrict__ queue_count,
+                                                                   unsigned long long queue_cap,
+                                                                   unsigned long long* __restrict__ ticket) {
+    static_assert(K >= 8 && K <= 15, "the filter bit choice needs >= 16 k-mer bits; 2k < 32");
+    constexpr int NF = (CW + 1) / 2;
+    extern __shared__ uint32_t s_kf[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid * 4; i < T.kfilter_words; i += SCREEN_THREADS * 4)
+        *reinterpret_cast<uint4*>(s_kf + i) = __ldg(reinterpret_cast<const uint4*>(T.kfilter + i));
+    __syncthreads();
+    const uint32_t n_fw = T.kfilter_words;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_kf);
+    const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
+    const unsigned long long n_tiles = (n_items + 31) / 32;
+    const bool wide = R.stride_words && !(R.stride_words & 1u) && !R.seg_read;  // every read starts 8-byte aligned
+    unsigned long long tile = 0;
+    if (lane == 0) tile = atomicAdd(ticket, 1ull);
+    tile = __shfl_sync(FULL, tile, 0);
+    while (tile < n_tiles) {
+        unsigned long long next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(ticket, 1ull);  // lands while this tile is screened
+        const unsigned long long item = tile * 32 + lane;
+        const bool have = item < n_items;
+        const unsigned long long r = have ? (R.seg_read ? (unsigned long long)__ldg(R.seg_read + item) : item) : 0ull;
+        uint32_t len = have ? __ldg(R.lens + r) : 0u;
+        if (len + 1 < wk) len = 0;  // too short or dropped: the sketch skips it too
+        const uint32_t nk_read = len ? len - K + 1 : 0;
+        const uint32_t seg_s = (have && R.seg_read) ? __ldg(R.seg_start + item) : 0u;
+        const uint32_t seg_e = R.seg_read ? min(seg_s + R.seg_len, nk_read) : nk_read;  // screen positions [seg_s, seg_e)
+        const uint32_t q0 = seg_s & ~15u;                                             // streamed from a word boundary
+        const uint32_t span = seg_e > seg_s ? seg_e - q0 : 0u;
+        const uint32_t span_max = __reduce_max_sync(FULL, span);
+        const uint32_t* wp = R.words + (have ? (R.stride_words ? r * R.stride_words : __ldg(R.word_off + r)) : 0ull) + (q0 >> 4);
+        const uint32_t nwords = span ? ((len + 15) >> 4) - (q0 >> 4) : 0u;  // words that may be read from wp
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < span_max; c0 += CW * 16) {
+            const uint32_t w0 = c0 >> 4;
+            uint32_t cw[CW + 2];
+            if (wide) {
+#pragma unroll
+                for (int i = 0; i <= CW; i += 2) {
+                    uint2 t = make_uint2(0u, 0u);
+                    if (w0 + i < nwords) t = __ldg(reinterpret_cast<const uint2*>(wp + w0 + i));  // nwords bounds the pair: the stride is even
+                    cw[i] = t.x;
+                    cw[i + 1] = (w0 + i + 1 < nwords) ? t.y : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i <= CW; ++i) cw[i] = (w0 + i < nwords) ? __ldg(wp + w0 + i) : 0u;
+            }
+            uint32_t f[NF];
+#pragma unroll
+            for (int i = 0; i < NF; ++i) f[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+                if (c0 + i * 16 < span_max) {  // warp-uniform: skip words past every lane's last position
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // 32 bits ENDING at the last base of the k-mer that starts at base j of word i; the older
+                        // bases above bit 2K are removed by the multiply
+                        const int n = 64 - 2 * (j + K);
+                        const uint32_t v = (n >= 32) ? (cw[i] >> ((n - 32) & 31)) : __funnelshift_r(cw[i + 1], cw[i], n & 31);
+                        const uint32_t p = v * (SCREEN_MUL << (32 - 2 * K));
+                        uint32_t word;
+                        if (V & 1) {
+                            uint32_t addr;
+                            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(__umulhi(p, n_fw)), "r"(SC.four), "r"(s_base));
+                            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+                        } else {
+                            word = s_kf[__umulhi(p, n_fw)];
+                        }
+                        const uint32_t s2 = (V & 2) ? __umulhi(p, SC.two21) : (p >> 11);
+                        const uint32_t t = __funnelshift_r(word, 0u, v) & __funnelshift_r(word, 0u, s2);
+                        asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %1, 1;\n\tsetp.ne.u32 q, t, 0;\n\t@q or.b32 %0, %0, %2;\n\t}"
+                            : "+r"(f[i >> 1])
+                            : "r"(t), "r"(1u << ((i & 1) * 16 + j)));
+                    }
+                }
+            }
+            // keep the flags of positions inside [seg_s, seg_e), count them, reserve queue space per warp
+            uint32_t cnt = 0;
+            {
+                const uint32_t lo_cut = (c0 == 0) ? (seg_s - q0) : 0u;                          // < 16
+                const uint32_t hi_cut = span > c0 ? min(span - c0, (uint32_t)(CW * 16)) : 0u;  // valid positions in this chunk
+#pragma unroll
+                for (int i = 0; i < NF; ++i) {
+                    const uint32_t base = i * 32;
+                    const uint32_t hi_n = hi_cut > base ? min(hi_cut - base, 32u) : 0u;
+                    uint32_t m = hi_n >= 32u ? 0xffffffffu : ((1u << hi_n) - 1u);
+                    if (i == 0) m &= ~((1u << lo_cut) - 1u);
+                    f[i] &= m;
+                    cnt += __popc(f[i]);
+                }
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total) {
+                unsigned long long o = 0;
+                if (lane == 0) o = atomicAdd(queue_count, (unsigned long long)total);
+                o = __shfl_sync(FULL, o, 0) + (incl - cnt);
+                const unsigned long long tag = (unsigned long long)(uint32_t)r << 32;
+#pragma unroll
+                for (int i = 0; i < NF; ++i) {
+                    uint32_t m = f[i];
+                    while (m) {
+                        const uint32_t bit = __ffs(m) - 1;
+                        m &= m - 1u;
+                        if (o < queue_cap) queue[o] = tag | (q0 + c0 + i * 32 + bit);
+                        ++o;
+                    }
+                }
+            }
+        }
+        tile = __shfl_sync(FULL, next_tile, 0);
+    }
+}
+
+// one thread per flagged (read, position).  W > 0: compile-time window (W <= 17 with k = 15, so the 2W-2+K bases around
+// the position fit four words): the words are fetched once, aligned so that every neighbour sits at a static offset,
+// and all 2W-1 canonical hashes are computed branch-free.  W == 0: any window, neighbours fetched one by one.
+template <int W, int K>
+__global__ void __launch_bounds__(256) resolve_kernel(DevReads R, DevTable T, uint32_t w_rt, uint32_t k_rt,
+                                                      const unsigned long long* __restrict__ queue,
+                                                      const unsigned long long* __restrict__ queue_count,
+                                                      unsigned long long queue_cap,
+                                                      unsigned long long* __restrict__ queue_need,
+                                                      unsigned long long* __restrict__ out_a,
+                                                      unsigned long long* __restrict__ out_b,
+                                                      unsigned long long* __restrict__ out_count, unsigned long long cap) {
+    static_assert(W == 0 || 2 * W - 2 + K <= 48, "window + k-mer must fit three aligned words");
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(queue_need, *queue_count);  // sticky over the chunks of a batch: the host regrows and redoes
+    const unsigned long long n = min(*queue_count, queue_cap);
+    const uint32_t w = W ? (uint32_t)W : w_rt, k = W ? (uint32_t)K : k_rt;
+    const uint32_t S = 32 - 2 * k;
+    const uint32_t hm = (S == 0) ? 0xffffffffu : ~((1u << S) - 1u);
+    auto canon_of = [&](uint32_t v, uint32_t& strand) {  // v: 32 bits starting at the k-mer's first base
+        const uint32_t F = v & hm;
+        uint32_t y = __brev(~v & hm);
+        y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+        const uint32_t hf = hash_left_aligned(F, S, hm), hr = hash_left_aligned(y << S, S, hm);
+        strand = hf <= hr ? 1u : 0u;
+        return min(hf, hr);
+    };
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long e0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); e0 < n;
+         e0 += (unsigned long long)gridDim.x * blockDim.x) {  // warp-uniform trip count: the hits are appended per warp
+      uint32_t emit_n = 0, rec_begin = 0, read_strand = 0, r = 0, pos = 0;
+      const unsigned long long e = e0 + lane;
+      do {
+        if (e >= n) break;
+        const unsigned long long q = queue[e];
+        r = (uint32_t)(q >> 32);
+        pos = (uint32_t)q;
+        const uint32_t len = __ldg(R.lens + r);
+        const uint32_t nk = len - k + 1;
+        const uint32_t* wp = R.words + (R.stride_words ? (unsigned long long)r * R.stride_words : __ldg(R.word_off + r));
+        const uint32_t nwords = (len + 15) >> 4;
+        uint32_t y[4] = {0u, 0u, 0u, 0u};
+        auto canon_at = [&](uint32_t x, uint32_t& strand) {  // generic path: fetch the two words of position x
+            const uint32_t wi = x >> 4;
+            const uint32_t a = __ldg(wp + wi), b = (wi + 1 < nwords) ? __ldg(wp + wi + 1) : 0u;
+            return canon_of(__funnelshift_l(b, a, 2u * (x & 15u)), strand);
+        };
+        uint32_t dummy, h;
+        if (W) {
+            const int start = (int)pos - (W - 1);  // may be negative near the read start: those words read as 0
+            const int sw = start >> 4;
+            const uint32_t sh = 2u * ((uint32_t)start & 15u);
+            uint32_t x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = (sw + i >= 0 && sw + i < (int)nwords) ? __ldg(wp + sw + i) : 0u;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) y[i] = __funnelshift_l(x[i + 1], x[i], sh);  // base `start + j` now sits at base j
+            constexpr int c = W - 1;
+            h = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), read_strand);
+        } else {
+            h = canon_at(pos, read_strand);
+        }
+        const uint32_t hv = h >> S;
+        // index probe first: most queue entries are false positives of the Bloom filter
+        uint32_t slot = table_slot(hv, T.slot_bits);
+        const uint32_t smask = (1u << T.slot_bits) - 1u;
+        uint32_t rec_n = 0;
+        while (true) {
+            const uint2 ent = __ldg(T.slots + slot);
+            if (ent.y == 0u) break;
+            if (ent.x == hv) {
+                rec_begin = ent.y & 0xffffffu;
+                rec_n = ent.y >> 24;
+                break;
+            }
+            slot = (slot + 1) & smask;
+        }
+        if (!rec_n) break;
+        // minimizer test: the neighbours with hash >= h on both sides must cover a window of w positions
+        uint32_t run = 1;
+        if (W) {
+            bool ok = true;
+#pragma unroll
+            for (int d = 1; d < (W ? W : 1); ++d) {
+                const int c = W - 1 - d;
+                const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
+                ok = ok && (uint32_t)d <= pos && hn >= h;
+                run += ok ? 1u : 0u;
+            }
+            ok = true;
+#pragma unroll
+            for (int d = 1; d < (W ? W : 1); ++d) {
+                const int c = W - 1 + d;
+                const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
+                ok = ok && pos + d < nk && hn >= h;
+                run += ok ? 1u : 0u;
+            }
+        } else {
+            for (uint32_t d = 1; d < w && d <= pos && run < w; ++d) {
+                if (canon_at(pos - d, dummy) < h) break;
+                ++run;
+            }
+            for (uint32_t d = 1; d < w && pos + d < nk && run < w; ++d) {
+                if (canon_at(pos + d, dummy) < h) break;
+                ++run;
+            }
+        }
+        if (run >= w) emit_n = rec_n;
+      } while (false);
+      // one atomic per warp: a single hit counter takes ~1 atomic per clock, the real entries come ~30 per read
+      uint32_t incl = emit_n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += t;
+      }
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      if (total) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+          base = __shfl_sync(FULL, base, 0) + (incl - emit_n);
+          for (uint32_t j = 0; j < emit_n; ++j) {
+              const uint2 rc = __ldg(T.recs + rec_begin + j);
+              const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
+              if (base + j < cap) {
+                  out_a[base + j] = ((unsigned long long)(R.read_id_base + r) << 32) | ((unsigned long long)(rc.y >> 1) << 16) |
+                                    ((unsigned long long)(fwd ^ 1u) << 15);
+                  out_b[base + j] = ((unsigned long long)pos << 32) | rc.x;
+              }
+          }
+      }
+    }
+}
+
+template <int K, int CW, int V>
+static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue,
+                            unsigned long long* counters, uint64_t queue_cap, int sm_count, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(screen_kernel<K, CW, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCREEN_MAX_FILTER_WORDS * 4));
+        configured = true;
+    }
+    const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
+    const unsigned long long n_ctas = (n_items + SCREEN_THREADS - 1) / SCREEN_THREADS;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(n_ctas, (unsigned long long)sm_count);  // one persistent CTA per SM
+    screen_kernel<K, CW, V><<<grid, SCREEN_THREADS, (size_t)T.kfilter_words * 4, st>>>(R, T, wk, ScreenConsts{4u, 1u << 21}, queue, counters, queue_cap, counters + 1);
+    ++g_launches;
+}
+
+#ifndef DRPRG_SCREEN_DEFAULT_VARIANT
+#define DRPRG_SCREEN_DEFAULT_VARIANT 0
+#endif
+template <int K, int CW>
+static void launch_screen_one(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue,
+                              unsigned long long* counters, uint64_t queue_cap, int sm_count, cudaStream_t st) {
+    static const int variant = [] {
+        const char* e = getenv("DRPRG_SCREEN_VARIANT");
+        return e ? atoi(e) & 3 : DRPRG_SCREEN_DEFAULT_VARIANT;
+    }();
+    switch (variant) {
+        case 1: return launch_screen_v<K, CW, 1>(R, T, wk, queue, counters, queue_cap, sm_count, st);
+        case 2: return launch_screen_v<K, CW, 2>(R, T, wk, queue, counters, queue_cap, sm_count, st);
+        case 3: return launch_screen_v<K, CW, 3>(R, T, wk, queue, counters, queue_cap, sm_count, st);
+        default: return launch_screen_v<K, CW, 0>(R, T, wk, queue, counters, queue_cap, sm_count, st);
+    }
+}
+
+// screen + resolve; counters = {queue length, ticket, largest queue length wanted (not reset here)}
+template <int K>
+static void launch_screened(const DevReads& R, const DevTable& T, uint32_t w, unsigned long long* a, unsigned long long* b,
+                            unsigned long long* cnt, uint64_t cap, int sm_count, uint32_t max_len,
+                            unsigned long long* queue, uint64_t queue_cap, unsigned long long* counters, cudaStream_t st) {
+    cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st);
+    if (!R.seg_read && max_len >= (uint32_t)K && max_len - K + 1 <= 10 * 16) launch_screen_one<K, 10>(R, T, w + K, queue, counters, queue_cap, sm_count, st);
+    else launch_screen_one<K, 8>(R, T, w + K, queue, counters, queue_cap, sm_count, st);
+    // ~2 queue entries per read; the grid-stride loop reads the real length on the device
+    const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((n_items * 2 + 255) / 256 + 1, 8ull * (unsigned)sm_count);
+    if (w == 11) resolve_kernel<11, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else if (w == 14) resolve_kernel<14, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else resolve_kernel<0, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    ++g_launches;
+}
+
 static int grid_for(int sm_count, uint64_t n_reads) {
     // persistent-style grid: a multiple of the SM count, capped by the work available
     long long want = (long long)((n_reads + WARPS - 1) / WARPS);
@@ -534,8 +871,15 @@ static int grid_for(int sm_count, uint64_t n_reads) {
 
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
-                          uint32_t max_len, cudaStream_t st) {
+                          uint32_t max_len, cudaStream_t st, unsigned long long* d_queue, uint64_t queue_cap,
+                          unsigned long long* d_screen_counters) {
     if (R.n_reads == 0) return;
+    static const bool screen_on = [] {
+        const char* e = getenv("DRPRG_SCREEN");  // DRPRG_SCREEN=0 sketches every read (A/B measurements, parity tests)
+        return !e || atoi(e) != 0;
+    }();
+    if (screen_on && d_queue && T.kfilter && (max_len <= SHORT_READ_MAX || R.seg_read) && k == 15)
+        return launch_screened<15>(R, T, w, d_hi, d_lo, d_hit_count, hit_cap, sm_count, max_len, d_queue, queue_cap, d_screen_counters, st);
     if ((max_len <= SHORT_READ_MAX || R.seg_read) && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, sm_count, st)) return;
     sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
     ++g_launches;
@@ -964,7 +1308,7 @@ constexpr uint32_t REC = 64, R_M = 0, R_MEAN = 8, R_PR = 16, R_LEN = 24, R_EOFF 
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ double lds64(uint32_t a) {

@@ -35,6 +35,10 @@ struct DevTable {
     const uint2* recs;       // {knode rank within locus, prg << 1 | strand}, grouped by hash
     const uint32_t* filter;  // blocked 2-bit Bloom pre-filter, 1 << filter_bits words
     uint32_t filter_bits;
+    // k-mer screen (k <= 15): every indexed minimizer k-mer in both orientations.  A read can only produce a hit if
+    // one of its forward k-mers is in this set, which is tested WITHOUT hashing (hash64 is a bijection).
+    const uint32_t* kfilter = nullptr;  // blocked 2-bit Bloom over k-mers, kfilter_words words (multiple of 4), copied to shared memory
+    uint32_t kfilter_words = 0;
 };
 
 struct Hit128 {  // sort key: (hi, lo) ascending == pandora MinimizerHit order
@@ -56,9 +60,17 @@ struct ModelParams {  // S6 output, computed on the host
 uint64_t launch_count();
 
 // S1+S2: sketch every read and probe the index; hits appended (unordered) through *hit_count
+// With a screen workspace (d_queue: queue_cap entries, d_screen_counters: {queue length, ticket, largest queue length
+// wanted}) and a screenable index (k = 15), a k-mer screen queues the positions whose k-mer may be indexed and only
+// those are hashed, probed and tested for minimizer status (identical hits).  The queue overflowed when
+// d_screen_counters[2] > queue_cap (the caller zeroes [2] before a batch and redoes the batch with a larger queue).
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
-                          uint32_t max_len, cudaStream_t st);
+                          uint32_t max_len, cudaStream_t st, unsigned long long* d_queue = nullptr, uint64_t queue_cap = 0,
+                          unsigned long long* d_screen_counters = nullptr);
+// host mirror of the screen's filter addressing (used when the index is uploaded)
+void screen_filter_insert(uint32_t* filter, uint32_t n_words, uint32_t kmer, uint32_t k);
+constexpr uint32_t SCREEN_MAX_FILTER_WORDS = 54 * 1024;  // 216 KB of shared memory
 // S1 only (parity hook): emits key = read << 32 | start, val = hash << 1 | strand
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st);

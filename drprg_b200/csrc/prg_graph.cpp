@@ -25,6 +25,30 @@ uint64_t hash64_host(uint64_t key, uint64_t mask) {
     return key;
 }
 
+// hash64 is a bijection on [0, mask]: every step (odd multiply, xor-shift, x -> x*(2^21-1) - 1) is invertible
+// modulo mask + 1.  The device k-mer screen needs the k-mer behind every indexed hash.
+uint64_t hash64_inverse_host(uint64_t key, uint64_t mask) {
+    auto inv_odd = [](uint64_t a) {  // Newton iteration for a^-1 mod 2^64
+        uint64_t x = a;
+        for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+        return x;
+    };
+    auto unxorshift = [&](uint64_t v, int s) {
+        uint64_t x = v;
+        for (int i = 0; i * s < 64; ++i) x = v ^ (x >> s);
+        return x;
+    };
+    key &= mask;
+    key = (key * inv_odd((1ull << 31) + 1)) & mask;
+    key = unxorshift(key, 28);
+    key = (key * inv_odd(21)) & mask;
+    key = unxorshift(key, 14);
+    key = (key * inv_odd(265)) & mask;
+    key = unxorshift(key, 24);
+    key = ((key + 1) * inv_odd((1ull << 21) - 1)) & mask;
+    return key;
+}
+
 std::string read_text_file(const std::string& path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("cannot open " + path);

@@ -52,6 +52,7 @@ struct HostIndex {
 };
 
 uint64_t hash64_host(uint64_t key, uint64_t mask);
+uint64_t hash64_inverse_host(uint64_t key, uint64_t mask);
 void parse_prg_text(const std::string& text, std::vector<Locus>& loci);
 void sketch_locus(Locus& L, uint32_t prg_id, uint32_t w, uint32_t k, std::vector<Record>& records);
 HostIndex build_host_index(const std::string& prg_text, uint32_t w, uint32_t k);

@@ -370,10 +370,11 @@ def test_pandora_cuda_cli_drop_in(tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"DRPRG_MLPATH_UNITS": "1"}, {"DRPRG_MLPATH_UNITS": "0"}, {"DRPRG_MLPATH_GENERIC": "1", "DRPRG_MLPATH_UNITS": "0"},
-                                 {"DRPRG_SKETCH_VARIANT": "0"}])
+                                 {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}])
 def test_alternative_kernel_variants_keep_parity(env):
-    """the ML-path kernel has three implementations (run-parallel units, record-addressed chain, generic lifting) and the
-    sketch kernel a switchable variant; each must give the oracle's results.  The switches are read once per process."""
+    """the ML-path kernel has three implementations (run-parallel units, record-addressed chain, generic lifting), the
+    sketch kernel a switchable variant and the k-mer screen in front of it can be turned off (every read sketched); each
+    must give the oracle's results.  The switches are read once per process."""
     import subprocess, sys
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
