@@ -678,24 +678,33 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
     }
 }
 
-// one thread per flagged (read, position).  W > 0: compile-time window (W <= 17 with k = 15, so the 2W-2+K bases around
-// the position fit four words): the words are fetched once, aligned so that every neighbour sits at a static offset,
-// and all 2W-1 canonical hashes are computed branch-free.  W == 0: any window, neighbours fetched one by one.
+// Resolve the flagged (read, position) pairs.  Phase 1, one thread per queue entry: canonical hash of the k-mer, index
+// probe — exact, so the Bloom filter's false positives (~80 % of the queue) end here; the survivors are compacted into
+// shared memory.  Phase 2, one thread per survivor in dense warps: the minimizer test restricted to that position.
+//   W > 0: compile-time window (2W-2+K bases around the position fit three aligned words): the words are fetched once,
+//          shifted so that every neighbour sits at a static offset, and all 2W-1 canonical hashes are computed branch-free;
+//   W == 0: any window, neighbours fetched one by one with early exit.
+constexpr int RESOLVE_THREADS = 256;
 template <int W, int K>
-__global__ void __launch_bounds__(256) resolve_kernel(DevReads R, DevTable T, uint32_t w_rt, uint32_t k_rt,
-                                                      const unsigned long long* __restrict__ queue,
-                                                      const unsigned long long* __restrict__ queue_count,
-                                                      unsigned long long queue_cap,
-                                                      unsigned long long* __restrict__ queue_need,
-                                                      unsigned long long* __restrict__ out_a,
-                                                      unsigned long long* __restrict__ out_b,
-                                                      unsigned long long* __restrict__ out_count, unsigned long long cap) {
+__global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, DevTable T, uint32_t w_rt, uint32_t k_rt,
+                                                                  const unsigned long long* __restrict__ queue,
+                                                                  const unsigned long long* __restrict__ queue_count,
+                                                                  unsigned long long queue_cap,
+                                                                  unsigned long long* __restrict__ queue_need,
+                                                                  unsigned long long* __restrict__ out_a,
+                                                                  unsigned long long* __restrict__ out_b,
+                                                                  unsigned long long* __restrict__ out_count,
+                                                                  unsigned long long cap) {
     static_assert(W == 0 || 2 * W - 2 + K <= 48, "window + k-mer must fit three aligned words");
+    __shared__ unsigned long long s_q[RESOLVE_THREADS];
+    __shared__ uint32_t s_rec[RESOLVE_THREADS];
+    __shared__ uint32_t s_n;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(queue_need, *queue_count);  // sticky over the chunks of a batch: the host regrows and redoes
     const unsigned long long n = min(*queue_count, queue_cap);
     const uint32_t w = W ? (uint32_t)W : w_rt, k = W ? (uint32_t)K : k_rt;
     const uint32_t S = 32 - 2 * k;
     const uint32_t hm = (S == 0) ? 0xffffffffu : ~((1u << S) - 1u);
+    const int tid = threadIdx.x, lane = tid & 31;
     auto canon_of = [&](uint32_t v, uint32_t& strand) {  // v: 32 bits starting at the k-mer's first base
         const uint32_t F = v & hm;
         uint32_t y = __brev(~v & hm);
@@ -704,110 +713,134 @@ __global__ void __launch_bounds__(256) resolve_kernel(DevReads R, DevTable T, ui
         strand = hf <= hr ? 1u : 0u;
         return min(hf, hr);
     };
-    const int lane = threadIdx.x & 31;
-    for (unsigned long long e0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); e0 < n;
-         e0 += (unsigned long long)gridDim.x * blockDim.x) {  // warp-uniform trip count: the hits are appended per warp
-      uint32_t emit_n = 0, rec_begin = 0, read_strand = 0, r = 0, pos = 0;
-      const unsigned long long e = e0 + lane;
-      do {
-        if (e >= n) break;
-        const unsigned long long q = queue[e];
-        r = (uint32_t)(q >> 32);
-        pos = (uint32_t)q;
-        const uint32_t len = __ldg(R.lens + r);
-        const uint32_t nk = len - k + 1;
-        const uint32_t* wp = R.words + (R.stride_words ? (unsigned long long)r * R.stride_words : __ldg(R.word_off + r));
-        const uint32_t nwords = (len + 15) >> 4;
-        uint32_t y[4] = {0u, 0u, 0u, 0u};
-        auto canon_at = [&](uint32_t x, uint32_t& strand) {  // generic path: fetch the two words of position x
-            const uint32_t wi = x >> 4;
-            const uint32_t a = __ldg(wp + wi), b = (wi + 1 < nwords) ? __ldg(wp + wi + 1) : 0u;
-            return canon_of(__funnelshift_l(b, a, 2u * (x & 15u)), strand);
-        };
-        uint32_t dummy, h;
-        if (W) {
-            const int start = (int)pos - (W - 1);  // may be negative near the read start: those words read as 0
-            const int sw = start >> 4;
-            const uint32_t sh = 2u * ((uint32_t)start & 15u);
-            uint32_t x[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = (sw + i >= 0 && sw + i < (int)nwords) ? __ldg(wp + sw + i) : 0u;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) y[i] = __funnelshift_l(x[i + 1], x[i], sh);  // base `start + j` now sits at base j
-            constexpr int c = W - 1;
-            h = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), read_strand);
-        } else {
-            h = canon_at(pos, read_strand);
-        }
-        const uint32_t hv = h >> S;
-        // index probe first: most queue entries are false positives of the Bloom filter
-        uint32_t slot = table_slot(hv, T.slot_bits);
-        const uint32_t smask = (1u << T.slot_bits) - 1u;
-        uint32_t rec_n = 0;
-        while (true) {
-            const uint2 ent = __ldg(T.slots + slot);
-            if (ent.y == 0u) break;
-            if (ent.x == hv) {
-                rec_begin = ent.y & 0xffffffu;
-                rec_n = ent.y >> 24;
-                break;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * RESOLVE_THREADS; base < n;
+         base += (unsigned long long)gridDim.x * RESOLVE_THREADS) {  // CTA-uniform trip count
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        // ---- phase 1
+        {
+            const unsigned long long e = base + tid;
+            uint32_t rec = 0;
+            unsigned long long q = 0;
+            if (e < n) {
+                q = queue[e];
+                const uint32_t r = (uint32_t)(q >> 32), pos = (uint32_t)q;
+                const uint32_t len = __ldg(R.lens + r);
+                const uint32_t* wp = R.words + (R.stride_words ? (unsigned long long)r * R.stride_words : __ldg(R.word_off + r));
+                const uint32_t wi = pos >> 4;
+                const uint32_t a = __ldg(wp + wi), b = (wi + 1 < ((len + 15) >> 4)) ? __ldg(wp + wi + 1) : 0u;
+                uint32_t strand;
+                const uint32_t hv = canon_of(__funnelshift_l(b, a, 2u * (pos & 15u)), strand) >> S;
+                uint32_t slot = table_slot(hv, T.slot_bits);
+                const uint32_t smask = (1u << T.slot_bits) - 1u;
+                while (true) {
+                    const uint2 ent = __ldg(T.slots + slot);
+                    if (ent.y == 0u) break;
+                    if (ent.x == hv) {
+                        rec = ent.y;  // rec_begin | rec_count << 24, count >= 1
+                        break;
+                    }
+                    slot = (slot + 1) & smask;
+                }
             }
-            slot = (slot + 1) & smask;
-        }
-        if (!rec_n) break;
-        // minimizer test: the neighbours with hash >= h on both sides must cover a window of w positions
-        uint32_t run = 1;
-        if (W) {
-            bool ok = true;
-#pragma unroll
-            for (int d = 1; d < (W ? W : 1); ++d) {
-                const int c = W - 1 - d;
-                const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
-                ok = ok && (uint32_t)d <= pos && hn >= h;
-                run += ok ? 1u : 0u;
-            }
-            ok = true;
-#pragma unroll
-            for (int d = 1; d < (W ? W : 1); ++d) {
-                const int c = W - 1 + d;
-                const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
-                ok = ok && pos + d < nk && hn >= h;
-                run += ok ? 1u : 0u;
-            }
-        } else {
-            for (uint32_t d = 1; d < w && d <= pos && run < w; ++d) {
-                if (canon_at(pos - d, dummy) < h) break;
-                ++run;
-            }
-            for (uint32_t d = 1; d < w && pos + d < nk && run < w; ++d) {
-                if (canon_at(pos + d, dummy) < h) break;
-                ++run;
+            const uint32_t bal = __ballot_sync(FULL, rec != 0u);
+            if (bal) {
+                uint32_t o = 0;
+                if (lane == 0) o = atomicAdd(&s_n, (uint32_t)__popc(bal));
+                o = __shfl_sync(FULL, o, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (rec) {
+                    s_q[o] = q;
+                    s_rec[o] = rec;
+                }
             }
         }
-        if (run >= w) emit_n = rec_n;
-      } while (false);
-      // one atomic per warp: a single hit counter takes ~1 atomic per clock, the real entries come ~30 per read
-      uint32_t incl = emit_n;
+        __syncthreads();
+        // ---- phase 2
+        const uint32_t nf = s_n;
+        if ((uint32_t)(tid & ~31) < nf) {  // warp-uniform
+            uint32_t emit_n = 0, rec_begin = 0, read_strand = 0, r = 0, pos = 0;
+            if ((uint32_t)tid < nf) {
+                const unsigned long long q = s_q[tid];
+                const uint32_t rec = s_rec[tid];
+                r = (uint32_t)(q >> 32);
+                pos = (uint32_t)q;
+                rec_begin = rec & 0xffffffu;
+                const uint32_t len = __ldg(R.lens + r);
+                const uint32_t nk = len - k + 1;
+                const uint32_t* wp = R.words + (R.stride_words ? (unsigned long long)r * R.stride_words : __ldg(R.word_off + r));
+                const uint32_t nwords = (len + 15) >> 4;
+                uint32_t run = 1, dummy;
+                if (W) {
+                    // minimizer test: the neighbours with hash >= h on both sides must cover a window of w positions
+                    const int start = (int)pos - (W - 1);  // may be negative near the read start: those words read as 0
+                    const int sw = start >> 4;
+                    const uint32_t sh = 2u * ((uint32_t)start & 15u);
+                    uint32_t x[4], y[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t t = __shfl_up_sync(FULL, incl, d);
-          if (lane >= d) incl += t;
-      }
-      const uint32_t total = __shfl_sync(FULL, incl, 31);
-      if (total) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
-          base = __shfl_sync(FULL, base, 0) + (incl - emit_n);
-          for (uint32_t j = 0; j < emit_n; ++j) {
-              const uint2 rc = __ldg(T.recs + rec_begin + j);
-              const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
-              if (base + j < cap) {
-                  out_a[base + j] = ((unsigned long long)(R.read_id_base + r) << 32) | ((unsigned long long)(rc.y >> 1) << 16) |
-                                    ((unsigned long long)(fwd ^ 1u) << 15);
-                  out_b[base + j] = ((unsigned long long)pos << 32) | rc.x;
-              }
-          }
-      }
+                    for (int i = 0; i < 4; ++i) x[i] = (sw + i >= 0 && sw + i < (int)nwords) ? __ldg(wp + sw + i) : 0u;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) y[i] = __funnelshift_l(x[i + 1], x[i], sh);  // base `start + j` now sits at base j
+                    y[3] = 0u;
+                    constexpr int c0 = W - 1;
+                    const uint32_t h = canon_of(__funnelshift_l(y[(c0 >> 4) + 1], y[c0 >> 4], 2 * (c0 & 15)), read_strand);
+                    bool ok = true;
+#pragma unroll
+                    for (int d = 1; d < (W ? W : 1); ++d) {
+                        const int c = W - 1 - d;
+                        const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
+                        ok = ok && (uint32_t)d <= pos && hn >= h;
+                        run += ok ? 1u : 0u;
+                    }
+                    ok = true;
+#pragma unroll
+                    for (int d = 1; d < (W ? W : 1); ++d) {
+                        const int c = W - 1 + d;
+                        const uint32_t hn = canon_of(__funnelshift_l(y[(c >> 4) + 1], y[c >> 4], 2 * (c & 15)), dummy);
+                        ok = ok && pos + d < nk && hn >= h;
+                        run += ok ? 1u : 0u;
+                    }
+                } else {
+                    auto canon_at = [&](uint32_t x, uint32_t& strand) {  // fetch the two words of position x
+                        const uint32_t wi = x >> 4;
+                        const uint32_t a = __ldg(wp + wi), b = (wi + 1 < nwords) ? __ldg(wp + wi + 1) : 0u;
+                        return canon_of(__funnelshift_l(b, a, 2u * (x & 15u)), strand);
+                    };
+                    const uint32_t h = canon_at(pos, read_strand);
+                    for (uint32_t d = 1; d < w && d <= pos && run < w; ++d) {
+                        if (canon_at(pos - d, dummy) < h) break;
+                        ++run;
+                    }
+                    for (uint32_t d = 1; d < w && pos + d < nk && run < w; ++d) {
+                        if (canon_at(pos + d, dummy) < h) break;
+                        ++run;
+                    }
+                }
+                if (run >= w) emit_n = rec >> 24;
+            }
+            // one atomic per warp: a single hit counter takes ~1 atomic per clock
+            uint32_t incl = emit_n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total) {
+                unsigned long long ob = 0;
+                if (lane == 0) ob = atomicAdd(out_count, (unsigned long long)total);
+                ob = __shfl_sync(FULL, ob, 0) + (incl - emit_n);
+                for (uint32_t j = 0; j < emit_n; ++j) {
+                    const uint2 rc = __ldg(T.recs + rec_begin + j);
+                    const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
+                    if (ob + j < cap) {
+                        out_a[ob + j] = ((unsigned long long)(R.read_id_base + r) << 32) | ((unsigned long long)(rc.y >> 1) << 16) |
+                                        ((unsigned long long)(fwd ^ 1u) << 15);
+                        out_b[ob + j] = ((unsigned long long)pos << 32) | rc.x;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -827,7 +860,7 @@ static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, u
 }
 
 #ifndef DRPRG_SCREEN_DEFAULT_VARIANT
-#define DRPRG_SCREEN_DEFAULT_VARIANT 0
+#define DRPRG_SCREEN_DEFAULT_VARIANT 1
 #endif
 template <int K, int CW>
 static void launch_screen_one(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue,
@@ -855,9 +888,9 @@ static void launch_screened(const DevReads& R, const DevTable& T, uint32_t w, un
     // ~2 queue entries per read; the grid-stride loop reads the real length on the device
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned grid = (unsigned)std::min<unsigned long long>((n_items * 2 + 255) / 256 + 1, 8ull * (unsigned)sm_count);
-    if (w == 11) resolve_kernel<11, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
-    else if (w == 14) resolve_kernel<14, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
-    else resolve_kernel<0, K><<<grid, 256, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    if (w == 11) resolve_kernel<11, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else if (w == 14) resolve_kernel<14, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else resolve_kernel<0, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
     ++g_launches;
 }
 
