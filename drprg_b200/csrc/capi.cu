@@ -200,7 +200,7 @@ struct drprg_index {
     cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr;  // ML-path kernel / genotype kernels run concurrently
     PinnedBuf<uint32_t> h_path, h_plen, h_u32;
     PinnedBuf<double> h_f64;
-    PinnedBuf<int32_t> h_gt;
+    PinnedBuf<int32_t> h_gt, h_acc;
     double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::string> contigs;
     std::string vcf;
@@ -223,7 +223,7 @@ struct drprg_index {
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
-        h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release();
+        h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release(); h_acc.release();
         for (auto& e : ev_ml)
             if (e) cudaEventDestroy(e);
         if (st_copy) cudaStreamDestroy(st_copy);
@@ -536,7 +536,8 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     CK(cudaEventRecord(X->ev[1], st));
     const uint32_t max_len = B->max_len;  // read_start < longest read
     sort_hits(X->temp.p, X->temp.cap, X->hi.p, X->lo.p, X->hi2.p, X->lo2.p, nh,
-              bits_for((uint64_t)B->R.read_id_base + B->R.n_reads), bits_for(max_len), 32, st);
+              bits_for((uint64_t)B->R.read_id_base + B->R.n_reads), bits_for(max_len), bits_for(X->max_locus_knodes),
+              bits_for(H.loci.size()), st);
     CK(cudaEventRecord(X->ev[2], st));
     int32_t* d_locus_reads = X->d_accum + 2ull * H.total_knodes();
     launch_cluster_filter(X->hi.p, X->lo.p, nh, X->opts.max_diff, X->d_thresh, X->clist.p, X->clist2.p, X->cend.p,
@@ -578,11 +579,12 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         t0 = t;
     };
     flush_scalars(X);
-    std::vector<int32_t> acc(X->n_accum);
-    CK(cudaMemcpy(acc.data(), X->d_accum, acc.size() * 4, cudaMemcpyDeviceToHost));
-    const int32_t* cov = acc.data();
-    const int32_t* locus_reads = acc.data() + 2ull * N;
-    const int32_t* sc = acc.data() + X->n_accum - 4;
+    X->h_acc.resize(X->n_accum);  // pinned: a pageable destination is staged through a bounce buffer (~0.1 ms for 0.3 MB)
+    CK(cudaMemcpyAsync(X->h_acc.data(), X->d_accum, X->n_accum * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int32_t* cov = X->h_acc.data();
+    const int32_t* locus_reads = X->h_acc.data() + 2ull * N;
+    const int32_t* sc = X->h_acc.data() + X->n_accum - 4;
     const uint64_t total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
     lap(0);
     // ---- S6: moments / model choice on the host, log-prob histogram on the device

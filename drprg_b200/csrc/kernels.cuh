@@ -78,7 +78,7 @@ void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long
 size_t sort_hits_temp_bytes(uint64_t n);
 void sort_hits(void* d_temp, size_t temp_bytes, unsigned long long* hi_in, unsigned long long* lo_in,
                unsigned long long* hi_tmp, unsigned long long* lo_tmp, uint64_t n, int read_bits, int start_bits,
-               int knode_bits, cudaStream_t st);  // result ends in (hi_in, lo_in)
+               int knode_bits, int prg_bits, cudaStream_t st);  // result ends in (hi_in, lo_in)
 // S3+S4: clusters per read, size and overlap filters; kept[i] in {0,1}; locus read counts accumulate
 void launch_cluster_filter(const unsigned long long* hi, const unsigned long long* lo, uint64_t n, uint32_t max_diff,
                            const uint32_t* d_thresh_per_prg, uint32_t* d_clist, uint32_t* d_clist2, uint32_t* d_cend,

@@ -370,7 +370,7 @@ def test_pandora_cuda_cli_drop_in(tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"DRPRG_MLPATH_UNITS": "1"}, {"DRPRG_MLPATH_UNITS": "0"}, {"DRPRG_MLPATH_GENERIC": "1", "DRPRG_MLPATH_UNITS": "0"},
-                                 {"DRPRG_MLPATH_LEVELS": "0"}, {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}])
+                                 {"DRPRG_MLPATH_LEVELS": "0"}, {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}, {"DRPRG_PACKED_SORT": "0"}])
 def test_alternative_kernel_variants_keep_parity(env):
     """the ML-path kernel has four implementations (level-parallel = default, run-parallel units, record-addressed chain,
     generic lifting), the
