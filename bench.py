@@ -24,6 +24,11 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
+# dram__bytes_read.sum + dram__bytes_write.sum of screen_kernel + resolve_kernel for one 1 M-read launch, and the pipe
+# utilisation of screen_kernel, from profiles/r1_screen.md (ncu --set full of this workload; constants, not measured live)
+NCU_TRAFFIC_BYTES = 107.1e6
+NCU_ISSUE = {"alu_pipe_active_pct": 66.9, "issue_active_pct": 61.8, "warp_instr_per_read": 68.4, "dram_read_mb_screen": 44.3,
+             "source": "profiles/r1_screen.md"}
 METRIC = "mapped reads/sec (pandora-map hot path: sketch+lookup+cluster+coverage+ML path+genotype)"
 UNIT = "reads/s"
 
@@ -183,7 +188,7 @@ def main():
         ix.genotype(wl.refs_path)
         for k_, v_ in ix.last_genotype_timings().items():
             stats.setdefault("gt_" + k_, []).append(v_)
-        return ix.vcf_bytes()
+        return ix.vcf_view()  # the step's result: the VCF text in host memory (zero-copy view of the library's buffer)
 
     def step_resident():
         return hot_path(resident)
@@ -238,6 +243,7 @@ def main():
     alg_bytes = n * (workload.STRIDE_WORDS * 4 + 4) + 16.0 * hits
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    vcf_text = bytes(vcf_text)
     n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
     kept_cluster_reads = int(ix.coverage()["locus_reads"].sum())  # reads (clusters) that support a panel locus, all ranks
     h2d = int(h_words.numel() * 4 + h_lens.numel() * 4)
@@ -254,16 +260,18 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "sketch_short_kernel<11,15,LOOKUP> (S1+S2: sketch + index lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "screen_kernel<15,10> + resolve_kernel<11,15> (S1+S2: k-mer screen of every read, then hash/probe/minimizer test of the flagged positions)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "int_issue_ceiling": {"alu_pipe_active_pct": 76.5, "issue_active_pct": 66.8, "warp_instr_per_read": 291,
-                                           "dram_read_mb_per_launch": 45.4, "source": "profiles/r1_sketch_short.md (ncu --set full, same workload; not measured live)"},
-                     "note": "this kernel carries all of the step's HBM traffic and ~98% of its instructions; it is bound by INT32 issue "
-                             "(ncu: ALU pipe 80% active, 302 warp-instr per read vs 49.7 B), not by HBM. The only kernel with a longer "
-                             "duration at this batch size is mlpath_kernel (30 warps, a serial dependency chain per locus, see "
-                             "stage_ms.gt_mlpath_kernel); it runs concurrently with the genotype kernels and the host VCF formatting. "
-                             "See DESIGN.md section 4 and profiles/."},
+                     "issue_ceiling": NCU_ISSUE,
+                     "note": "the two kernels of the sketch+lookup stage carry all of the step's HBM traffic; kernel_ms is the CUDA-event time "
+                             "around the pair on the launch stream. screen_kernel streams each read once (DRAM read = the input, see "
+                             "profiles/) and is bound by the ALU pipe (shift/logic) and shared-memory bank conflicts of the Bloom probes "
+                             "(~70 warp-instructions per read), not by HBM; `traffic` is dram read+write of both kernels from the "
+                             "committed ncu capture (cold caches: resolve_kernel re-reads queue and words that are L2 hits in a real step). "
+                             "The longest single launch of the step is mlpath_level_kernel (30 warps, a latency chain per locus, "
+                             "stage_ms.gt_mlpath_kernel), which overlaps the genotype kernels and the VCF text. See DESIGN.md section 4."},
         "stage_ms": {k_: float(np.mean(v_)) for k_, v_ in st.items() if k_ != "hits"},
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <map>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -172,7 +173,7 @@ struct drprg_index {
     unsigned long long* d_counters = nullptr;  // [0] hit count, [1] kept count
     unsigned long long* h_counters = nullptr;  // pinned
     uint64_t last_n_hits = 0;
-    cudaEvent_t ev[5]{};
+    cudaEvent_t ev[6]{};  // [5]: end of the sketch+lookup kernels (before the host reads the hit count)
     float timings[4] = {0, 0, 0, 0};
     // genotype state
     std::string refs_path;
@@ -523,6 +524,7 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
                                  X->queue.p, X->queue.cap, X->d_counters + 2);
         }
         CK(cudaGetLastError());
+        CK(cudaEventRecord(X->ev[5], st));
         CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         nh = X->h_counters[0];
@@ -549,7 +551,7 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(X->h_counters + 1, X->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&X->timings[i], X->ev[i], X->ev[i + 1]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&X->timings[i], X->ev[i], X->ev[i == 0 ? 5 : i + 1]));
     X->last_n_hits = nh;
     X->total_bases += B->total_bases;
     X->n_reads += B->R.n_reads;
@@ -659,6 +661,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     GenotypeArrays& G = X->GA;
     // S8 + text for a given record list (uses the cached device CSR while the list is the cached one)
     auto run_s8_and_format = [&](cudaStream_t s8) {
+        const double ts0 = now_ms();
         if (X->records != X->csr_records || G.rec_off.empty() || !X->sample_records.empty()) {
             G.rec_off.assign(1, 0);
             G.allele_off.assign(1, 0);
@@ -709,7 +712,10 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             std::copy(X->h_f64.begin() + na, X->h_f64.begin() + 2 * (size_t)na, G.lik.begin());
             std::copy(X->h_f64.begin() + 2 * (size_t)na, X->h_f64.end(), G.gt_conf.begin());
         }
-        X->vcf = format_vcf(H, X->records, G, X->contigs, sample_name);
+        const double tf0 = now_ms();
+        format_vcf(H, X->records, G, X->contigs, sample_name, X->vcf);
+        static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+        if (timing) fprintf(stderr, "[drprg-cuda] s8 kernels+copies %.3f ms, vcf text %.3f ms\n", tf0 - ts0, now_ms() - tf0);
     };
     // ---- speculative pass: every locus with reads present, cached merged site tables
     {
@@ -1069,6 +1075,10 @@ int drprg_cuda_write_vcf(drprg_index* X, const char* path) {
     API_END
 }
 const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->vcf.c_str() : ""; }
+const char* drprg_cuda_vcf_view(drprg_index* X, uint64_t* len) {
+    if (len) *len = X->have_gt ? X->vcf.size() : 0;
+    return X->have_gt ? X->vcf.data() : "";
+}
 
 int drprg_cuda_index_info(drprg_index* X, drprg_index_info* o) {
     API_BEGIN o->w = X->H.w;

@@ -579,9 +579,9 @@ size_t format_g6(double v, char* out) {
     return (size_t)(o - out);
 }
 
-std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
-                       const std::vector<std::string>& contigs, const std::string& sample) {
-    std::string s;
+void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
+                const std::vector<std::string>& contigs, const std::string& sample, std::string& s) {
+    s.clear();  // keeps its capacity: a fresh ~1 MB string would be mmap'ed and page-faulted in on every sample
     s.reserve(4096 + recs.size() * 256);
     char date[32];
     time_t t = time(nullptr);
@@ -674,7 +674,9 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
         return (size_t)(o - buf.data());
     };
     const size_t parts_n = recs.size() >= 512 ? 16 : 1;
-    std::vector<std::vector<char>> parts(parts_n);
+    static thread_local std::vector<std::vector<char>> parts_tls;  // reused across samples (same reason as `s`)
+    std::vector<std::vector<char>>& parts = parts_tls;  // the workers must see THIS thread's buffers, not their own
+    if (parts.size() < parts_n) parts.resize(parts_n);
     std::vector<size_t> used(parts_n, 0);
     parallel_for(parts_n, [&](size_t t) {
         used[t] = format_range(recs.size() * t / parts_n, recs.size() * (t + 1) / parts_n, parts[t]);
@@ -685,7 +687,6 @@ std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>&
     parallel_for(parts_n, [&](size_t t) {
         if (used[t]) memcpy(&s[at[t]], parts[t].data(), used[t]);
     });
-    return s;
 }
 
 // ---------------------------------------------------------------------------- IO ---

@@ -80,8 +80,8 @@ struct GenotypeArrays {  // flattened over records / alleles, device results cop
     std::vector<double> gaps, lik, gt_conf;
     std::vector<int32_t> gt;
 };
-std::string format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
-                       const std::vector<std::string>& contigs, const std::string& sample);
+void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
+                const std::vector<std::string>& contigs, const std::string& sample, std::string& out);
 
 size_t format_g6(double v, char* out);  // printf("%g") text of v, out has room for 40 chars
 std::map<std::string, std::string> load_fasta(const std::string& path);

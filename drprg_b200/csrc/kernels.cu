@@ -552,7 +552,7 @@ void screen_filter_insert(uint32_t* filter, uint32_t n_words, uint32_t kmer, uin
 // V: pipe-balance variants (the ALU pipe — SHF/LOP3/LEA — binds first, the multiplier pipe has room):
 //   bit 0: shared-memory address by IMAD with a run-time 4 instead of LEA;  bit 1: the second bit index by
 //   multiply-high with a run-time 2^21 instead of a shift.
-struct ScreenConsts { uint32_t four, two21; };
+struct ScreenConsts { uint32_t four, two21, prefetch; };
 template <int K, int CW, int V>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, DevTable T, uint32_t wk, ScreenConsts SC,
                                                                    unsigned long long* __restrict__ queue,
@@ -571,12 +571,24 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_tiles = (n_items + 31) / 32;
     const bool wide = R.stride_words && !(R.stride_words & 1u) && !R.seg_read;  // every read starts 8-byte aligned
-    unsigned long long tile = 0;
-    if (lane == 0) tile = atomicAdd(ticket, 1ull);
+    // tickets are drawn two tiles ahead: the next tile's id is known when a tile starts, so its words can be
+    // prefetched into L2 while this tile is screened (a cold read otherwise costs the full HBM latency per tile)
+    unsigned long long tile = 0, next_tile = 0;
+    if (lane == 0) {
+        tile = atomicAdd(ticket, 1ull);
+        next_tile = atomicAdd(ticket, 1ull);
+    }
     tile = __shfl_sync(FULL, tile, 0);
+    next_tile = __shfl_sync(FULL, next_tile, 0);
     while (tile < n_tiles) {
-        unsigned long long next_tile = 0;
-        if (lane == 0) next_tile = atomicAdd(ticket, 1ull);  // lands while this tile is screened
+        unsigned long long after_next = 0;
+        if (lane == 0) after_next = atomicAdd(ticket, 1ull);  // lands while this tile is screened
+        if (SC.prefetch && !R.seg_read && R.stride_words && next_tile * 32 + lane < n_items) {
+            const uint32_t* np = R.words + (next_tile * 32 + lane) * R.stride_words;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np + R.stride_words - 1));
+            if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.lens + next_tile * 32));
+        }
         const unsigned long long item = tile * 32 + lane;
         const bool have = item < n_items;
         const unsigned long long r = have ? (R.seg_read ? (unsigned long long)__ldg(R.seg_read + item) : item) : 0ull;
@@ -674,7 +686,8 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
                 }
             }
         }
-        tile = __shfl_sync(FULL, next_tile, 0);
+        tile = next_tile;
+        next_tile = __shfl_sync(FULL, after_next, 0);
     }
 }
 
@@ -852,10 +865,14 @@ static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, u
         cudaFuncSetAttribute(screen_kernel<K, CW, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCREEN_MAX_FILTER_WORDS * 4));
         configured = true;
     }
+    static const uint32_t prefetch = [] {
+        const char* e = getenv("DRPRG_SCREEN_PREFETCH");
+        return e ? (uint32_t)atoi(e) : 1u;
+    }();
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_ctas = (n_items + SCREEN_THREADS - 1) / SCREEN_THREADS;
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_ctas, (unsigned long long)sm_count);  // one persistent CTA per SM
-    screen_kernel<K, CW, V><<<grid, SCREEN_THREADS, (size_t)T.kfilter_words * 4, st>>>(R, T, wk, ScreenConsts{4u, 1u << 21}, queue, counters, queue_cap, counters + 1);
+    screen_kernel<K, CW, V><<<grid, SCREEN_THREADS, (size_t)T.kfilter_words * 4, st>>>(R, T, wk, ScreenConsts{4u, 1u << 21, prefetch}, queue, counters, queue_cap, counters + 1);
     ++g_launches;
 }
 

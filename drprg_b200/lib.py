@@ -58,7 +58,7 @@ SYMBOLS = [
     "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
     "drprg_cuda_batch_wrap_device", "drprg_cuda_batch_free", "drprg_cuda_sample_begin", "drprg_cuda_map_batch",
     "drprg_cuda_accum_device_ptr", "drprg_cuda_accum_download", "drprg_cuda_accum_upload", "drprg_cuda_genotype",
-    "drprg_cuda_write_vcf", "drprg_cuda_vcf_text", "drprg_cuda_index_info", "drprg_cuda_locus_name",
+    "drprg_cuda_write_vcf", "drprg_cuda_vcf_text", "drprg_cuda_vcf_view", "drprg_cuda_index_info", "drprg_cuda_locus_name",
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
@@ -76,6 +76,7 @@ def lib():
         L.drprg_cuda_last_error.restype = C.c_char_p
         L.drprg_cuda_locus_name.restype = C.c_char_p
         L.drprg_cuda_vcf_text.restype = C.c_char_p
+        L.drprg_cuda_vcf_view.restype = C.c_void_p
         for f in ("drprg_cuda_pack_reads", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits", "drprg_cuda_gt_mlpath"):
             getattr(L, f).restype = C.c_int64
         L.drprg_cuda_launch_count.restype = C.c_uint64
@@ -272,6 +273,12 @@ class Index:
     def vcf_bytes(self):
         """the VCF text as bytes (no UTF-8 decode: the text is ~1 MB per sample)"""
         return lib().drprg_cuda_vcf_text(self.h)
+
+    def vcf_view(self):
+        """zero-copy view of the VCF text in the library's host buffer (valid until the next genotype call)"""
+        n = C.c_uint64(0)
+        p = lib().drprg_cuda_vcf_view(self.h, C.byref(n))
+        return memoryview((C.c_char * n.value).from_address(p)) if n.value else memoryview(b"")
 
     def write_vcf(self, path):
         _check(lib().drprg_cuda_write_vcf(self.h, str(path).encode()), "write_vcf")

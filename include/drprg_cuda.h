@@ -108,6 +108,8 @@ int drprg_cuda_accum_upload(drprg_index*, const int32_t* in, uint64_t n_int32);
 int drprg_cuda_genotype(drprg_index*, const char* vcf_refs_fasta /* NULL = top path */, const char* sample_name);
 int drprg_cuda_write_vcf(drprg_index*, const char* path);
 const char* drprg_cuda_vcf_text(drprg_index*);
+/* the same text without a copy: pointer + length, valid until the next drprg_cuda_genotype on this handle */
+const char* drprg_cuda_vcf_view(drprg_index*, uint64_t* len);
 
 /* ---- introspection / parity hooks (same .so, used by tests and bench) --------------------------- */
 typedef struct {
