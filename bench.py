@@ -225,10 +225,11 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
-        return float(t.item()) / steps, lib.launch_count() - l0, out, dict(stats)
+        return float(t.item()) / steps, lib.launch_count() - l0, out, {k_: list(v_) for k_, v_ in stats.items()}
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("DRPRG_BENCH_NO_SAMPLER"):
+        sampler.start()
     ms_step, launches, vcf_text, st = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
@@ -273,6 +274,8 @@ def main():
                              "The longest single launch of the step is mlpath_level_kernel (30 warps, a latency chain per locus, "
                              "stage_ms.gt_mlpath_kernel), which overlaps the genotype kernels and the VCF text. See DESIGN.md section 4."},
         "stage_ms": {k_: float(np.mean(v_)) for k_, v_ in st.items() if k_ != "hits"},
+        **({"stage_ms_per_step": {k_: [round(float(x), 4) for x in v_] for k_, v_ in st.items() if k_ in ("sketch_lookup", "gt_s8+vcf_text")}}
+           if os.environ.get("DRPRG_BENCH_VERBOSE") else {}),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -169,6 +169,7 @@ struct drprg_index {
     DBuf<unsigned long long> hi, lo, hi2, lo2;
     DBuf<uint32_t> clist, clist2, cend, keys, keys2;
     DBuf<unsigned long long> queue;  // k-mer screen: flagged (read, position) pairs
+    DBuf<uint32_t> queue_kmer;       // ... and their k-mers
     DBuf<uint8_t> calive, kept, temp;
     unsigned long long* d_counters = nullptr;  // [0] hit count, [1] kept count
     unsigned long long* h_counters = nullptr;  // pinned
@@ -218,7 +219,7 @@ struct drprg_index {
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
         hi.release(); lo.release(); hi2.release(); lo2.release();
-        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release(); queue.release();
+        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release(); queue.release(); queue_kmer.release();
         calive.release(); kept.release(); temp.release();
         d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
@@ -504,7 +505,10 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     // whole-genome reads give ~0.35 hits per 150 bp read; a targeted run overflows once, regrows to the exact count and re-sketches
     uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 256));
     ensure_hit_capacity(X, cap);
-    if (X->T.kfilter) X->queue.ensure(std::max<uint64_t>(X->queue.cap, B->total_bases / 32 + (1u << 20)));  // ~1.6 flagged positions per 150 bp read
+    if (X->T.kfilter) {  // ~2 flagged positions per 150 bp read
+        X->queue.ensure(std::max<uint64_t>(X->queue.cap, B->total_bases / 32 + (1u << 20)));
+        X->queue_kmer.ensure(X->queue.cap);
+    }
     uint64_t nh = 0;
     CK(cudaEventRecord(X->ev[0], st));
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -521,7 +525,7 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
                 Rc.read_id_base = B->R.read_id_base + (uint32_t)lo;
             }
             launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st,
-                                 X->queue.p, X->queue.cap, X->d_counters + 2);
+                                 X->queue.p, std::min(X->queue.cap, X->queue_kmer.cap), X->d_counters + 2, X->queue_kmer.p);
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(X->ev[5], st));
@@ -529,10 +533,13 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
         CK(cudaStreamSynchronize(st));
         nh = X->h_counters[0];
         const uint64_t nq = X->h_counters[4];  // largest screen queue any chunk wanted
-        if (nh <= X->hi.cap && nq <= X->queue.cap) break;
+        if (nh <= X->hi.cap && nq <= std::min(X->queue.cap, X->queue_kmer.cap)) break;
         if (attempt == 2) throw std::runtime_error("hit buffer overflow");
         if (nh > X->hi.cap) ensure_hit_capacity(X, nh);
-        if (nq > X->queue.cap) X->queue.ensure(nq);
+        if (nq > X->queue.cap) {
+            X->queue.ensure(nq);
+            X->queue_kmer.ensure(X->queue.cap);
+        }
         CK(cudaEventRecord(X->ev[0], st));
     }
     CK(cudaEventRecord(X->ev[1], st));

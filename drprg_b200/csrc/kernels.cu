@@ -556,6 +556,7 @@ struct ScreenConsts { uint32_t four, two21, prefetch; };
 template <int K, int CW, int V>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, DevTable T, uint32_t wk, ScreenConsts SC,
                                                                    unsigned long long* __restrict__ queue,
+                                                                   uint32_t* __restrict__ queue_kmer,
                                                                    unsigned long long* __restrict__ queue_count,
                                                                    unsigned long long queue_cap,
                                                                    unsigned long long* __restrict__ ticket) {
@@ -680,7 +681,13 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
                     while (m) {
                         const uint32_t bit = __ffs(m) - 1;
                         m &= m - 1u;
-                        if (o < queue_cap) queue[o] = tag | (q0 + c0 + i * 32 + bit);
+                        if (o < queue_cap) {
+                            queue[o] = tag | (q0 + c0 + i * 32 + bit);
+                            // the k-mer travels with the entry, so the resolve kernel's index probe needs no access to the read
+                            const bool up = bit >= 16u;
+                            const uint32_t a = up ? cw[2 * i + 1] : cw[2 * i], b = up ? cw[2 * i + 2] : cw[2 * i + 1];
+                            queue_kmer[o] = __funnelshift_l(b, a, 2u * (bit & 15u)) >> (32 - 2 * K);
+                        }
                         ++o;
                     }
                 }
@@ -701,6 +708,7 @@ constexpr int RESOLVE_THREADS = 256;
 template <int W, int K>
 __global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, DevTable T, uint32_t w_rt, uint32_t k_rt,
                                                                   const unsigned long long* __restrict__ queue,
+                                                                  const uint32_t* __restrict__ queue_kmer,
                                                                   const unsigned long long* __restrict__ queue_count,
                                                                   unsigned long long queue_cap,
                                                                   unsigned long long* __restrict__ queue_need,
@@ -737,13 +745,8 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, De
             unsigned long long q = 0;
             if (e < n) {
                 q = queue[e];
-                const uint32_t r = (uint32_t)(q >> 32), pos = (uint32_t)q;
-                const uint32_t len = __ldg(R.lens + r);
-                const uint32_t* wp = R.words + (R.stride_words ? (unsigned long long)r * R.stride_words : __ldg(R.word_off + r));
-                const uint32_t wi = pos >> 4;
-                const uint32_t a = __ldg(wp + wi), b = (wi + 1 < ((len + 15) >> 4)) ? __ldg(wp + wi + 1) : 0u;
                 uint32_t strand;
-                const uint32_t hv = canon_of(__funnelshift_l(b, a, 2u * (pos & 15u)), strand) >> S;
+                const uint32_t hv = canon_of(queue_kmer[e] << S, strand) >> S;  // the queued k-mer, left aligned
                 uint32_t slot = table_slot(hv, T.slot_bits);
                 const uint32_t smask = (1u << T.slot_bits) - 1u;
                 while (true) {
@@ -858,7 +861,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, De
 }
 
 template <int K, int CW, int V>
-static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue,
+static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue, uint32_t* queue_kmer,
                             unsigned long long* counters, uint64_t queue_cap, int sm_count, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -872,7 +875,7 @@ static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, u
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_ctas = (n_items + SCREEN_THREADS - 1) / SCREEN_THREADS;
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_ctas, (unsigned long long)sm_count);  // one persistent CTA per SM
-    screen_kernel<K, CW, V><<<grid, SCREEN_THREADS, (size_t)T.kfilter_words * 4, st>>>(R, T, wk, ScreenConsts{4u, 1u << 21, prefetch}, queue, counters, queue_cap, counters + 1);
+    screen_kernel<K, CW, V><<<grid, SCREEN_THREADS, (size_t)T.kfilter_words * 4, st>>>(R, T, wk, ScreenConsts{4u, 1u << 21, prefetch}, queue, queue_kmer, counters, queue_cap, counters + 1);
     ++g_launches;
 }
 
@@ -880,17 +883,17 @@ static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, u
 #define DRPRG_SCREEN_DEFAULT_VARIANT 1
 #endif
 template <int K, int CW>
-static void launch_screen_one(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue,
+static void launch_screen_one(const DevReads& R, const DevTable& T, uint32_t wk, unsigned long long* queue, uint32_t* queue_kmer,
                               unsigned long long* counters, uint64_t queue_cap, int sm_count, cudaStream_t st) {
     static const int variant = [] {
         const char* e = getenv("DRPRG_SCREEN_VARIANT");
         return e ? atoi(e) & 3 : DRPRG_SCREEN_DEFAULT_VARIANT;
     }();
     switch (variant) {
-        case 1: return launch_screen_v<K, CW, 1>(R, T, wk, queue, counters, queue_cap, sm_count, st);
-        case 2: return launch_screen_v<K, CW, 2>(R, T, wk, queue, counters, queue_cap, sm_count, st);
-        case 3: return launch_screen_v<K, CW, 3>(R, T, wk, queue, counters, queue_cap, sm_count, st);
-        default: return launch_screen_v<K, CW, 0>(R, T, wk, queue, counters, queue_cap, sm_count, st);
+        case 1: return launch_screen_v<K, CW, 1>(R, T, wk, queue, queue_kmer, counters, queue_cap, sm_count, st);
+        case 2: return launch_screen_v<K, CW, 2>(R, T, wk, queue, queue_kmer, counters, queue_cap, sm_count, st);
+        case 3: return launch_screen_v<K, CW, 3>(R, T, wk, queue, queue_kmer, counters, queue_cap, sm_count, st);
+        default: return launch_screen_v<K, CW, 0>(R, T, wk, queue, queue_kmer, counters, queue_cap, sm_count, st);
     }
 }
 
@@ -898,16 +901,17 @@ static void launch_screen_one(const DevReads& R, const DevTable& T, uint32_t wk,
 template <int K>
 static void launch_screened(const DevReads& R, const DevTable& T, uint32_t w, unsigned long long* a, unsigned long long* b,
                             unsigned long long* cnt, uint64_t cap, int sm_count, uint32_t max_len,
-                            unsigned long long* queue, uint64_t queue_cap, unsigned long long* counters, cudaStream_t st) {
+                            unsigned long long* queue, uint32_t* queue_kmer, uint64_t queue_cap, unsigned long long* counters,
+                            cudaStream_t st) {
     cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st);
-    if (!R.seg_read && max_len >= (uint32_t)K && max_len - K + 1 <= 10 * 16) launch_screen_one<K, 10>(R, T, w + K, queue, counters, queue_cap, sm_count, st);
-    else launch_screen_one<K, 8>(R, T, w + K, queue, counters, queue_cap, sm_count, st);
+    if (!R.seg_read && max_len >= (uint32_t)K && max_len - K + 1 <= 10 * 16) launch_screen_one<K, 10>(R, T, w + K, queue, queue_kmer, counters, queue_cap, sm_count, st);
+    else launch_screen_one<K, 8>(R, T, w + K, queue, queue_kmer, counters, queue_cap, sm_count, st);
     // ~2 queue entries per read; the grid-stride loop reads the real length on the device
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned grid = (unsigned)std::min<unsigned long long>((n_items * 2 + 255) / 256 + 1, 8ull * (unsigned)sm_count);
-    if (w == 11) resolve_kernel<11, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
-    else if (w == 14) resolve_kernel<14, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
-    else resolve_kernel<0, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    if (w == 11) resolve_kernel<11, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, queue_kmer, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else if (w == 14) resolve_kernel<14, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, queue_kmer, counters, queue_cap, counters + 2, a, b, cnt, cap);
+    else resolve_kernel<0, K><<<grid, RESOLVE_THREADS, 0, st>>>(R, T, w, K, queue, queue_kmer, counters, queue_cap, counters + 2, a, b, cnt, cap);
     ++g_launches;
 }
 
@@ -922,14 +926,14 @@ static int grid_for(int sm_count, uint64_t n_reads) {
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
                           uint32_t max_len, cudaStream_t st, unsigned long long* d_queue, uint64_t queue_cap,
-                          unsigned long long* d_screen_counters) {
+                          unsigned long long* d_screen_counters, uint32_t* d_queue_kmer) {
     if (R.n_reads == 0) return;
     static const bool screen_on = [] {
         const char* e = getenv("DRPRG_SCREEN");  // DRPRG_SCREEN=0 sketches every read (A/B measurements, parity tests)
         return !e || atoi(e) != 0;
     }();
-    if (screen_on && d_queue && T.kfilter && (max_len <= SHORT_READ_MAX || R.seg_read) && k == 15)
-        return launch_screened<15>(R, T, w, d_hi, d_lo, d_hit_count, hit_cap, sm_count, max_len, d_queue, queue_cap, d_screen_counters, st);
+    if (screen_on && d_queue && d_queue_kmer && T.kfilter && (max_len <= SHORT_READ_MAX || R.seg_read) && k == 15)
+        return launch_screened<15>(R, T, w, d_hi, d_lo, d_hit_count, hit_cap, sm_count, max_len, d_queue, d_queue_kmer, queue_cap, d_screen_counters, st);
     if ((max_len <= SHORT_READ_MAX || R.seg_read) && launch_short<true>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap, sm_count, st)) return;
     sketch_kernel<true><<<grid_for(sm_count, R.n_reads), WARPS * 32, 0, st>>>(R, T, w, k, d_hi, d_lo, d_hit_count, hit_cap);
     ++g_launches;

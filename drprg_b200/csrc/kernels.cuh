@@ -60,14 +60,14 @@ struct ModelParams {  // S6 output, computed on the host
 uint64_t launch_count();
 
 // S1+S2: sketch every read and probe the index; hits appended (unordered) through *hit_count
-// With a screen workspace (d_queue: queue_cap entries, d_screen_counters: {queue length, ticket, largest queue length
+// With a screen workspace (d_queue + d_queue_kmer: queue_cap entries each, d_screen_counters: {queue length, ticket, largest queue length
 // wanted}) and a screenable index (k = 15), a k-mer screen queues the positions whose k-mer may be indexed and only
 // those are hashed, probed and tested for minimizer status (identical hits).  The queue overflowed when
 // d_screen_counters[2] > queue_cap (the caller zeroes [2] before a batch and redoes the batch with a larger queue).
 void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint32_t k, unsigned long long* d_hi,
                           unsigned long long* d_lo, unsigned long long* d_hit_count, uint64_t hit_cap, int sm_count,
                           uint32_t max_len, cudaStream_t st, unsigned long long* d_queue = nullptr, uint64_t queue_cap = 0,
-                          unsigned long long* d_screen_counters = nullptr);
+                          unsigned long long* d_screen_counters = nullptr, uint32_t* d_queue_kmer = nullptr);
 // host mirror of the screen's filter addressing (used when the index is uploaded)
 void screen_filter_insert(uint32_t* filter, uint32_t n_words, uint32_t kmer, uint32_t k);
 constexpr uint32_t SCREEN_MAX_FILTER_WORDS = 54 * 1024;  // 216 KB of shared memory
