@@ -7,9 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdrprg_cuda.so")
-SOURCES = ["kernels.cu", "capi.cu", "prg_graph.cpp", "genotype_host.cpp"]
+SOURCES = ["kernels.cu", "capi.cu", "ingest.cu", "prg_graph.cpp", "genotype_host.cpp"]
 EXTRA = ["pandora_cuda_main.cpp"]
-HEADERS = ["kernels.cuh", "prg_graph.hpp", "genotype_host.hpp", "../../include/drprg_cuda.h"]
+HEADERS = ["kernels.cuh", "prg_graph.hpp", "genotype_host.hpp", "ingest.hpp", "../../include/drprg_cuda.h"]
 
 
 def nvcc():

@@ -19,6 +19,7 @@
 
 #include "../../include/drprg_cuda.h"
 #include "genotype_host.hpp"
+#include "ingest.hpp"
 #include "kernels.cuh"
 #include "prg_graph.hpp"
 
@@ -552,7 +553,8 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     launch_cluster_filter(X->hi.p, X->lo.p, nh, X->opts.max_diff, X->d_thresh, X->clist.p, X->clist2.p, X->cend.p,
                           X->calive.p, X->kept.p, d_locus_reads, st);
     CK(cudaEventRecord(X->ev[3], st));
-    launch_coverage(X->hi.p, X->lo.p, X->kept.p, nh, X->d_knode_base, X->keys.p, X->keys2.p, X->temp.p, X->temp.cap, 32,
+    launch_coverage(X->hi.p, X->lo.p, X->kept.p, nh, X->d_knode_base, X->keys.p, X->keys2.p, X->temp.p, X->temp.cap,
+                    bits_for(2ull * H.total_knodes()),
                     X->d_accum, X->d_counters + 1, st);
     CK(cudaEventRecord(X->ev[4], st));
     CK(cudaGetLastError());
@@ -822,6 +824,35 @@ void free_batch(drprg_batch* b) {
     delete b;
 }
 
+// long reads: cut every read into segments of 40*w k-mer positions so that the thread-per-item kernels get evenly
+// sized work (a 10 kb read becomes ~23 items instead of one warp-long loop)
+void build_segments(drprg_index* X, drprg_batch* B, const uint32_t* lens, uint64_t n, uint64_t total_bases, cudaStream_t cs) {
+    const uint32_t w = X->H.w, k = X->H.k, seg_len = 40 * w;
+    std::vector<uint32_t> sr, ss;
+    sr.reserve(total_bases / seg_len + n);
+    ss.reserve(total_bases / seg_len + n);
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint32_t len = lens[r];
+        if (len + 1 < w + k) continue;
+        const uint32_t nk = len - k + 1;
+        for (uint32_t s0 = 0; s0 < nk; s0 += seg_len) {
+            sr.push_back((uint32_t)r);
+            ss.push_back(s0);
+        }
+    }
+    if (sr.empty()) return;
+    B->b_seg = sr.size() * 4;
+    B->d_seg_read = (uint32_t*)g_pool.get(B->b_seg, X->device);
+    B->d_seg_start = (uint32_t*)g_pool.get(B->b_seg, X->device);
+    CK(cudaMemcpyAsync(B->d_seg_read, sr.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(B->d_seg_start, ss.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
+    CK(cudaStreamSynchronize(cs));  // the staging vectors die with this scope
+    B->R.seg_read = B->d_seg_read;
+    B->R.seg_start = B->d_seg_start;
+    B->R.n_segs = sr.size();
+    B->R.seg_len = seg_len;
+}
+
 drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t* word_off, uint32_t stride, const uint32_t* lens,
                           uint64_t n, uint64_t total_bases, uint32_t id_base, cudaStream_t st) {
     need_device(X);
@@ -866,36 +897,58 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
     B->R = DevReads{B->d_words, B->d_off, stride, B->d_lens, n, id_base};
     B->total_bases = total_bases;
     B->max_len = ml;
-    if (ml > SHORT_READ_MAX) {
-        // long reads: cut every read into segments of 40*w k-mer positions so that the thread-per-item sketch kernel
-        // gets evenly sized work (a 10 kb read becomes ~23 items instead of one warp-long loop)
-        const uint32_t w = X->H.w, k = X->H.k, seg_len = 40 * w;
-        std::vector<uint32_t> sr, ss;
-        sr.reserve(total_bases / seg_len + n);
-        ss.reserve(total_bases / seg_len + n);
-        for (uint64_t r = 0; r < n; ++r) {
-            const uint32_t len = lens[r];
-            if (len + 1 < w + k) continue;
-            const uint32_t nk = len - k + 1;
-            for (uint32_t s0 = 0; s0 < nk; s0 += seg_len) {
-                sr.push_back((uint32_t)r);
-                ss.push_back(s0);
-            }
-        }
-        if (!sr.empty()) {
-            B->b_seg = sr.size() * 4;
-            B->d_seg_read = (uint32_t*)g_pool.get(B->b_seg, X->device);
-            B->d_seg_start = (uint32_t*)g_pool.get(B->b_seg, X->device);
-            CK(cudaMemcpyAsync(B->d_seg_read, sr.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(B->d_seg_start, ss.data(), B->b_seg, cudaMemcpyHostToDevice, cs));
-            CK(cudaStreamSynchronize(cs));  // the staging vectors die with this scope
-            B->R.seg_read = B->d_seg_read;
-            B->R.seg_start = B->d_seg_start;
-            B->R.n_segs = sr.size();
-            B->R.seg_len = seg_len;
-        }
-    }
+    if (ml > SHORT_READ_MAX) build_segments(X, B.get(), lens, n, total_bases, cs);
     return B.release();
+}
+
+// A reads file as a device-resident batch.  Strict 4-line FASTQ (plain or gzip) is parsed and packed ON THE DEVICE
+// (ingest.cu); FASTA and anything unusual goes through the host parser and an upload.  DRPRG_HOST_INGEST=1 forces the
+// host parser (tests compare the two).
+struct FileBatch {
+    drprg_batch* B = nullptr;
+    uint64_t n_dropped = 0;
+    uint32_t first_read_len = 0;
+    bool on_device = false;
+};
+FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threads) {
+    need_device(X);
+    CK(cudaSetDevice(X->device));
+    FileBatch F;
+    static const bool host_only = getenv("DRPRG_HOST_INGEST") != nullptr && atoi(getenv("DRPRG_HOST_INGEST")) != 0;
+    IngestResult I;
+    if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0)) {
+        std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
+        B->owned = true;
+        B->device = X->device;
+        B->d_words = I.d_words;
+        B->d_lens = I.d_lens;
+        B->d_off = I.d_word_off;
+        B->b_words = I.b_words;
+        B->b_lens = I.b_lens;
+        B->b_off = I.b_off;
+        B->R = DevReads{I.d_words, I.d_word_off, I.stride_words, I.d_lens, I.n_reads, 0};
+        B->total_bases = I.total_bases;
+        B->max_len = I.stride_words ? I.stride_words * 16u : I.max_len;
+        if (I.max_len > SHORT_READ_MAX) {  // the segment table is built from the lengths on the host
+            std::vector<uint32_t> lens(I.n_reads);
+            CK(cudaMemcpy(lens.data(), I.d_lens, I.n_reads * 4, cudaMemcpyDeviceToHost));
+            build_segments(X, B.get(), lens.data(), I.n_reads, I.total_bases, 0);
+        }
+        F.B = B.release();
+        F.n_dropped = I.n_dropped;
+        F.first_read_len = I.first_read_len;
+        F.on_device = true;
+        return F;
+    }
+    PackedReads pr;
+    load_reads_packed(reads_path, threads, pr);
+    const uint64_t n = pr.lens.size();
+    if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
+    F.B = upload_batch(X, pr.words.data(), pr.word_off.data(), 0, pr.lens.data(), n, pr.total_bases, 0, 0);
+    CK(cudaStreamSynchronize(0));  // pr dies with this scope
+    F.n_dropped = pr.n_dropped;
+    F.first_read_len = pr.first_read_len;
+    return F;
 }
 
 int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir, const drprg_map_opts* o,
@@ -903,15 +956,15 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     need_device(X);
     const double t0 = now_ms();
     std::ofstream log(std::string(outdir) + "/pandora.log");
-    PackedReads pr;
-    load_reads_packed(reads_path, o ? o->threads : 1, pr);
+    FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1);
+    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(F.B, free_batch);
+    struct {
+        uint64_t n_dropped, total_bases;
+    } pr{F.n_dropped, B->total_bases};
     const double t1 = now_ms();
-    sample_begin(X, o, pr.first_read_len);
+    sample_begin(X, o, F.first_read_len);
     uint64_t nh = 0, nk = 0;
-    const uint64_t n = pr.lens.size();
-    if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
-    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(
-        upload_batch(X, pr.words.data(), pr.word_off.data(), 0, pr.lens.data(), n, pr.total_bases, 0, 0), free_batch);
+    const uint64_t n = B->R.n_reads;
     map_batch(X, B.get(), 0, &nh, &nk);
     const double t2 = now_ms();
     genotype(X, vcf_refs, "sample");
@@ -935,7 +988,7 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     if (stats) *stats = s;
     log << "drprg-cuda map: reads=" << n << " dropped=" << pr.n_dropped << " bases=" << pr.total_bases << " hits=" << nh
         << " kept=" << nk << " loci=" << s.n_loci_present << " records=" << s.n_records << " E=" << s.exp_depth_covg
-        << "\nkernel ms: sketch_lookup=" << X->timings[0] << " sort=" << X->timings[1] << " cluster=" << X->timings[2]
+        << " ingest=" << (F.on_device ? "device" : "host") << "\nkernel ms: sketch_lookup=" << X->timings[0] << " sort=" << X->timings[1] << " cluster=" << X->timings[2]
         << " coverage=" << X->timings[3] << "\nwall ms: ingest=" << s.ms_ingest << " map=" << s.ms_map
         << " genotype=" << s.ms_genotype << " total=" << s.ms_total << "\n";
     return 0;
@@ -1026,6 +1079,18 @@ int drprg_cuda_batch_wrap_device(drprg_index* X, const void* d_words, const void
     B->total_bases = total_bases;
     B->max_len = stride_words ? stride_words * 16u : UINT32_MAX;
     *out = B;
+    return 0;
+    API_END
+}
+int drprg_cuda_batch_from_fastx(drprg_index* X, const char* path, uint32_t threads, drprg_batch** out, uint64_t* n_reads,
+                                uint64_t* total_bases, uint64_t* n_dropped, uint32_t* first_read_len, int* parsed_on_device) {
+    API_BEGIN FileBatch F = batch_from_file(X, path, threads);
+    *out = F.B;
+    if (n_reads) *n_reads = F.B->R.n_reads;
+    if (total_bases) *total_bases = F.B->total_bases;
+    if (n_dropped) *n_dropped = F.n_dropped;
+    if (first_read_len) *first_read_len = F.first_read_len;
+    if (parsed_on_device) *parsed_on_device = F.on_device ? 1 : 0;
     return 0;
     API_END
 }

@@ -1,0 +1,22 @@
+// Device-side FASTQ ingest: raw text to the GPU, parsed and 2-bit packed there.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+namespace drprg {
+
+struct IngestResult {  // device buffers from cudaMalloc, owned by the caller
+    uint32_t* d_words = nullptr;
+    uint64_t* d_word_off = nullptr;  // nullptr with a fixed stride
+    uint32_t* d_lens = nullptr;
+    size_t b_words = 0, b_off = 0, b_lens = 0;
+    uint32_t stride_words = 0, max_len = 0, first_read_len = 0;
+    uint64_t n_reads = 0, total_bases = 0, n_dropped = 0;
+};
+
+// false: the input is not strict 4-line FASTQ below 4 GiB of text (the caller uses the host parser); throws on IO errors
+bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st);
+
+}  // namespace drprg

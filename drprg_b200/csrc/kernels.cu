@@ -1172,10 +1172,10 @@ void launch_cluster_filter(const unsigned long long* hi, const unsigned long lon
 // ============================================================================================
 __global__ void cov_keys_kernel(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ lo,
                                 const uint8_t* __restrict__ kept, unsigned long long n,
-                                const uint32_t* __restrict__ knode_base, uint32_t* __restrict__ keys) {
+                                const uint32_t* __restrict__ knode_base, uint32_t* __restrict__ keys, uint32_t sentinel) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t key = 0xffffffffu;
+    uint32_t key = sentinel;  // above every real key: discarded hits sort to the end
     if (kept[i]) {
         const unsigned long long h = hi[i];
         const uint32_t g = knode_base[hit_prg(h)] + (uint32_t)lo[i];
@@ -1185,12 +1185,12 @@ __global__ void cov_keys_kernel(const unsigned long long* __restrict__ hi, const
 }
 
 __global__ void cov_runs_kernel(const uint32_t* __restrict__ keys, unsigned long long n, int32_t* __restrict__ cov,
-                                unsigned long long* __restrict__ n_kept) {
+                                unsigned long long* __restrict__ n_kept, uint32_t sentinel) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
     if (i > 0 && keys[i - 1] == key) return;
-    if (key == 0xffffffffu) {  // first discarded hit: everything before it was kept
+    if (key == sentinel) {  // first discarded hit: everything before it was kept
         *n_kept += i;
         return;
     }
@@ -1216,10 +1216,12 @@ void launch_coverage(const unsigned long long* hi, const unsigned long long* lo,
     if (n == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    cov_keys_kernel<<<blocks, threads, 0, st>>>(hi, lo, kept, n, d_knode_base, d_keys);
-    (void)key_bits;  // discarded hits carry 0xffffffff, so all 32 bits take part
-    cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_keys, d_keys_sorted, (int64_t)n, 0, 32, st);
-    cov_runs_kernel<<<blocks, threads, 0, st>>>(d_keys_sorted, n, d_cov, d_n_kept);
+    // real keys use key_bits bits; discarded hits carry 1 << key_bits, so only key_bits + 1 bits are sorted
+    const int kb = key_bits < 31 ? key_bits : 31;
+    const uint32_t sentinel = kb < 31 ? (1u << kb) : 0xffffffffu;
+    cov_keys_kernel<<<blocks, threads, 0, st>>>(hi, lo, kept, n, d_knode_base, d_keys, sentinel);
+    cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_keys, d_keys_sorted, (int64_t)n, 0, kb + 1, st);
+    cov_runs_kernel<<<blocks, threads, 0, st>>>(d_keys_sorted, n, d_cov, d_n_kept, sentinel);
     g_launches += 3;
 }
 

@@ -55,7 +55,7 @@ def make_opts(threads=1, min_cluster_size=10, illumina=False, genome_size=441153
 SYMBOLS = [
     "drprg_cuda_version", "drprg_cuda_last_error", "drprg_cuda_device_count", "drprg_cuda_index_load",
     "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_map_genotype", "drprg_cuda_map_genotype_batch",
-    "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
+    "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_batch_from_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
     "drprg_cuda_batch_wrap_device", "drprg_cuda_batch_free", "drprg_cuda_sample_begin", "drprg_cuda_map_batch",
     "drprg_cuda_accum_device_ptr", "drprg_cuda_accum_download", "drprg_cuda_accum_upload", "drprg_cuda_genotype",
     "drprg_cuda_write_vcf", "drprg_cuda_vcf_text", "drprg_cuda_vcf_view", "drprg_cuda_index_info", "drprg_cuda_locus_name",
@@ -109,6 +109,23 @@ def pack_reads(data, off, stride_words=0):
     if r < 0:
         raise DrprgCudaError(L.drprg_cuda_last_error().decode())
     return words[:cap], woff, out_lens[:n]
+
+
+def read_fastx(path, threads=8):
+    """host parser (fasta/fastq, plain or gzip) -> (words, word_off, lens, n_reads, total_bases, first_read_len)"""
+    L = lib()
+    words, woff, lens = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
+    n, tb, fl = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    _check(L.drprg_cuda_read_fastx(str(path).encode(), C.c_uint32(threads), C.byref(words), C.byref(woff), C.byref(lens),
+                                   C.byref(n), C.byref(tb), C.byref(fl)), "drprg_cuda_read_fastx")
+    try:
+        o = np.ctypeslib.as_array(woff, (n.value + 1,)).copy()
+        w = np.ctypeslib.as_array(words, (max(1, int(o[-1])),)).copy()[:int(o[-1])]
+        l = np.ctypeslib.as_array(lens, (max(1, n.value),)).copy()[:n.value]
+    finally:
+        for p in (words, woff, lens):
+            L.drprg_cuda_host_free(p)
+    return w, o, l, n.value, tb.value, fl.value
 
 
 class Batch:
@@ -197,6 +214,18 @@ class Index:
                                            C.c_void_p(stream), C.byref(h))
         _check(rc, "drprg_cuda_batch_upload")
         return Batch(self, h, len(lens))
+
+    def batch_from_fastx(self, path, threads=8):
+        """a reads file as a device-resident batch: strict 4-line FASTQ (plain/gzip) is parsed and packed on the GPU, anything
+        else by the host parser.  Returns (Batch, info)."""
+        h = C.c_void_p()
+        n, tb, nd = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        fl, dev = C.c_uint32(0), C.c_int(0)
+        rc = lib().drprg_cuda_batch_from_fastx(self.h, str(path).encode(), C.c_uint32(threads), C.byref(h), C.byref(n), C.byref(tb),
+                                               C.byref(nd), C.byref(fl), C.byref(dev))
+        _check(rc, "drprg_cuda_batch_from_fastx")
+        return Batch(self, h, n.value), dict(n_reads=n.value, total_bases=tb.value, n_dropped=nd.value, first_read_len=fl.value,
+                                             parsed_on_device=bool(dev.value))
 
     def upload_ptrs(self, words_ptr, lens_ptr, n_reads, stride_words, total_bases, read_id_base=0, stream=0, woff_ptr=None):
         """H2D from raw host pointers (e.g. pinned torch tensors) without numpy staging."""

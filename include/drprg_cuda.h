@@ -91,6 +91,10 @@ int drprg_cuda_batch_upload(drprg_index*, const uint32_t* words, const uint64_t*
 int drprg_cuda_batch_wrap_device(drprg_index*, const void* d_words, const void* d_word_off, uint32_t stride_words,
                                  const void* d_lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base,
                                  drprg_batch** out);
+/* a reads file (fasta/fastq, plain or gzip: src/predict.rs:166-170) as a device-resident batch.  Strict 4-line FASTQ is
+ * sent to the device as raw text and parsed + 2-bit packed there; other inputs use the host parser and an upload. */
+int drprg_cuda_batch_from_fastx(drprg_index*, const char* path, uint32_t threads, drprg_batch** out, uint64_t* n_reads,
+                                uint64_t* total_bases, uint64_t* n_dropped, uint32_t* first_read_len, int* parsed_on_device);
 void drprg_cuda_batch_free(drprg_batch*);
 
 /* start a sample: zero the coverage accumulators, fix the options (thresholds depend on -c/-I and on the

@@ -394,3 +394,79 @@ def test_hit_buffer_regrows_on_targeted_reads():
     gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10)
     assert len(gh["read"]) > (1 << 20)
     assert_map_equal(gx, mr, gh)
+
+
+def _fastq_bytes(reads, crlf=False, final_newline=True):
+    nl = b"\r\n" if crlf else b"\n"
+    t = b"".join(b"@read%d some comment" % i + nl + r + nl + b"+" + nl + b"I" * len(r) + nl for i, r in enumerate(reads))
+    return t if final_newline else t[:-len(nl)]
+
+
+def _map_file_both_ways(gx, path, opts):
+    """(hits, info) through the device FASTQ parser and through the host parser + upload"""
+    out = []
+    b, info = gx.batch_from_fastx(path)
+    gx.sample_begin(opts, info["first_read_len"])
+    nh, nk = gx.map_batch(b)
+    out.append((gx.last_hits(nh), info, gx.coverage()))
+    words, woff, lens, n, tb, fl = lib.read_fastx(path)
+    gx.sample_begin(opts, fl)
+    nh, nk = gx.map_batch(gx.upload(words, woff, lens, total_bases=tb))
+    out.append((gx.last_hits(nh), dict(n_reads=n, total_bases=tb, first_read_len=fl), gx.coverage()))
+    return out
+
+
+@pytest.mark.parametrize("variant", ["plain", "gzip", "crlf", "no_final_newline"])
+def test_device_fastq_ingest_matches_host_parser(tmp_path, variant):
+    """the reads file goes to the GPU as text and is parsed + 2-bit packed there; the batch must be the
+    one the host parser builds (same reads, lengths, dropped reads, hits and coverage)."""
+    import gzip
+    d, o = sim.toy_dataset(TOY_PRG, TOY_REFS, depth=30, decoys=2, seed=4)
+    reads = [d[int(o[i]):int(o[i + 1])].tobytes() for i in range(len(o) - 1)]
+    reads[3] = reads[3][:70] + b"N" + reads[3][71:]      # dropped by pandora: non-ACGT
+    reads[5] = reads[5].lower()                          # case-insensitive
+    reads[7] = reads[7][:20]                             # shorter than w + k - 1
+    reads[9] = b""                                       # empty sequence line
+    reads[11] = reads[11][:149] + b"x"                   # bad base in the last word
+    text = _fastq_bytes(reads, crlf=(variant == "crlf"), final_newline=(variant != "no_final_newline"))
+    path = tmp_path / ("r.fq.gz" if variant == "gzip" else "r.fq")
+    path.write_bytes(gzip.compress(text) if variant == "gzip" else text)
+    gx = lib.Index(TOY_PRG, 11, 15, device=0)
+    (hd, idev, cd), (hh, ihost, ch) = _map_file_both_ways(gx, path, lib.make_opts(illumina=True, genome_size=2000))
+    assert idev["parsed_on_device"]
+    assert idev["n_reads"] == ihost["n_reads"] == len(reads)
+    assert idev["total_bases"] == ihost["total_bases"] == sum(len(r) for r in reads)
+    assert idev["first_read_len"] == ihost["first_read_len"] == len(reads[0])
+    assert idev["n_dropped"] == 2
+    assert len(hd["read"]) > 500
+    for key in ("read", "prg", "fwd", "start", "knode", "kept"):
+        assert len(hd[key]) == len(hh[key]) and (hd[key] == hh[key]).all(), key
+    for key in ("fwd", "rev", "locus_reads"):
+        assert (cd[key] == ch[key]).all()
+    assert cd["total_bases"] == ch["total_bases"] and cd["n_reads"] == ch["n_reads"]
+
+
+def test_device_fastq_ingest_long_reads_and_fallbacks(tmp_path):
+    """ragged layout + segment table for long reads; FASTA, wrapped or blank-line input falls back to the host parser"""
+    p, prg, refs = small_panel()
+    d, o, g, pl = long_reads_sample(p, 200)
+    reads = [d[int(o[i]):int(o[i + 1])].tobytes() for i in range(len(o) - 1)]
+    fq = tmp_path / "long.fq"
+    fq.write_bytes(_fastq_bytes(reads))
+    gx = lib.Index(prg, 11, 15, device=0)
+    opts = lib.make_opts(illumina=False, genome_size=len(g))
+    (hd, idev, cd), (hh, ihost, ch) = _map_file_both_ways(gx, fq, opts)
+    assert idev["parsed_on_device"] and idev["n_reads"] == len(reads)
+    assert len(hd["read"]) > 1000
+    for key in ("read", "prg", "fwd", "start", "knode", "kept"):
+        assert len(hd[key]) == len(hh[key]) and (hd[key] == hh[key]).all(), key
+    assert (cd["fwd"] == ch["fwd"]).all() and (cd["rev"] == ch["rev"]).all()
+    # fallbacks
+    fa = tmp_path / "r.fa"
+    fa.write_bytes(b"".join(b">r%d\n" % i + r[:80] + b"\n" + r[80:160] + b"\n" for i, r in enumerate(reads[:20])))
+    b, info = gx.batch_from_fastx(fa)
+    assert not info["parsed_on_device"] and info["n_reads"] == 20
+    blank = tmp_path / "blank.fq"
+    blank.write_bytes(_fastq_bytes(reads[:10]) + b"\n")
+    b, info = gx.batch_from_fastx(blank)
+    assert not info["parsed_on_device"] and info["n_reads"] == 10

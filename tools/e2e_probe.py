@@ -1,16 +1,38 @@
-import sys, time
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
-import numpy as np, torch
-from drprg_b200 import lib, workload
-wl = workload.Config2(); d, o = wl.reads(1000000, 0); words, _, lens = lib.pack_reads(d, o, 10)
-ix = lib.Index(wl.prg_path, 11, 15); opts = lib.make_opts(illumina=True)
-hw = torch.from_numpy(words.view(np.int32)).pin_memory(); hl = torch.from_numpy(lens.view(np.int32)).pin_memory()
-n = len(lens); tb = int(o[-1])
-for i in range(6):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    b = ix.upload_ptrs(hw.data_ptr(), hl.data_ptr(), n, 10, tb); t1 = time.perf_counter()
-    ix.sample_begin(opts, 150); t2 = time.perf_counter()
-    ix.map_batch(b); t3 = time.perf_counter()
-    ix.genotype(wl.refs_path); t4 = time.perf_counter()
-    v = ix.vcf_bytes(); b.free(); t5 = time.perf_counter()
-    print("upload %.3f begin %.3f map %.3f gt %.3f vcf+free %.3f total %.3f ms" % tuple(x * 1e3 for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0)), ix.last_timings())
+"""Drop-in call from a FASTQ file (drprg_cuda_map_genotype): wall time with the device FASTQ parser vs the host parser.
+   python tools/e2e_probe.py [n_reads]"""
+import sys, os, subprocess, json, tempfile, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1 and sys.argv[1] == "run":
+    from drprg_b200 import lib, workload, sim
+    fq, gz, prg, refs = sys.argv[2:6]
+    ix = lib.Index(prg, 11, 15); opts = lib.make_opts(illumina=True, threads=16)
+    out = tempfile.mkdtemp()
+    res = {}
+    for name, path in (("plain", fq), ("gzip", gz)):
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter(); st = ix.map_genotype(path, refs, out, opts); ts.append((time.perf_counter() - t0) * 1e3)
+        res[name] = dict(wall_ms_min=round(min(ts[1:]), 2), ingest_ms=round(st["ms_ingest"], 2), map_ms=round(st["ms_map"], 2),
+                         genotype_ms=round(st["ms_genotype"], 2), n_reads=st["n_reads"], records=st["n_records"])
+    import hashlib
+    res["vcf_sha1"] = hashlib.sha1(b"".join(l for l in open(os.path.join(out, "pandora_genotyped.vcf"), "rb") if not l.startswith(b"##fileDate"))).hexdigest()[:12]
+    print(json.dumps({"host_ingest": os.environ.get("DRPRG_HOST_INGEST", "0"), **res}))
+else:
+    from drprg_b200 import workload, sim
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+    wl = workload.Config2(); d, o = wl.reads(n, 0)
+    tmp = tempfile.mkdtemp()
+    fq, gz = os.path.join(tmp, "r.fq"), os.path.join(tmp, "r.fq.gz")
+    import numpy as np
+    # fast FASTQ writer (1 M reads)
+    L = 150
+    reads = d.reshape(n, L)
+    rec = np.empty((n, 8 + 1 + L + 3 + L + 1), np.uint8)
+    ids = np.char.zfill(np.arange(n).astype(str), 7).astype("S7")
+    rec[:, 0] = ord("@"); rec[:, 1:8] = np.frombuffer(ids.tobytes(), np.uint8).reshape(n, 7); rec[:, 8] = 10
+    rec[:, 9:9 + L] = reads; rec[:, 9 + L] = 10; rec[:, 10 + L] = ord("+"); rec[:, 11 + L] = 10
+    rec[:, 12 + L:12 + 2 * L] = ord("I"); rec[:, 12 + 2 * L] = 10
+    rec.tofile(fq)
+    subprocess.run(f"gzip -1 -c {fq} > {gz}", shell=True, check=True)
+    for h in ("0", "1"):
+        subprocess.run([sys.executable, __file__, "run", fq, gz, wl.prg_path, wl.refs_path], env=dict(os.environ, DRPRG_HOST_INGEST=h))
