@@ -26,8 +26,8 @@ import numpy as np
 
 # dram__bytes_read.sum + dram__bytes_write.sum of screen_kernel + resolve_kernel for one 1 M-read launch, and the pipe
 # utilisation of screen_kernel, from profiles/r1_screen.md (ncu --set full of this workload; constants, not measured live)
-NCU_TRAFFIC_BYTES = 107.1e6
-NCU_ISSUE = {"alu_pipe_active_pct": 66.9, "issue_active_pct": 61.8, "warp_instr_per_read": 68.4, "dram_read_mb_screen": 44.3,
+NCU_TRAFFIC_BYTES = 81.3e6
+NCU_ISSUE = {"alu_pipe_active_pct": 64.5, "issue_active_pct": 65.9, "warp_instr_per_read": 75.6, "dram_read_mb_screen": 44.3,
              "source": "profiles/r1_screen.md"}
 METRIC = "mapped reads/sec (pandora-map hot path: sketch+lookup+cluster+coverage+ML path+genotype)"
 UNIT = "reads/s"

@@ -394,10 +394,12 @@ void upload_index(drprg_index* X) {
             }
             std::vector<std::vector<uint32_t>> by(max_lev + 1);
             for (uint32_t r = n >= 2 ? n - 1 : 0; r-- > 0;) by[lev[r]].push_back(r);
-            for (uint32_t v = 1; v <= max_lev; ++v) {
-                level_nodes.insert(level_nodes.end(), by[v].begin(), by[v].end());
-                level_start.push_back((uint32_t)level_nodes.size());
-            }
+            for (uint32_t v = 1; v <= max_lev; ++v)
+                for (size_t c = 0; c < by[v].size(); c += 32) {  // rounds of at most 32 nodes: one per lane
+                    const size_t hi = std::min(by[v].size(), c + 32);
+                    level_nodes.insert(level_nodes.end(), by[v].begin() + c, by[v].begin() + hi);
+                    level_start.push_back((uint32_t)level_nodes.size());
+                }
             locus_level_off.push_back((uint32_t)level_start.size() - 1);
         }
         X->d_locus_level_off = to_device(locus_level_off);
