@@ -152,7 +152,7 @@ struct drprg_index {
     uint32_t *d_filter = nullptr, *d_knode_base = nullptr, *d_edge_off = nullptr, *d_edges = nullptr;
     uint8_t *d_is_terminal = nullptr, *d_needs_mean = nullptr;
     uint32_t *d_locus_unit_off = nullptr, *d_unit_start = nullptr, *d_unit_nodes = nullptr;
-    uint32_t *d_locus_level_off = nullptr, *d_level_start = nullptr, *d_level_nodes = nullptr;
+    uint32_t *d_locus_level_off = nullptr, *d_level_start = nullptr, *d_level_nodes = nullptr, *d_level_singles = nullptr;
     float mean_run_len = 0.f;
     uint32_t table_slots = 0, filter_words = 0;
     uint64_t n_edges = 0, n_ivs = 0;
@@ -216,7 +216,7 @@ struct drprg_index {
         cudaSetDevice(device);
         for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
                         (void*)d_is_terminal, (void*)d_needs_mean, (void*)d_locus_unit_off, (void*)d_unit_start, (void*)d_unit_nodes, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
-                        (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist, (void*)d_kfilter, (void*)d_locus_level_off, (void*)d_level_start, (void*)d_level_nodes})
+                        (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist, (void*)d_kfilter, (void*)d_locus_level_off, (void*)d_level_start, (void*)d_level_nodes, (void*)d_level_singles})
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
         hi.release(); lo.release(); hi2.release(); lo2.release();
@@ -380,7 +380,7 @@ void upload_index(drprg_index* X) {
         X->d_unit_nodes = to_device(unit_nodes);
     }
     {   // level order for the level-parallel ML-path kernel: level = 1 + max level of the successors (terminus = 0)
-        std::vector<uint32_t> locus_level_off(1, 0), level_start(1, 0), level_nodes;
+        std::vector<uint32_t> locus_level_off(1, 0), level_start(1, 0), level_nodes, level_singles;
         for (size_t l = 0; l < H.loci.size(); ++l) {
             const Locus& L = H.loci[l];
             const uint32_t n = (uint32_t)L.kpath.size();
@@ -394,17 +394,20 @@ void upload_index(drprg_index* X) {
             }
             std::vector<std::vector<uint32_t>> by(max_lev + 1);
             for (uint32_t r = n >= 2 ? n - 1 : 0; r-- > 0;) by[lev[r]].push_back(r);
-            for (uint32_t v = 1; v <= max_lev; ++v)
-                for (size_t c = 0; c < by[v].size(); c += 32) {  // rounds of at most 32 nodes: one per lane
-                    const size_t hi = std::min(by[v].size(), c + 32);
-                    level_nodes.insert(level_nodes.end(), by[v].begin() + c, by[v].begin() + hi);
-                    level_start.push_back((uint32_t)level_nodes.size());
-                }
+            for (uint32_t v = 1; v <= max_lev; ++v) {  // single-successor nodes first: they go to their own warps
+                std::stable_partition(by[v].begin(), by[v].end(), [&](uint32_t r) { return L.kout[r].size() == 1; });
+                uint32_t ns = 0;
+                for (uint32_t r : by[v]) ns += L.kout[r].size() == 1;
+                level_nodes.insert(level_nodes.end(), by[v].begin(), by[v].end());
+                level_start.push_back((uint32_t)level_nodes.size());
+                level_singles.push_back(ns);
+            }
             locus_level_off.push_back((uint32_t)level_start.size() - 1);
         }
         X->d_locus_level_off = to_device(locus_level_off);
         X->d_level_start = to_device(level_start);
         X->d_level_nodes = to_device(level_nodes);
+        X->d_level_singles = to_device(level_singles);
     }
     X->n_accum = 2ull * N + H.loci.size() + 4;
     CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
@@ -641,7 +644,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
                   X->d_len.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
                   X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start, X->d_unit_nodes, X->mean_run_len, X->st_ml,
-                  X->d_locus_level_off, X->d_level_start, X->d_level_nodes);
+                  X->d_locus_level_off, X->d_level_start, X->d_level_nodes, X->d_level_singles);
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());
     X->h_path.resize(N);

@@ -1723,116 +1723,122 @@ __global__ void mlpath_unit_kernel(uint32_t n_loci, const uint32_t* __restrict__
 // ---- level-parallel variant --------------------------------------------------------------------------------
 // A node only needs its successors' finished records, so all nodes at the same distance-to-sink ("level": 1 + the
 // largest level among the successors) are independent: the alleles of a bubble advance side by side.  The host
-// sorts every locus by level; lane i of the locus's warp takes the i-th node of the current level and runs exactly
+// sorts every locus by level, single-successor nodes first within a level.  A locus gets a CTA of four warps: warps
+// 0-1 take the level's single-successor nodes, warps 2-3 the nodes with a choice, one node per lane, so the two code
+// paths run on different schedulers instead of serialising inside one warp (a lone warp issues one instruction every
+// ~6 cycles here: the kernel is bound by its own instruction latency, not by shared memory).  Each node runs exactly
 // the per-node step of mlpath_rec_kernel (successors still visited in rank order, so pandora's order-dependent
-// tie-breaking is unchanged), then the warp synchronises.  The serial chain shrinks from the number of nodes to the
-// number of levels (benchmark panel: 38 251 nodes -> 15 128 levels, widest level 22 nodes).
-__global__ void mlpath_level_kernel(uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
-                                    const uint32_t* __restrict__ edges, const double* __restrict__ prob,
-                                    const int32_t* __restrict__ locus_reads, const uint8_t* __restrict__ needs_mean,
-                                    MlUnitsDev L, ModelParams P, uint32_t* __restrict__ path, uint32_t* __restrict__ path_len,
-                                    uint32_t max_nodes, uint32_t max_edges) {
+// tie-breaking is unchanged); the CTA synchronises between levels.  The serial chain shrinks from the number of nodes
+// to the number of levels (benchmark panel: 38 251 nodes -> 15 128 levels, widest level 22 nodes).
+constexpr int ML_LEVEL_THREADS = 128;
+__global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
+    uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
+    const uint32_t* __restrict__ edges, const double* __restrict__ prob, const int32_t* __restrict__ locus_reads,
+    const uint8_t* __restrict__ needs_mean, MlUnitsDev L, const uint32_t* __restrict__ level_singles, ModelParams P,
+    uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t max_nodes, uint32_t max_edges) {
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
-    const uint32_t lane = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
     if (locus_reads[l] <= 0 || n < 2) {
-        if (lane == 0) path_len[l] = 0xffffffffu;
+        if (tid == 0) path_len[l] = 0xffffffffu;
         return;
     }
     const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
     const uint32_t recs = (uint32_t)__cvta_generic_to_shared(s_dyn);
     const uint32_t edg = recs + (max_nodes + 1) * REC;
     const uint32_t lvn = edg + (max_edges + 1) * 4u;  // record addresses in level order
-    const uint32_t lvs = lvn + max_nodes * 4u;        // level boundaries (indices into lvn)
-    for (uint32_t i = lane; i <= n; i += 32) {
+    const uint32_t lvs = lvn + max_nodes * 4u;        // per level: first index into lvn, number of single-successor nodes
+    for (uint32_t i = tid; i <= n; i += ML_LEVEL_THREADS) {
         const uint32_t a = recs + i * REC;
         if (i < n) sts64(a + R_PR, prob[base + i]);
         sts32(a + R_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
     }
-    for (uint32_t i = lane; i < n_edges; i += 32) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
+    for (uint32_t i = tid; i < n_edges; i += ML_LEVEL_THREADS) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
     const uint32_t u0 = L.locus_unit_off[l], n_levels = L.locus_unit_off[l + 1] - u0;
     const uint32_t s00 = L.unit_start[u0];
-    for (uint32_t i = lane; i <= n_levels; i += 32) sts32(lvs + 4u * i, L.unit_start[u0 + i] - s00);
-    for (uint32_t i = lane; i + 1 < n; i += 32) sts32(lvn + 4u * i, recs + L.unit_nodes[s00 + i] * REC);
+    for (uint32_t i = tid; i <= n_levels; i += ML_LEVEL_THREADS) {
+        sts32(lvs + 8u * i, L.unit_start[u0 + i] - s00);
+        sts32(lvs + 8u * i + 4u, i < n_levels ? level_singles[u0 + i] : 0u);
+    }
+    for (uint32_t i = tid; i + 1 < n; i += ML_LEVEL_THREADS) sts32(lvn + 4u * i, recs + L.unit_nodes[s00 + i] * REC);
     const double tol = 0.000001;
     const uint32_t term = recs + (n - 1) * REC;
     const uint32_t steps2 = P.window - 2;
-    if (lane == 0) {
+    if (tid == 0) {
         sts64(term + R_M, 0.0);
         sts32(term + R_LEN, 0u);
 #pragma unroll
         for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // includes R_T
     }
-    __syncwarp();
-    uint32_t s1 = lds32(lvs);
+    __syncthreads();
+    const bool single_warp = warp < 2;
+    const uint32_t sub = (warp & 1u) + 2u * lane;  // this lane's slot among the level's nodes of its kind (64 per pass)
     for (uint32_t u = 0; u < n_levels; ++u) {
-        const uint32_t s0 = s1;
-        s1 = lds32(lvs + 4u * (u + 1));
-        for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
-            if (i0 + lane < s1) {
-                const uint32_t a = lds32(lvn + 4u * (i0 + lane));
-                double Mj = 0.0;
-                uint32_t lenj = 0, prevj = term;
-                const double pj = lds64(a + R_PR);
+        const uint32_t s0 = lds32(lvs + 8u * u), ns = lds32(lvs + 8u * u + 4u), s1 = lds32(lvs + 8u * u + 8u);
+        const uint32_t lo = single_warp ? s0 : s0 + ns, hi = single_warp ? s0 + ns : s1;
+        for (uint32_t idx = lo + sub; idx < hi; idx += 64) {
+            const uint32_t a = lds32(lvn + 4u * idx);
+            double Mj = 0.0;
+            uint32_t lenj = 0, prevj = term;
+            const double pj = lds64(a + R_PR);
+            const uint32_t e0w = lds32(a + R_EOFF);
+            const uint32_t e0 = e0w & ~3u;
+            if (single_warp) {
+                // single successor: pandora's comparison against the initial -FLT_MAX accepts any successor that is
+                // not a dead end
+                const uint32_t v = lds32(e0);
+                const uint32_t lv = lds32(v + R_LEN);
+                const uint32_t tv = lds32(v + R_T);
+                const double Mv = lds64(v + R_M);
+                if (v == term || lv > 0u) {
+                    mlpath_link(a, v, steps2);  // independent of the sums below: overlaps them
+                    prevj = v;
+                    lenj = 1 + lv;
+                    Mj = pj + Mv;
+                    if (lenj > P.window) {
+                        Mj -= lds64(tv + R_PR);
+                        lenj -= 1;
+                    }
+                }
+            } else {
                 const uint32_t e1 = lds32(a + REC + R_EOFF) & ~3u;
-                const uint32_t e0w = lds32(a + R_EOFF);
-                const uint32_t e0 = e0w & ~3u;
-                if (e1 - e0 == 4u) {
-                    // single successor: pandora's comparison against the initial -FLT_MAX accepts any successor that is
-                    // not a dead end
-                    const uint32_t v = lds32(e0);
+                double max_mean = -(double)FLT_MAX;
+                uint32_t max_len = 0;
+                for (uint32_t e = e0; e < e1; e += 4u) {
+                    const uint32_t v = lds32(e);
+                    const bool is_term = (v == term);
                     const uint32_t lv = lds32(v + R_LEN);
                     const uint32_t tv = lds32(v + R_T);
+                    const double mean_v = lds64(v + R_MEAN);
                     const double Mv = lds64(v + R_M);
-                    if (v == term || lv > 0u) {
-                        mlpath_link(a, v, steps2);
-                        prevj = v;
-                        lenj = 1 + lv;
-                        Mj = pj + Mv;
-                        if (lenj > P.window) {
-                            Mj -= lds64(tv + R_PR);
-                            lenj -= 1;
-                        }
+                    const bool take = is_term ? (P.thresh > max_mean + tol)
+                                              : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
+                    if (!take) continue;
+                    Mj = pj + Mv;
+                    lenj = 1 + lv;
+                    prevj = v;
+                    if (lenj > P.window) {
+                        Mj -= lds64(tv + R_PR);
+                        lenj -= 1;
                     }
-                } else {
-                    double max_mean = -(double)FLT_MAX;
-                    uint32_t max_len = 0;
-                    for (uint32_t e = e0; e < e1; e += 4u) {
-                        const uint32_t v = lds32(e);
-                        const bool is_term = (v == term);
-                        const uint32_t lv = lds32(v + R_LEN);
-                        const uint32_t tv = lds32(v + R_T);
-                        const double mean_v = lds64(v + R_MEAN);
-                        const double Mv = lds64(v + R_M);
-                        const bool take = is_term ? (P.thresh > max_mean + tol)
-                                                  : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
-                        if (!take) continue;
-                        Mj = pj + Mv;
-                        lenj = 1 + lv;
-                        prevj = v;
-                        if (lenj > P.window) {
-                            Mj -= lds64(tv + R_PR);
-                            lenj -= 1;
-                        }
-                        max_mean = is_term ? P.thresh : mean_v;
-                        if (!is_term) max_len = lv;
-                    }
-                    if (lenj) mlpath_link(a, prevj, steps2);
+                    max_mean = is_term ? P.thresh : mean_v;
+                    if (!is_term) max_len = lv;
                 }
-                if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) sts32(a + R_UP + 4 * v, term);
-                }
-                sts64(a + R_M, Mj);
-                sts32(a + R_LEN, lenj);
-                if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
+                if (lenj) mlpath_link(a, prevj, steps2);
             }
+            if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
+#pragma unroll
+                for (int v = 0; v < 8; ++v) sts32(a + R_UP + 4 * v, term);
+            }
+            sts64(a + R_M, Mj);
+            sts32(a + R_LEN, lenj);
+            if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         uint32_t cnt = 0, p = lds32(recs + R_UP);
         while (p != term && cnt < n) {
             path[base + cnt++] = (p - recs) / REC;
@@ -1848,7 +1854,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean,
                    const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes,
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off, const uint32_t* d_level_start,
-                   const uint32_t* d_level_nodes) {
+                   const uint32_t* d_level_nodes, const uint32_t* d_level_singles) {
     if (!n_loci) return;
     {   // default: level-parallel kernel (any of the older switches selects the older kernels)
         static const bool levels_on = [] {
@@ -1856,17 +1862,17 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
             if (e) return atoi(e) != 0;
             return !getenv("DRPRG_MLPATH_UNITS") && !getenv("DRPRG_MLPATH_GENERIC");
         }();
-        const size_t lvl_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4 + (size_t)max_locus_knodes * 8 + 16;
-        if (levels_on && d_level_nodes && d_needs_mean && P.window >= 2 && P.window <= 128 && lvl_smem <= 220u * 1024u) {
+        const size_t lvl_smem = ((size_t)max_locus_knodes + 1) * REC + (size_t)(max_locus_edges + 1) * 4 + (size_t)max_locus_knodes * 12 + 32;
+        if (levels_on && d_level_nodes && d_level_singles && d_needs_mean && P.window >= 2 && P.window <= 128 && lvl_smem <= 220u * 1024u) {
             static size_t configured = 0;
             if (lvl_smem > configured) {
                 cudaFuncSetAttribute(mlpath_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lvl_smem);
                 configured = lvl_smem;
             }
             MlUnitsDev L{d_locus_level_off, d_level_start, d_level_nodes};
-            mlpath_level_kernel<<<n_loci, 32, lvl_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads,
-                                                              d_needs_mean, L, P, d_path, d_path_len, max_locus_knodes,
-                                                              max_locus_edges);
+            mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob,
+                                                                            d_locus_reads, d_needs_mean, L, d_level_singles, P, d_path,
+                                                                            d_path_len, max_locus_knodes, max_locus_edges);
             ++g_launches;
             return;
         }
