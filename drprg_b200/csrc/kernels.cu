@@ -1730,6 +1730,34 @@ __global__ void mlpath_unit_kernel(uint32_t n_loci, const uint32_t* __restrict__
 // the per-node step of mlpath_rec_kernel (successors still visited in rank order, so pandora's order-dependent
 // tie-breaking is unchanged); the CTA synchronises between levels.  The serial chain shrinks from the number of nodes
 // to the number of levels (benchmark panel: 38 251 nodes -> 15 128 levels, widest level 22 nodes).
+// sum / length on the level kernel's critical path.  The length is an integer <= 128, so the correctly rounded quotient
+// comes from a table of correctly rounded reciprocals and two Markstein corrections (q += fma(-q, n, a) * y): five
+// dependent FP64 operations instead of the ~15 of the generic division sequence.  The first correction makes q
+// faithful, the second one makes it RN(a / n) because y = RN(1 / n) (Markstein's theorem; also checked against the
+// hardware division on 7.7e8 random and adversarial operands, tools/divtest.c).  n == 0 gives NaN like 0.0 / 0.
+__constant__ double c_rcp_small[129];
+static void upload_rcp_table() {
+    static bool done = false;  // per process; every device of the process gets it at its first launch
+    static int done_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done && done_dev == dev) return;
+    double h[129];
+    h[0] = 0.0;
+    for (int n = 1; n <= 128; ++n) h[n] = 1.0 / (double)n;
+    cudaMemcpyToSymbol(c_rcp_small, h, sizeof h);
+    done = true;
+    done_dev = dev;
+}
+__device__ __forceinline__ double div_small(double a, uint32_t n) {
+    if (n == 0u) return __longlong_as_double(0x7ff8000000000000ll);  // what 0.0 / 0 gives: never compares true
+    const double y = c_rcp_small[n], b = (double)n;
+    double q = a * y;
+    q = fma(fma(-q, b, a), y, q);
+    q = fma(fma(-q, b, a), y, q);
+    return q;
+}
+
 constexpr int ML_LEVEL_THREADS = 128;
 __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
@@ -1834,7 +1862,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
             }
             sts64(a + R_M, Mj);
             sts32(a + R_LEN, lenj);
-            if (e0w & 1u) sts64(a + R_MEAN, Mj / (double)lenj);  // 0/0 = NaN for a dead end: never chosen, like pandora
+            if (e0w & 1u) sts64(a + R_MEAN, div_small(Mj, lenj));  // 0/0 = NaN for a dead end: never chosen, like pandora
         }
         __syncthreads();
     }
@@ -1870,6 +1898,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                 configured = lvl_smem;
             }
             MlUnitsDev L{d_locus_level_off, d_level_start, d_level_nodes};
+            upload_rcp_table();
             mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob,
                                                                             d_locus_reads, d_needs_mean, L, d_level_singles, P, d_path,
                                                                             d_path_len, max_locus_knodes, max_locus_edges);
