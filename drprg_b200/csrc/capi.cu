@@ -187,7 +187,7 @@ struct drprg_index {
         SiteKeySet known;
     };
     std::vector<LocusSites> sites;
-    std::vector<uint32_t> loci_by_name;
+    std::vector<uint32_t> loci_by_name, loci_by_size;
     FitParams fit;
     std::vector<std::vector<uint32_t>> mlpaths;
     std::vector<char> present;
@@ -429,6 +429,9 @@ void upload_index(drprg_index* X) {
     for (uint32_t l = 0; l < H.loci.size(); ++l) X->loci_by_name[l] = l;
     std::sort(X->loci_by_name.begin(), X->loci_by_name.end(),
               [&](uint32_t a, uint32_t b) { return H.loci[a].name < H.loci[b].name; });
+    X->loci_by_size = X->loci_by_name;
+    std::stable_sort(X->loci_by_size.begin(), X->loci_by_size.end(),
+                     [&](uint32_t a, uint32_t b) { return H.loci[a].kpath.size() > H.loci[b].kpath.size(); });
 }
 
 int load_common(const std::string& text, uint32_t w, uint32_t k, int device, drprg_index** out) {
@@ -750,7 +753,9 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     run_s8_and_format(X->st_gt);
     lap(3);
     // ---- verify the speculation against the ML paths
+    const double tw0 = now_ms();
     CK(cudaStreamSynchronize(X->st_ml));
+    const double tw1 = now_ms();
     {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, X->ev_ml[0], X->ev_ml[1]));
@@ -768,7 +773,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     };
     std::vector<LocusOut> lout(P);
     parallel_for(P, [&](size_t li) {
-        const uint32_t l = (uint32_t)li;
+        const uint32_t l = X->loci_by_size[li];  // biggest first: the pool hands loci out in order
         if (locus_reads[l] <= 0 || plen[l] == 0xffffffffu || plen[l] == 0) return;
         const Locus& L = H.loci[l];
         LocusOut& O = lout[l];
@@ -785,7 +790,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             O.sample_merged = merge_records(L, S.ref_path, std::move(all));
             O.use_cached = false;
         }
-    });
+    }, 16);
     bool speculation_ok = true;
     for (uint32_t l = 0; l < P; ++l) {
         if (lout[l].present) {
@@ -793,6 +798,10 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             X->mlpaths[l] = std::move(lout[l].kp);
         }
         if ((locus_reads[l] > 0) != lout[l].present || !lout[l].use_cached) speculation_ok = false;
+    }
+    {
+        static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+        if (timing) fprintf(stderr, "[drprg-cuda] ml wait %.3f ms, verify %.3f ms\n", tw1 - tw0, now_ms() - tw1);
     }
     lap(4);
     if (!speculation_ok) {  // slow path: rebuild the record list exactly and redo S8 + text
