@@ -470,3 +470,56 @@ def test_device_fastq_ingest_long_reads_and_fallbacks(tmp_path):
     blank.write_bytes(_fastq_bytes(reads[:10]) + b"\n")
     b, info = gx.batch_from_fastx(blank)
     assert not info["parsed_on_device"] and info["n_reads"] == 10
+
+
+def _panel_path_reads(seed, n, lens_choices):
+    """reads cut from the toy panel's reference sequences (so their minimizers are indexed), random strand, a few
+    substitutions, assorted lengths; plus homopolymer / repeat / non-ACGT / random decoys"""
+    rng = np.random.default_rng(seed)
+    refs = [l.strip() for l in open(TOY_REFS) if not l.startswith(">")]
+    comp = str.maketrans("ACGT", "TGCA")
+    strs = []
+    for i in range(n):
+        g = refs[int(rng.integers(0, len(refs)))]
+        L = int(lens_choices[i % len(lens_choices)])
+        st = int(rng.integers(0, max(1, len(g) - L)))
+        r = list(g[st:st + L])
+        for _ in range(int(rng.integers(0, 3))):
+            if r:
+                r[int(rng.integers(0, len(r)))] = "ACGT"[int(rng.integers(0, 4))]
+        r = "".join(r)
+        if rng.integers(0, 2):
+            r = r.translate(comp)[::-1]
+        strs.append(r)
+    strs += ["A" * 300, "ACGT" * 100, "AC" * 80 + "GATTACA" * 30, "", "ACGTN" * 30, strs[0].lower(),
+             strs[1][:30] + "N" + strs[1][31:], refs[0][:25], refs[0][:24], refs[0][:640], refs[1][:641]]
+    strs += ["".join("ACGT"[j] for j in rng.integers(0, 4, size=int(L))) for L in rng.integers(0, 700, size=60)]
+    return strs
+
+
+@pytest.mark.parametrize("w", [11, 14, 1, 5, 19, 32])
+def test_screened_lookup_edge_cases(w):
+    """k = 15 batches go through the k-mer screen + resolve kernels: hits must equal the oracle's for every window size
+    (compiled W = 11, 14 and the generic resolve), read lengths around the word / chunk / segment boundaries, ragged and
+    fixed-stride layouts, both strands, ties, dropped reads"""
+    k = 15
+    lens = [25, 26, 31, 32, 33, 47, 48, 49, 100, 127, 128, 129, 142, 143, 144, 145, 150, 151, 159, 160, 161, 174, 175, 176,
+            200, 255, 256, 257, 300, 454, 455, 456, 500, 639, 640]
+    strs = _panel_path_reads(100 + w, 350, lens)
+    data, off = reads_from_strings(strs)
+    gx, ox, mr, gh, oo = run_both(TOY_PRG, TOY_REFS, data, off, w=w, k=k, genome_size=2000, c=2)
+    assert len(gh["read"]) > 2000
+    assert_map_equal(gx, mr, gh)
+    gx2, ox2, mr2, gh2, _ = run_both(TOY_PRG, TOY_REFS, data, off, w=w, k=k, genome_size=2000, c=2, stride_words=44)
+    for key in gh:
+        assert (gh[key] == gh2[key]).all(), key
+    # short-read-only batch (the one-chunk screen instantiation) and a long-read batch (segments)
+    short = [s for s in strs if len(s) <= 160]
+    d2, o2 = reads_from_strings(short)
+    gx3, ox3, mr3, gh3, _ = run_both(TOY_PRG, TOY_REFS, d2, o2, w=w, k=k, genome_size=2000, c=2, stride_words=10)
+    assert_map_equal(gx3, mr3, gh3)
+    refs = [l.strip() for l in open(TOY_REFS) if not l.startswith(">")]
+    longs = [refs[0] + refs[1][:300], refs[1], refs[0][:700] + "ACGT" * 200 + refs[1][100:], "A" * 1500, refs[0][:641]] + short[:20]
+    d3, o3 = reads_from_strings(longs)
+    gx4, ox4, mr4, gh4, _ = run_both(TOY_PRG, TOY_REFS, d3, o3, w=w, k=k, genome_size=2000, c=2, illumina=False)
+    assert_map_equal(gx4, mr4, gh4)
