@@ -663,32 +663,35 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
                     cnt += __popc(f[i]);
                 }
             }
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
             if (total) {
                 unsigned long long o = 0;
-                if (lane == 0) o = atomicAdd(queue_count, (unsigned long long)total);
-                o = __shfl_sync(FULL, o, 0) + (incl - cnt);
-                const unsigned long long tag = (unsigned long long)(uint32_t)r << 32;
+                if (lane == 0) o = atomicAdd(queue_count, (unsigned long long)total);  // in flight during the prefix scan
+                uint32_t incl = cnt;
 #pragma unroll
-                for (int i = 0; i < NF; ++i) {
-                    uint32_t m = f[i];
-                    while (m) {
-                        const uint32_t bit = __ffs(m) - 1;
-                        m &= m - 1u;
-                        if (o < queue_cap) {
-                            queue[o] = tag | (q0 + c0 + i * 32 + bit);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                o = __shfl_sync(FULL, o, 0);
+                // a warp whose entries do not all fit writes none of them: the host sees the overflow in the counter and
+                // redoes the batch with a larger queue, so one bounds test per warp is enough
+                if (o + total <= queue_cap) {
+                    unsigned long long* qp = queue + o + (incl - cnt);
+                    uint32_t* kp = queue_kmer + o + (incl - cnt);
+                    const uint32_t tag = (uint32_t)r, pos0 = q0 + c0;
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        uint32_t m = f[i];
+                        while (m) {
+                            const uint32_t bit = __ffs(m) - 1;
+                            m &= m - 1u;
+                            *reinterpret_cast<uint2*>(qp++) = make_uint2(pos0 + i * 32 + bit, tag);  // read << 32 | position
                             // the k-mer travels with the entry, so the resolve kernel's index probe needs no access to the read
                             const bool up = bit >= 16u;
                             const uint32_t a = up ? cw[2 * i + 1] : cw[2 * i], b = up ? cw[2 * i + 2] : cw[2 * i + 1];
-                            queue_kmer[o] = __funnelshift_l(b, a, 2u * (bit & 15u)) >> (32 - 2 * K);
+                            *kp++ = __funnelshift_l(b, a, 2u * (bit & 15u)) >> (32 - 2 * K);
                         }
-                        ++o;
                     }
                 }
             }
@@ -721,7 +724,8 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, De
     __shared__ uint32_t s_rec[RESOLVE_THREADS];
     __shared__ uint32_t s_n;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(queue_need, *queue_count);  // sticky over the chunks of a batch: the host regrows and redoes
-    const unsigned long long n = min(*queue_count, queue_cap);
+    if (*queue_count > queue_cap) return;  // overflow: the queue has unwritten slots and the batch is redone anyway
+    const unsigned long long n = *queue_count;
     const uint32_t w = W ? (uint32_t)W : w_rt, k = W ? (uint32_t)K : k_rt;
     const uint32_t S = 32 - 2 * k;
     const uint32_t hm = (S == 0) ? 0xffffffffu : ~((1u << S) - 1u);
@@ -869,8 +873,8 @@ static void launch_screen_v(const DevReads& R, const DevTable& T, uint32_t wk, u
         configured = true;
     }
     static const uint32_t prefetch = [] {
-        const char* e = getenv("DRPRG_SCREEN_PREFETCH");
-        return e ? (uint32_t)atoi(e) : 1u;
+        const char* e = getenv("DRPRG_SCREEN_PREFETCH");  // L2 prefetch of the next tile: measured neutral (cold == warm L2 time), off
+        return e ? (uint32_t)atoi(e) : 0u;
     }();
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_ctas = (n_items + SCREEN_THREADS - 1) / SCREEN_THREADS;
