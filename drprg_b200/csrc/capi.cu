@@ -200,7 +200,10 @@ struct drprg_index {
     DBuf<int32_t> d_gt_i32;
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     cudaEvent_t ev_ml[2] = {nullptr, nullptr};
-    cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr;  // ML-path kernel / genotype kernels run concurrently
+    cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr, st_acc = nullptr;
+    cudaEvent_t ev_acc[2] = {nullptr, nullptr};
+    uint32_t* d_hist1000 = nullptr;
+    PinnedBuf<uint32_t> h_small;  // coverage histogram | locus read counts | scalars  // ML-path kernel / genotype kernels run concurrently
     PinnedBuf<uint32_t> h_path, h_plen, h_u32;
     PinnedBuf<double> h_f64;
     PinnedBuf<int32_t> h_gt, h_acc;
@@ -230,6 +233,11 @@ struct drprg_index {
         for (auto& e : ev_ml)
             if (e) cudaEventDestroy(e);
         if (st_copy) cudaStreamDestroy(st_copy);
+        if (st_acc) cudaStreamDestroy(st_acc);
+        for (auto& e : ev_acc)
+            if (e) cudaEventDestroy(e);
+        if (d_hist1000) cudaFree(d_hist1000);
+        h_small.release();
         if (st_ml) cudaStreamDestroy(st_ml);
         if (st_gt) cudaStreamDestroy(st_gt);
     }
@@ -424,6 +432,7 @@ void upload_index(drprg_index* X) {
     }
     X->d_knode_locus = to_device(knode_locus);
     CK(cudaMalloc(&X->d_hist, 200 * sizeof(uint32_t)));
+    CK(cudaMalloc(&X->d_hist1000, 1000 * sizeof(uint32_t)));
     X->sites.assign(H.loci.size(), drprg_index::LocusSites());
     X->loci_by_name.resize(H.loci.size());
     for (uint32_t l = 0; l < H.loci.size(); ++l) X->loci_by_name[l] = l;
@@ -598,16 +607,34 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         t0 = t;
     };
     flush_scalars(X);
-    X->h_acc.resize(X->n_accum);  // pinned: a pageable destination is staged through a bounce buffer (~0.1 ms for 0.3 MB)
-    CK(cudaMemcpyAsync(X->h_acc.data(), X->d_accum, X->n_accum * 4, cudaMemcpyDeviceToHost, st));
+    if (!X->st_ml) {
+        CK(cudaStreamCreateWithFlags(&X->st_ml, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&X->st_gt, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&X->st_acc, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&X->ev_acc[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&X->ev_acc[1], cudaEventDisableTiming));
+    }
+    // On the critical path the host only needs the 1000-bin coverage histogram (built on the device), the locus read
+    // counts and the scalars: 4 KB.  The full accumulator (0.3 MB, pinned destination) is needed when the ML paths are
+    // verified; it comes down on its own stream, ordered after whatever produced the accumulator on `st` (map_batch, or
+    // the caller's allreduce).
+    X->h_acc.resize(X->n_accum);
+    CK(cudaEventRecord(X->ev_acc[0], st));
+    CK(cudaStreamWaitEvent(X->st_acc, X->ev_acc[0], 0));
+    CK(cudaMemcpyAsync(X->h_acc.data(), X->d_accum, X->n_accum * 4, cudaMemcpyDeviceToHost, X->st_acc));
+    CK(cudaEventRecord(X->ev_acc[1], X->st_acc));
+    launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
+    X->h_small.resize(1000 + (size_t)P + 4);
+    CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, ((size_t)P + 4) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const int32_t* cov = X->h_acc.data();
-    const int32_t* locus_reads = X->h_acc.data() + 2ull * N;
-    const int32_t* sc = X->h_acc.data() + X->n_accum - 4;
+    const int32_t* cov = X->h_acc.data();  // valid after ev_acc[1]
+    const int32_t* locus_reads = (const int32_t*)(X->h_small.data() + 1000);
+    const int32_t* sc = locus_reads + P;
     const uint64_t total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
     lap(0);
-    // ---- S6: moments / model choice on the host, log-prob histogram on the device
-    X->fit = fit_parameters(H, cov, locus_reads, total_bases, X->opts);
+    // ---- S6: moments / model choice on the host, histograms on the device
+    X->fit = fit_parameters_hist(H, X->h_small.data(), locus_reads, total_bases, X->opts);
     ModelParams MP{};
     MP.bin = X->fit.bin;
     MP.nb_p = X->fit.nb_p;
@@ -634,10 +661,6 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     // while S8 (per-allele statistics + likelihoods) and the VCF text are produced SPECULATIVELY for the common
     // outcome "every locus with reads is present, no extra records"; the outcome is verified afterwards and
     // anything that deviates is redone on the slow path.
-    if (!X->st_ml) {
-        CK(cudaStreamCreateWithFlags(&X->st_ml, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&X->st_gt, cudaStreamNonBlocking));
-    }
     if (!X->ev_ml[0]) {
         CK(cudaEventCreate(&X->ev_ml[0]));
         CK(cudaEventCreate(&X->ev_ml[1]));
@@ -755,6 +778,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     // ---- verify the speculation against the ML paths
     const double tw0 = now_ms();
     CK(cudaStreamSynchronize(X->st_ml));
+    CK(cudaEventSynchronize(X->ev_acc[1]));  // the full accumulator is on the host from here on
     const double tw1 = now_ms();
     {
         float ms = 0;

@@ -136,20 +136,29 @@ double host_node_log_prob(const FitParams& P, uint32_t k, uint32_t f, uint32_t r
 
 FitParams fit_parameters(const HostIndex& H, const int32_t* cov, const int32_t* locus_reads, uint64_t total_bases,
                          const SampleOpts& o) {
+    uint32_t hist[1000] = {0};
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        if (locus_reads[l] <= 0) continue;
+        for (uint32_t g = H.knode_base[l] + 1; g + 1 < H.knode_base[l + 1]; ++g) {
+            uint32_t c = sat16(cov[2 * g]) + sat16(cov[2 * g + 1]);
+            if (c < 1000) ++hist[c];
+        }
+    }
+    return fit_parameters_hist(H, hist, locus_reads, total_bases, o);
+}
+
+// the same fit from a ready histogram of per-node total coverage (built on the device by cov_hist_kernel)
+FitParams fit_parameters_hist(const HostIndex& H, const uint32_t* hist, const int32_t* locus_reads, uint64_t total_bases,
+                              const SampleOpts& o) {
     FitParams P;
     P.e_rate = o.e_rate;
     P.covg = (uint32_t)(total_bases / std::max<uint32_t>(1u, o.genome_size));
     P.E = P.covg;
-    uint32_t hist[1000] = {0};
     uint64_t reads = 0, present = 0;
     for (size_t l = 0; l < H.loci.size(); ++l) {
         if (locus_reads[l] <= 0) continue;
         ++present;
         reads += (uint64_t)locus_reads[l];
-        for (uint32_t g = H.knode_base[l] + 1; g + 1 < H.knode_base[l + 1]; ++g) {
-            uint32_t c = sat16(cov[2 * g]) + sat16(cov[2 * g + 1]);
-            if (c < 1000) ++hist[c];
-        }
     }
     if (!present) {
         P.min_kmer_covg = P.E / 10;

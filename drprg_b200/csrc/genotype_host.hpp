@@ -45,6 +45,8 @@ struct FitParams {
 // everything of estimate_parameters except the probability threshold (set from the device histogram)
 FitParams fit_parameters(const HostIndex& H, const int32_t* cov, const int32_t* locus_reads, uint64_t total_bases,
                          const SampleOpts& o);
+FitParams fit_parameters_hist(const HostIndex& H, const uint32_t* hist1000, const int32_t* locus_reads, uint64_t total_bases,
+                              const SampleOpts& o);
 int prob_threshold(const uint32_t* hist200);
 double host_node_log_prob(const FitParams& P, uint32_t k, uint32_t f, uint32_t r, bool terminal);
 

@@ -1284,6 +1284,33 @@ __global__ void prob_hist_kernel(const double* __restrict__ prob, uint32_t total
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
+// histogram of the per-node total coverage (0..999) over the inner k-mer nodes of the loci present in the sample:
+// the data-parallel half of pandora's estimate_parameters moments / peak search (the 1000-bin scans stay on the host)
+__global__ void cov_hist_kernel(const int32_t* __restrict__ cov, uint32_t total, const uint8_t* __restrict__ is_terminal,
+                                const uint32_t* __restrict__ knode_locus, const int32_t* __restrict__ locus_reads,
+                                uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[1000];
+    for (int i = threadIdx.x; i < 1000; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x)
+        if (!is_terminal[g] && locus_reads[knode_locus[g]] > 0) {
+            const uint32_t c = cov_sat(max(cov[2 * g], 0)) + cov_sat(max(cov[2 * g + 1], 0));
+            if (c < 1000u) atomicAdd(&sh[c], 1u);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1000; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+void launch_cov_hist(const int32_t* d_cov, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
+                     const int32_t* d_locus_reads, uint32_t* d_hist1000, cudaStream_t st) {
+    cudaMemsetAsync(d_hist1000, 0, 1000 * sizeof(uint32_t), st);
+    if (!total) return;
+    const unsigned grid = std::min<unsigned>((total + 1023) / 1024, 64u);
+    cov_hist_kernel<<<grid, 1024, 0, st>>>(d_cov, total, d_is_terminal, d_knode_locus, d_locus_reads, d_hist1000);
+    ++g_launches;
+}
+
 void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
                       const int32_t* d_locus_reads, uint32_t* d_hist, cudaStream_t st) {
     cudaMemsetAsync(d_hist, 0, 200 * sizeof(uint32_t), st);

@@ -99,6 +99,8 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off = nullptr,
                    const uint32_t* d_level_start = nullptr, const uint32_t* d_level_nodes = nullptr,
                    const uint32_t* d_level_singles = nullptr);
+void launch_cov_hist(const int32_t* d_cov, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
+                     const int32_t* d_locus_reads, uint32_t* d_hist1000, cudaStream_t st);
 void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
                       const int32_t* d_locus_reads, uint32_t* d_hist, cudaStream_t st);
 // S8: per-allele coverage statistics, then per-record likelihoods / GT / GT_CONF
