@@ -523,3 +523,25 @@ def test_screened_lookup_edge_cases(w):
     d3, o3 = reads_from_strings(longs)
     gx4, ox4, mr4, gh4, _ = run_both(TOY_PRG, TOY_REFS, d3, o3, w=w, k=k, genome_size=2000, c=2, illumina=False)
     assert_map_equal(gx4, mr4, gh4)
+
+
+def test_chunked_upload_and_its_overflow_path():
+    """a host upload of >= 8 MB is split into four chunks whose screen/resolve kernels start as each chunk lands.  Targeted
+    reads overflow the initial hit buffer in a middle chunk: the batch is redone with larger buffers and must equal the
+    oracle (and a second sample on the same handle, which needs no redo, must give the same hits)."""
+    p, prg, refs = small_panel()
+    hap = sim.sample_haplotype(p, 5, 0.1)
+    g, placements = sim.make_genome(p, [h[0] for h in hap], size=60_000, seed=6, min_sep=3000)
+    regions = [(s, ln) for s, ln, st in placements]
+    d, o = sim.simulate_reads(g, 230_000, 150, seed=9, sub_rate=0.002, regions=regions)
+    gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10)   # 9.2 MB of words: chunked
+    assert len(gh["read"]) > (2 << 20)
+    assert_map_equal(gx, mr, gh)
+    # second sample on the same handle: buffers are large enough now, no redo, same answer
+    words, woff, lens = lib.pack_reads(d, o, 10)
+    gx.sample_begin(lib.make_opts(illumina=True, genome_size=len(g), min_cluster_size=10), 150)
+    nh, nk = gx.map_batch(gx.upload(words, woff, lens, total_bases=int(o[-1]), stride_words=10))
+    h2 = gx.last_hits(nh)
+    for key in gh:
+        assert (gh[key] == h2[key]).all(), key
+    assert_map_equal(gx, mr, h2)
