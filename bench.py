@@ -152,6 +152,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the map path has no CPU fallback")
+    # the root rank runs the genotype step (VCF text, ML-path verification on the host): it gets the host cores its
+    # sibling ranks do not need; must be set before the library creates its worker pool
+    os.environ.setdefault("DRPRG_THREADS", str(sharded.host_threads_for_rank(rank, world)))
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -185,6 +188,9 @@ def main():
         stats.setdefault("hits", []).append(nh)
         if world > 1:
             sharded.allreduce_accum(ix)  # the genotype step's first device->host copy is ordered after it on the same stream
+            if rank != 0:                # one VCF per sample: S6-S8 run on the root rank only
+                torch.cuda.current_stream().synchronize()
+                return None
         ix.genotype(wl.refs_path)
         for k_, v_ in ix.last_genotype_timings().items():
             stats.setdefault("gt_" + k_, []).append(v_)
@@ -244,7 +250,7 @@ def main():
     alg_bytes = n * (workload.STRIDE_WORDS * 4 + 4) + 16.0 * hits
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    vcf_text = bytes(vcf_text)
+    vcf_text = bytes(vcf_text) if vcf_text is not None else b""
     n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
     kept_cluster_reads = int(ix.coverage()["locus_reads"].sum())  # reads (clusters) that support a panel locus, all ranks
     h2d = int(h_words.numel() * 4 + h_lens.numel() * 4)

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <deque>
@@ -62,8 +63,15 @@ class WorkerPool {
 
   private:
     WorkerPool() {
+        // one process per GPU shares the host with its sibling ranks: the pool takes this rank's share of the cores
+        // (DRPRG_THREADS overrides; LOCAL_WORLD_SIZE is what torchrun sets), otherwise 8 ranks x 16 spinning threads
+        // would fight over the same cores
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned n = std::min(15u, hw > 1 ? hw - 1 : 0);
+        unsigned ranks = 1, budget = 0;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+        if (const char* e = getenv("DRPRG_THREADS")) budget = (unsigned)std::max(1, atoi(e));
+        if (!budget) budget = std::max(1u, hw / ranks);
+        const unsigned n = std::min(15u, budget > 1 ? budget - 1 : 0);
         for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
         for (auto& w : workers_) w.detach();
     }

@@ -1,7 +1,8 @@
 """Read-sharded multi-GPU driver (BASELINE config 3): one process per GPU, the index is
 replicated, each rank maps a contiguous shard of the reads, and the packed int32 accumulator
 [coverage | locus read counts | scalars] is summed in place with ONE allreduce (NCCL over NVLink via
-torch.distributed) before the replicated genotype step.  Integer sums => bit-exact for any world size."""
+torch.distributed) before the genotype step, which only the root rank has to run (one VCF per sample; SURVEY §8e:
+"S7/S8 on rank 0").  Integer sums => bit-exact for any world size."""
 from __future__ import annotations
 
 import numpy as np
@@ -41,6 +42,16 @@ def allreduce_accum(index, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def host_threads_for_rank(rank: int, world: int, cores: int | None = None) -> int:
+    """Host threads a rank's library pool should use (DRPRG_THREADS): the root rank formats the VCF and verifies the ML
+    paths, the others only feed their GPU, so the root gets what the sibling ranks do not need."""
+    import os
+    cores = cores or os.cpu_count() or 1
+    if world <= 1:
+        return cores
+    return max(2, cores - 2 * (world - 1)) if rank == 0 else 2
 
 
 def allreduce_accum_host(accum: np.ndarray, group=None) -> np.ndarray:

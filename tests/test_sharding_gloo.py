@@ -54,3 +54,10 @@ def test_shard_bounds_partition():
             b = [sharded.shard_bounds(n, g, r) for r in range(g)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+
+
+def test_host_threads_per_rank():
+    from drprg_b200 import sharded
+    assert sharded.host_threads_for_rank(0, 1, 16) == 16
+    assert sharded.host_threads_for_rank(0, 8, 32) == 18 and sharded.host_threads_for_rank(3, 8, 32) == 2
+    assert sharded.host_threads_for_rank(0, 8, 8) == 2
