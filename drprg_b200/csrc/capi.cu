@@ -166,6 +166,7 @@ struct drprg_index {
     bool sample_open = false;
     uint32_t first_read_len = 0;
     uint32_t* d_thresh = nullptr;
+    std::vector<uint32_t> thresh_on_device;
     // workspace
     DBuf<unsigned long long> hi, lo, hi2, lo2;
     DBuf<uint32_t> clist, clist2, cend, keys, keys2;
@@ -501,7 +502,10 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
         uint32_t lbt = (uint32_t)(std::min(X->H.loci[l].min_path_len, expected) * fraction);
         thr[l] = std::max(lbt, X->opts.min_cluster_size);
     }
-    if (!thr.empty()) CK(cudaMemcpy(X->d_thresh, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+    if (thr != X->thresh_on_device) {  // unchanged between the samples of a batch: skip the synchronous copy
+        if (!thr.empty()) CK(cudaMemcpy(X->d_thresh, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+        X->thresh_on_device = thr;
+    }
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
     X->total_bases = X->n_reads = 0;
     X->scalars_in_buffer = false;

@@ -164,6 +164,7 @@ def assert_genotype_equal(gx, ox, mr, oo, refs):
     np.testing.assert_allclose(gr["gt_conf"], orr["gt_conf"], rtol=1e-9, atol=1e-9)
     strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
     assert strip(gx.vcf()) == strip(og.vcf())
+    assert bytes(gx.vcf_view()) == gx.vcf_bytes()  # the zero-copy view is the same text
     return og
 
 
