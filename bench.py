@@ -26,8 +26,8 @@ import numpy as np
 
 # dram__bytes_read.sum + dram__bytes_write.sum of screen_kernel + resolve_kernel for one 1 M-read launch, and the pipe
 # utilisation of screen_kernel, from profiles/r1_screen.md (ncu --set full of this workload; constants, not measured live)
-NCU_TRAFFIC_BYTES = 81.3e6
-NCU_ISSUE = {"alu_pipe_active_pct": 64.5, "issue_active_pct": 65.9, "warp_instr_per_read": 75.6, "dram_read_mb_screen": 44.3,
+NCU_TRAFFIC_BYTES = 80.2e6
+NCU_ISSUE = {"alu_pipe_active_pct": 62.6, "issue_active_pct": 66.4, "warp_instr_per_read": 72.0, "dram_read_mb_screen": 44.3,
              "source": "profiles/r1_screen.md"}
 METRIC = "mapped reads/sec (pandora-map hot path: sketch+lookup+cluster+coverage+ML path+genotype)"
 UNIT = "reads/s"
@@ -275,7 +275,7 @@ def main():
                      "note": "the two kernels of the sketch+lookup stage carry all of the step's HBM traffic; kernel_ms is the CUDA-event time "
                              "around the pair on the launch stream. screen_kernel streams each read once (DRAM read = the input, see "
                              "profiles/) and is bound by the ALU pipe (shift/logic) and shared-memory bank conflicts of the Bloom probes "
-                             "(~70 warp-instructions per read), not by HBM; `traffic` is dram read+write of both kernels from the "
+                             "(~72 warp-instructions per read), not by HBM; `traffic` is dram read+write of both kernels from the "
                              "committed ncu capture (cold caches: resolve_kernel re-reads queue and words that are L2 hits in a real step). "
                              "The longest single launch of the step is mlpath_level_kernel (30 warps, a latency chain per locus, "
                              "stage_ms.gt_mlpath_kernel), which overlaps the genotype kernels and the VCF text. See DESIGN.md section 4."},
