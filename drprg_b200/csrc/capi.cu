@@ -301,14 +301,20 @@ void upload_index(drprg_index* X) {
         }
         std::sort(kmers.begin(), kmers.end());
         kmers.erase(std::unique(kmers.begin(), kmers.end()), kmers.end());
+        // The filter is capped by one SM's shared memory (1.77 Mbit).  Beyond ~300 k k-mers (4x the Mtb-scale panel) more
+        // than a third of its bits are set, over 10 % of all read positions are flagged and resolving them costs as much
+        // as sketching every read: such an index keeps the sketch kernels.
+        const bool screen_pays = kmers.size() <= 300000;
         // ~24 filter bits per k-mer, capped by the shared memory of one SM
         uint32_t nw = (uint32_t)std::min<uint64_t>(SCREEN_MAX_FILTER_WORDS, std::max<uint64_t>(1024, (kmers.size() * 24 + 31) / 32));
         nw = (nw + 3) & ~3u;
         std::vector<uint32_t> kfilter(nw, 0);
         for (uint32_t x : kmers) screen_filter_insert(kfilter.data(), nw, x, H.k);
-        X->d_kfilter = to_device(kfilter);
-        X->T.kfilter = X->d_kfilter;
-        X->T.kfilter_words = nw;
+        if (screen_pays) {
+            X->d_kfilter = to_device(kfilter);
+            X->T.kfilter = X->d_kfilter;
+            X->T.kfilter_words = nw;
+        }
     }
     // ---- k-mer graphs
     const uint32_t N = H.total_knodes();
