@@ -964,7 +964,8 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
     FileBatch F;
     static const bool host_only = getenv("DRPRG_HOST_INGEST") != nullptr && atoi(getenv("DRPRG_HOST_INGEST")) != 0;
     IngestResult I;
-    if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0)) {
+    const int dev = X->device;
+    if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); })) {
         std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
         B->owned = true;
         B->device = X->device;

@@ -14,8 +14,10 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -39,6 +41,7 @@ namespace {
     } while (0)
 
 constexpr size_t STAGE_BYTES = 32u << 20;
+double now_ms_i() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Staging {  // process-wide pinned double buffer + grow-only device text / scratch buffers (one ingest at a time)
     std::mutex m;
@@ -51,6 +54,8 @@ struct Staging {  // process-wide pinned double buffer + grow-only device text /
     size_t nl_cap = 0;
     void* d_temp = nullptr;
     size_t temp_cap = 0;
+    uint32_t* d_rec = nullptr;  // per record: sequence start | raw length | bad flag (3 x rec_cap)
+    size_t rec_cap = 0;
     unsigned long long* d_scalars = nullptr;  // [0] n newlines, [1] bad framing, [2] max len, [3] total bases, [4] dropped
     unsigned long long* h_scalars = nullptr;
     void ensure_host() {
@@ -80,13 +85,14 @@ struct Staging {  // process-wide pinned double buffer + grow-only device text /
         }
     }
     void release_device() {
-        for (void* p : {(void*)d_text, (void*)d_nl, d_temp, (void*)d_scalars})
+        for (void* p : {(void*)d_text, (void*)d_nl, d_temp, (void*)d_scalars, (void*)d_rec})
             if (p) cudaFree(p);
         d_text = nullptr;
         d_nl = nullptr;
         d_temp = nullptr;
         d_scalars = nullptr;
-        text_cap = nl_cap = temp_cap = 0;
+        d_rec = nullptr;
+        text_cap = nl_cap = temp_cap = rec_cap = 0;
     }
 } g_stage;
 
@@ -243,7 +249,8 @@ struct ByteSource {
 
 }  // namespace
 
-bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st) {
+bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
+                         const std::function<void*(size_t)>& alloc) {
     out = IngestResult();
     ByteSource src;
     src.fd = open(path.c_str(), O_RDONLY);
@@ -263,6 +270,8 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
     if (!is_gz && src.fsize >= 0xfff00000ull) return false;  // 32-bit text offsets
 
     std::lock_guard<std::mutex> lock(g_stage.m);
+    static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+    const double ti0 = now_ms_i();
     ICK(cudaSetDevice(device));
     g_stage.ensure_host();
     g_stage.ensure_device(device, is_gz ? std::max<size_t>(src.fsize * 4, 1u << 20) : src.fsize + 1);
@@ -284,6 +293,8 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
         total += n;
     }
     if (total == 0) return false;
+    if (timing) ICK(cudaStreamSynchronize(st));
+    const double ti1 = now_ms_i();
     // ---- newline offsets
     const char* text = g_stage.d_text;
     ICK(cudaMemsetAsync(g_stage.d_scalars, 0, 8 * sizeof(unsigned long long), st));
@@ -328,18 +339,24 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
         ICK(cudaStreamSynchronize(st));
         ++n_lines;
     }
+    const double ti2 = now_ms_i();
     if (n_lines == 0 || (n_lines & 3u)) return false;  // blank or wrapped lines: host parser
     const uint64_t n = n_lines / 4;
     if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
     // ---- records
-    uint32_t *d_start = nullptr, *d_rawlen = nullptr, *d_bad = nullptr;
-    ICK(cudaMalloc(&d_start, n * 4));
-    ICK(cudaMalloc(&d_rawlen, n * 4));
-    ICK(cudaMalloc(&d_bad, n * 4));
-    auto cleanup = [&]() {
-        cudaFree(d_start);
-        cudaFree(d_rawlen);
-        cudaFree(d_bad);
+    if (n > g_stage.rec_cap) {  // grow-only scratch: cudaMalloc / cudaFree per sample cost more than the kernels
+        if (g_stage.d_rec) cudaFree(g_stage.d_rec);
+        g_stage.d_rec = nullptr;
+        g_stage.rec_cap = n + n / 8 + 1024;
+        ICK(cudaMalloc(&g_stage.d_rec, g_stage.rec_cap * 3 * sizeof(uint32_t)));
+    }
+    uint32_t *d_start = g_stage.d_rec, *d_rawlen = g_stage.d_rec + g_stage.rec_cap, *d_bad = g_stage.d_rec + 2 * g_stage.rec_cap;
+    auto cleanup = [&]() {};
+    auto dev_alloc = [&](size_t bytes) -> void* {
+        if (alloc) return alloc(bytes);
+        void* p = nullptr;
+        ICK(cudaMalloc(&p, bytes));
+        return p;
     };
     try {
         ICK(cudaMemsetAsync(d_bad, 0, n * 4, st));
@@ -358,18 +375,18 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
         out.first_read_len = first_len;
         out.n_reads = n;
         out.b_lens = std::max<uint64_t>(1, n) * 4;
-        ICK(cudaMalloc(&out.d_lens, out.b_lens));
+        out.d_lens = (uint32_t*)dev_alloc(out.b_lens);
         if (out.max_len <= SHORT_READ_MAX) {
             uint32_t stride = std::max(1u, (out.max_len + 15) / 16);
             stride += stride & 1u;  // even: every read starts 8-byte aligned (wide loads in the screen kernel)
             out.stride_words = stride;
             out.b_words = (n * (uint64_t)stride + 2) * 4;
-            ICK(cudaMalloc(&out.d_words, out.b_words));
+            out.d_words = (uint32_t*)dev_alloc(out.b_words);
             const uint64_t items = n * (uint64_t)stride;
             pack_stride_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n, stride, out.d_words, d_bad);
         } else {
             out.b_off = (n + 1) * 8;
-            ICK(cudaMalloc(&out.d_word_off, out.b_off));
+            out.d_word_off = (uint64_t*)dev_alloc(out.b_off);
             unsigned long long* d_nw = nullptr;
             ICK(cudaMalloc(&d_nw, (n + 1) * 8));
             ICK(cudaMemsetAsync(d_nw + n, 0, 8, st));
@@ -383,7 +400,7 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
             ICK(cudaStreamSynchronize(st));
             cudaFree(d_nw);
             out.b_words = (total_words + 2) * 4;
-            ICK(cudaMalloc(&out.d_words, out.b_words));
+            out.d_words = (uint32_t*)dev_alloc(out.b_words);
             pack_ragged_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n,
                                                                                 (const unsigned long long*)out.d_word_off, out.d_words, d_bad);
         }
@@ -400,6 +417,9 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
         throw;
     }
     cleanup();
+    if (timing)
+        fprintf(stderr, "[drprg-cuda] ingest: %.1f MB text, read+H2D %.2f ms, newline scan %.2f ms, records+pack %.2f ms\n", total / 1e6,
+                ti1 - ti0, ti2 - ti1, now_ms_i() - ti2);
     return true;
 }
 

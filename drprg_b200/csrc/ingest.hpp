@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <string>
 
 namespace drprg {
@@ -17,6 +18,8 @@ struct IngestResult {  // device buffers from cudaMalloc, owned by the caller
 };
 
 // false: the input is not strict 4-line FASTQ below 4 GiB of text (the caller uses the host parser); throws on IO errors
-bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st);
+// `alloc` supplies the output buffers (e.g. from the caller's buffer pool); default: cudaMalloc
+bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
+                         const std::function<void*(size_t)>& alloc = nullptr);
 
 }  // namespace drprg
