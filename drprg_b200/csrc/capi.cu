@@ -12,6 +12,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -958,14 +959,35 @@ struct FileBatch {
     uint32_t first_read_len = 0;
     bool on_device = false;
 };
-FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threads) {
+struct Inflated {  // a gzip reads file inflated ahead of time (batch mode)
+    char* p = nullptr;
+    size_t n = 0;
+    std::string error;
+    Inflated() = default;
+    Inflated(const Inflated&) = delete;
+    Inflated(Inflated&& o) noexcept : p(o.p), n(o.n), error(std::move(o.error)) { o.p = nullptr; }
+    Inflated& operator=(Inflated&& o) noexcept {
+        if (this != &o) {
+            free(p);
+            p = o.p;
+            n = o.n;
+            error = std::move(o.error);
+            o.p = nullptr;
+        }
+        return *this;
+    }
+    ~Inflated() { free(p); }
+};
+
+FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threads, const Inflated* pre = nullptr) {
     need_device(X);
     CK(cudaSetDevice(X->device));
     FileBatch F;
     static const bool host_only = getenv("DRPRG_HOST_INGEST") != nullptr && atoi(getenv("DRPRG_HOST_INGEST")) != 0;
     IngestResult I;
     const int dev = X->device;
-    if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); })) {
+    if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); },
+                                          pre ? pre->p : nullptr, pre ? pre->n : 0)) {
         std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
         B->owned = true;
         B->device = X->device;
@@ -1001,11 +1023,11 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
 }
 
 int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir, const drprg_map_opts* o,
-               drprg_map_stats* stats) {
+               drprg_map_stats* stats, const Inflated* pre = nullptr) {
     need_device(X);
     const double t0 = now_ms();
     std::ofstream log(std::string(outdir) + "/pandora.log");
-    FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1);
+    FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1, pre);
     std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(F.B, free_batch);
     struct {
         uint64_t n_dropped, total_bases;
@@ -1081,7 +1103,32 @@ int drprg_cuda_map_genotype(drprg_index* X, const char* reads_path, const char* 
 }
 int drprg_cuda_map_genotype_batch(drprg_index* X, size_t n, const char* const* reads_paths, const char* vcf_refs,
                                   const char* const* outdirs, const drprg_map_opts* o, drprg_map_stats* stats) {
-    API_BEGIN for (size_t i = 0; i < n; ++i) run_sample(X, reads_paths[i], vcf_refs, outdirs[i], o, stats ? stats + i : nullptr);
+    API_BEGIN
+    // gzip inputs are inflate-bound (one zlib stream = one core, ~0.6 s per million reads): the next few samples are
+    // inflated on spare threads while the GPU works on the current one
+    const size_t window = std::max<size_t>(1, std::min<size_t>({n, (size_t)(o && o->threads ? o->threads : 1), (size_t)8}));
+    std::vector<std::future<Inflated>> ahead(n);
+    auto prefetch = [&](size_t i) {
+        if (i >= n || !file_is_gzip(reads_paths[i])) return;
+        const std::string path = reads_paths[i];
+        ahead[i] = std::async(std::launch::async, [path]() {
+            Inflated r;
+            try {
+                inflate_file(path, &r.p, &r.n);
+            } catch (const std::exception& e) {
+                r.error = e.what();
+            }
+            return r;
+        });
+    };
+    for (size_t i = 0; i < window; ++i) prefetch(i);
+    for (size_t i = 0; i < n; ++i) {
+        Inflated pre;
+        if (ahead[i].valid()) pre = ahead[i].get();
+        prefetch(i + window);
+        if (!pre.error.empty()) throw std::runtime_error(pre.error);
+        run_sample(X, reads_paths[i], vcf_refs, outdirs[i], o, stats ? stats + i : nullptr, pre.p ? &pre : nullptr);
+    }
     return 0;
     API_END
 }

@@ -860,6 +860,25 @@ void slurp(const std::string& path, RawText& buf) {
     buf.n = n;
 }
 
+}  // namespace
+// whole file inflated into one malloc'ed buffer (the batch driver runs this ahead of the GPU on spare threads)
+bool inflate_file(const std::string& path, char** out, size_t* n) {
+    RawText buf;
+    slurp(path, buf);
+    *out = buf.p;
+    *n = buf.n;
+    buf.p = nullptr;
+    return true;
+}
+bool file_is_gzip(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    unsigned char m[2] = {0, 0};
+    const size_t got = fread(m, 1, 2, fp);
+    fclose(fp);
+    return got == 2 && m[0] == 0x1f && m[1] == 0x8b;
+}
+namespace {
 struct Piece {
     std::vector<uint32_t> words, lens;
     std::vector<uint32_t> nwords;  // per read

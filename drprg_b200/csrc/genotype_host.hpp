@@ -97,6 +97,8 @@ struct PackedReads {
     uint32_t first_read_len = 0;
 };
 void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& out);
+bool inflate_file(const std::string& path, char** out, size_t* n);  // malloc'ed; caller frees
+bool file_is_gzip(const std::string& path);
 int64_t pack_ascii(const uint8_t* ascii, const uint64_t* off, uint64_t n, uint32_t stride_words, uint32_t* words,
                    uint64_t words_cap, uint64_t* word_off, uint32_t* lens);
 

@@ -200,6 +200,7 @@ __global__ void finish_lens_kernel(const uint32_t* __restrict__ raw_len, const u
 struct ByteSource {
     int fd = -1;
     gzFile gz = nullptr;
+    const char* mem = nullptr;  // text already in host memory (a gzip file inflated ahead of time by the batch driver)
     size_t fsize = 0, pos = 0;
     bool eof = false;
     ~ByteSource() {
@@ -232,6 +233,10 @@ struct ByteSource {
         parallel_for(T, [&](size_t t) {
             const size_t lo = want * t / T, hi = want * (t + 1) / T;
             size_t done = 0;
+            if (mem) {
+                memcpy(buf + lo, mem + pos + lo, hi - lo);
+                done = hi - lo;
+            }
             while (lo + done < hi) {
                 const ssize_t r = pread(fd, buf + lo + done, hi - lo - done, (off_t)(pos + lo + done));
                 if (r <= 0) break;
@@ -250,15 +255,23 @@ struct ByteSource {
 }  // namespace
 
 bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
-                         const std::function<void*(size_t)>& alloc) {
+                         const std::function<void*(size_t)>& alloc, const char* mem, size_t mem_size) {
     out = IngestResult();
     ByteSource src;
-    src.fd = open(path.c_str(), O_RDONLY);
-    if (src.fd < 0) throw std::runtime_error("cannot open " + path);
     unsigned char magic[2] = {0, 0};
-    const ssize_t got = pread(src.fd, magic, 2, 0);
-    src.fsize = (size_t)lseek(src.fd, 0, SEEK_END);
-    const bool is_gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    ssize_t got = 0;
+    if (mem) {
+        src.mem = mem;
+        src.fsize = mem_size;
+        got = (ssize_t)std::min<size_t>(2, mem_size);
+        memcpy(magic, mem, (size_t)got);
+    } else {
+        src.fd = open(path.c_str(), O_RDONLY);
+        if (src.fd < 0) throw std::runtime_error("cannot open " + path);
+        got = pread(src.fd, magic, 2, 0);
+        src.fsize = (size_t)lseek(src.fd, 0, SEEK_END);
+    }
+    const bool is_gz = !mem && got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     if (is_gz) {
         lseek(src.fd, 0, SEEK_SET);
         src.gz = gzdopen(src.fd, "rb");

@@ -18,8 +18,9 @@ struct IngestResult {  // device buffers from cudaMalloc, owned by the caller
 };
 
 // false: the input is not strict 4-line FASTQ below 4 GiB of text (the caller uses the host parser); throws on IO errors
-// `alloc` supplies the output buffers (e.g. from the caller's buffer pool); default: cudaMalloc
+// `alloc` supplies the output buffers (e.g. from the caller's buffer pool); default: cudaMalloc.  With `mem` the text is
+// taken from host memory instead of the file (a gzip file inflated ahead of time).
 bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
-                         const std::function<void*(size_t)>& alloc = nullptr);
+                         const std::function<void*(size_t)>& alloc = nullptr, const char* mem = nullptr, size_t mem_size = 0);
 
 }  // namespace drprg

@@ -260,12 +260,12 @@ def test_batch_of_samples_config5(tmp_path):
     import ctypes as C
     p, prg, refs = small_panel()
     gx, ox = both_indexes(prg, 11, 15)
-    n_samples = 3
+    n_samples = 4
     reads, outs, datas = [], [], []
     for s in range(n_samples):
         d, o, g, pl = panel_sample(p, 20000, seed=100 + 7 * s)
-        fq = tmp_path / f"s{s}.fq"
-        sim.write_fastq(str(fq), d, o)
+        fq = tmp_path / (f"s{s}.fq.gz" if s % 2 else f"s{s}.fq")  # gzip samples are inflated ahead of time on spare threads
+        sim.write_fastq(str(fq), d, o, gz=bool(s % 2))
         od = tmp_path / f"out{s}"
         od.mkdir()
         reads.append(str(fq).encode()); outs.append(str(od).encode()); datas.append((d, o, len(g)))
@@ -273,7 +273,7 @@ def test_batch_of_samples_config5(tmp_path):
     arr_r = (C.c_char_p * n_samples)(*reads)
     arr_o = (C.c_char_p * n_samples)(*outs)
     stats = (lib.MapStats * n_samples)()
-    go = lib.make_opts(illumina=True, genome_size=200_000)
+    go = lib.make_opts(illumina=True, genome_size=200_000, threads=4)
     rc = L.drprg_cuda_map_genotype_batch(gx.h, C.c_size_t(n_samples), arr_r, refs.encode(), arr_o, C.byref(go), stats)
     assert rc == 0, L.drprg_cuda_last_error()
     strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
