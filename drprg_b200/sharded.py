@@ -13,6 +13,12 @@ def shard_bounds(n_reads: int, world: int, rank: int):
     return n_reads * rank // world, n_reads * (rank + 1) // world
 
 
+def sample_shard(items, world: int, rank: int):
+    """Batch mode (BASELINE config 5): samples are independent, rank r takes samples r, r + G, r + 2G, ... — replicas
+    only, no collective (each rank calls drprg_cuda_map_genotype_batch on its share)."""
+    return list(items)[rank::world]
+
+
 def encode_scalars(total_bases: int, n_reads: int):
     """lo24/hi split keeps every int32 partial sum in range for any realistic shard count."""
     return np.array([total_bases & 0xFFFFFF, total_bases >> 24, n_reads & 0xFFFFFF, n_reads >> 24], np.int32)

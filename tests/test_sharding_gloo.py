@@ -61,3 +61,12 @@ def test_host_threads_per_rank():
     assert sharded.host_threads_for_rank(0, 1, 16) == 16
     assert sharded.host_threads_for_rank(0, 8, 32) == 18 and sharded.host_threads_for_rank(3, 8, 32) == 2
     assert sharded.host_threads_for_rank(0, 8, 8) == 2
+
+
+def test_sample_shard_covers_every_sample_once():
+    from drprg_b200 import sharded
+    items = [f"s{i}.fq.gz" for i in range(96)]
+    for g in (1, 2, 4, 8):
+        parts = [sharded.sample_shard(items, g, r) for r in range(g)]
+        assert sorted(sum(parts, [])) == sorted(items)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
