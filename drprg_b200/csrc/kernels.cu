@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1) screen_kernel(DevReads R, D
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_kf);
     const unsigned long long n_items = R.seg_read ? R.n_segs : R.n_reads;
     const unsigned long long n_tiles = (n_items + 31) / 32;
-    const bool wide = R.stride_words && !(R.stride_words & 1u) && !R.seg_read;  // every read starts 8-byte aligned
+    const bool wide = R.stride_words && !(R.stride_words & 1u) && !R.seg_read &&
+                      (reinterpret_cast<unsigned long long>(R.words) & 7ull) == 0ull;  // every read starts 8-byte aligned
     // tickets are drawn two tiles ahead: the next tile's id is known when a tile starts, so its words can be
     // prefetched into L2 while this tile is screened (a cold read otherwise costs the full HBM latency per tile)
     unsigned long long tile = 0, next_tile = 0;
