@@ -89,7 +89,11 @@ class WorkerPool {
         while (true) {
             // the parallel sections of one sample follow each other within ~0.1 ms: spin briefly before sleeping, a futex
             // wake-up of 15 threads costs more than the work of a section
-            for (int spin = 0; spin < 4000 && gen_hint_.load(std::memory_order_acquire) == seen; ++spin) {
+            static const int spin_max = [] {
+                const char* e = getenv("DRPRG_SPIN");
+                return e ? atoi(e) : 4000;
+            }();
+            for (int spin = 0; spin < spin_max && gen_hint_.load(std::memory_order_acquire) == seen; ++spin) {
 #if defined(__x86_64__)
                 __builtin_ia32_pause();
 #endif
