@@ -667,7 +667,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     if (any_present) X->fit.thresh = prob_threshold(hist);
     MP.thresh = (double)X->fit.thresh;
     lap(1);
-    // ---- S7 on the device: the ML-path kernel is a serial chain per locus (~1 ms).  It only decides which loci
+    // ---- S7 on the device: the ML-path kernel is a latency chain per locus (~0.4 ms).  It only decides which loci
     // are reported and whether the path spells alleles the site tables lack (rare), so it runs on its own stream
     // while S8 (per-allele statistics + likelihoods) and the VCF text are produced SPECULATIVELY for the common
     // outcome "every locus with reads is present, no extra records"; the outcome is verified afterwards and

@@ -1940,7 +1940,8 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
     }
     // The run-parallel kernel pays ~1.5k cycles of per-unit overhead (warp syncs, ~50 loads per lane): it wins when
     // runs of single-successor nodes are long (sparse panels) and loses on bubble-dense graphs (the benchmark panel:
-    // 32 % of the nodes have a choice, mean run 2.6 nodes: 1.23 ms vs 0.78 ms), so it is chosen by run length.
+    // 32 % of the nodes have a choice, mean run 2.6 nodes: 1.23 ms vs 0.78 ms for the chain kernel), so among the older
+    // kernels it is chosen by run length; the level-parallel kernel above is the default.
     static const char* force_units = getenv("DRPRG_MLPATH_UNITS");
     const bool want_units = force_units ? atoi(force_units) != 0 : mean_run_len >= 8.0f;
     if (want_units) {
