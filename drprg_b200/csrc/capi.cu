@@ -162,6 +162,7 @@ struct drprg_index {
     uint64_t n_accum = 0;
     uint64_t total_bases = 0, n_reads = 0;
     bool scalars_in_buffer = false;
+    bool hist_on_host = false;  // h_small holds the coverage histogram + locus read counts of the current accumulators
     // sample state
     SampleOpts opts;
     bool sample_open = false;
@@ -516,6 +517,7 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
     X->total_bases = X->n_reads = 0;
     X->scalars_in_buffer = false;
+    X->hist_on_host = false;
     X->sample_open = true;
     X->have_gt = false;
 }
@@ -586,8 +588,18 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
                     X->d_accum, X->d_counters + 1, st);
     CK(cudaEventRecord(X->ev[4], st));
     CK(cudaGetLastError());
+    {   // what the genotype step needs first (coverage histogram, locus read counts: 4 KB) rides on this batch's final
+        // synchronisation; it stays valid unless the accumulators change before drprg_cuda_genotype (another batch
+        // recomputes it, an allreduce through accum_device_ptr invalidates it)
+        const uint32_t N = H.total_knodes(), P = (uint32_t)H.loci.size();
+        launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
+        X->h_small.resize(1000 + (size_t)P + 4);
+        CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaMemcpyAsync(X->h_counters + 1, X->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    X->hist_on_host = true;
     for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&X->timings[i], X->ev[i], X->ev[i == 0 ? 5 : i + 1]));
     X->last_n_hits = nh;
     X->total_bases += B->total_bases;
@@ -617,7 +629,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         X->gt_ms[i] = t - t0;
         t0 = t;
     };
-    flush_scalars(X);
+    const bool reuse_hist = X->hist_on_host;  // downloaded at the end of the last map_batch, accumulators untouched since
+    if (!reuse_hist) flush_scalars(X);
     if (!X->st_ml) {
         CK(cudaStreamCreateWithFlags(&X->st_ml, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&X->st_gt, cudaStreamNonBlocking));
@@ -634,15 +647,18 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     CK(cudaStreamWaitEvent(X->st_acc, X->ev_acc[0], 0));
     CK(cudaMemcpyAsync(X->h_acc.data(), X->d_accum, X->n_accum * 4, cudaMemcpyDeviceToHost, X->st_acc));
     CK(cudaEventRecord(X->ev_acc[1], X->st_acc));
-    launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
-    X->h_small.resize(1000 + (size_t)P + 4);
-    CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, ((size_t)P + 4) * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    uint64_t total_bases = X->total_bases;  // this process's batches; after an allreduce the summed scalars are read back
+    if (!reuse_hist) {
+        launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
+        X->h_small.resize(1000 + (size_t)P + 4);
+        CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, ((size_t)P + 4) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int32_t* sc = (const int32_t*)(X->h_small.data() + 1000) + P;
+        total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
+    }
     const int32_t* cov = X->h_acc.data();  // valid after ev_acc[1]
     const int32_t* locus_reads = (const int32_t*)(X->h_small.data() + 1000);
-    const int32_t* sc = locus_reads + P;
-    const uint64_t total_bases = (uint64_t)(uint32_t)sc[0] + ((uint64_t)(uint32_t)sc[1] << 24);
     lap(0);
     // ---- S6: moments / model choice on the host, histograms on the device
     X->fit = fit_parameters_hist(H, X->h_small.data(), locus_reads, total_bases, X->opts);
@@ -1206,6 +1222,7 @@ int drprg_cuda_accum_device_ptr(drprg_index* X, void** d_ptr, uint64_t* n_int32)
     API_BEGIN need_device(X);
     CK(cudaSetDevice(X->device));
     flush_scalars(X);
+    X->hist_on_host = false;  // the caller may change the accumulators (allreduce)
     *d_ptr = X->d_accum;
     *n_int32 = X->n_accum;
     return 0;
@@ -1225,6 +1242,7 @@ int drprg_cuda_accum_upload(drprg_index* X, const int32_t* in, uint64_t n) {
     if (n != X->n_accum) throw std::runtime_error("accumulator size mismatch");
     CK(cudaSetDevice(X->device));
     CK(cudaMemcpy(X->d_accum, in, n * 4, cudaMemcpyHostToDevice));
+    X->hist_on_host = false;
     X->scalars_in_buffer = true;
     return 0;
     API_END
