@@ -207,7 +207,7 @@ struct drprg_index {
     cudaEvent_t ev_acc[2] = {nullptr, nullptr};
     uint32_t* d_hist1000 = nullptr;
     PinnedBuf<uint32_t> h_small;  // coverage histogram | locus read counts | scalars  // ML-path kernel / genotype kernels run concurrently
-    PinnedBuf<uint32_t> h_path, h_plen, h_u32;
+    PinnedBuf<uint32_t> h_path, h_plen, h_u32, h_done;
     PinnedBuf<double> h_f64;
     PinnedBuf<int32_t> h_gt, h_acc;
     double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -232,7 +232,7 @@ struct drprg_index {
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
-        h_path.release(); h_plen.release(); h_u32.release(); h_f64.release(); h_gt.release(); h_acc.release();
+        h_path.release(); h_plen.release(); h_u32.release(); h_done.release(); h_f64.release(); h_gt.release(); h_acc.release();
         for (auto& e : ev_ml)
             if (e) cudaEventDestroy(e);
         if (st_copy) cudaStreamDestroy(st_copy);
@@ -692,18 +692,26 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         CK(cudaEventCreate(&X->ev_ml[0]));
         CK(cudaEventCreate(&X->ev_ml[1]));
     }
-    CK(cudaMemsetAsync(X->d_path.p, 0, (size_t)N * 4, X->st_ml));  // absent loci leave their slice unwritten
-    CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
-    launch_mlpath(P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p,
-                  X->d_len.p, X->d_up.p, N, X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges,
-                  X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start, X->d_unit_nodes, X->mean_run_len, X->st_ml,
-                  X->d_locus_level_off, X->d_level_start, X->d_level_nodes, X->d_level_singles);
-    CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
-    CK(cudaGetLastError());
     X->h_path.resize(N);
     X->h_plen.resize(P);
-    CK(cudaMemcpyAsync(X->h_path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost, X->st_ml));
-    CK(cudaMemcpyAsync(X->h_plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost, X->st_ml));
+    X->h_done.resize(P);
+    std::fill(X->h_done.begin(), X->h_done.end(), 0u);
+    CK(cudaMemsetAsync(X->d_path.p, 0, (size_t)N * 4, X->st_ml));  // absent loci leave their slice unwritten
+    CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
+    // The level-parallel kernel writes every locus's path straight into pinned host memory (UVA: the same pointers
+    // are valid on the device) and raises a per-locus flag, so the host can verify the small loci while the big ones
+    // are still running; the older kernels leave the paths in device memory and are copied back as a whole.
+    const bool ml_streamed = launch_mlpath(
+        P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p, X->d_len.p, X->d_up.p, N,
+        X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges, X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start,
+        X->d_unit_nodes, X->mean_run_len, X->st_ml, X->d_locus_level_off, X->d_level_start, X->d_level_nodes, X->d_level_singles,
+        X->h_path.data(), X->h_plen.data(), X->h_done.data());
+    CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
+    CK(cudaGetLastError());
+    if (!ml_streamed) {
+        CK(cudaMemcpyAsync(X->h_path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost, X->st_ml));
+        CK(cudaMemcpyAsync(X->h_plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost, X->st_ml));
+    }
     // ---- reference paths / site tables (read independent, cached per --vcf-refs file)
     const std::string rp = vcf_refs ? vcf_refs : "";
     if (rp != X->refs_path) {
@@ -804,16 +812,28 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     lap(3);
     // ---- verify the speculation against the ML paths
     const double tw0 = now_ms();
-    CK(cudaStreamSynchronize(X->st_ml));
+    if (!ml_streamed) CK(cudaStreamSynchronize(X->st_ml));
     CK(cudaEventSynchronize(X->ev_acc[1]));  // the full accumulator is on the host from here on
     const double tw1 = now_ms();
-    {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, X->ev_ml[0], X->ev_ml[1]));
-        X->gt_ms[6] = ms;  // device time of the ML-path kernel (overlapped with S8 + VCF text on the host)
-    }
     const uint32_t* path = X->h_path.data();
     const uint32_t* plen = X->h_plen.data();
+    const volatile uint32_t* done = X->h_done.data();
+    std::atomic<bool> ml_failed{false};
+    auto wait_for_locus = [&](uint32_t l) {  // streamed mode: spin until the kernel has published locus l
+        if (!ml_streamed) return true;
+        for (uint64_t spin = 0; done[l] == 0u; ++spin) {
+            if (ml_failed.load(std::memory_order_relaxed)) return false;
+            if ((spin & 0xffffu) == 0xffffu && cudaStreamQuery(X->st_ml) != cudaErrorNotReady && done[l] == 0u) {
+                ml_failed = true;  // the stream ended (or failed) without publishing: never spin forever
+                return false;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return true;
+    };
     X->mlpaths.assign(P, {});
     X->present.assign(P, 0);
     struct LocusOut {
@@ -824,8 +844,10 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     };
     std::vector<LocusOut> lout(P);
     parallel_for(P, [&](size_t li) {
-        const uint32_t l = X->loci_by_size[li];  // biggest first: the pool hands loci out in order
-        if (locus_reads[l] <= 0 || plen[l] == 0xffffffffu || plen[l] == 0) return;
+        // the pool hands loci out in order: biggest first when all paths are already there; smallest first when they are
+        // streamed (small loci finish first, and only the biggest one's check is left when the kernel ends)
+        const uint32_t l = ml_streamed ? X->loci_by_size[P - 1 - li] : X->loci_by_size[li];
+        if (locus_reads[l] <= 0 || !wait_for_locus(l) || plen[l] == 0xffffffffu || plen[l] == 0) return;
         const Locus& L = H.loci[l];
         LocusOut& O = lout[l];
         O.kp.assign(path + H.knode_base[l], path + H.knode_base[l] + plen[l]);
@@ -842,6 +864,13 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             O.use_cached = false;
         }
     }, 16);
+    CK(cudaStreamSynchronize(X->st_ml));
+    if (ml_failed.load()) throw std::runtime_error("the ML-path kernel ended without publishing every locus");
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, X->ev_ml[0], X->ev_ml[1]));
+        X->gt_ms[6] = ms;  // device time of the ML-path kernel (overlapped with S8 + VCF text on the host)
+    }
     bool speculation_ok = true;
     for (uint32_t l = 0; l < P; ++l) {
         if (lout[l].present) {

@@ -1795,14 +1795,21 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
     const uint32_t* __restrict__ edges, const double* __restrict__ prob, const int32_t* __restrict__ locus_reads,
     const uint8_t* __restrict__ needs_mean, MlUnitsDev L, const uint32_t* __restrict__ level_singles, ModelParams P,
-    uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t max_nodes, uint32_t max_edges) {
+    uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t max_nodes, uint32_t max_edges,
+    volatile uint32_t* done) {  // done != nullptr: path / path_len are host-mapped and done[l] tells the host that locus l is there
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t base = knode_base[l], n = knode_base[l + 1] - base;
     if (locus_reads[l] <= 0 || n < 2) {
-        if (tid == 0) path_len[l] = 0xffffffffu;
+        if (tid == 0) {
+            path_len[l] = 0xffffffffu;
+            if (done) {
+                __threadfence_system();
+                done[l] = 1u;
+            }
+        }
         return;
     }
     const uint32_t e_base = edge_off[base], n_edges = edge_off[base + n] - e_base;
@@ -1905,17 +1912,22 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
             p = lds32(p + R_UP);
         }
         path_len[l] = cnt;
+        if (done) {  // the loci finish at different times (170 .. 860 levels): the host verifies each one as it lands
+            __threadfence_system();
+            done[l] = 1u;
+        }
     }
 }
 
-void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
+bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
                    uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean,
                    const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes,
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off, const uint32_t* d_level_start,
-                   const uint32_t* d_level_nodes, const uint32_t* d_level_singles) {
-    if (!n_loci) return;
+                   const uint32_t* d_level_nodes, const uint32_t* d_level_singles, uint32_t* h_path, uint32_t* h_path_len,
+                   uint32_t* h_done) {
+    if (!n_loci) return false;
     {   // default: level-parallel kernel (any of the older switches selects the older kernels)
         static const bool levels_on = [] {
             const char* e = getenv("DRPRG_MLPATH_LEVELS");
@@ -1931,11 +1943,13 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
             }
             MlUnitsDev L{d_locus_level_off, d_level_start, d_level_nodes};
             upload_rcp_table();
-            mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob,
-                                                                            d_locus_reads, d_needs_mean, L, d_level_singles, P, d_path,
-                                                                            d_path_len, max_locus_knodes, max_locus_edges);
+            const bool streamed = h_path && h_path_len && h_done;  // results straight into host-mapped memory, locus by locus
+            mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(
+                n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, d_needs_mean, L, d_level_singles, P,
+                streamed ? h_path : d_path, streamed ? h_path_len : d_path_len, max_locus_knodes, max_locus_edges,
+                streamed ? h_done : nullptr);
             ++g_launches;
-            return;
+            return streamed;
         }
     }
     // The run-parallel kernel pays ~1.5k cycles of per-unit overhead (warp syncs, ~50 loads per lane): it wins when
@@ -1958,7 +1972,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                                                              d_needs_mean, U, P, d_path, d_path_len, max_locus_knodes,
                                                              max_locus_edges);
             ++g_launches;
-            return;
+            return false;
         }
     }
     // shared memory: per k-mer node sum, mean, score (f64), length, LV lifting pointers, edge offset (u32);
@@ -1986,7 +2000,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
             mlpath_rec_kernel<<<n_loci, 32, rec_smem, st>>>(n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads,
                                                            d_needs_mean, P, d_path, d_path_len, max_locus_knodes);
             ++g_launches;
-            return;
+            return false;
         }
     }
     auto go = [&](auto kernel) {
@@ -2000,6 +2014,7 @@ void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
         default: go(mlpath_kernel<LV_MAX>); break;
     }
     ++g_launches;
+    return false;
 }
 
 // ============================================================================================

@@ -91,14 +91,17 @@ void launch_coverage(const unsigned long long* hi, const unsigned long long* lo,
 // S7: per-node log-probabilities then one warp per locus for the ML-path DP
 void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t* d_is_terminal, ModelParams P,
                       double* d_prob, cudaStream_t st);
-void launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
+// returns true when the results are streamed into the host-mapped h_path / h_path_len with per-locus h_done flags
+// (level-parallel kernel); otherwise they are in d_path / d_path_len when the stream has finished
+bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t* d_edge_off, const uint32_t* d_edges,
                    const double* d_prob, const int32_t* d_locus_reads, ModelParams P, double* d_M, uint32_t* d_len,
                    uint32_t* d_up, uint32_t total_knodes, uint32_t* d_path, uint32_t* d_path_len,
                    uint32_t max_locus_knodes, uint32_t max_locus_edges, const uint8_t* d_needs_mean,
                    const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes,
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off = nullptr,
                    const uint32_t* d_level_start = nullptr, const uint32_t* d_level_nodes = nullptr,
-                   const uint32_t* d_level_singles = nullptr);
+                   const uint32_t* d_level_singles = nullptr, uint32_t* h_path = nullptr, uint32_t* h_path_len = nullptr,
+                   uint32_t* h_done = nullptr);
 void launch_cov_hist(const int32_t* d_cov, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
                      const int32_t* d_locus_reads, uint32_t* d_hist1000, cudaStream_t st);
 void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
