@@ -204,7 +204,10 @@ struct drprg_index {
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     cudaEvent_t ev_ml[2] = {nullptr, nullptr};
     cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr, st_acc = nullptr;
-    cudaEvent_t ev_acc[2] = {nullptr, nullptr};
+    cudaEvent_t ev_acc[3] = {nullptr, nullptr, nullptr};  // [2]: node scores + threshold ready on `st`
+    double* d_thresh_f64 = nullptr;
+    int* d_thresh_i32 = nullptr;
+    PinnedBuf<int> h_thresh;
     uint32_t* d_hist1000 = nullptr;
     PinnedBuf<uint32_t> h_small;  // coverage histogram | locus read counts | scalars  // ML-path kernel / genotype kernels run concurrently
     PinnedBuf<uint32_t> h_path, h_plen, h_u32, h_done;
@@ -240,6 +243,9 @@ struct drprg_index {
         for (auto& e : ev_acc)
             if (e) cudaEventDestroy(e);
         if (d_hist1000) cudaFree(d_hist1000);
+        if (d_thresh_f64) cudaFree(d_thresh_f64);
+        if (d_thresh_i32) cudaFree(d_thresh_i32);
+        h_thresh.release();
         h_small.release();
         if (st_ml) cudaStreamDestroy(st_ml);
         if (st_gt) cudaStreamDestroy(st_gt);
@@ -637,6 +643,9 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         CK(cudaStreamCreateWithFlags(&X->st_acc, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&X->ev_acc[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&X->ev_acc[1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&X->ev_acc[2], cudaEventDisableTiming));
+        CK(cudaMalloc(&X->d_thresh_f64, sizeof(double)));
+        CK(cudaMalloc(&X->d_thresh_i32, sizeof(int)));
     }
     // On the critical path the host only needs the 1000-bin coverage histogram (built on the device), the locus read
     // counts and the scalars: 4 KB.  The full accumulator (0.3 MB, pinned destination) is needed when the ML paths are
@@ -676,12 +685,15 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     X->d_up.ensure((size_t)N * LV_MAX); X->d_path.ensure(N); X->d_path_len.ensure(P);
     launch_node_prob(X->d_accum, N, X->d_is_terminal, MP, X->d_prob.p, st);
     launch_prob_hist(X->d_prob.p, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist, st);
-    uint32_t hist[200];
-    CK(cudaMemcpy(hist, X->d_hist, sizeof hist, cudaMemcpyDeviceToHost));
     bool any_present = false;
     for (uint32_t l = 0; l < P; ++l) any_present = any_present || locus_reads[l] > 0;
-    if (any_present) X->fit.thresh = prob_threshold(hist);
-    MP.thresh = (double)X->fit.thresh;
+    // the threshold (valley of the 200-bin histogram) is found on the device too: the ML-path kernel reads it from
+    // device memory and starts without a host round trip; the host picks the value up later
+    launch_prob_thresh(X->d_hist, any_present, X->fit.thresh, X->d_thresh_f64, X->d_thresh_i32, st);
+    X->h_thresh.resize(1);
+    CK(cudaMemcpyAsync(X->h_thresh.data(), X->d_thresh_i32, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(X->ev_acc[2], st));
+    MP.thresh = (double)X->fit.thresh;  // placeholder for kernels that do not read it (S8); S7 uses d_thresh_f64
     lap(1);
     // ---- S7 on the device: the ML-path kernel is a latency chain per locus (~0.4 ms).  It only decides which loci
     // are reported and whether the path spells alleles the site tables lack (rare), so it runs on its own stream
@@ -696,6 +708,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     X->h_plen.resize(P);
     X->h_done.resize(P);
     std::fill(X->h_done.begin(), X->h_done.end(), 0u);
+    CK(cudaStreamWaitEvent(X->st_ml, X->ev_acc[2], 0));  // node scores and threshold are produced on `st`
     CK(cudaMemsetAsync(X->d_path.p, 0, (size_t)N * 4, X->st_ml));  // absent loci leave their slice unwritten
     CK(cudaEventRecord(X->ev_ml[0], X->st_ml));
     // The level-parallel kernel writes every locus's path straight into pinned host memory (UVA: the same pointers
@@ -705,7 +718,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         P, X->d_knode_base, X->d_edge_off, X->d_edges, X->d_prob.p, X->d_accum + 2ull * N, MP, X->d_M.p, X->d_len.p, X->d_up.p, N,
         X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges, X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start,
         X->d_unit_nodes, X->mean_run_len, X->st_ml, X->d_locus_level_off, X->d_level_start, X->d_level_nodes, X->d_level_singles,
-        X->h_path.data(), X->h_plen.data(), X->h_done.data());
+        X->h_path.data(), X->h_plen.data(), X->h_done.data(), X->d_thresh_f64);
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());
     if (!ml_streamed) {
@@ -809,6 +822,9 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     }
     lap(2);
     run_s8_and_format(X->st_gt);
+    CK(cudaEventSynchronize(X->ev_acc[2]));  // long done: the threshold the device chose
+    X->fit.thresh = X->h_thresh.data()[0];
+    MP.thresh = (double)X->fit.thresh;
     lap(3);
     // ---- verify the speculation against the ML paths
     const double tw0 = now_ms();

@@ -1320,6 +1320,41 @@ void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_
     ++g_launches;
 }
 
+// pandora's find_prob_thresh on the 200-bin histogram (same scan as prob_threshold() on the host): the valley between
+// the error peak and the signal peak.  One thread; lets the ML-path kernel start without a host round trip.
+__global__ void prob_thresh_kernel(const uint32_t* __restrict__ ph, int any_present, int fallback, double* __restrict__ out_f64,
+                                   int* __restrict__ out_i32) {
+    if (threadIdx.x || blockIdx.x) return;
+    int t = fallback;
+    if (any_present) {
+        int p1 = 0, p2 = -1;
+        for (int i = 1; i < 200; ++i)
+            if (ph[i] > ph[p1]) p1 = i;  // first maximum
+        for (int i = 0; i < 200; ++i) {
+            const int d = i > p1 ? i - p1 : p1 - i;
+            if (d <= 10 || ph[i] == 0) continue;
+            if (p2 < 0 || ph[i] > ph[p2]) p2 = i;
+        }
+        if (p2 < 0) {
+            t = p1 - 200 - 10 > -200 ? p1 - 200 - 10 : -200;
+        } else {
+            const int a = p1 < p2 ? p1 : p2, b = p1 < p2 ? p2 : p1;
+            int m = a;
+            for (int i = a + 1; i <= b; ++i)
+                if (ph[i] < ph[m]) m = i;  // first minimum
+            t = m - 200;
+        }
+    }
+    *out_i32 = t;
+    *out_f64 = (double)t;
+}
+
+void launch_prob_thresh(const uint32_t* d_hist200, bool any_present, int fallback, double* d_thresh_f64, int* d_thresh_i32,
+                        cudaStream_t st) {
+    prob_thresh_kernel<<<1, 32, 0, st>>>(d_hist200, any_present ? 1 : 0, fallback, d_thresh_f64, d_thresh_i32);
+    ++g_launches;
+}
+
 // One warp per locus.  The recurrence is a chain (node j needs its successors), and the choice
 // among successors is order dependent (1e-6 tolerance, longer path wins ties), so lane 0 walks the
 // nodes in reverse rank order; the windowed mean needs the node `window` steps down the chosen
@@ -1796,7 +1831,8 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint32_t* __restrict__ edges, const double* __restrict__ prob, const int32_t* __restrict__ locus_reads,
     const uint8_t* __restrict__ needs_mean, MlUnitsDev L, const uint32_t* __restrict__ level_singles, ModelParams P,
     uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t max_nodes, uint32_t max_edges,
-    volatile uint32_t* done) {  // done != nullptr: path / path_len are host-mapped and done[l] tells the host that locus l is there
+    volatile uint32_t* done,     // done != nullptr: path / path_len are host-mapped and done[l] tells the host that locus l is there
+    const double* d_thresh) {    // != nullptr: the probability threshold is read from device memory (computed by prob_thresh_kernel)
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
@@ -1831,6 +1867,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     }
     for (uint32_t i = tid; i + 1 < n; i += ML_LEVEL_THREADS) sts32(lvn + 4u * i, recs + L.unit_nodes[s00 + i] * REC);
     const double tol = 0.000001;
+    const double thresh = d_thresh ? *d_thresh : P.thresh;
     const uint32_t term = recs + (n - 1) * REC;
     const uint32_t steps2 = P.window - 2;
     if (tid == 0) {
@@ -1880,7 +1917,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                     const uint32_t tv = lds32(v + R_T);
                     const double mean_v = lds64(v + R_MEAN);
                     const double Mv = lds64(v + R_M);
-                    const bool take = is_term ? (P.thresh > max_mean + tol)
+                    const bool take = is_term ? (thresh > max_mean + tol)
                                               : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
                     if (!take) continue;
                     Mj = pj + Mv;
@@ -1890,7 +1927,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                         Mj -= lds64(tv + R_PR);
                         lenj -= 1;
                     }
-                    max_mean = is_term ? P.thresh : mean_v;
+                    max_mean = is_term ? thresh : mean_v;
                     if (!is_term) max_len = lv;
                 }
                 if (lenj) mlpath_link(a, prevj, steps2);
@@ -1926,7 +1963,7 @@ bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    const uint32_t* d_locus_unit_off, const uint32_t* d_unit_start, const uint32_t* d_unit_nodes,
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off, const uint32_t* d_level_start,
                    const uint32_t* d_level_nodes, const uint32_t* d_level_singles, uint32_t* h_path, uint32_t* h_path_len,
-                   uint32_t* h_done) {
+                   uint32_t* h_done, const double* d_thresh) {
     if (!n_loci) return false;
     {   // default: level-parallel kernel (any of the older switches selects the older kernels)
         static const bool levels_on = [] {
@@ -1947,10 +1984,16 @@ bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
             mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(
                 n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, d_needs_mean, L, d_level_singles, P,
                 streamed ? h_path : d_path, streamed ? h_path_len : d_path_len, max_locus_knodes, max_locus_edges,
-                streamed ? h_done : nullptr);
+                streamed ? h_done : nullptr, d_thresh);
             ++g_launches;
             return streamed;
         }
+    }
+    if (d_thresh) {  // the older kernels take the threshold by value: one small read-back
+        double t = P.thresh;
+        cudaMemcpyAsync(&t, d_thresh, sizeof t, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        P.thresh = t;
     }
     // The run-parallel kernel pays ~1.5k cycles of per-unit overhead (warp syncs, ~50 loads per lane): it wins when
     // runs of single-successor nodes are long (sparse panels) and loses on bubble-dense graphs (the benchmark panel:

@@ -101,7 +101,10 @@ bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
                    float mean_run_len, cudaStream_t st, const uint32_t* d_locus_level_off = nullptr,
                    const uint32_t* d_level_start = nullptr, const uint32_t* d_level_nodes = nullptr,
                    const uint32_t* d_level_singles = nullptr, uint32_t* h_path = nullptr, uint32_t* h_path_len = nullptr,
-                   uint32_t* h_done = nullptr);
+                   uint32_t* h_done = nullptr, const double* d_thresh = nullptr);
+// the probability threshold from the 200-bin histogram, on the device (d_thresh_f64 feeds launch_mlpath)
+void launch_prob_thresh(const uint32_t* d_hist200, bool any_present, int fallback, double* d_thresh_f64, int* d_thresh_i32,
+                        cudaStream_t st);
 void launch_cov_hist(const int32_t* d_cov, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
                      const int32_t* d_locus_reads, uint32_t* d_hist1000, cudaStream_t st);
 void launch_prob_hist(const double* d_prob, uint32_t total, const uint8_t* d_is_terminal, const uint32_t* d_knode_locus,
