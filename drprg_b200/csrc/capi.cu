@@ -1311,6 +1311,11 @@ const char* drprg_cuda_vcf_view(drprg_index* X, uint64_t* len) {
     return X->have_gt ? X->vcf.data() : "";
 }
 
+uint64_t drprg_cuda_hash64(uint64_t kmer, uint32_t k) { return hash64_host(kmer, k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1)); }
+uint64_t drprg_cuda_hash64_inverse(uint64_t hash, uint32_t k) {
+    return hash64_inverse_host(hash, k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1));
+}
+
 int drprg_cuda_index_info(drprg_index* X, drprg_index_info* o) {
     API_BEGIN o->w = X->H.w;
     o->k = X->H.k;

@@ -62,7 +62,7 @@ SYMBOLS = [
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
-    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count",
+    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse",
 ]
 
 
@@ -80,6 +80,9 @@ def lib():
         for f in ("drprg_cuda_pack_reads", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits", "drprg_cuda_gt_mlpath"):
             getattr(L, f).restype = C.c_int64
         L.drprg_cuda_launch_count.restype = C.c_uint64
+        for f in ("drprg_cuda_hash64", "drprg_cuda_hash64_inverse"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_uint64, C.c_uint32]
         _LIB = L
     return _LIB
 

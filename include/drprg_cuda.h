@@ -116,6 +116,9 @@ const char* drprg_cuda_vcf_text(drprg_index*);
 const char* drprg_cuda_vcf_view(drprg_index*, uint64_t* len);
 
 /* ---- introspection / parity hooks (same .so, used by tests and bench) --------------------------- */
+/* pandora's hash64 on a 2k-bit k-mer and its inverse (the k-mer screen is built from the inverse): host functions */
+uint64_t drprg_cuda_hash64(uint64_t kmer, uint32_t k);
+uint64_t drprg_cuda_hash64_inverse(uint64_t hash, uint32_t k);
 typedef struct {
     uint32_t w, k, n_loci, total_knodes;
     uint64_t n_records, n_edges, n_path_intervals;

@@ -147,3 +147,29 @@ def test_read_file_ingest_matches_packer(tmp_path, fmt, gz, threads):
     assert (np.ctypeslib.as_array(words, (len(w2),)) == w2).all()
     for p in (words, woff, lens):
         L.drprg_cuda_host_free(p)
+
+
+def test_hash64_is_inverted_exactly():
+    """the k-mer screen is built from hash64's inverse: inverse(hash(x)) == x and hash(inverse(h)) == h for every k, and
+    the host hash agrees with the oracle's"""
+    import oracle_py as O
+    L = lib.lib()
+    rng = np.random.default_rng(5)
+    for k in (3, 7, 11, 15, 16, 21, 31):
+        mask = (1 << (2 * k)) - 1
+        for x in [0, 1, mask, mask >> 1] + [int(v) & mask for v in rng.integers(0, 2 ** 62, size=300)]:
+            h = L.drprg_cuda_hash64(x, k)
+            assert h <= mask
+            assert L.drprg_cuda_hash64_inverse(h, k) == x
+            assert L.drprg_cuda_hash64(L.drprg_cuda_hash64_inverse(x, k), k) == x
+    # against the oracle's sketch: a read of exactly w + k - 1 = k bases with w = 1 has one minimizer = min(hash(fwd), hash(rc))
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for s_ in ("ACGTACGTACGTACG", "TTTTTGGGGGCCCCC", "GATTACAGATTACAG"):
+        fwd = 0
+        for c in s_:
+            fwd = (fwd << 2) | code[c]
+        rc = 0
+        for c in reversed(s_):
+            rc = (rc << 2) | (3 - code[c])
+        hs, st, sd = O.sketch(s_.encode(), 1, 15)
+        assert len(hs) == 1 and int(hs[0]) == min(L.drprg_cuda_hash64(fwd, 15), L.drprg_cuda_hash64(rc, 15))
