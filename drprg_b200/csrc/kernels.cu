@@ -1828,6 +1828,44 @@ __device__ __forceinline__ double div_small(double a, uint32_t n) {
     return q;
 }
 
+// The level kernel's own record layout (64 B), arranged for vector shared-memory accesses: a lone warp per scheduler
+// pays ~6 cycles per instruction, so fewer, wider accesses matter more than anything else here.
+//   0 sum f64 | 8 mean f64 | 16 score f64 | 24 len u32 | 28 T u32 | 32 edge-list address u32 | 36 up[0..6] u32
+// sum+mean come with one LDS.128, len+T with one LDS.64; up[1..6] sit at 40/48/56 and are stored as three STS.64.
+constexpr uint32_t L_M = 0, L_MEAN = 8, L_PR = 16, L_LEN = 24, L_T = 28, L_EOFF = 32, L_UP = 36;
+static_assert(L_MEAN == L_M + 8 && L_T == L_LEN + 4 && (L_UP + 4) % 8 == 0 && L_UP + 28 == REC, "vector accesses rely on this layout");
+__device__ __forceinline__ void lds_sum_mean(uint32_t a, double& m, double& mean) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m), "=d"(mean) : "r"(a + L_M));
+}
+__device__ __forceinline__ void lds_len_t(uint32_t a, uint32_t& len, uint32_t& t) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(len), "=r"(t) : "r"(a + L_LEN));
+}
+__device__ __forceinline__ void sts_pair32(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y));
+}
+// lifting pointers of a (successor v) and T(a) = succ^(window-2)(v): the two pointer chases are issued interleaved like
+// mlpath_link; the stores are batched: up[0] | (up[1],up[2]) | (up[3],up[4]) | (up[5],up[6]); T is returned
+__device__ __forceinline__ uint32_t level_link(uint32_t a, uint32_t v, uint32_t steps2) {
+    uint32_t up[7];
+    up[0] = v;
+    uint32_t x = v, t = v;
+#pragma unroll
+    for (int l = 0; l < 7; ++l) {
+        const uint32_t xn = (l < 6) ? lds32(x + L_UP + 4 * l) : 0u;              // level l+1 of a
+        const uint32_t tn = ((steps2 >> l) & 1u) ? lds32(t + L_UP + 4 * l) : t;  // walk window-2 steps from v
+        if (l < 6) {
+            up[l + 1] = xn;
+            x = xn;
+        }
+        t = tn;
+    }
+    sts32(a + L_UP, up[0]);
+    sts_pair32(a + L_UP + 4, up[1], up[2]);
+    sts_pair32(a + L_UP + 12, up[3], up[4]);
+    sts_pair32(a + L_UP + 20, up[5], up[6]);
+    return t;
+}
+
 constexpr int ML_LEVEL_THREADS = 128;
 __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
@@ -1858,8 +1896,8 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint32_t lvs = lvn + max_nodes * 4u;        // per level: first index into lvn, number of single-successor nodes
     for (uint32_t i = tid; i <= n; i += ML_LEVEL_THREADS) {
         const uint32_t a = recs + i * REC;
-        if (i < n) sts64(a + R_PR, prob[base + i]);
-        sts32(a + R_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
+        if (i < n) sts64(a + L_PR, prob[base + i]);
+        sts32(a + L_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
     }
     for (uint32_t i = tid; i < n_edges; i += ML_LEVEL_THREADS) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
     const uint32_t u0 = L.locus_unit_off[l], n_levels = L.locus_unit_off[l + 1] - u0;
@@ -1874,10 +1912,10 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint32_t term = recs + (n - 1) * REC;
     const uint32_t steps2 = P.window - 2;
     if (tid == 0) {
-        sts64(term + R_M, 0.0);
-        sts32(term + R_LEN, 0u);
+        sts64(term + L_M, 0.0);
+        sts_pair32(term + L_LEN, 0u, term);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) sts32(term + R_UP + 4 * v, term);  // includes R_T
+        for (int v = 0; v < 7; ++v) sts32(term + L_UP + 4 * v, term);
     }
     __syncthreads();
     const bool single_warp = warp < 2;
@@ -1889,37 +1927,38 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
             const uint32_t a = lds32(lvn + 4u * idx);
             double Mj = 0.0;
             uint32_t lenj = 0, prevj = term;
-            const double pj = lds64(a + R_PR);
-            const uint32_t e0w = lds32(a + R_EOFF);
+            const double pj = lds64(a + L_PR);
+            const uint32_t e0w = lds32(a + L_EOFF);
             const uint32_t e0 = e0w & ~3u;
+            uint32_t Tj = term;
             if (single_warp) {
                 // single successor: pandora's comparison against the initial -FLT_MAX accepts any successor that is
                 // not a dead end
                 const uint32_t v = lds32(e0);
-                const uint32_t lv = lds32(v + R_LEN);
-                const uint32_t tv = lds32(v + R_T);
-                const double Mv = lds64(v + R_M);
+                uint32_t lv, tv;
+                lds_len_t(v, lv, tv);
+                const double Mv = lds64(v + L_M);
                 if (v == term || lv > 0u) {
-                    mlpath_link(a, v, steps2);  // independent of the sums below: overlaps them
+                    Tj = level_link(a, v, steps2);  // independent of the sums below: overlaps them
                     prevj = v;
                     lenj = 1 + lv;
                     Mj = pj + Mv;
                     if (lenj > P.window) {
-                        Mj -= lds64(tv + R_PR);
+                        Mj -= lds64(tv + L_PR);
                         lenj -= 1;
                     }
                 }
             } else {
-                const uint32_t e1 = lds32(a + REC + R_EOFF) & ~3u;
+                const uint32_t e1 = lds32(a + REC + L_EOFF) & ~3u;
                 double max_mean = -(double)FLT_MAX;
                 uint32_t max_len = 0;
                 for (uint32_t e = e0; e < e1; e += 4u) {
                     const uint32_t v = lds32(e);
                     const bool is_term = (v == term);
-                    const uint32_t lv = lds32(v + R_LEN);
-                    const uint32_t tv = lds32(v + R_T);
-                    const double mean_v = lds64(v + R_MEAN);
-                    const double Mv = lds64(v + R_M);
+                    uint32_t lv, tv;
+                    lds_len_t(v, lv, tv);
+                    double Mv, mean_v;
+                    lds_sum_mean(v, Mv, mean_v);
                     const bool take = is_term ? (thresh > max_mean + tol)
                                               : ((mean_v > max_mean + tol) || (max_mean - mean_v <= tol && lv > max_len));
                     if (!take) continue;
@@ -1927,29 +1966,33 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                     lenj = 1 + lv;
                     prevj = v;
                     if (lenj > P.window) {
-                        Mj -= lds64(tv + R_PR);
+                        Mj -= lds64(tv + L_PR);
                         lenj -= 1;
                     }
                     max_mean = is_term ? thresh : mean_v;
                     if (!is_term) max_len = lv;
                 }
-                if (lenj) mlpath_link(a, prevj, steps2);
+                if (lenj) Tj = level_link(a, prevj, steps2);
             }
             if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
 #pragma unroll
-                for (int v = 0; v < 8; ++v) sts32(a + R_UP + 4 * v, term);
+                for (int v = 0; v < 7; ++v) sts32(a + L_UP + 4 * v, term);
             }
-            sts64(a + R_M, Mj);
-            sts32(a + R_LEN, lenj);
-            if (e0w & 1u) sts64(a + R_MEAN, div_small(Mj, lenj));  // 0/0 = NaN for a dead end: never chosen, like pandora
+            sts_pair32(a + L_LEN, lenj, Tj);
+            if (e0w & 1u) {  // 0/0 = NaN for a dead end: never chosen, like pandora
+                const double mean_j = div_small(Mj, lenj);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + L_M), "d"(Mj), "d"(mean_j));
+            } else {
+                sts64(a + L_M, Mj);
+            }
         }
         __syncthreads();
     }
     if (tid == 0) {
-        uint32_t cnt = 0, p = lds32(recs + R_UP);
+        uint32_t cnt = 0, p = lds32(recs + L_UP);
         while (p != term && cnt < n) {
             path[base + cnt++] = (p - recs) / REC;
-            p = lds32(p + R_UP);
+            p = lds32(p + L_UP);
         }
         path_len[l] = cnt;
         if (done) {  // the loci finish at different times (170 .. 860 levels): the host verifies each one as it lands
