@@ -1893,7 +1893,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint32_t recs = (uint32_t)__cvta_generic_to_shared(s_dyn);
     const uint32_t edg = recs + (max_nodes + 1) * REC;
     const uint32_t lvn = edg + (max_edges + 1) * 4u;  // record addresses in level order
-    const uint32_t lvs = lvn + max_nodes * 4u;        // per level: first index into lvn, number of single-successor nodes
+    const uint32_t lvs = (lvn + max_nodes * 4u + 7u) & ~7u;  // per level: first index into lvn, number of single-successor nodes (8-byte aligned pairs)
     for (uint32_t i = tid; i <= n; i += ML_LEVEL_THREADS) {
         const uint32_t a = recs + i * REC;
         if (i < n) sts64(a + L_PR, prob[base + i]);
@@ -1919,10 +1919,18 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     }
     __syncthreads();
     const bool single_warp = warp < 2;
-    const uint32_t sub = (warp & 1u) + 2u * lane;  // this lane's slot among the level's nodes of its kind (64 per pass)
+    uint32_t sub = (warp & 1u) + 2u * lane;  // this lane's slot among the level's nodes of its kind (64 per pass)
+    asm volatile("" : "+r"(sub));            // keep it in a register: recomputing it every level costs issue slots
+    // level bounds: one LDS.64 per level ({first index, number of single-successor nodes} of the NEXT level; the
+    // current pair is carried in registers)
+    uint32_t s0, ns;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(s0), "=r"(ns) : "r"(lvs));
     for (uint32_t u = 0; u < n_levels; ++u) {
-        const uint32_t s0 = lds32(lvs + 8u * u), ns = lds32(lvs + 8u * u + 4u), s1 = lds32(lvs + 8u * u + 8u);
+        uint32_t s1, ns1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(s1), "=r"(ns1) : "r"(lvs + 8u * (u + 1)));
         const uint32_t lo = single_warp ? s0 : s0 + ns, hi = single_warp ? s0 + ns : s1;
+        s0 = s1;
+        ns = ns1;
         for (uint32_t idx = lo + sub; idx < hi; idx += 64) {
             const uint32_t a = lds32(lvn + 4u * idx);
             double Mj = 0.0;
