@@ -217,6 +217,7 @@ struct drprg_index {
     std::vector<std::string> contigs;
     std::string vcf;
     bool have_gt = false;
+    bool ml_in_flight = false;  // the ML-path kernel of an unfinished drprg_cuda_genotype may still be writing h_path / h_done
     DBuf<double> d_prob, d_M;
     DBuf<uint32_t> d_len, d_up, d_path, d_path_len;
 
@@ -259,14 +260,11 @@ void upload_index(drprg_index* X) {
     if (H.w > (uint32_t)W_MAX) throw std::runtime_error("w > 32 is not supported by the device kernels");
     if (H.loci.size() > 65535) throw std::runtime_error("more than 65535 loci");
     // ---- hash table + pre-filter
-    std::vector<uint2> recs(H.records.size());
+    std::vector<uint2> recs;
+    recs.reserve(H.records.size() + 16);
     size_t distinct = 0;
-    for (size_t i = 0; i < H.records.size(); ++i) {
-        const Record& r = H.records[i];
-        recs[i] = make_uint2(r.knode, (r.prg << 1) | r.strand);
-        if (i == 0 || H.records[i - 1].hash != r.hash) ++distinct;
-    }
-    if (recs.size() >= (1u << 24)) throw std::runtime_error("too many index records");
+    for (size_t i = 0; i < H.records.size(); ++i)
+        if (i == 0 || H.records[i - 1].hash != H.records[i].hash) ++distinct;
     uint32_t sb = 10;
     while ((1ull << sb) < distinct * 2) ++sb;
     uint32_t fb = 8;
@@ -276,11 +274,16 @@ void upload_index(drprg_index* X) {
     for (size_t i = 0; i < H.records.size();) {
         size_t j = i;
         while (j < H.records.size() && H.records[j].hash == H.records[i].hash) ++j;
-        if (j - i > 255) throw std::runtime_error("a minimizer occurs in more than 255 k-mer nodes");
+        // a minimizer in 255 or more k-mer nodes (pandora has no limit): count 255 = "the real count is in a header
+        // pseudo-record in front of the group" (rec_span in kernels.cu)
+        const uint32_t count = (uint32_t)(j - i), begin = (uint32_t)recs.size();
+        if (count >= 255u) recs.push_back(make_uint2(count, 0xffffffffu));
+        for (size_t q = i; q < j; ++q) recs.push_back(make_uint2(H.records[q].knode, (H.records[q].prg << 1) | H.records[q].strand));
+        if (recs.size() >= (1u << 24)) throw std::runtime_error("too many index records");
         const uint32_t h = (uint32_t)H.records[i].hash;
         uint32_t s = (h * 0x9E3779B1u) >> (32 - sb);
         while (slots[s].y != 0) s = (s + 1) & ((1u << sb) - 1);
-        slots[s] = make_uint2(h, (uint32_t)i | ((uint32_t)(j - i) << 24));
+        slots[s] = make_uint2(h, begin | (std::min(count, 255u) << 24));
         filter[h & ((1u << fb) - 1)] |= (1u << ((h >> fb) & 31)) | (1u << ((h >> (fb + 5)) & 31));
         i = j;
     }
@@ -635,6 +638,22 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         X->gt_ms[i] = t - t0;
         t0 = t;
     };
+    // a previous call that threw after launching the ML-path kernel may have left it running: it writes into the pinned
+    // path / flag buffers this call is about to reset
+    if (X->ml_in_flight) {
+        cudaStreamSynchronize(X->st_ml);
+        X->ml_in_flight = false;
+    }
+    // --vcf-refs is loaded before anything is launched (a bad path must not leave kernels behind)
+    {
+        const std::string rp = vcf_refs ? vcf_refs : "";
+        if (rp != X->refs_path) {
+            X->refs = rp.empty() ? std::map<std::string, std::string>() : load_fasta(rp);
+            X->refs_path = rp;
+            for (auto& s : X->sites) s = drprg_index::LocusSites();
+            X->csr_records.clear();
+        }
+    }
     const bool reuse_hist = X->hist_on_host;  // downloaded at the end of the last map_batch, accumulators untouched since
     if (!reuse_hist) flush_scalars(X);
     if (!X->st_ml) {
@@ -719,20 +738,14 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         X->d_path.p, X->d_path_len.p, X->max_locus_knodes, X->max_locus_edges, X->d_needs_mean, X->d_locus_unit_off, X->d_unit_start,
         X->d_unit_nodes, X->mean_run_len, X->st_ml, X->d_locus_level_off, X->d_level_start, X->d_level_nodes, X->d_level_singles,
         X->h_path.data(), X->h_plen.data(), X->h_done.data(), X->d_thresh_f64);
+    X->ml_in_flight = true;
     CK(cudaEventRecord(X->ev_ml[1], X->st_ml));
     CK(cudaGetLastError());
     if (!ml_streamed) {
         CK(cudaMemcpyAsync(X->h_path.data(), X->d_path.p, (size_t)N * 4, cudaMemcpyDeviceToHost, X->st_ml));
         CK(cudaMemcpyAsync(X->h_plen.data(), X->d_path_len.p, (size_t)P * 4, cudaMemcpyDeviceToHost, X->st_ml));
     }
-    // ---- reference paths / site tables (read independent, cached per --vcf-refs file)
-    const std::string rp = vcf_refs ? vcf_refs : "";
-    if (rp != X->refs_path) {
-        X->refs = rp.empty() ? std::map<std::string, std::string>() : load_fasta(rp);
-        X->refs_path = rp;
-        for (auto& s : X->sites) s = drprg_index::LocusSites();
-        X->csr_records.clear();
-    }
+    // ---- reference paths / site tables (read independent, cached per --vcf-refs file, loaded above)
     auto ensure_sites = [&](uint32_t l) {
         auto& S = X->sites[l];
         if (S.ready) return;
@@ -880,7 +893,12 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             O.use_cached = false;
         }
     }, 16);
-    CK(cudaStreamSynchronize(X->st_ml));
+    {
+        const cudaError_t mle = cudaStreamSynchronize(X->st_ml);
+        X->ml_in_flight = false;
+        if (mle != cudaSuccess)
+            throw std::runtime_error(std::string("ML-path kernel failed: ") + cudaGetErrorString(mle));
+    }
     if (ml_failed.load()) throw std::runtime_error("the ML-path kernel ended without publishing every locus");
     {
         float ms = 0;
@@ -1087,7 +1105,10 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
                drprg_map_stats* stats, const Inflated* pre = nullptr) {
     need_device(X);
     const double t0 = now_ms();
+    // like the reference (File::create of pandora.log comes first, src/lib.rs:592-593): an unusable outdir fails before
+    // any GPU work is done
     std::ofstream log(std::string(outdir) + "/pandora.log");
+    if (!log) throw std::runtime_error(std::string("cannot write ") + outdir + "/pandora.log");
     FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1, pre);
     std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(F.B, free_batch);
     struct {
@@ -1499,6 +1520,55 @@ int drprg_cuda_gt_allele_knodes(drprg_index* X, uint32_t* out) {
         for (auto& kn : r->allele_kn)
             for (uint32_t x : kn) out[e++] = x;
     return 0;
+}
+int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec_off, const uint32_t* mean_fwd,
+                             const uint32_t* mean_rev, const double* gaps, uint32_t exp_depth, double genotyping_error_rate,
+                             double min_gt_conf, double* lik, int32_t* gt, double* gt_conf) {
+    API_BEGIN
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device visible: drprg-cuda has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::runtime_error("bad device ordinal");
+    CK(cudaSetDevice(device));
+    if (!n_records) return 0;
+    const uint32_t na = rec_off[n_records];
+    DBuf<uint32_t> d_u32;
+    DBuf<double> d_f64;
+    DBuf<int32_t> d_i32;
+    d_u32.ensure((size_t)n_records + 1 + 2 * (size_t)na);
+    d_f64.ensure(2 * (size_t)na + n_records);
+    d_i32.ensure(n_records);
+    uint32_t *d_off = d_u32.p, *d_mf = d_off + n_records + 1, *d_mr = d_mf + na;
+    double *d_gaps = d_f64.p, *d_lik = d_gaps + na, *d_conf = d_lik + na;
+    struct Guard {
+        DBuf<uint32_t>& a; DBuf<double>& b; DBuf<int32_t>& c;
+        ~Guard() { a.release(); b.release(); c.release(); }
+    } guard{d_u32, d_f64, d_i32};
+    CK(cudaMemcpy(d_off, rec_off, ((size_t)n_records + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_mf, mean_fwd, (size_t)na * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_mr, mean_rev, (size_t)na * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_gaps, gaps, (size_t)na * 8, cudaMemcpyHostToDevice));
+    DevGenotype G{};
+    G.n_records = n_records;
+    G.n_alleles = na;
+    G.rec_off = d_off;
+    G.mean_fwd = d_mf;
+    G.mean_rev = d_mr;
+    G.gaps = d_gaps;
+    G.lik = d_lik;
+    G.gt_conf = d_conf;
+    G.gt = d_i32.p;
+    ModelParams MP{};
+    MP.exp_depth = exp_depth;
+    MP.gt_err = genotyping_error_rate > 0 ? genotyping_error_rate : 0.01;
+    MP.gt_conf = min_gt_conf;
+    launch_genotype_rows(G, MP, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(lik, d_lik, (size_t)na * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gt_conf, d_conf, (size_t)n_records * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gt, d_i32.p, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    return 0;
+    API_END
 }
 int drprg_cuda_last_timings(drprg_index* X, float* out4) {
     memcpy(out4, X->timings, sizeof X->timings);

@@ -1,0 +1,97 @@
+// Hand-written sm_100a kernels for the map hot path: read sketching + index lookup (S1+S2), hit
+// clustering (S3/S4), k-mer coverage (S5), ML path (S7) and genotyping (S8).  These replace the
+// per-read and per-locus loops of `pandora map` that drprg launches at
+// /root/reference/src/lib.rs:580-642 (argv :594-609, src/predict.rs:288-294); stage semantics
+// follow pandora's Seq::minimizer_sketch, add_read_hits, define_clusters, filter_clusters(2),
+// add_hits_to_kmergraphs, KmerGraphWithCoverage::find_max_path and SampleInfo.
+// This file: S8 (per-allele statistics, likelihoods, GT, GT_CONF).
+#include <algorithm>
+#include <cfloat>
+#include <cstdlib>
+
+#include "kernels_common.cuh"
+
+namespace drprg {
+
+// ============================================================================================
+// S8 : per-allele statistics and genotype likelihoods
+// ============================================================================================
+__global__ void allele_stats_kernel(const int32_t* __restrict__ cov, DevGenotype G, uint32_t min_kmer_covg) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= G.n_alleles) return;
+    const uint32_t b = G.allele_off[a], e = G.allele_off[a + 1], n = e - b;
+    uint32_t sf = 0, sr = 0, gaps = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t g = G.allele_kn[i];
+        const uint32_t f = cov_sat(cov[2 * g]), r = cov_sat(cov[2 * g + 1]);
+        sf += f;
+        sr += r;
+        if (f + r < min_kmer_covg) ++gaps;
+    }
+    // integer median by rank selection (n is a handful of k-mers): no scratch memory needed
+    uint32_t med[2] = {0, 0};
+    if (n) {
+        const uint32_t r_hi = n / 2, r_lo = (n % 2) ? n / 2 : n / 2 - 1;
+        for (int s = 0; s < 2; ++s) {
+            uint32_t v_lo = 0, v_hi = 0;
+            for (uint32_t i = b; i < e; ++i) {
+                const uint32_t vi = cov_sat(cov[2 * G.allele_kn[i] + s]);
+                uint32_t less = 0, leq = 0;
+                for (uint32_t j = b; j < e; ++j) {
+                    const uint32_t vj = cov_sat(cov[2 * G.allele_kn[j] + s]);
+                    less += vj < vi;
+                    leq += vj <= vi;
+                }
+                if (less <= r_lo && r_lo < leq) v_lo = vi;
+                if (less <= r_hi && r_hi < leq) v_hi = vi;
+            }
+            med[s] = (n % 2) ? v_hi : (v_lo + v_hi) / 2;
+        }
+    }
+    G.sum_fwd[a] = sf;
+    G.sum_rev[a] = sr;
+    G.mean_fwd[a] = n ? sf / n : 0;
+    G.mean_rev[a] = n ? sr / n : 0;
+    G.med_fwd[a] = med[0];
+    G.med_rev[a] = med[1];
+    G.gaps[a] = n ? (double)gaps / (double)n : 0.0;
+}
+
+__global__ void genotype_kernel(DevGenotype G, ModelParams P) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.n_records) return;
+    const uint32_t b = G.rec_off[r], e = G.rec_off[r + 1];
+    const double E = (double)P.exp_depth;
+    double total = 0.0;
+    for (uint32_t a = b; a < e; ++a) total += (double)G.mean_fwd[a] + (double)G.mean_rev[a];
+    const double lnE = log(E), lnerr = log(P.gt_err), ln1m = log(1.0 - exp(-E));
+    uint32_t best = b;
+    for (uint32_t a = b; a < e; ++a) {
+        const double c = (double)G.mean_fwd[a] + (double)G.mean_rev[a];
+        const double g = G.gaps[a];
+        const double L = -E + c * lnE - lgamma(c + 1.0) + (total - c) * lnerr - E * g + ln1m * (1.0 - g);
+        G.lik[a] = L;
+        if (L > G.lik[best]) best = a;
+    }
+    double second = -INFINITY;
+    for (uint32_t a = b; a < e; ++a)
+        if (a != best && G.lik[a] > second) second = G.lik[a];
+    const double conf = (e - b > 1) ? fabs(G.lik[best] - second) : 0.0;
+    G.gt_conf[r] = conf;
+    G.gt[r] = (conf >= P.gt_conf) ? (int32_t)(best - b) : -1;
+}
+
+void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st) {
+    if (!G.n_records) return;
+    allele_stats_kernel<<<(G.n_alleles + 127) / 128, 128, 0, st>>>(d_cov, G, P.min_kmer_covg);
+    genotype_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, P);
+    g_launches += 2;
+}
+
+void launch_genotype_rows(const DevGenotype& G, ModelParams P, cudaStream_t st) {
+    if (!G.n_records) return;
+    genotype_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, P);
+    ++g_launches;
+}
+
+}  // namespace drprg

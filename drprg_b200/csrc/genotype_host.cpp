@@ -887,6 +887,7 @@ struct Piece {
     std::vector<uint32_t> words, lens;
     std::vector<uint32_t> nwords;  // per read
     uint64_t total_bases = 0, n_dropped = 0;
+    uint32_t first_raw_len = 0;  // length of the piece's first read before the non-ACGT drop
 };
 
 inline size_t line_end(const RawText& b, size_t p) {
@@ -927,6 +928,7 @@ void parse_piece(const RawText& b, size_t lo, size_t hi, bool fastq, Piece& out)
         uint32_t l = 0;
         pack_one((const uint8_t*)s, len, out.words.data() + at, l);
         if (l == 0 && len > 0) ++out.n_dropped;
+        if (out.lens.empty()) out.first_raw_len = len;
         out.lens.push_back(l);
         out.nwords.push_back(nw);
         out.total_bases += len;
@@ -939,14 +941,41 @@ void parse_piece(const RawText& b, size_t lo, size_t hi, bool fastq, Piece& out)
             continue;
         }
         if (fastq) {
+            // kseq-style record (what pandora's reader accepts): '@' header, sequence lines up to the '+' line, then
+            // quality lines until they are as long as the sequence.  Strict 4-line records take the first branch.
             if (b[p] != '@') throw std::runtime_error("malformed FASTQ record");
             size_t s0 = e + 1, s1 = s0 < b.size() ? line_end(b, s0) : b.size();
             size_t len = s1 > s0 ? s1 - s0 : 0;
             if (len && b[s0 + len - 1] == '\r') --len;
-            emit(b.data() + std::min(s0, b.size()), (uint32_t)len);
-            size_t plus_end = s1 < b.size() ? line_end(b, s1 + 1) : b.size();
-            size_t qual_end = plus_end < b.size() ? line_end(b, plus_end + 1) : b.size();
-            p = qual_end + 1;
+            size_t nxt = s1 + 1;  // start of the line after the first sequence line
+            if (nxt >= b.size() || b[nxt] == '+') {
+                emit(b.data() + std::min(s0, b.size()), (uint32_t)len);
+            } else {  // wrapped sequence
+                seq.assign(b.data() + s0, len);
+                while (nxt < b.size() && b[nxt] != '+') {
+                    size_t le = line_end(b, nxt);
+                    size_t l2 = le - nxt;
+                    if (l2 && b[nxt + l2 - 1] == '\r') --l2;
+                    seq.append(b.data() + nxt, l2);
+                    nxt = le + 1;
+                }
+                if (nxt >= b.size()) throw std::runtime_error("malformed FASTQ record: no '+' line");
+                len = seq.size();
+                emit(seq.data(), (uint32_t)len);
+            }
+            size_t q = nxt < b.size() ? line_end(b, nxt) + 1 : b.size();  // past the '+' line
+            size_t qlen = 0;
+            bool first_qual = true;
+            while (q < b.size() && (first_qual || qlen < len)) {
+                size_t le = line_end(b, q);
+                size_t l2 = le - q;
+                if (l2 && b[q + l2 - 1] == '\r') --l2;
+                qlen += l2;
+                q = le + 1;
+                first_qual = false;
+            }
+            if (qlen > len && len) throw std::runtime_error("malformed FASTQ record: quality longer than sequence");
+            p = q;
         } else {
             if (b[p] != '>') throw std::runtime_error("malformed FASTA record");
             p = e + 1;
@@ -974,12 +1003,33 @@ void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& o
     if (first >= buf.size()) return;
     const bool fastq = buf[first] == '@';
     if (!fastq && buf[first] != '>') throw std::runtime_error("unrecognised read file format: " + path);
-    const size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), (size_t)16, buf.size() / (1 << 20) + 1}));
-    std::vector<size_t> cut(T + 1, buf.size());
-    cut[0] = first;
-    for (size_t t = 1; t < T; ++t) cut[t] = std::max(cut[t - 1], next_record(buf, first + (buf.size() - first) * t / T, fastq));
-    std::vector<Piece> pieces(T);
-    parallel_for(T, [&](size_t t) { parse_piece(buf, cut[t], cut[t + 1], fastq, pieces[t]); }, T);
+    size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), (size_t)16, buf.size() / (1 << 20) + 1}));
+    if (fastq && T > 1) {
+        // the parallel cut finds record starts by the strict 4-line pattern ('@' line, '+' two lines later); a wrapped
+        // (multi-line) FASTQ is parsed by one thread instead.  Probe the first records.
+        size_t p = first;
+        for (int rec = 0; rec < 64 && p < buf.size() && T > 1; ++rec) {
+            size_t l1 = line_end(buf, p), l2 = l1 < buf.size() ? line_end(buf, l1 + 1) : buf.size();
+            size_t l3 = l2 < buf.size() ? line_end(buf, l2 + 1) : buf.size(), l4 = l3 < buf.size() ? line_end(buf, l3 + 1) : buf.size();
+            if (buf[p] != '@' || l2 + 1 >= buf.size() || buf[l2 + 1] != '+') T = 1;
+            p = l4 + 1;
+        }
+    }
+    std::vector<size_t> cut;
+    std::vector<Piece> pieces;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        cut.assign(T + 1, buf.size());
+        cut[0] = first;
+        for (size_t t = 1; t < T; ++t) cut[t] = std::max(cut[t - 1], next_record(buf, first + (buf.size() - first) * t / T, fastq));
+        pieces.assign(T, Piece());
+        try {
+            parallel_for(T, [&](size_t t) { parse_piece(buf, cut[t], cut[t + 1], fastq, pieces[t]); }, T);
+            break;
+        } catch (const std::exception&) {
+            if (T == 1 || attempt) throw;
+            T = 1;  // records that only look irregular from a mid-file cut: one thread, from the top
+        }
+    }
     // stitch
     std::vector<uint64_t> rbase(T + 1, 0), wbase(T + 1, 0);
     for (size_t t = 0; t < T; ++t) {
@@ -1003,19 +1053,9 @@ void load_reads_packed(const std::string& path, uint32_t threads, PackedReads& o
     }, T);
     out.word_off[rbase[T]] = wbase[T];
     // pandora's short-read cluster threshold uses the length of the first read
-    for (size_t t = 0; t < T && out.first_read_len == 0; ++t)
+    for (size_t t = 0; t < T; ++t)
         if (!pieces[t].nwords.empty()) {
-            // length before the non-ACGT drop: recover it from the raw text of the first record
-            size_t p = cut[t];
-            size_t e = line_end(buf, p);
-            if (fastq) {
-                size_t s1 = e < buf.size() ? line_end(buf, e + 1) : buf.size();
-                size_t len = s1 > e + 1 ? s1 - e - 1 : 0;
-                if (len && buf[e + len] == '\r') --len;
-                out.first_read_len = (uint32_t)len;
-            } else {
-                out.first_read_len = pieces[t].lens[0] ? pieces[t].lens[0] : (uint32_t)(pieces[t].nwords[0] * 16);
-            }
+            out.first_read_len = pieces[t].first_raw_len;
             break;
         }
 }

@@ -120,5 +120,7 @@ struct DevGenotype {
     int32_t* gt;
 };
 void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st);
+// the likelihood / GT / GT_CONF kernel alone, on per-allele rows already in G.mean_fwd / G.mean_rev / G.gaps
+void launch_genotype_rows(const DevGenotype& G, ModelParams P, cudaStream_t st);
 
 }  // namespace drprg

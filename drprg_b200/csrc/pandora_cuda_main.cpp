@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <string>
+#include <system_error>
 #include <vector>
 
 #include "../../include/drprg_cuda.h"
@@ -65,7 +67,14 @@ int main(int argc, char** argv) {
         fprintf(stderr, "pandora_cuda: need <prg> <reads>\n");
         return 2;
     }
-    if (system(("mkdir -p '" + outdir + "'").c_str()) != 0) return 1;
+    {   // pandora creates its output directory; no shell is involved (the path is user input)
+        std::error_code ec;
+        std::filesystem::create_directories(outdir, ec);
+        if (ec) {
+            fprintf(stderr, "pandora_cuda: cannot create %s: %s\n", outdir.c_str(), ec.message().c_str());
+            return 1;
+        }
+    }
     const int device = getenv("DRPRG_CUDA_DEVICE") ? atoi(getenv("DRPRG_CUDA_DEVICE")) : 0;
     drprg_index* idx = nullptr;
     if (drprg_cuda_index_load(pos[0].c_str(), w, k, device, &idx) != 0) {

@@ -62,7 +62,7 @@ SYMBOLS = [
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
-    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse",
+    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse",
 ]
 
 
@@ -363,6 +363,21 @@ class Index:
                                            str(outdir).encode(), C.byref(o), C.byref(st))
         _check(rc, "drprg_cuda_map_genotype")
         return st.asdict()
+
+
+def genotype_rows(rec_off, mean_fwd, mean_rev, gaps, exp_depth, err=0.01, min_gt_conf=0.0, device=0):
+    """the product's genotype_kernel on caller-supplied per-allele rows (parity hook for the reference's VCF fixtures)"""
+    rec_off = np.ascontiguousarray(rec_off, np.uint32)
+    mf = np.ascontiguousarray(mean_fwd, np.uint32)
+    mr = np.ascontiguousarray(mean_rev, np.uint32)
+    g = np.ascontiguousarray(gaps, np.float64)
+    nr, na = len(rec_off) - 1, int(rec_off[-1])
+    assert len(mf) == na and len(mr) == na and len(g) == na
+    lik = np.zeros(na, np.float64); gt = np.zeros(nr, np.int32); conf = np.zeros(nr, np.float64)
+    rc = lib().drprg_cuda_genotype_rows(C.c_int(device), C.c_uint32(nr), _p(rec_off), _p(mf), _p(mr), _p(g), C.c_uint32(int(exp_depth)),
+                                        C.c_double(err), C.c_double(min_gt_conf), _p(lik), _p(gt), _p(conf))
+    _check(rc, "drprg_cuda_genotype_rows")
+    return lik, gt, conf
 
 
 def launch_count():

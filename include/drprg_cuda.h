@@ -146,6 +146,13 @@ int drprg_cuda_gt_records(drprg_index*, uint32_t* locus, uint32_t* pos, uint32_t
 int drprg_cuda_gt_alleles(drprg_index*, double* lik, double* gaps, uint32_t* mean_fwd, uint32_t* mean_rev,
                           uint32_t* med_fwd, uint32_t* med_rev, uint32_t* sum_fwd, uint32_t* sum_rev, uint32_t* n_knodes);
 int drprg_cuda_gt_allele_knodes(drprg_index*, uint32_t* out);
+/* S8's likelihood / GT / GT_CONF kernel on caller-supplied per-allele rows: rec_off[n_records+1] -> alleles, per allele the
+ * MEAN_FWD_COVG, MEAN_REV_COVG and GAPS a pandora VCF record carries (e.g. /root/reference/tests/cases/predict/in.vcf), the
+ * sample's integer expected depth E, -E error rate and --gt-conf.  Outputs lik[n_alleles], gt[n_records] (-1 = null call),
+ * gt_conf[n_records].  This is the genotype_kernel of the product path, so the reference's VCF fixtures check it directly. */
+int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec_off, const uint32_t* mean_fwd,
+                             const uint32_t* mean_rev, const double* gaps, uint32_t exp_depth, double genotyping_error_rate,
+                             double min_gt_conf, double* lik, int32_t* gt, double* gt_conf);
 /* kernel timing of the last map_batch in ms (CUDA events on its stream): [sketch_lookup, sort, cluster, coverage] */
 int drprg_cuda_last_timings(drprg_index*, float* out4);
 /* host wall time of the last drprg_cuda_genotype in ms: [accumulator download, parameter fit + log-prob histogram,

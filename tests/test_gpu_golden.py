@@ -1,0 +1,61 @@
+"""The CUDA genotype kernel against the vectors the REFERENCE holds: every data row of the seven pandora VCF
+fixtures under /root/reference/tests/cases/predict (copied to tests/golden/) goes through genotype_kernel — the
+kernel of the product path — by the C-ABI hook drprg_cuda_genotype_rows, and its LIKELIHOOD / GT / GT_CONF must
+reproduce what pandora printed (6 significant digits).  Same rows, tolerances and hand-edited exclusions as the
+oracle's pin in tests/test_oracle_golden.py."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from drprg_b200 import lib
+from test_oracle_golden import FIXTURE_E, HAND_EDITED, vcf_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def fixture_rows(golden, name):
+    keys, rec_off, mf, mr, gaps, want, gts, confs = [], [0], [], [], [], [], [], []
+    for f, v in vcf_rows(os.path.join(golden, name)):
+        if (name, f[0], int(f[1])) in HAND_EDITED:
+            continue
+        a = [int(x) for x in v["MEAN_FWD_COVG"].split(",")]
+        mf += a
+        mr += [int(x) for x in v["MEAN_REV_COVG"].split(",")]
+        gaps += [float(x) for x in v["GAPS"].split(",")]
+        want += [float(x) for x in v["LIKELIHOOD"].split(",")]
+        rec_off.append(rec_off[-1] + len(a))
+        gts.append(v["GT"])
+        confs.append(float(v["GT_CONF"]))
+        keys.append((f[0], f[1]))
+    return keys, rec_off, mf, mr, gaps, want, gts, confs
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURE_E))
+def test_genotype_kernel_reproduces_reference_vcf_rows(golden, name):
+    keys, rec_off, mf, mr, gaps, want, gts, confs = fixture_rows(golden, name)
+    lik, gt, conf = lib.genotype_rows(rec_off, mf, mr, gaps, FIXTURE_E[name])
+    n_alleles = 0
+    for r, key in enumerate(keys):
+        b, e = rec_off[r], rec_off[r + 1]
+        for a in range(b, e):
+            # 6 significant digits printed; GAPS is itself rounded to 6 digits and multiplied by E
+            assert math.isclose(lik[a], want[a], rel_tol=2e-5, abs_tol=2e-3), (name, key, lik[b:e], want[b:e])
+            n_alleles += 1
+        if gts[r] == ".":
+            continue
+        srt = sorted(lik[b:e], reverse=True)
+        if len(srt) > 1 and srt[0] - srt[1] > 1e-3:
+            assert int(gts[r]) == int(gt[r]), (name, key)
+        assert math.isclose(conf[r], confs[r], rel_tol=2e-4, abs_tol=5e-3), (name, key, conf[r], confs[r])
+    assert n_alleles >= 12
+
+
+def test_genotype_rows_zero_depth_and_min_conf(golden):
+    # zero-depth site: every allele gets exactly -2E, GT 0, GT_CONF 0 (ERR4796933.pandora.vcf ethA 19: -144,-144)
+    lik, gt, conf = lib.genotype_rows([0, 2], [0, 0], [0, 0], [1.0, 1.0], 72)
+    assert lik.tolist() == [-144.0, -144.0] and gt.tolist() == [0] and conf.tolist() == [0.0]
+    # --gt-conf above the confidence nulls the call
+    lik, gt, conf = lib.genotype_rows([0, 2], [40, 0], [30, 1], [0.0, 1.0], 72, min_gt_conf=1e6)
+    assert gt.tolist() == [-1] and conf[0] > 100

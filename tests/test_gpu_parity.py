@@ -344,6 +344,9 @@ def test_config2_full_size_properties_and_oracle():
     N = ox.total_knodes
     assert (whole[:2 * N:2] == f).all() and (whole[1:2 * N:2] == r).all()
     assert (whole[2 * N:2 * N + ox.n_loci] == mr.locus_reads()).all()
+    oh = mr.hits()  # every hit and its kept flag, at full size
+    for hk in ("read", "prg", "fwd", "start", "knode", "kept"):
+        assert len(h[hk]) == len(oh[hk]) and (h[hk] == oh[hk]).all(), hk
     og = O.Genotype(ox, mr, oo, wl.refs_path)
     assert [l for l in og.vcf().splitlines() if not l.startswith("##fileDate")] == vcf_whole
 
@@ -395,6 +398,33 @@ def test_hit_buffer_regrows_on_targeted_reads():
     gx, ox, mr, gh, oo = run_both(prg, refs, d, o, genome_size=len(g), stride_words=10)
     assert len(gh["read"]) > (1 << 20)
     assert_map_equal(gx, mr, gh)
+
+
+def test_minimizer_in_more_than_255_kmer_nodes():
+    """a minimizer k-mer shared by 300 loci has 300 index records: the slot's 8-bit count escapes to a header record
+    (pandora has no limit); hits must equal the oracle's"""
+    rng = np.random.default_rng(77)
+    shared = "".join("ACGT"[i] for i in rng.integers(0, 4, size=90))
+    loci = []
+    for i in range(300):
+        tail = "".join("ACGT"[j] for j in rng.integers(0, 4, size=40))
+        loci.append(f">rep{i}\n{shared}{tail}\n")
+    text = "".join(loci)
+    gx, ox = lib.Index(text=text, w=11, k=15, device=0), O.Index(text=text, w=11, k=15)
+    rec = ox.records()
+    _, counts = np.unique(rec["hash"], return_counts=True)
+    assert counts.max() >= 300
+    reads = [shared[:80], shared[5:90], shared + "ACGTACGTAC", loci[7].split("\n")[1], "".join("ACGT"[j] for j in rng.integers(0, 4, size=150))]
+    data, off = reads_from_strings(reads)
+    oo = O.make_opts(illumina=True, genome_size=100000, min_cluster_size=2)
+    go = lib.make_opts(illumina=True, genome_size=100000, min_cluster_size=2)
+    mr = O.MapRun(ox, data, off, oo)
+    for stride in (0, 10):
+        words, woff, lens = lib.pack_reads(data, off, stride)
+        gx.sample_begin(go, 80)
+        nh, nk = gx.map_batch(gx.upload(words, woff, lens, total_bases=int(off[-1]), stride_words=stride))
+        assert nh > 3000
+        assert_map_equal(gx, mr, gx.last_hits(nh))
 
 
 def _fastq_bytes(reads, crlf=False, final_newline=True):

@@ -149,6 +149,33 @@ def test_read_file_ingest_matches_packer(tmp_path, fmt, gz, threads):
         L.drprg_cuda_host_free(p)
 
 
+def test_wrapped_fastq_is_parsed_like_kseq(tmp_path):
+    """multi-line (wrapped) FASTQ, which pandora's kseq-based reader accepts: sequence lines up to '+', quality lines
+    until they are as long as the sequence — including quality lines that start with '@' or '+'"""
+    rng = np.random.default_rng(11)
+    strs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(L))) for L in rng.integers(1, 500, size=400)]
+    strs[3] = strs[3][:5] + "N" + strs[3][6:]
+    path = tmp_path / "wrapped.fq"
+    with open(path, "w") as f:
+        for i, s_ in enumerate(strs):
+            q = "".join(chr(33 + int(x)) for x in rng.integers(0, 41, size=len(s_)))
+            if i % 7 == 0:
+                q = "@" + q[1:]
+            if i % 11 == 0:
+                q = "+" + q[1:]
+            wrap = 60 if i % 3 else 10 ** 9   # every third record stays on one line
+            f.write(f"@r{i}\n" + "\n".join(s_[j:j + wrap] for j in range(0, len(s_), wrap)) + "\n+\n")
+            f.write("\n".join(q[j:j + wrap] for j in range(0, len(q), wrap)) + "\n")
+    for threads in (1, 8):
+        words, woff, lens, n, tb, fl = lib.read_fastx(path, threads=threads)
+        data = np.frombuffer("".join(strs).encode(), np.uint8)
+        off = np.zeros(len(strs) + 1, np.uint64)
+        off[1:] = np.cumsum([len(s_) for s_ in strs])
+        w2, o2, l2 = lib.pack_reads(data, off)
+        assert n == len(strs) and tb == int(off[-1]) and fl == len(strs[0])
+        assert (lens == l2).all() and (woff == o2).all() and (words == w2).all()
+
+
 def test_hash64_is_inverted_exactly():
     """the k-mer screen is built from hash64's inverse: inverse(hash(x)) == x and hash(inverse(h)) == h for every k, and
     the host hash agrees with the oracle's"""
