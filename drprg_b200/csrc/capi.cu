@@ -117,11 +117,6 @@ struct DevPool {
     }
 } g_pool;
 
-int bits_for(uint64_t v) {
-    int b = 1;
-    while (b < 64 && (v >> b)) ++b;
-    return b;
-}
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -168,17 +163,28 @@ struct drprg_index {
     bool sample_open = false;
     uint32_t first_read_len = 0;
     uint32_t* d_thresh = nullptr;
+    uint32_t min_thresh = 0;
     std::vector<uint32_t> thresh_on_device;
     // workspace
-    DBuf<unsigned long long> hi, lo, hi2, lo2;
-    DBuf<uint32_t> clist, clist2, cend, keys, keys2;
+    DBuf<unsigned long long> hi, lo;  // unordered hits from the lookup kernels
+    DBuf<unsigned long long> gkey;    // hits grouped by read (sorted within a read after the cluster kernels)
+    DBuf<uint8_t> gkept;
+    DBuf<uint32_t> act_read, act_base, act_count, act_lk, lk_ovf, big_list, cov_keys, scratch[10];
+    DBuf<int32_t> read_count;         // per read of a batch; all zero between batches
+    DBuf<uint32_t> read_base;
+    DBuf<int32_t> partials;           // per-stretch coverage partials (cov_count_kernel): n_partials x n_accum
+    uint32_t n_partials = 0;
     DBuf<unsigned long long> queue;  // k-mer screen: flagged (read, position) pairs
     DBuf<uint32_t> queue_kmer;       // ... and their k-mers
-    DBuf<uint8_t> calive, kept, temp;
-    unsigned long long* d_counters = nullptr;  // [0] hit count, [1] kept count
+    unsigned long long* d_counters = nullptr;  // CTR_* of kernels.cuh
     unsigned long long* h_counters = nullptr;  // pinned
-    uint64_t last_n_hits = 0;
-    cudaEvent_t ev[6]{};  // [5]: end of the sketch+lookup kernels (before the host reads the hit count)
+    uint64_t last_n_hits = 0, last_n_active = 0;
+    uint32_t last_id_base = 0;
+    // read-sharded runs: where this GPU's coverage goes (nullptr = its own accumulator; otherwise the root GPU's
+    // accumulator, peer-mapped, updated with red.global.add by cov_merge_kernel)
+    int32_t* reduce_dst = nullptr;
+    bool accum_shared = false;  // other GPUs add into this accumulator: the histogram taken at the end of map_batch is not final
+    cudaEvent_t ev[6]{};  // batch timeline: start, lookup done, hits grouped, clustered, coverage merged
     float timings[4] = {0, 0, 0, 0};
     // genotype state
     std::string refs_path;
@@ -229,9 +235,12 @@ struct drprg_index {
                         (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist, (void*)d_kfilter, (void*)d_locus_level_off, (void*)d_level_start, (void*)d_level_nodes, (void*)d_level_singles})
             if (p) cudaFree(p);
         if (h_counters) cudaFreeHost(h_counters);
-        hi.release(); lo.release(); hi2.release(); lo2.release();
-        clist.release(); clist2.release(); cend.release(); keys.release(); keys2.release(); queue.release(); queue_kmer.release();
-        calive.release(); kept.release(); temp.release();
+        hi.release(); lo.release(); gkey.release(); gkept.release();
+        act_read.release(); act_base.release(); act_count.release(); act_lk.release(); lk_ovf.release(); big_list.release(); cov_keys.release();
+        for (auto& b : scratch) b.release();
+        read_count.release(); read_base.release();
+        partials.release();
+        queue.release(); queue_kmer.release();
         d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
@@ -259,6 +268,9 @@ void upload_index(drprg_index* X) {
     if (H.k > (uint32_t)K_MAX) throw std::runtime_error("k > 16 is not supported by the device kernels (2k must fit 32 bits)");
     if (H.w > (uint32_t)W_MAX) throw std::runtime_error("w > 32 is not supported by the device kernels");
     if (H.loci.size() > 65535) throw std::runtime_error("more than 65535 loci");
+    for (size_t l = 0; l < H.loci.size(); ++l)
+        if (H.loci[l].kpath.size() >= (1ull << GKEY_KNODE_BITS)) throw std::runtime_error("a locus has more than 4 M k-mer nodes");
+    if (2ull * H.total_knodes() + H.loci.size() >= (1ull << 31)) throw std::runtime_error("too many k-mer nodes for 32-bit coverage keys");
     // ---- hash table + pre-filter
     std::vector<uint2> recs;
     recs.reserve(H.records.size() + 16);
@@ -439,8 +451,9 @@ void upload_index(drprg_index* X) {
     CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
     CK(cudaMalloc(&X->d_thresh, std::max<size_t>(1, H.loci.size()) * sizeof(uint32_t)));
-    CK(cudaMalloc(&X->d_counters, 8 * sizeof(unsigned long long)));  // [0] hits, [1] kept hits, [2] screen queue length, [3] screen ticket, [4] largest queue length wanted
-    CK(cudaMallocHost(&X->h_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&X->d_counters, CTR_COUNT * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&X->h_counters, CTR_COUNT * sizeof(unsigned long long)));
+
     for (auto& e : X->ev) CK(cudaEventCreate(&e));
     std::vector<uint32_t> knode_locus(N);
     for (size_t l = 0; l < H.loci.size(); ++l) {
@@ -519,6 +532,7 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
         uint32_t lbt = (uint32_t)(std::min(X->H.loci[l].min_path_len, expected) * fraction);
         thr[l] = std::max(lbt, X->opts.min_cluster_size);
     }
+    X->min_thresh = thr.empty() ? 0u : *std::min_element(thr.begin(), thr.end());
     if (thr != X->thresh_on_device) {  // unchanged between the samples of a batch: skip the synchronous copy
         if (!thr.empty()) CK(cudaMemcpy(X->d_thresh, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
         X->thresh_on_device = thr;
@@ -532,31 +546,54 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
 }
 
 void ensure_hit_capacity(drprg_index* X, uint64_t cap) {
-    X->hi.ensure(cap); X->lo.ensure(cap); X->hi2.ensure(cap); X->lo2.ensure(cap);
-    X->clist.ensure(cap); X->clist2.ensure(cap); X->cend.ensure(cap); X->keys.ensure(cap); X->keys2.ensure(cap);
-    X->calive.ensure(cap); X->kept.ensure(cap);
-    X->temp.ensure(std::max(sort_hits_temp_bytes(cap), sort_cov_temp_bytes(cap)));
+    if (cap >= 0xfffffff0ull) throw std::runtime_error("more than 2^32 hits in one batch: split the batch");
+    if (cap <= X->hi.cap) return;
+    X->hi.ensure(cap);
+    const size_t c = X->hi.cap;  // every per-hit buffer follows the hit buffer's capacity
+    X->lo.ensure(c); X->gkey.ensure(c); X->gkept.ensure(c);
+    X->act_read.ensure(c); X->act_base.ensure(c); X->act_count.ensure(c);
+    X->act_lk.ensure(2 * c); X->lk_ovf.ensure(c);
+    X->big_list.ensure(c / CLUSTER_WARP_MAX + 16);
+    X->cov_keys.ensure(c);
+    for (auto& b : X->scratch) b.ensure(c);
+    X->n_partials = cov_max_stretches(c, X->sm_count);
+    X->partials.ensure((size_t)X->n_partials * X->n_accum);
+}
+
+void ensure_read_capacity(drprg_index* X, uint64_t n_reads) {
+    if (n_reads <= X->read_count.cap) return;
+    X->read_count.ensure(n_reads);
+    X->read_base.ensure(X->read_count.cap);
+    CK(cudaMemset(X->read_count.p, 0, X->read_count.cap * sizeof(int32_t)));  // the kernels leave it zero after every batch
 }
 
 void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits, uint64_t* n_kept) {
     if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
     CK(cudaSetDevice(X->device));
     const HostIndex& H = X->H;
-    // whole-genome reads give ~0.35 hits per 150 bp read; a targeted run overflows once, regrows to the exact count and re-sketches
-    uint64_t cap = std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 256));
-    ensure_hit_capacity(X, cap);
+    if (B->max_len != UINT32_MAX && B->max_len >= (1u << GKEY_START_BITS)) throw std::runtime_error("reads of 32 Mb or more are not supported");
+    // whole-genome reads give ~0.35 hits per 150 bp read; a targeted run overflows once, regrows to the exact count and is redone
+    ensure_hit_capacity(X, std::max<uint64_t>(X->hi.cap, std::max<uint64_t>(1u << 20, B->total_bases / 256)));
+    ensure_read_capacity(X, B->R.n_reads);
     if (X->T.kfilter) {  // ~2 flagged positions per 150 bp read
         X->queue.ensure(std::max<uint64_t>(X->queue.cap, B->total_bases / 32 + (1u << 20)));
         X->queue_kmer.ensure(X->queue.cap);
     }
+    const uint32_t N = H.total_knodes(), P = (uint32_t)H.loci.size();
     uint64_t nh = 0;
-    CK(cudaEventRecord(X->ev[0], st));
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        CK(cudaMemsetAsync(X->d_counters, 0, 5 * sizeof(unsigned long long), st));
+    // The whole batch is enqueued without a host round trip: the kernels after the lookup read their sizes from the
+    // device counters.  A buffer that turned out too small is noticed at the end (the kernels downstream of an overflow
+    // skip their work, the accumulators are untouched) and the batch is redone with larger buffers.
+    for (int attempt = 0;; ++attempt) {
+        const uint64_t queue_cap = X->T.kfilter ? std::min(X->queue.cap, X->queue_kmer.cap) : 0;
+        CK(cudaMemsetAsync(X->d_counters, 0, CTR_COUNT * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(X->ev[0], st));
         for (int c = 0; c < B->n_chunks; ++c) {
             DevReads Rc = B->R;
+            Rc.hit_count = X->read_count.p;
             if (B->n_chunks > 1) {
                 const uint64_t lo = B->chunk_lo[c], hi = B->chunk_lo[c + 1];
+                Rc.hit_count = X->read_count.p + lo;
                 if (B->ev[c]) CK(cudaStreamWaitEvent(st, B->ev[c], 0));
                 Rc.words = B->R.stride_words ? B->R.words + lo * B->R.stride_words : B->R.words;
                 Rc.word_off = B->R.word_off ? B->R.word_off + lo : nullptr;
@@ -564,57 +601,59 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
                 Rc.n_reads = hi - lo;
                 Rc.read_id_base = B->R.read_id_base + (uint32_t)lo;
             }
-            launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters, X->hi.cap, X->sm_count, B->max_len, st,
-                                 X->queue.p, std::min(X->queue.cap, X->queue_kmer.cap), X->d_counters + 2, X->queue_kmer.p);
+            launch_sketch_lookup(Rc, X->T, H.w, H.k, X->hi.p, X->lo.p, X->d_counters + CTR_HITS, X->hi.cap, X->sm_count, B->max_len, st,
+                                 X->queue.p, queue_cap, X->d_counters + CTR_QUEUE, X->queue_kmer.p);
         }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(X->ev[5], st));
-        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(X->ev[1], st));
+        PostBuffers PB{};
+        PB.hi = X->hi.p; PB.lo = X->lo.p; PB.ctr = X->d_counters;
+        PB.read_count = X->read_count.p; PB.read_base = X->read_base.p;
+        PB.act_read = X->act_read.p; PB.act_base = X->act_base.p; PB.act_count = X->act_count.p;
+        PB.act_lk = X->act_lk.p; PB.lk_ovf = X->lk_ovf.p;
+        PB.big_list = X->big_list.p; PB.gkey = X->gkey.p; PB.gkept = X->gkept.p; PB.cov_keys = X->cov_keys.p;
+        for (int i = 0; i < 10; ++i) PB.scratch[i] = X->scratch[i].p;
+        PB.partials = X->partials.p; PB.n_partials = X->n_partials;
+        launch_postprocess(PB, PostCaps{X->hi.cap, queue_cap}, B->R.read_id_base, B->R.n_reads, X->opts.max_diff, X->min_thresh, X->d_thresh,
+                           X->d_knode_base, N, P, X->reduce_dst ? X->reduce_dst : X->d_accum, X->reduce_dst ? 1 : 0, X->sm_count, st,
+                           X->ev[2], X->ev[3]);
+        CK(cudaEventRecord(X->ev[4], st));
+        CK(cudaGetLastError());
+        if (!X->reduce_dst) {
+            // what the genotype step needs first (coverage histogram, locus read counts: 4 KB) rides on this batch's final
+            // synchronisation; it stays valid unless the accumulators change before drprg_cuda_genotype (another batch
+            // recomputes it, a reduce from other GPUs invalidates it)
+            launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
+            X->h_small.resize(1000 + (size_t)P + 4);
+            CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(X->h_counters, X->d_counters, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        nh = X->h_counters[0];
-        const uint64_t nq = X->h_counters[4];  // largest screen queue any chunk wanted
-        if (nh <= X->hi.cap && nq <= std::min(X->queue.cap, X->queue_kmer.cap)) break;
+        nh = X->h_counters[CTR_HITS];
+        const uint64_t nq = X->h_counters[CTR_QUEUE_NEED];  // largest screen queue any chunk wanted
+        if (nh <= X->hi.cap && nq <= queue_cap) break;
         if (attempt == 2) throw std::runtime_error("hit buffer overflow");
+        // the lookup kernels counted hits per read that were never scattered: the counters must be zero before the redo
+        CK(cudaMemsetAsync(X->read_count.p, 0, X->read_count.cap * sizeof(int32_t), st));
         if (nh > X->hi.cap) ensure_hit_capacity(X, nh);
-        if (nq > X->queue.cap) {
+        if (nq > queue_cap) {
             X->queue.ensure(nq);
             X->queue_kmer.ensure(X->queue.cap);
         }
-        CK(cudaEventRecord(X->ev[0], st));
     }
-    CK(cudaEventRecord(X->ev[1], st));
-    const uint32_t max_len = B->max_len;  // read_start < longest read
-    sort_hits(X->temp.p, X->temp.cap, X->hi.p, X->lo.p, X->hi2.p, X->lo2.p, nh,
-              bits_for((uint64_t)B->R.read_id_base + B->R.n_reads), bits_for(max_len), bits_for(X->max_locus_knodes),
-              bits_for(H.loci.size()), st);
-    CK(cudaEventRecord(X->ev[2], st));
-    int32_t* d_locus_reads = X->d_accum + 2ull * H.total_knodes();
-    launch_cluster_filter(X->hi.p, X->lo.p, nh, X->opts.max_diff, X->d_thresh, X->clist.p, X->clist2.p, X->cend.p,
-                          X->calive.p, X->kept.p, d_locus_reads, st);
-    CK(cudaEventRecord(X->ev[3], st));
-    launch_coverage(X->hi.p, X->lo.p, X->kept.p, nh, X->d_knode_base, X->keys.p, X->keys2.p, X->temp.p, X->temp.cap,
-                    bits_for(2ull * H.total_knodes()),
-                    X->d_accum, X->d_counters + 1, st);
-    CK(cudaEventRecord(X->ev[4], st));
-    CK(cudaGetLastError());
-    {   // what the genotype step needs first (coverage histogram, locus read counts: 4 KB) rides on this batch's final
-        // synchronisation; it stays valid unless the accumulators change before drprg_cuda_genotype (another batch
-        // recomputes it, an allreduce through accum_device_ptr invalidates it)
-        const uint32_t N = H.total_knodes(), P = (uint32_t)H.loci.size();
-        launch_cov_hist(X->d_accum, N, X->d_is_terminal, X->d_knode_locus, X->d_accum + 2ull * N, X->d_hist1000, st);
-        X->h_small.resize(1000 + (size_t)P + 4);
-        CK(cudaMemcpyAsync(X->h_small.data(), X->d_hist1000, 1000 * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(X->h_small.data() + 1000, X->d_accum + 2ull * N, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaMemcpyAsync(X->h_counters + 1, X->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    X->hist_on_host = true;
-    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&X->timings[i], X->ev[i], X->ev[i == 0 ? 5 : i + 1]));
+    X->hist_on_host = !X->reduce_dst && !X->accum_shared;
+    CK(cudaEventElapsedTime(&X->timings[0], X->ev[0], X->ev[1]));
+    CK(cudaEventElapsedTime(&X->timings[1], X->ev[1], X->ev[2]));
+    CK(cudaEventElapsedTime(&X->timings[2], X->ev[2], X->ev[3]));
+    CK(cudaEventElapsedTime(&X->timings[3], X->ev[3], X->ev[4]));
     X->last_n_hits = nh;
+    X->last_n_active = X->h_counters[CTR_ACTIVE];
+    X->last_id_base = B->R.read_id_base;
     X->total_bases += B->total_bases;
     X->n_reads += B->R.n_reads;
     if (n_hits) *n_hits = nh;
-    if (n_kept) *n_kept = nh ? X->h_counters[1] : 0;
+    if (n_kept) *n_kept = X->h_counters[CTR_KEPT];
 }
 
 void flush_scalars(drprg_index* X) {
@@ -1449,21 +1488,38 @@ int64_t drprg_cuda_last_hits(drprg_index* X, uint32_t* read, uint32_t* start, ui
     try {
         need_device(X);
         CK(cudaSetDevice(X->device));
-        const uint64_t n = X->last_n_hits;
+        const uint64_t n = X->last_n_hits, na = X->last_n_active;
         if (n > cap) return -(int64_t)n;
-        std::vector<unsigned long long> hi(n), lo(n);
+        // the device keeps the hits grouped by read (slices in no particular order, sorted within a read): pandora's
+        // order (read, prg, strand, read_start, k-mer node) is restored here by ordering the slices by read id
+        std::vector<unsigned long long> key(n);
+        std::vector<uint8_t> kp(n);
+        std::vector<uint32_t> ar(na), ab(na), ac(na);
         if (n) {
-            CK(cudaMemcpy(hi.data(), X->hi.p, n * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(lo.data(), X->lo.p, n * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(kept, X->kept.p, n, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(key.data(), X->gkey.p, n * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(kp.data(), X->gkept.p, n, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ar.data(), X->act_read.p, na * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ab.data(), X->act_base.p, na * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ac.data(), X->act_count.p, na * 4, cudaMemcpyDeviceToHost));
         }
-        for (uint64_t i = 0; i < n; ++i) {
-            read[i] = (uint32_t)(hi[i] >> 32);
-            prg[i] = (uint32_t)(hi[i] >> 16) & 0xffff;
-            fwd[i] = (uint8_t)((((uint32_t)hi[i] >> 15) & 1) ^ 1);
-            start[i] = (uint32_t)(lo[i] >> 32);
-            knode[i] = (uint32_t)lo[i];
+        std::vector<uint32_t> ord(na);
+        for (uint32_t i = 0; i < na; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ar[a] < ar[b]; });
+        uint64_t o = 0;
+        for (uint32_t a : ord) {
+            // reads that cannot keep anything are not sorted on the device; their flags are all 0, so sorting the keys alone is exact
+            if (!std::is_sorted(key.begin() + ab[a], key.begin() + ab[a] + ac[a])) std::sort(key.begin() + ab[a], key.begin() + ab[a] + ac[a]);
+            for (uint32_t j = ab[a]; j < ab[a] + ac[a]; ++j, ++o) {
+                const unsigned long long k = key[j];
+                read[o] = X->last_id_base + ar[a];
+                prg[o] = (uint32_t)(k >> 48);
+                fwd[o] = (uint8_t)(((k >> 47) & 1ull) ^ 1ull);
+                start[o] = (uint32_t)(k >> GKEY_KNODE_BITS) & ((1u << GKEY_START_BITS) - 1u);
+                knode[o] = (uint32_t)k & ((1u << GKEY_KNODE_BITS) - 1u);
+                kept[o] = kp[j];
+            }
         }
+        if (o != n) throw std::runtime_error("grouped hits do not add up");
         return (int64_t)n;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -5,12 +5,12 @@
 //
 // This file: S3 - S5 (hit grouping, clustering + filters, k-mer coverage) with no library sort and no host round trip.
 //
-// The lookup kernels append hits in no particular order.  pandora orders them (read, prg, strand, read_start, k-mer
-// node) and everything downstream is per read, so nothing here sorts globally:
-//   count_reads_kernel    per-read hit counters; the first hit of a read enrols it in the list of active reads
-//                         (~1.4 % of whole-genome reads touch the panel)
-//   assign_kernel         every active read gets a contiguous slice of the grouped-hit array (order of the slices is
-//                         immaterial: all later results are sums) and a class: <= 64 hits -> a warp, more -> a CTA
+// The lookup kernels append hits in no particular order and count them per read as they go.  pandora orders the hits
+// (read, prg, strand, read_start, k-mer node) and everything downstream is per read, so nothing here sorts globally:
+//   assign_kernel         one pass over the per-read hit counters: every read with hits ("active", ~1.4 % of whole-genome
+//                         reads) gets a contiguous slice of the grouped-hit array (block scan, one slice allocation per
+//                         CTA; the order of the slices is immaterial, all later results are sums) and a class:
+//                         <= 64 hits -> a warp, more -> a CTA
 //   scatter_kernel        hits move into their read's slice as ONE 64-bit key prg | strand | read_start | k-mer node whose
 //                         integer order is pandora's MinimizerHit order within a read; the per-read counters count back
 //                         down to zero, so they never need a memset
@@ -19,13 +19,15 @@
 //                         surviving clusters (usually one)
 //   cluster_cta_kernel    one CTA per long read: the same with a shared-memory (or, beyond 8 k hits, in-place global)
 //                         bitonic sort and a block scan for the cluster boundaries
-//   both emit, for every kept hit, the coverage key 2 * k-mer node + strand, and one key 2N + locus per kept cluster
-//   cov_tile_kernel       S5: sorted-key reduction without atomics.  A persistent CTA sorts tiles of 8 k keys in shared
-//                         memory, turns them into (key, run length) and adds the run lengths to its PRIVATE partial
-//                         accumulator (each key occurs once per tile after the sort: plain adds, no conflicts)
+//   both write, next to every grouped hit, its coverage key 2 * k-mer node + strand (or "none" when the hit is dropped),
+//   and per read the keys 2N + locus of its kept clusters: no allocation, no atomics
+//   cov_count_kernel      S5 without atomics: a job = (range of 6 k counters, stretch of 32 k key slots); its CTA keeps a
+//                         PRIVATE copy of the range's counters per warp in shared memory, every warp compacts the keys
+//                         of its share of the stretch that fall into the range and counts them, equal keys of one step
+//                         combined by match.any: every increment is a plain read-modify-write with a single writer
 //   cov_merge_kernel      column sum of the partials into the sample's accumulator — or, on a read-sharded run, straight
 //                         into the ROOT GPU's accumulator over NVLink with red.global.add (integers: bit-exact for any
-//                         number of GPUs), which is the whole "allreduce" of the path
+//                         number of GPUs), which is the whole "allreduce" of the path; also counts the kept hits
 // Overflowing buffers are detected at the end of the batch (the kernels skip their work when a counter exceeds its
 // capacity, the accumulators stay untouched) and the batch is redone with larger buffers.
 #include <algorithm>
@@ -55,47 +57,74 @@ __device__ __forceinline__ bool batch_overflowed(const unsigned long long* __res
 // ============================================================================================
 // grouping by read
 // ============================================================================================
-__global__ void count_reads_kernel(const unsigned long long* __restrict__ hi, unsigned long long* __restrict__ ctr, PostCaps C,
-                                   uint32_t read_id_base, int32_t* __restrict__ read_count, uint32_t* __restrict__ act_read) {
+constexpr int AS_THREADS = 256, AS_PER = 4;  // a CTA step covers 1024 reads: four consecutive counters per thread (one 16-byte load)
+__global__ void __launch_bounds__(AS_THREADS) assign_kernel(unsigned long long* __restrict__ ctr, PostCaps C, unsigned long long n_reads,
+                                                            const int32_t* __restrict__ read_count, uint32_t* __restrict__ act_read,
+                                                            uint32_t* __restrict__ act_base, uint32_t* __restrict__ act_count,
+                                                            uint32_t* __restrict__ read_base, uint32_t* __restrict__ big_list) {
+    __shared__ unsigned long long s_warp[AS_THREADS / 32];
+    __shared__ unsigned long long s_base[3];
     if (batch_overflowed(ctr, C)) return;
-    const unsigned long long n = ctr[CTR_HITS];
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(hi[i] >> 32) - read_id_base;
-        if (atomicAdd(read_count + r, 1) == 0) act_read[atomicAdd(ctr + CTR_ACTIVE, 1ull)] = r;
-    }
-}
-
-__global__ void assign_kernel(unsigned long long* __restrict__ ctr, PostCaps C, const int32_t* __restrict__ read_count,
-                              const uint32_t* __restrict__ act_read, uint32_t* __restrict__ act_base,
-                              uint32_t* __restrict__ act_count, uint32_t* __restrict__ read_base,
-                              uint32_t* __restrict__ big_list) {
-    if (batch_overflowed(ctr, C)) return;
-    const unsigned long long n = ctr[CTR_ACTIVE];
-    const int lane = threadIdx.x & 31;
-    for (unsigned long long a0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; a0 < n;
-         a0 += (unsigned long long)gridDim.x * blockDim.x) {  // warp-uniform trip count
-        const unsigned long long a = a0 + lane;
-        uint32_t r = 0, c = 0;
-        if (a < n) {
-            r = act_read[a];
-            c = (uint32_t)read_count[r];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long step = (unsigned long long)AS_THREADS * AS_PER;
+    for (unsigned long long r0 = (unsigned long long)blockIdx.x * step; r0 < n_reads; r0 += (unsigned long long)gridDim.x * step) {
+        const unsigned long long r = r0 + (unsigned long long)tid * AS_PER;
+        uint32_t c[AS_PER] = {0u, 0u, 0u, 0u};
+        if (r + AS_PER <= n_reads) {  // read_count comes from cudaMalloc and r is a multiple of 4: the 16-byte load is aligned
+            const int4 v = __ldg(reinterpret_cast<const int4*>(read_count + r));
+            c[0] = (uint32_t)v.x; c[1] = (uint32_t)v.y; c[2] = (uint32_t)v.z; c[3] = (uint32_t)v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < AS_PER; ++q)
+                if (r + q < n_reads) c[q] = (uint32_t)read_count[r + q];
         }
-        uint32_t incl = c;
+        // one scan for three running sums: hits (bits 0..39), active reads (40..51), long reads (52..63)
+        unsigned long long pre[AS_PER + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int q = 0; q < AS_PER; ++q)
+            pre[q + 1] = pre[q] + ((unsigned long long)c[q] | (c[q] ? 1ull << 40 : 0ull) | (c[q] > CLUSTER_WARP_MAX ? 1ull << 52 : 0ull));
+        const unsigned long long mine = pre[AS_PER];
+        unsigned long long incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            const unsigned long long t = ((unsigned long long)__shfl_up_sync(FULL, (uint32_t)(incl >> 32), d) << 32) | __shfl_up_sync(FULL, (uint32_t)incl, d);
             if (lane >= d) incl += t;
         }
-        unsigned long long base = 0;
-        if (lane == 31) base = atomicAdd(ctr + CTR_CURSOR, (unsigned long long)incl);  // one slice allocation per warp
-        base = __shfl_sync(FULL, base, 31) + (incl - c);
-        if (a < n) {
-            act_base[a] = (uint32_t)base;
-            act_count[a] = c;
-            read_base[r] = (uint32_t)base;
-            if (c > CLUSTER_WARP_MAX) big_list[atomicAdd(ctr + CTR_BIG, 1ull)] = (uint32_t)a;
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long v = lane < AS_THREADS / 32 ? s_warp[lane] : 0ull;
+            unsigned long long w = v;
+#pragma unroll
+            for (int d = 1; d < AS_THREADS / 32; d <<= 1) {
+                const unsigned long long t = ((unsigned long long)__shfl_up_sync(FULL, (uint32_t)(w >> 32), d) << 32) | __shfl_up_sync(FULL, (uint32_t)w, d);
+                if (lane >= d) w += t;
+            }
+            if (lane < AS_THREADS / 32) s_warp[lane] = w - v;  // exclusive warp offsets
+            if (lane == AS_THREADS / 32 - 1 && w) {          // one allocation per CTA step for the three lists
+                s_base[0] = atomicAdd(ctr + CTR_CURSOR, w & ((1ull << 40) - 1ull));
+                s_base[1] = atomicAdd(ctr + CTR_ACTIVE, (w >> 40) & 0xfffull);
+                s_base[2] = ((w >> 52) & 0xfffull) ? atomicAdd(ctr + CTR_BIG, (w >> 52) & 0xfffull) : 0ull;
+            }
         }
+        __syncthreads();
+        if (mine) {
+            const unsigned long long excl0 = s_warp[wid] + incl - mine;
+#pragma unroll
+            for (int q = 0; q < AS_PER; ++q) {
+                if (!c[q]) continue;
+                const unsigned long long excl = excl0 + pre[q];
+                const uint32_t base = (uint32_t)(s_base[0] + (excl & ((1ull << 40) - 1ull)));
+                const uint32_t a = (uint32_t)(s_base[1] + ((excl >> 40) & 0xfffull));
+                act_read[a] = (uint32_t)(r + q);
+                act_base[a] = base;
+                act_count[a] = c[q];
+                read_base[r + q] = base;
+                if (c[q] > CLUSTER_WARP_MAX) big_list[s_base[2] + ((excl >> 52) & 0xfffull)] = a;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -204,21 +233,6 @@ __device__ void filter_clusters_warp(uint32_t ncl, const ClusterArrays& A, int l
     }
 }
 
-// ---- coverage-key emission shared by the two cluster kernels: one slot allocation per warp --------------------
-__device__ __forceinline__ uint32_t warp_alloc(unsigned long long* counter, uint32_t mine, int lane, uint32_t& total) {
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
-    }
-    total = __shfl_sync(FULL, incl, 31);
-    unsigned long long base = 0;
-    if (total && lane == 31) base = atomicAdd(counter, (unsigned long long)total);
-    base = __shfl_sync(FULL, base, 31);
-    return (uint32_t)base + (incl - mine);
-}
-
 // ============================================================================================
 // one warp per read with <= 64 hits
 // ============================================================================================
@@ -234,10 +248,39 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
     return ((unsigned long long)__shfl_sync(FULL, (uint32_t)(v >> 32), src) << 32) | __shfl_sync(FULL, (uint32_t)v, src);
 }
 
+// bitonic network over the 32 * NREG keys of a warp, fully unrolled (every shuffle distance and direction is static)
+template <int NREG>
+__device__ __forceinline__ void warp_sort64(unsigned long long& x0, unsigned long long& x1, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * NREG; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {  // k == 64: the last merge is ascending over all 64 elements
+                const unsigned long long lo = x0 < x1 ? x0 : x1, hi = x0 < x1 ? x1 : x0;
+                x0 = lo;
+                x1 = hi;
+            } else {
+                const bool lower = (lane & j) == 0;
+                {
+                    const unsigned long long y = shfl_xor64(x0, j);
+                    const bool take_min = lower == ((lane & k) == 0);
+                    x0 = ((x0 < y) == take_min) ? x0 : y;
+                }
+                if (NREG == 2) {
+                    const unsigned long long y = shfl_xor64(x1, j);
+                    const bool take_min = lower == (((lane + 32) & k) == 0);
+                    x1 = ((x1 < y) == take_min) ? x1 : y;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CW_WARPS * 32) cluster_warp_kernel(
     unsigned long long* __restrict__ ctr, PostCaps C, const uint32_t* __restrict__ act_base, const uint32_t* __restrict__ act_count,
-    unsigned long long* __restrict__ gkey, uint8_t* __restrict__ gkept, uint32_t max_diff, const uint32_t* __restrict__ thresh,
-    const uint32_t* __restrict__ knode_base, uint32_t locus_key_base, uint32_t* __restrict__ cov_keys) {
+    unsigned long long* __restrict__ gkey, uint8_t* __restrict__ gkept, uint32_t max_diff, uint32_t min_thresh, const uint32_t* __restrict__ thresh,
+    const uint32_t* __restrict__ knode_base, uint32_t locus_key_base, uint32_t* __restrict__ cov_keys, uint32_t* __restrict__ act_lk,
+    uint32_t* __restrict__ lk_ovf) {
     __shared__ uint32_t s_u32[CW_WARPS][6][64];  // first, last, size, pf, ord, ord2
     __shared__ uint32_t s_alive[CW_WARPS][64];
     if (batch_overflowed(ctr, C)) return;
@@ -247,33 +290,23 @@ __global__ void __launch_bounds__(CW_WARPS * 32) cluster_warp_kernel(
         const uint32_t c = act_count[a];
         if (c > CLUSTER_WARP_MAX) continue;  // the CTA kernel's read
         const uint32_t base = act_base[a];
+        if (c <= min_thresh) {  // no cluster of this read can exceed any locus's size threshold (stray hits): nothing is kept
+            if ((uint32_t)lane < c) {
+                gkept[base + lane] = 0;
+                cov_keys[base + lane] = COV_KEY_NONE;
+            }
+            if ((uint32_t)lane + 32u < c) {
+                gkept[base + 32 + lane] = 0;
+                cov_keys[base + 32 + lane] = COV_KEY_NONE;
+            }
+            if (lane < 2) act_lk[2 * a + lane] = COV_KEY_NONE;
+            continue;
+        }
         // element i lives in lane i & 31, register i >> 5; padding sorts to the end
         unsigned long long x0 = (uint32_t)lane < c ? gkey[base + lane] : ~0ull;
         unsigned long long x1 = (uint32_t)lane + 32u < c ? gkey[base + 32 + lane] : ~0ull;
-        const bool two = c > 32u;  // warp-uniform
-        const int top = two ? 64 : 32;
-        for (int k = 2; k <= top; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j == 32) {  // k == 64: the last merge is ascending over all 64 elements
-                    if (x0 > x1) {
-                        const unsigned long long t = x0;
-                        x0 = x1;
-                        x1 = t;
-                    }
-                } else {
-                    const bool lower = (lane & j) == 0;
-                    {
-                        const unsigned long long y = shfl_xor64(x0, j);
-                        const bool asc = (lane & k) == 0;
-                        x0 = (lower == asc) ? (x0 < y ? x0 : y) : (x0 < y ? y : x0);
-                    }
-                    if (two) {
-                        const unsigned long long y = shfl_xor64(x1, j);
-                        const bool asc = ((lane + 32) & k) == 0;
-                        x1 = (lower == asc) ? (x1 < y ? x1 : y) : (x1 < y ? y : x1);
-                    }
-                }
-            }
+        if (c > 32u) warp_sort64<2>(x0, x1, lane);  // warp-uniform
+        else warp_sort64<1>(x0, x1, lane);
         if ((uint32_t)lane < c) gkey[base + lane] = x0;  // the slice stays sorted for the hooks / later consumers
         if ((uint32_t)lane + 32u < c) gkey[base + 32 + lane] = x1;
         // ---- define_clusters: a hit opens a cluster when prg or strand change or the gap exceeds max_diff
@@ -305,8 +338,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32) cluster_warp_kernel(
         const unsigned long long BP = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
         const uint32_t ncl = (uint32_t)__popcll(BP);
         if (ncl == 0u) {
-            if ((uint32_t)lane < c) gkept[base + lane] = 0;
-            if ((uint32_t)lane + 32u < c) gkept[base + 32 + lane] = 0;
+            if ((uint32_t)lane < c) {
+                gkept[base + lane] = 0;
+                cov_keys[base + lane] = COV_KEY_NONE;
+            }
+            if ((uint32_t)lane + 32u < c) {
+                gkept[base + 32 + lane] = 0;
+                cov_keys[base + 32 + lane] = COV_KEY_NONE;
+            }
+            if (lane < 2) act_lk[2 * a + lane] = COV_KEY_NONE;
             continue;
         }
         bool alive[2] = {pass[0], pass[1]};
@@ -338,20 +378,21 @@ __global__ void __launch_bounds__(CW_WARPS * 32) cluster_warp_kernel(
                 if (pass[r]) alive[r] = s_alive[wid][(uint32_t)__popcll(BP & ((1ull << cb[r]) - 1ull))] != 0u;
         }
         // ---- add_clusters_to_pangraph: kept flags, one coverage key per kept hit, one locus key per kept cluster
-        if ((uint32_t)lane < c) gkept[base + lane] = alive[0] ? 1 : 0;
-        if ((uint32_t)lane + 32u < c) gkept[base + 32 + lane] = alive[1] ? 1 : 0;
-        const uint32_t mine = (alive[0] ? 1u : 0u) + (alive[1] ? 1u : 0u) + ((alive[0] && begin_pass[0]) ? 1u : 0u) +
-                              ((alive[1] && begin_pass[1]) ? 1u : 0u);
-        uint32_t total;
-        uint32_t o = warp_alloc(ctr + CTR_COVKEYS, mine, lane, total);
-        const uint32_t nkept = __popc(__ballot_sync(FULL, alive[0])) + __popc(__ballot_sync(FULL, alive[1]));
-        if (lane == 0 && nkept) atomicAdd(ctr + CTR_KEPT, (unsigned long long)nkept);
+        const uint32_t k0m = __ballot_sync(FULL, alive[0] && begin_pass[0]), k1m = __ballot_sync(FULL, alive[1] && begin_pass[1]);
+        const unsigned long long KB = (unsigned long long)k0m | ((unsigned long long)k1m << 32);  // begins of the kept clusters
+        if (lane < 2 && (uint32_t)__popcll(KB) <= (uint32_t)lane) act_lk[2 * a + lane] = COV_KEY_NONE;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            if (!alive[r]) continue;
+            const uint32_t i = (uint32_t)lane + 32u * r;
+            if (i >= c) continue;
             const unsigned long long xr = r ? x1 : x0;
-            cov_keys[o++] = 2u * (knode_base[gk_prg(xr)] + gk_knode(xr)) + gk_rev(xr);
-            if (begin_pass[r]) cov_keys[o++] = locus_key_base + gk_prg(xr);
+            gkept[base + i] = alive[r] ? 1 : 0;
+            cov_keys[base + i] = alive[r] ? 2u * (knode_base[gk_prg(xr)] + gk_knode(xr)) + gk_rev(xr) : COV_KEY_NONE;
+            if (alive[r] && begin_pass[r]) {
+                const uint32_t t = (uint32_t)__popcll(KB & ((1ull << i) - 1ull));
+                if (t < 2u) act_lk[2 * a + t] = locus_key_base + gk_prg(xr);
+                else lk_ovf[atomicAdd(ctr + CTR_LKOVF, 1ull)] = locus_key_base + gk_prg(xr);  // a third kept cluster on one short read: rare
+            }
         }
     }
 }
@@ -395,9 +436,9 @@ __global__ void __launch_bounds__(CC_THREADS) cluster_cta_kernel(
     unsigned long long* __restrict__ ctr, PostCaps C, const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ act_base,
     const uint32_t* __restrict__ act_count, unsigned long long* __restrict__ gkey, uint8_t* __restrict__ gkept, uint32_t max_diff,
     const uint32_t* __restrict__ thresh, const uint32_t* __restrict__ knode_base, uint32_t locus_key_base,
-    uint32_t* __restrict__ cov_keys, BigScratch B) {
+    uint32_t* __restrict__ cov_keys, uint32_t* __restrict__ act_lk, uint32_t* __restrict__ lk_ovf, BigScratch B) {
     extern __shared__ unsigned long long s_keys[];
-    __shared__ uint32_t s_carry, s_ncl, s_warp_max[CC_THREADS / 32];
+    __shared__ uint32_t s_carry, s_ncl, s_nlk, s_warp_max[CC_THREADS / 32];
     if (batch_overflowed(ctr, C)) return;
     const unsigned long long n_big = ctr[CTR_BIG];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -417,7 +458,9 @@ __global__ void __launch_bounds__(CC_THREADS) cluster_cta_kernel(
         if (tid == 0) {
             s_carry = 0;
             s_ncl = 0;
+            s_nlk = 0;
         }
+        if (tid < 2) act_lk[2 * a + tid] = COV_KEY_NONE;
         __syncthreads();
         // ---- define_clusters: cbeg[i] = index of the last hit <= i that opens a cluster (running maximum)
         for (uint32_t i0 = 0; i0 < c; i0 += CC_THREADS) {
@@ -472,26 +515,17 @@ __global__ void __launch_bounds__(CC_THREADS) cluster_cta_kernel(
         }
         __syncthreads();
         // ---- kept flags + coverage keys
-        for (uint32_t i0 = 0; i0 < c; i0 += CC_THREADS) {
-            const uint32_t i = i0 + tid;
-            bool keep = false, is_begin = false;
-            unsigned long long k0 = 0;
-            if (i < c) {
-                const uint32_t b = B.cbeg[base + i];
-                const uint32_t sl = B.slot[base + b];
-                keep = sl != 0xffffffffu && B.alive[base + sl] != 0u;
-                is_begin = keep && b == i;
-                k0 = K[i];
-                gkept[base + i] = keep ? 1 : 0;
-            }
-            const uint32_t mine = (keep ? 1u : 0u) + (is_begin ? 1u : 0u);
-            uint32_t total;
-            uint32_t o = warp_alloc(ctr + CTR_COVKEYS, mine, lane, total);
-            const uint32_t nkept = __popc(__ballot_sync(FULL, keep));
-            if (lane == 0 && nkept) atomicAdd(ctr + CTR_KEPT, (unsigned long long)nkept);
-            if (keep) {
-                cov_keys[o++] = 2u * (knode_base[gk_prg(k0)] + gk_knode(k0)) + gk_rev(k0);
-                if (is_begin) cov_keys[o++] = locus_key_base + gk_prg(k0);
+        for (uint32_t i = tid; i < c; i += CC_THREADS) {
+            const uint32_t b = B.cbeg[base + i];
+            const uint32_t sl = B.slot[base + b];
+            const bool keep = sl != 0xffffffffu && B.alive[base + sl] != 0u;
+            const unsigned long long k0 = K[i];
+            gkept[base + i] = keep ? 1 : 0;
+            cov_keys[base + i] = keep ? 2u * (knode_base[gk_prg(k0)] + gk_knode(k0)) + gk_rev(k0) : COV_KEY_NONE;
+            if (keep && b == i) {  // one locus key per kept cluster: the first two next to the read, the rest in the overflow list
+                const uint32_t t = atomicAdd(&s_nlk, 1u);
+                if (t < 2u) act_lk[2 * a + t] = locus_key_base + gk_prg(k0);
+                else lk_ovf[atomicAdd(ctr + CTR_LKOVF, 1ull)] = locus_key_base + gk_prg(k0);
             }
         }
         __syncthreads();
@@ -499,98 +533,163 @@ __global__ void __launch_bounds__(CC_THREADS) cluster_cta_kernel(
 }
 
 // ============================================================================================
-// S5 : coverage by sorted-key reduction, no atomics on the counters
+// S5 : coverage without atomics.
+// The key slots of a batch ([one per grouped hit | two per active read | overflow list], "none" where nothing is
+// counted) are cut into STRETCHES of 64 k slots and the key space into RANGES of 6 k counters.  A job = (range, stretch):
+// its CTA keeps one PRIVATE copy of the range's counters per warp in shared memory (16 warps x 6144 x 16 bit = 192 KB);
+// every warp walks its own sixteenth of the stretch, ignores keys outside the range, and combines equal keys of one step
+// with match.any, so every increment is a plain read-modify-write with a single writer.  The sixteen copies are then
+// summed and STORED (not added) to the job's own piece of partial[stretch][range]; cov_merge_kernel sums over the
+// stretches.  A slot is read once per range (13 times for the Mtb-scale panel, from L2).
 // ============================================================================================
-constexpr int CT_THREADS = 512;
-constexpr uint32_t CT_TILE = 8192;
+constexpr int CV_THREADS = 512, CV_WARPS = CV_THREADS / 32;
+constexpr uint32_t CV_RANGE = 6144;            // counters per range
+constexpr uint32_t CV_STRETCH_MIN = 8192;      // a stretch is sized so that (ranges x stretches) fills the grid once, within these
+constexpr uint32_t CV_STRETCH_MAX = 983040;    // bounds: a warp sees a sixteenth of it and its counters are 16 bit (61 440 < 65 536)
+constexpr uint32_t CV_UNROLL = 8;              // independent slot loads in flight per lane; 8 x 32 slots are compacted, then counted
 
-__global__ void __launch_bounds__(CT_THREADS) cov_tile_kernel(const unsigned long long* __restrict__ ctr, PostCaps C,
-                                                             const uint32_t* __restrict__ cov_keys, int32_t* __restrict__ partials,
-                                                             uint32_t n_accum) {
-    __shared__ uint32_t s_k[CT_TILE];
+// slots per stretch for n slots when `waves` stretches fit the grid at once; a multiple of 512 (16 warps x 32 lanes)
+__host__ __device__ __forceinline__ unsigned long long cov_stretch_len(unsigned long long n, uint32_t waves) {
+    unsigned long long len = (n + waves - 1) / waves;
+    len = (len + 511ull) & ~511ull;
+    return len < CV_STRETCH_MIN ? CV_STRETCH_MIN : (len > CV_STRETCH_MAX ? CV_STRETCH_MAX : len);
+}
+
+// key slots of a batch, concatenated: [per grouped hit | two per active read | overflow list]
+struct CovSlots {
+    const uint32_t *cov_keys, *act_lk, *lk_ovf;
+    unsigned long long n0, n1, n2;
+    __device__ __forceinline__ uint32_t at(unsigned long long i, unsigned long long end) const {  // slots from `end` on read as "none"
+        if (i >= end) return COV_KEY_NONE;
+        if (i < n0) return __ldg(cov_keys + i);
+        i -= n0;
+        if (i < n1) return __ldg(act_lk + i);
+        return __ldg(lk_ovf + (i - n1));
+    }
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1) cov_count_kernel(const unsigned long long* __restrict__ ctr, PostCaps C, CovSlots S,
+                                                                 int32_t* __restrict__ partials, uint32_t max_stretches,
+                                                                 uint32_t n_accum, uint32_t n_keys) {
+    extern __shared__ unsigned short s_cnt[];  // [CV_WARPS][CV_RANGE] counters, then [CV_WARPS][CV_UNROLL * 32] compacted keys
     if (batch_overflowed(ctr, C)) return;
-    const unsigned long long n = ctr[CTR_COVKEYS];
-    const unsigned long long n_tiles = (n + CT_TILE - 1) / CT_TILE;
-    int32_t* mine = partials + (size_t)blockIdx.x * n_accum;
-    const int tid = threadIdx.x;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long t0 = tile * CT_TILE;
-        const uint32_t m = (uint32_t)min((unsigned long long)CT_TILE, n - t0);
-        for (uint32_t i = tid; i < m; i += CT_THREADS) s_k[i] = cov_keys[t0 + i];
+    S.n0 = ctr[CTR_HITS];
+    S.n1 = 2ull * ctr[CTR_ACTIVE];
+    S.n2 = ctr[CTR_LKOVF];
+    const unsigned long long n = S.n0 + S.n1 + S.n2;
+    const uint32_t n_range = (n_keys + CV_RANGE - 1) / CV_RANGE;
+    const unsigned long long stretch_len = cov_stretch_len(n, max(1u, gridDim.x / n_range));
+    const uint32_t n_stretch = (uint32_t)min((unsigned long long)max_stretches, (n + stretch_len - 1) / stretch_len);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned short* mine = s_cnt + (size_t)wid * CV_RANGE;
+    unsigned short* list = s_cnt + (size_t)CV_WARPS * CV_RANGE + (size_t)wid * (CV_UNROLL * 32);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t job = blockIdx.x; job < n_stretch * n_range; job += gridDim.x) {
+        const uint32_t stretch = job / n_range, k_lo = (job % n_range) * CV_RANGE;
+        const uint32_t k_n = min(CV_RANGE, n_keys - k_lo);
+        for (uint32_t i = tid; i < CV_WARPS * CV_RANGE / 8; i += CV_THREADS) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        block_bitonic(s_k, m, tid, CT_THREADS);
-        // the first element of every run of equal keys finds the run's end and adds its length: after the sort a key is
-        // touched by exactly one thread of this CTA, and the partial belongs to this CTA alone
-        for (uint32_t i = tid; i < m; i += CT_THREADS) {
-            const uint32_t key = s_k[i];
-            if (i > 0 && s_k[i - 1] == key) continue;
-            uint32_t e = i + 1;
-            while (e < m && e < i + 8u && s_k[e] == key) ++e;
-            if (e < m && s_k[e] == key) {  // a long run (deep coverage): first index with s_k[idx] > key
-                uint32_t lo = e, hi = m;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_k[mid] <= key) lo = mid + 1;
-                    else hi = mid;
-                }
-                e = lo;
+        // this warp's share of the stretch, CV_UNROLL x 32 slots at a time (the loads of the next group are issued first)
+        const unsigned long long s_lo = (unsigned long long)stretch * stretch_len + (unsigned long long)wid * (stretch_len / CV_WARPS);
+        const unsigned long long s_hi = min(n, s_lo + stretch_len / CV_WARPS);
+        uint32_t cur[CV_UNROLL], nxt[CV_UNROLL];
+#pragma unroll
+        for (uint32_t u = 0; u < CV_UNROLL; ++u) cur[u] = S.at(s_lo + u * 32 + lane, s_hi);
+        for (unsigned long long g0 = s_lo; g0 < s_hi; g0 += CV_UNROLL * 32) {
+#pragma unroll
+            for (uint32_t u = 0; u < CV_UNROLL; ++u) nxt[u] = S.at(g0 + (CV_UNROLL + u) * 32 + lane, s_hi);
+            // compact the keys of this group that fall into the range ("none" is far above every range)
+            uint32_t cnt = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < CV_UNROLL; ++u) {
+                const uint32_t rel = cur[u] - k_lo;
+                const bool own = rel < k_n;
+                const uint32_t m = __ballot_sync(FULL, own);
+                if (own) list[cnt + __popc(m & lt)] = (unsigned short)rel;
+                cnt += __popc(m);
             }
-            mine[key] += (int32_t)(e - i);
+            __syncwarp();
+            // count them: equal keys of one step are combined, the lowest lane of each group adds
+            for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+                const bool have = e0 + lane < cnt;
+                const uint32_t rel = have ? list[e0 + lane] : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(FULL, rel);
+                if (have && lane == __ffs(peers) - 1) mine[rel] = (unsigned short)(mine[rel] + __popc(peers));
+                __syncwarp();
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < CV_UNROLL; ++u) cur[u] = nxt[u];
+        }
+        __syncthreads();
+        // sum the sixteen copies and store the job's piece of the partial (it is this job's alone: a store, not an add)
+        int32_t* out = partials + (size_t)stretch * n_accum + k_lo;
+        for (uint32_t k = tid; k < k_n; k += CV_THREADS) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int w = 0; w < CV_WARPS; ++w) v += s_cnt[(size_t)w * CV_RANGE + k];
+            out[k] = (int32_t)v;
         }
         __syncthreads();
     }
 }
 
-// Column sum of the partials of the CTAs that had tiles into `dst` (re-zeroing them for the next batch).  dst is the
-// sample's accumulator on this GPU, or — remote != 0 — the ROOT GPU's accumulator mapped over NVLink, which receives one
-// fire-and-forget red.global.add per non-zero counter: the fused form of the path's only collective.
-__global__ void cov_merge_kernel(const unsigned long long* __restrict__ ctr, PostCaps C, int32_t* __restrict__ partials,
-                                 uint32_t n_partials, uint32_t n_accum, uint32_t n_keys, int32_t* __restrict__ dst, int remote) {
+// Column sum over the stretches into `dst`.  dst is the sample's accumulator on this GPU, or — remote != 0 — the ROOT
+// GPU's accumulator mapped over NVLink, which receives one fire-and-forget red.global.add per non-zero counter: the
+// fused form of the path's only collective.  The coverage counters (keys below 2N) also add up to the number of kept hits.
+__global__ void cov_merge_kernel(unsigned long long* __restrict__ ctr, PostCaps C, const int32_t* __restrict__ partials,
+                                 uint32_t max_stretches, uint32_t count_grid, uint32_t n_accum, uint32_t n_keys, uint32_t n_cov_keys,
+                                 int32_t* __restrict__ dst, int remote) {
     if (batch_overflowed(ctr, C)) return;
-    const unsigned long long n_tiles = (ctr[CTR_COVKEYS] + CT_TILE - 1) / CT_TILE;
-    const uint32_t used = (uint32_t)min((unsigned long long)n_partials, n_tiles);
+    const unsigned long long n = ctr[CTR_HITS] + 2ull * ctr[CTR_ACTIVE] + ctr[CTR_LKOVF];
+    const unsigned long long stretch_len = cov_stretch_len(n, max(1u, count_grid / ((n_keys + CV_RANGE - 1) / CV_RANGE)));
+    const uint32_t used = (uint32_t)min((unsigned long long)max_stretches, (n + stretch_len - 1) / stretch_len);
+    unsigned long long kept = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_keys; k += gridDim.x * blockDim.x) {
         int32_t sum = 0;
-        for (uint32_t g = 0; g < used; ++g) {
-            int32_t* p = partials + (size_t)g * n_accum + k;
-            const int32_t v = *p;
-            if (v) {
-                sum += v;
-                *p = 0;
-            }
-        }
+        for (uint32_t g = 0; g < used; ++g) sum += partials[(size_t)g * n_accum + k];
         if (!sum) continue;
-        if (remote) asm volatile("red.global.add.s32 [%0], %1;" ::"l"(dst + k), "r"(sum) : "memory");
+        if (k < n_cov_keys) kept += (unsigned long long)sum;
+        if (remote) asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst + k), "r"(sum) : "memory");
         else dst[k] += sum;
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) kept += ((unsigned long long)__shfl_xor_sync(FULL, (uint32_t)(kept >> 32), d) << 32) | __shfl_xor_sync(FULL, (uint32_t)kept, d);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(ctr + CTR_KEPT, kept);
 }
 
-uint32_t cov_partial_ctas(int sm_count) { return (uint32_t)sm_count; }
+// stretches a hit capacity can produce: [hit_cap | 2 per active read <= 2 hit_cap | overflow <= hit_cap] slots
+uint32_t cov_max_stretches(uint64_t hit_cap, int sm_count) {
+    return (uint32_t)std::max<uint64_t>((uint64_t)sm_count, (4 * hit_cap + CV_STRETCH_MAX - 1) / CV_STRETCH_MAX) + 1;
+}
 
 void launch_postprocess(const PostBuffers& P, PostCaps C, uint32_t read_id_base, uint64_t n_reads, uint32_t max_diff,
-                        const uint32_t* d_thresh_per_prg, const uint32_t* d_knode_base, uint32_t total_knodes, uint32_t n_loci,
+                        uint32_t min_thresh, const uint32_t* d_thresh_per_prg, const uint32_t* d_knode_base, uint32_t total_knodes, uint32_t n_loci,
                         int32_t* d_accum_dst, int remote_dst, int sm_count, cudaStream_t st, cudaEvent_t ev_grouped,
                         cudaEvent_t ev_clustered) {
-    (void)n_reads;
     const unsigned sm = (unsigned)sm_count;
-    count_reads_kernel<<<sm * 4, 256, 0, st>>>(P.hi, P.ctr, C, read_id_base, P.read_count, P.act_read);
-    assign_kernel<<<sm, 256, 0, st>>>(P.ctr, C, P.read_count, P.act_read, P.act_base, P.act_count, P.read_base, P.big_list);
-    scatter_kernel<<<sm * 4, 256, 0, st>>>(P.hi, P.lo, P.ctr, C, read_id_base, P.read_count, P.read_base, P.gkey);
+    const uint64_t as_step = (uint64_t)AS_THREADS * AS_PER;
+    const unsigned as_grid = (unsigned)std::min<uint64_t>((n_reads + as_step - 1) / as_step, (uint64_t)sm * 8);
+    if (as_grid) assign_kernel<<<as_grid, AS_THREADS, 0, st>>>(P.ctr, C, n_reads, P.read_count, P.act_read, P.act_base, P.act_count, P.read_base, P.big_list);
+    scatter_kernel<<<sm * 16, 256, 0, st>>>(P.hi, P.lo, P.ctr, C, read_id_base, P.read_count, P.read_base, P.gkey);
     if (ev_grouped) cudaEventRecord(ev_grouped, st);
     const uint32_t locus_key_base = 2u * total_knodes;
-    cluster_warp_kernel<<<sm * 4, CW_WARPS * 32, 0, st>>>(P.ctr, C, P.act_base, P.act_count, P.gkey, P.gkept, max_diff, d_thresh_per_prg,
-                                                         d_knode_base, locus_key_base, P.cov_keys);
+    cluster_warp_kernel<<<sm * 4, CW_WARPS * 32, 0, st>>>(P.ctr, C, P.act_base, P.act_count, P.gkey, P.gkept, max_diff, min_thresh, d_thresh_per_prg,
+                                                         d_knode_base, locus_key_base, P.cov_keys, P.act_lk, P.lk_ovf);
     ensure_dyn_smem(cluster_cta_kernel, (size_t)CC_SMEM_KEYS * 8);
     BigScratch B{P.scratch[0], P.scratch[1], P.scratch[2], P.scratch[3], P.scratch[4], P.scratch[5], P.scratch[6], P.scratch[7],
                  P.scratch[8], P.scratch[9]};
     cluster_cta_kernel<<<sm * 2, CC_THREADS, (size_t)CC_SMEM_KEYS * 8, st>>>(P.ctr, C, P.big_list, P.act_base, P.act_count, P.gkey,
                                                                             P.gkept, max_diff, d_thresh_per_prg, d_knode_base,
-                                                                            locus_key_base, P.cov_keys, B);
+                                                                            locus_key_base, P.cov_keys, P.act_lk, P.lk_ovf, B);
     if (ev_clustered) cudaEventRecord(ev_clustered, st);
     const uint32_t n_accum = 2u * total_knodes + n_loci + 4u, n_keys = 2u * total_knodes + n_loci;
-    cov_tile_kernel<<<P.n_partials, CT_THREADS, 0, st>>>(P.ctr, C, P.cov_keys, P.partials, n_accum);
-    cov_merge_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(P.ctr, C, P.partials, P.n_partials, n_accum, n_keys, d_accum_dst, remote_dst);
-    g_launches += 7;
+    const size_t cv_smem = (size_t)CV_WARPS * (CV_RANGE + CV_UNROLL * 32) * sizeof(unsigned short);
+    ensure_dyn_smem(cov_count_kernel, cv_smem);
+    CovSlots S{P.cov_keys, P.act_lk, P.lk_ovf, 0, 0, 0};
+    cov_count_kernel<<<sm, CV_THREADS, cv_smem, st>>>(P.ctr, C, S, P.partials, P.n_partials, n_accum, n_keys);
+    cov_merge_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(P.ctr, C, P.partials, P.n_partials, sm, n_accum, n_keys, 2u * total_knodes, d_accum_dst,
+                                                          remote_dst);
+    g_launches += 6;
 }
 
 }  // namespace drprg

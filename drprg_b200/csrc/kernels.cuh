@@ -26,6 +26,9 @@ struct DevReads {
     const uint32_t* seg_start = nullptr;
     uint64_t n_segs = 0;
     uint32_t seg_len = 0;
+    // optional per-read hit counters (index = read within this DevReads): the lookup kernels add the hits they emit, which
+    // is what groups the hits by read afterwards (cluster.cu)
+    int32_t* hit_count = nullptr;
 };
 
 // minimizer index resident in HBM (small: lives in L2)
@@ -74,20 +77,52 @@ constexpr uint32_t SCREEN_MAX_FILTER_WORDS = 54 * 1024;  // 216 KB of shared mem
 // S1 only (parity hook): emits key = read << 32 | start, val = hash << 1 | strand
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st);
-// 128-bit radix sort of the hits by (hi, lo); temp storage managed by the caller
-size_t sort_hits_temp_bytes(uint64_t n);
-void sort_hits(void* d_temp, size_t temp_bytes, unsigned long long* hi_in, unsigned long long* lo_in,
-               unsigned long long* hi_tmp, unsigned long long* lo_tmp, uint64_t n, int read_bits, int start_bits,
-               int knode_bits, int prg_bits, cudaStream_t st);  // result ends in (hi_in, lo_in)
-// S3+S4: clusters per read, size and overlap filters; kept[i] in {0,1}; locus read counts accumulate
-void launch_cluster_filter(const unsigned long long* hi, const unsigned long long* lo, uint64_t n, uint32_t max_diff,
-                           const uint32_t* d_thresh_per_prg, uint32_t* d_clist, uint32_t* d_clist2, uint32_t* d_cend,
-                           uint8_t* d_calive, uint8_t* d_kept, int32_t* d_locus_reads, cudaStream_t st);
-// S5: coverage keys -> sort -> run lengths added to the accumulator (no atomics)
-size_t sort_cov_temp_bytes(uint64_t n);
-void launch_coverage(const unsigned long long* hi, const unsigned long long* lo, const uint8_t* kept, uint64_t n,
-                     const uint32_t* d_knode_base, uint32_t* d_keys, uint32_t* d_keys_sorted, void* d_temp,
-                     size_t temp_bytes, int key_bits, int32_t* d_cov, unsigned long long* d_n_kept, cudaStream_t st);
+// ---- S3-S5: hits grouped by read, per-read sort + clustering, coverage by sorted-key reduction (cluster.cu) ------
+// device counters of one batch (unsigned long long each)
+enum : int {
+    CTR_HITS = 0,        // hits appended by the lookup kernels
+    CTR_KEPT = 1,        // kept hits
+    CTR_QUEUE = 2,       // k-mer screen: queue length of the current chunk
+    CTR_TICKET = 3,      // k-mer screen: tile ticket
+    CTR_QUEUE_NEED = 4,  // largest queue length any chunk wanted
+    CTR_ACTIVE = 5,      // reads with at least one hit
+    CTR_CURSOR = 6,      // grouped-hit slices handed out
+    CTR_BIG = 7,         // active reads with more than CLUSTER_WARP_MAX hits
+    CTR_LKOVF = 8,       // locus keys beyond two kept clusters per read
+    CTR_COUNT = 16
+};
+constexpr uint32_t CLUSTER_WARP_MAX = 64;  // hits of a read one warp sorts in registers; longer reads get a CTA
+// grouped-hit key: prg 16 | reverse 1 | read_start 25 | k-mer node rank 22 (limits checked at index load / upload)
+constexpr int GKEY_KNODE_BITS = 22, GKEY_START_BITS = 25;
+constexpr uint32_t COV_KEY_NONE = 0xffffffffu;  // "no coverage key in this slot"
+struct PostCaps {
+    unsigned long long hit_cap, queue_cap;
+};
+struct PostBuffers {
+    const unsigned long long *hi, *lo;  // unordered hits from the lookup kernels
+    unsigned long long* ctr;            // CTR_COUNT counters
+    int32_t* read_count;                // per read of the batch: filled by the lookup kernels, all zero again after the scatter
+    uint32_t* read_base;                // per read
+    uint32_t *act_read, *act_base, *act_count;  // active reads (hit_cap entries)
+    uint32_t* act_lk;                   // 2 per active read: locus keys of its first two kept clusters
+    uint32_t* lk_ovf;                   // locus keys of further kept clusters (hit_cap entries)
+    uint32_t* big_list;                 // indices into the active list (hit_cap / 64 + 16 entries)
+    unsigned long long* gkey;           // grouped hits (hit_cap), sorted within each read's slice after the cluster kernels
+    uint8_t* gkept;                     // kept flag per grouped hit
+    uint32_t* cov_keys;                 // per grouped hit: its coverage key, COV_KEY_NONE when the hit is not kept
+    uint32_t* scratch[10];              // hit_cap each: long-read clustering
+    int32_t* partials;                  // n_partials x n_accum: per-stretch coverage partials (cov_count_kernel)
+    uint32_t n_partials;
+};
+uint32_t cov_max_stretches(uint64_t hit_cap, int sm_count);  // rows of PostBuffers::partials a hit capacity needs
+// everything after the lookup kernels for one batch; results are added to d_accum_dst: the sample's accumulator
+// [2*total_knodes coverage | n_loci locus reads | 4 scalars] on this GPU, or (remote_dst != 0) the root GPU's accumulator
+// mapped over NVLink, updated with red.global.add
+// min_thresh = smallest entry of d_thresh_per_prg (a read with no more hits than that keeps nothing)
+void launch_postprocess(const PostBuffers& P, PostCaps C, uint32_t read_id_base, uint64_t n_reads, uint32_t max_diff,
+                        uint32_t min_thresh, const uint32_t* d_thresh_per_prg, const uint32_t* d_knode_base, uint32_t total_knodes, uint32_t n_loci,
+                        int32_t* d_accum_dst, int remote_dst, int sm_count, cudaStream_t st, cudaEvent_t ev_grouped,
+                        cudaEvent_t ev_clustered);
 // S7: per-node log-probabilities then one warp per locus for the ML-path DP
 void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t* d_is_terminal, ModelParams P,
                       double* d_prob, cudaStream_t st);

@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(WARPS * 32) sketch_kernel(DevReads R, DevTable
                         const uint32_t total = __shfl_sync(FULL, incl, 31);
                         if (total) {
                             unsigned long long base = 0;
-                            if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+                            if (lane == 0) {
+                                base = atomicAdd(out_count, (unsigned long long)total);
+                                if (R.hit_count) atomicAdd(R.hit_count + r, (int32_t)total);
+                            }
                             base = __shfl_sync(FULL, base, 0) + (incl - rec_n);
                             for (uint32_t j = 0; j < rec_n; ++j) {
                                 const uint2 rc = __ldg(T.recs + rec_begin + j);
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(THREADS) sketch_short_kernel(DevReads R, DevTa
                     }
                     if (rec_n) {
                         const unsigned long long base = atomicAdd(out_count, (unsigned long long)rec_n);
+                        if (R.hit_count) atomicAdd(R.hit_count + r, (int32_t)rec_n);
                         for (uint32_t q = 0; q < rec_n; ++q) {
                             const uint2 rc = __ldg(T.recs + rec_begin + q);
                             const uint32_t fwd = ((rc.y & 1u) == read_strand) ? 1u : 0u;
@@ -848,6 +852,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) resolve_kernel(DevReads R, De
                     }
                 }
                 if (run >= w) emit_n = rec_n;
+                if (emit_n && R.hit_count) atomicAdd(R.hit_count + r, (int32_t)emit_n);
             }
             // one atomic per warp: a single hit counter takes ~1 atomic per clock
             uint32_t incl = emit_n;
