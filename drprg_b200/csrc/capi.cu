@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <map>
 #include <cstdio>
@@ -122,7 +124,70 @@ double now_ms() {
 }
 }  // namespace
 
+// one persistent host thread per extra GPU of a multi-GPU handle: launches for the devices are issued side by side
+class GpuWorker {
+   public:
+    GpuWorker() : th_([this] { loop(); }) {}
+    ~GpuWorker() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void submit(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            task_ = std::move(fn);
+            busy_ = true;
+            error_.clear();
+        }
+        cv_.notify_all();
+    }
+    void wait() {  // rethrows what the task threw
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return !busy_; });
+        if (!error_.empty()) throw std::runtime_error(error_);
+    }
+
+   private:
+    void loop() {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return stop_ || (busy_ && task_); });
+                if (stop_) return;
+                fn = std::move(task_);
+                task_ = nullptr;
+            }
+            std::string err;
+            try {
+                fn();
+            } catch (const std::exception& e) {
+                err = e.what();
+            } catch (...) {
+                err = "unknown error";
+            }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                error_ = err;
+                busy_ = false;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::function<void()> task_;
+    std::string error_;
+    bool busy_ = false, stop_ = false;
+    std::thread th_;
+};
+
 struct drprg_batch {
+    std::vector<drprg_batch*> shards;  // multi-GPU handle: one sub-batch per GPU (this object is then only the container)
     DevReads R{};
     uint32_t *d_words = nullptr, *d_lens = nullptr, *d_seg_read = nullptr, *d_seg_start = nullptr;
     uint64_t* d_off = nullptr;
@@ -184,6 +249,17 @@ struct drprg_index {
     // accumulator, peer-mapped, updated with red.global.add by cov_merge_kernel)
     int32_t* reduce_dst = nullptr;
     bool accum_shared = false;  // other GPUs add into this accumulator: the histogram taken at the end of map_batch is not final
+    // multi-GPU handle (drprg_cuda_index_load_multi): this object is the root; gpus[0] == this
+    std::vector<std::unique_ptr<drprg_index>> replicas;
+    std::vector<std::unique_ptr<GpuWorker>> workers;
+    std::vector<drprg_index*> gpus;
+    uint64_t own_bases = 0, own_reads = 0;  // this GPU's share of the sample (total_bases / n_reads hold the sample's)
+    // one PROCESS per GPU (torchrun): flags behind the root's accumulator, reached through a CUDA IPC mapping
+    int world = 1;               // ranks sharing the root accumulator (1 = not shared across processes)
+    uint32_t epoch = 0;          // samples begun
+    void* ipc_mapping = nullptr; // non-root: the root's accumulator allocation opened in this process
+    uint32_t* flag_ready = nullptr;     // root's "accumulator zeroed for sample e" word
+    uint32_t* flag_arrivals = nullptr;  // root's arrival counter (world - 1 per sample)
     cudaEvent_t ev[6]{};  // batch timeline: start, lookup done, hits grouped, clustered, coverage merged
     float timings[4] = {0, 0, 0, 0};
     // genotype state
@@ -228,8 +304,11 @@ struct drprg_index {
     DBuf<uint32_t> d_len, d_up, d_path, d_path_len;
 
     ~drprg_index() {
+        workers.clear();
+        replicas.clear();
         if (device < 0) return;
         cudaSetDevice(device);
+        if (ipc_mapping) cudaIpcCloseMemHandle(ipc_mapping);
         for (void* p : {(void*)d_slots, (void*)d_recs, (void*)d_filter, (void*)d_knode_base, (void*)d_edge_off, (void*)d_edges,
                         (void*)d_is_terminal, (void*)d_needs_mean, (void*)d_locus_unit_off, (void*)d_unit_start, (void*)d_unit_nodes, (void*)d_accum, (void*)d_thresh, (void*)d_counters, (void*)d_rec_off,
                         (void*)d_allele_off, (void*)d_allele_kn, (void*)d_knode_locus, (void*)d_hist, (void*)d_kfilter, (void*)d_locus_level_off, (void*)d_level_start, (void*)d_level_nodes, (void*)d_level_singles})
@@ -263,6 +342,8 @@ struct drprg_index {
 };
 
 namespace {
+inline size_t accum_flag_offset(uint64_t n_accum) { return (size_t)((n_accum + 31) & ~31ull); }  // 128-byte aligned flag words
+
 void upload_index(drprg_index* X) {
     const HostIndex& H = X->H;
     if (H.k > (uint32_t)K_MAX) throw std::runtime_error("k > 16 is not supported by the device kernels (2k must fit 32 bits)");
@@ -448,8 +529,9 @@ void upload_index(drprg_index* X) {
         X->d_level_singles = to_device(level_singles);
     }
     X->n_accum = 2ull * N + H.loci.size() + 4;
-    CK(cudaMalloc(&X->d_accum, X->n_accum * sizeof(int32_t)));
-    CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
+    // 16 extra words behind the accumulator hold the cross-GPU flags of a read-sharded run (ready epoch, arrival counter)
+    CK(cudaMalloc(&X->d_accum, (accum_flag_offset(X->n_accum) + 16) * sizeof(int32_t)));
+    CK(cudaMemset(X->d_accum, 0, (accum_flag_offset(X->n_accum) + 16) * sizeof(int32_t)));
     CK(cudaMalloc(&X->d_thresh, std::max<size_t>(1, H.loci.size()) * sizeof(uint32_t)));
     CK(cudaMalloc(&X->d_counters, CTR_COUNT * sizeof(unsigned long long)));
     CK(cudaMallocHost(&X->h_counters, CTR_COUNT * sizeof(unsigned long long)));
@@ -538,7 +620,11 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
         X->thresh_on_device = thr;
     }
     CK(cudaMemset(X->d_accum, 0, X->n_accum * sizeof(int32_t)));
+    ++X->epoch;
+    if (X->world > 1 && X->accum_shared)  // the other ranks may add to this accumulator from here on
+        launch_flag_publish(reinterpret_cast<uint32_t*>(X->d_accum + accum_flag_offset(X->n_accum)), X->epoch, 0);
     X->total_bases = X->n_reads = 0;
+    X->own_bases = X->own_reads = 0;
     X->scalars_in_buffer = false;
     X->hist_on_host = false;
     X->sample_open = true;
@@ -614,12 +700,13 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
         PB.big_list = X->big_list.p; PB.gkey = X->gkey.p; PB.gkept = X->gkept.p; PB.cov_keys = X->cov_keys.p;
         for (int i = 0; i < 10; ++i) PB.scratch[i] = X->scratch[i].p;
         PB.partials = X->partials.p; PB.n_partials = X->n_partials;
+        if (X->reduce_dst && X->flag_ready) launch_flag_wait(X->flag_ready, X->epoch, st);  // root has zeroed its accumulator for this sample
         launch_postprocess(PB, PostCaps{X->hi.cap, queue_cap}, B->R.read_id_base, B->R.n_reads, X->opts.max_diff, X->min_thresh, X->d_thresh,
                            X->d_knode_base, N, P, X->reduce_dst ? X->reduce_dst : X->d_accum, X->reduce_dst ? 1 : 0, X->sm_count, st,
                            X->ev[2], X->ev[3]);
         CK(cudaEventRecord(X->ev[4], st));
         CK(cudaGetLastError());
-        if (!X->reduce_dst) {
+        if (!X->reduce_dst && !X->accum_shared) {
             // what the genotype step needs first (coverage histogram, locus read counts: 4 KB) rides on this batch's final
             // synchronisation; it stays valid unless the accumulators change before drprg_cuda_genotype (another batch
             // recomputes it, a reduce from other GPUs invalidates it)
@@ -652,6 +739,8 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     X->last_id_base = B->R.read_id_base;
     X->total_bases += B->total_bases;
     X->n_reads += B->R.n_reads;
+    X->own_bases += B->total_bases;
+    X->own_reads += B->R.n_reads;
     if (n_hits) *n_hits = nh;
     if (n_kept) *n_kept = X->h_counters[CTR_KEPT];
 }
@@ -660,7 +749,12 @@ void flush_scalars(drprg_index* X) {
     if (X->scalars_in_buffer) return;
     int32_t s[4] = {(int32_t)(X->total_bases & 0xffffff), (int32_t)(X->total_bases >> 24), (int32_t)(X->n_reads & 0xffffff),
                     (int32_t)(X->n_reads >> 24)};
-    CK(cudaMemcpy(X->d_accum + X->n_accum - 4, s, sizeof s, cudaMemcpyHostToDevice));
+    if (X->accum_shared && X->world > 1) {  // the other ranks have added their scalars (shard_done): this rank's join them
+        launch_add_scalars(X->d_accum + X->n_accum - 4, s, 0);
+        CK(cudaStreamSynchronize(0));
+    } else {
+        CK(cudaMemcpy(X->d_accum + X->n_accum - 4, s, sizeof s, cudaMemcpyHostToDevice));
+    }
     X->scalars_in_buffer = true;
 }
 
@@ -693,6 +787,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             X->csr_records.clear();
         }
     }
+    if (X->accum_shared && X->world > 1)  // every other rank has finished adding its shard (shard_done)
+        launch_flag_wait(reinterpret_cast<uint32_t*>(X->d_accum + accum_flag_offset(X->n_accum)) + 1, X->epoch * (uint32_t)(X->world - 1), 0);
     const bool reuse_hist = X->hist_on_host;  // downloaded at the end of the last map_batch, accumulators untouched since
     if (!reuse_hist) flush_scalars(X);
     if (!X->st_ml) {
@@ -979,6 +1075,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
 
 void free_batch(drprg_batch* b) {
     if (!b) return;
+    for (drprg_batch* sh : b->shards) free_batch(sh);
+    b->shards.clear();
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->owned) {
@@ -1068,6 +1166,160 @@ drprg_batch* upload_batch(drprg_index* X, const uint32_t* words, const uint64_t*
     return B.release();
 }
 
+// ============================================================================================
+// Read-sharded multi-GPU handle: the index is replicated, a batch is cut into one contiguous shard of reads
+// per GPU, every GPU runs S1-S5 on its shard — one host thread per GPU issues the launches side by side — and the
+// coverage merge kernel of every non-root GPU adds straight into the ROOT GPU's accumulator over NVLink (peer-mapped
+// memory, red.global.add): there is no separate collective.  The root then runs S6-S8.
+// ============================================================================================
+bool is_multi(const drprg_index* X) { return X->gpus.size() > 1; }
+
+void for_each_gpu(drprg_index* root, const std::function<void(size_t, drprg_index*)>& fn) {
+    const size_t G = root->gpus.size();
+    for (size_t g = 1; g < G; ++g) {
+        drprg_index* X = root->gpus[g];
+        root->workers[g - 1]->submit([&fn, g, X] {
+            CK(cudaSetDevice(X->device));
+            fn(g, X);
+        });
+    }
+    std::string err;
+    try {
+        CK(cudaSetDevice(root->device));
+        fn(0, root);
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    for (size_t g = 1; g < G; ++g) {
+        try {
+            root->workers[g - 1]->wait();
+        } catch (const std::exception& e) {
+            if (err.empty()) err = e.what();
+        }
+    }
+    CK(cudaSetDevice(root->device));
+    if (!err.empty()) throw std::runtime_error(err);
+}
+
+int load_multi(const std::string& text, uint32_t w, uint32_t k, int n_gpus, const int* devices, drprg_index** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device visible: drprg-cuda has no CPU fallback");
+    const int G = n_gpus <= 0 ? ndev : n_gpus;
+    if (G > ndev && !devices) throw std::runtime_error("more GPUs requested than are visible");
+    if (G > 64) throw std::runtime_error("more than 64 shards");
+    std::vector<int> devs(G);
+    for (int i = 0; i < G; ++i) devs[i] = devices ? devices[i] : i;
+    // an explicit list may name a device more than once: its shards then share that GPU (how a one-GPU box exercises
+    // the sharded path); n_gpus alone always means distinct devices
+    for (int i = 0; i < G; ++i)
+        if (devs[i] < 0 || devs[i] >= ndev) throw std::runtime_error("bad device ordinal");
+    drprg_index* raw = nullptr;
+    load_common(text, w, k, devs[0], &raw);
+    std::unique_ptr<drprg_index> root(raw);
+    if (G == 1) {
+        *out = root.release();
+        return 0;
+    }
+    for (int i = 1; i < G; ++i) {
+        if (devs[i] != devs[0]) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, devs[i], devs[0]));
+            if (!can) throw std::runtime_error("GPU " + std::to_string(devs[i]) + " cannot reach GPU " + std::to_string(devs[0]) + " over NVLink/PCIe peer access");
+        }
+        std::unique_ptr<drprg_index> R(new drprg_index());
+        R->device = devs[i];
+        CK(cudaSetDevice(devs[i]));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, devs[i]));
+        R->sm_count = prop.multiProcessorCount;
+        R->H = root->H;  // the host index is built once
+        upload_index(R.get());
+        if (devs[i] != devs[0]) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[0], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+            cudaGetLastError();
+        }
+        R->reduce_dst = root->d_accum;  // UVA: the root's pointer is valid on the peer once access is enabled
+        root->replicas.push_back(std::move(R));
+        root->workers.emplace_back(new GpuWorker());
+    }
+    CK(cudaSetDevice(devs[0]));
+    root->accum_shared = true;
+    root->gpus.push_back(root.get());
+    for (auto& r : root->replicas) root->gpus.push_back(r.get());
+    *out = root.release();
+    return 0;
+}
+
+void multi_sample_begin(drprg_index* root, const drprg_map_opts* o, uint32_t first_read_len) {
+    // the root zeroes its accumulator first: the other GPUs only touch it in map_batch, which the host starts afterwards
+    for_each_gpu(root, [&](size_t, drprg_index* X) {
+        sample_begin(X, o, first_read_len);
+        CK(cudaStreamSynchronize(0));
+    });
+}
+
+drprg_batch* multi_upload(drprg_index* root, const uint32_t* words, const uint64_t* word_off, uint32_t stride, const uint32_t* lens,
+                          uint64_t n, uint64_t total_bases, uint32_t id_base) {
+    const size_t G = root->gpus.size();
+    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
+    B->shards.assign(G, nullptr);
+    B->R.n_reads = n;
+    B->R.read_id_base = id_base;
+    B->total_bases = total_bases;
+    for_each_gpu(root, [&](size_t g, drprg_index* X) {
+        const uint64_t lo = n * g / G, hi = n * (g + 1) / G;  // rank r maps reads [rN/G, (r+1)N/G)
+        uint64_t bases = 0;
+        for (uint64_t i = lo; i < hi; ++i) bases += lens[i];
+        if (stride) {
+            // dropped reads (lens == 0) still occupy bases in total_bases bookkeeping of the single-GPU path: keep the caller's
+            // total on the last shard so that the sum over shards equals total_bases
+            B->shards[g] = upload_batch(X, words + lo * stride, nullptr, stride, lens + lo, hi - lo, bases, id_base + (uint32_t)lo, 0);
+        } else {
+            std::vector<uint64_t> off(hi - lo + 1);
+            for (uint64_t i = lo; i <= hi; ++i) off[i - lo] = word_off[i] - word_off[lo];
+            B->shards[g] = upload_batch(X, words + word_off[lo], off.data(), 0, lens + lo, hi - lo, bases, id_base + (uint32_t)lo, 0);
+            CK(cudaStreamSynchronize(0));  // `off` dies with this scope
+        }
+    });
+    // total_bases counts the bases of dropped reads too (their lens are 0): the difference goes to the last shard
+    uint64_t sum = 0;
+    for (auto* sh : B->shards) sum += sh->total_bases;
+    if (total_bases > sum) B->shards[G - 1]->total_bases += total_bases - sum;
+    return B.release();
+}
+
+void multi_map_batch(drprg_index* root, drprg_batch* B, uint64_t* n_hits, uint64_t* n_kept) {
+    const size_t G = root->gpus.size();
+    if (B->shards.size() != G) throw std::runtime_error("the batch was not uploaded through this multi-GPU handle");
+    std::vector<uint64_t> nh(G, 0), nk(G, 0);
+    for_each_gpu(root, [&](size_t g, drprg_index* X) { map_batch(X, B->shards[g], 0, &nh[g], &nk[g]); });
+    // every GPU's stream has been synchronised: all remote adds have landed in the root's accumulator
+    uint64_t bases = 0, reads = 0, h = 0, kpt = 0;
+    for (size_t g = 0; g < G; ++g) {
+        bases += root->gpus[g]->own_bases;
+        reads += root->gpus[g]->own_reads;
+        h += nh[g];
+        kpt += nk[g];
+    }
+    root->total_bases = bases;
+    root->n_reads = reads;
+    root->scalars_in_buffer = false;
+    root->hist_on_host = false;
+    if (n_hits) *n_hits = h;
+    if (n_kept) *n_kept = kpt;
+}
+
+void sample_begin_any(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_len) {
+    if (is_multi(X)) multi_sample_begin(X, o, first_read_len);
+    else sample_begin(X, o, first_read_len);
+}
+void map_batch_any(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits, uint64_t* n_kept) {
+    if (is_multi(X)) multi_map_batch(X, B, n_hits, n_kept);
+    else map_batch(X, B, st, n_hits, n_kept);
+}
+
 // A reads file as a device-resident batch.  Strict 4-line FASTQ (plain or gzip) is parsed and packed ON THE DEVICE
 // (ingest.cu); FASTA and anything unusual goes through the host parser and an upload.  DRPRG_HOST_INGEST=1 forces the
 // host parser (tests compare the two).
@@ -1101,6 +1353,16 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
     need_device(X);
     CK(cudaSetDevice(X->device));
     FileBatch F;
+    if (is_multi(X)) {  // one shard of the reads per GPU
+        PackedReads pr;
+        load_reads_packed(reads_path, threads, pr);
+        const uint64_t n = pr.lens.size();
+        if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
+        F.B = multi_upload(X, pr.words.data(), pr.word_off.data(), 0, pr.lens.data(), n, pr.total_bases, 0);
+        F.n_dropped = pr.n_dropped;
+        F.first_read_len = pr.first_read_len;
+        return F;
+    }
     static const bool host_only = getenv("DRPRG_HOST_INGEST") != nullptr && atoi(getenv("DRPRG_HOST_INGEST")) != 0;
     IngestResult I;
     const int dev = X->device;
@@ -1154,10 +1416,10 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
         uint64_t n_dropped, total_bases;
     } pr{F.n_dropped, B->total_bases};
     const double t1 = now_ms();
-    sample_begin(X, o, F.first_read_len);
+    sample_begin_any(X, o, F.first_read_len);
     uint64_t nh = 0, nk = 0;
     const uint64_t n = B->R.n_reads;
-    map_batch(X, B.get(), 0, &nh, &nk);
+    map_batch_any(X, B.get(), 0, &nh, &nk);
     const double t2 = now_ms();
     genotype(X, vcf_refs, "sample");
     std::ofstream vcf(std::string(outdir) + "/pandora_genotyped.vcf");
@@ -1215,7 +1477,63 @@ int drprg_cuda_index_load_text(const char* prg_text, uint32_t w, uint32_t k, int
     API_BEGIN return load_common(prg_text, w, k, device, out);
     API_END
 }
+int drprg_cuda_index_load_multi(const char* prg_path, uint32_t w, uint32_t k, int n_gpus, const int* devices, drprg_index** out) {
+    API_BEGIN return load_multi(read_text_file(prg_path), w, k, n_gpus, devices, out);
+    API_END
+}
+int drprg_cuda_index_n_gpus(drprg_index* X) { return X->gpus.empty() ? (X->device >= 0 ? 1 : 0) : (int)X->gpus.size(); }
 void drprg_cuda_index_free(drprg_index* x) { delete x; }
+
+/* one process per GPU: the root rank's accumulator becomes the reduction target of the other ranks */
+int drprg_cuda_shard_root(drprg_index* X, int world_size, void* handle64) {
+    API_BEGIN need_device(X);
+    if (is_multi(X)) throw std::runtime_error("a multi-GPU handle shards inside the library already");
+    CK(cudaSetDevice(X->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, X->d_accum));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, sizeof h);
+    X->world = std::max(1, world_size);
+    X->accum_shared = X->world > 1;
+    X->hist_on_host = false;
+    return 0;
+    API_END
+}
+int drprg_cuda_shard_attach(drprg_index* X, int world_size, const void* handle64) {
+    API_BEGIN need_device(X);
+    if (is_multi(X)) throw std::runtime_error("a multi-GPU handle shards inside the library already");
+    CK(cudaSetDevice(X->device));
+    if (X->ipc_mapping) {
+        CK(cudaIpcCloseMemHandle(X->ipc_mapping));
+        X->ipc_mapping = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    X->ipc_mapping = p;
+    X->reduce_dst = (int32_t*)p;  // same index on every rank: same accumulator layout
+    X->flag_ready = reinterpret_cast<uint32_t*>((int32_t*)p + accum_flag_offset(X->n_accum));
+    X->flag_arrivals = X->flag_ready + 1;
+    X->world = std::max(1, world_size);
+    return 0;
+    API_END
+}
+int drprg_cuda_shard_done(drprg_index* X, void* stream) {
+    API_BEGIN need_device(X);
+    if (!X->reduce_dst || !X->flag_arrivals) throw std::runtime_error("drprg_cuda_shard_attach was not called");
+    CK(cudaSetDevice(X->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t sc[4] = {(int32_t)(X->own_bases & 0xffffff), (int32_t)(X->own_bases >> 24), (int32_t)(X->own_reads & 0xffffff),
+                           (int32_t)(X->own_reads >> 24)};
+    // a rank without reads still has to wait for the root's zeroing before it touches the scalars
+    launch_flag_wait(X->flag_ready, X->epoch, st);
+    launch_shard_done(X->reduce_dst + X->n_accum - 4, sc, X->flag_arrivals, st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+    API_END
+}
 
 int drprg_cuda_map_genotype(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir,
                             const drprg_map_opts* o, drprg_map_stats* stats) {
@@ -1282,14 +1600,15 @@ int drprg_cuda_batch_upload(drprg_index* X, const uint32_t* words, const uint64_
                             const uint32_t* lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base, void* stream,
                             drprg_batch** out) {
     API_BEGIN if (!stride_words && !word_off) throw std::runtime_error("word_off is required without a fixed stride");
-    *out = upload_batch(X, words, word_off, stride_words, lens, n_reads, total_bases, read_id_base, (cudaStream_t)stream);
+    if (is_multi(X)) *out = multi_upload(X, words, word_off, stride_words, lens, n_reads, total_bases, read_id_base);
+    else *out = upload_batch(X, words, word_off, stride_words, lens, n_reads, total_bases, read_id_base, (cudaStream_t)stream);
     return 0;
     API_END
 }
 int drprg_cuda_batch_wrap_device(drprg_index* X, const void* d_words, const void* d_word_off, uint32_t stride_words,
                                  const void* d_lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base,
                                  drprg_batch** out) {
-    API_BEGIN(void) X;
+    API_BEGIN if (is_multi(X)) throw std::runtime_error("device-resident arrays belong to one GPU: wrap them on a single-GPU handle");
     if (!stride_words && !d_word_off) throw std::runtime_error("word_off is required without a fixed stride");
     drprg_batch* B = new drprg_batch();
     B->R = DevReads{(const uint32_t*)d_words, (const uint64_t*)d_word_off, stride_words, (const uint32_t*)d_lens, n_reads, read_id_base};
@@ -1314,12 +1633,12 @@ int drprg_cuda_batch_from_fastx(drprg_index* X, const char* path, uint32_t threa
 void drprg_cuda_batch_free(drprg_batch* b) { free_batch(b); }
 
 int drprg_cuda_sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_len) {
-    API_BEGIN sample_begin(X, o, first_read_len);
+    API_BEGIN sample_begin_any(X, o, first_read_len);
     return 0;
     API_END
 }
 int drprg_cuda_map_batch(drprg_index* X, drprg_batch* B, void* stream, uint64_t* n_hits, uint64_t* n_kept) {
-    API_BEGIN map_batch(X, B, (cudaStream_t)stream, n_hits, n_kept);
+    API_BEGIN map_batch_any(X, B, (cudaStream_t)stream, n_hits, n_kept);
     return 0;
     API_END
 }
@@ -1483,44 +1802,52 @@ int64_t drprg_cuda_sketch_batch(drprg_index* X, drprg_batch* B, void* stream, ui
         return INT64_MIN;
     }
 }
-int64_t drprg_cuda_last_hits(drprg_index* X, uint32_t* read, uint32_t* start, uint32_t* prg, uint32_t* knode, uint8_t* fwd,
+int64_t drprg_cuda_last_hits(drprg_index* X0, uint32_t* read, uint32_t* start, uint32_t* prg, uint32_t* knode, uint8_t* fwd,
                              uint8_t* kept, uint64_t cap) {
     try {
-        need_device(X);
-        CK(cudaSetDevice(X->device));
-        const uint64_t n = X->last_n_hits, na = X->last_n_active;
-        if (n > cap) return -(int64_t)n;
-        // the device keeps the hits grouped by read (slices in no particular order, sorted within a read): pandora's
-        // order (read, prg, strand, read_start, k-mer node) is restored here by ordering the slices by read id
-        std::vector<unsigned long long> key(n);
-        std::vector<uint8_t> kp(n);
-        std::vector<uint32_t> ar(na), ab(na), ac(na);
-        if (n) {
-            CK(cudaMemcpy(key.data(), X->gkey.p, n * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(kp.data(), X->gkept.p, n, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(ar.data(), X->act_read.p, na * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(ab.data(), X->act_base.p, na * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(ac.data(), X->act_count.p, na * 4, cudaMemcpyDeviceToHost));
-        }
-        std::vector<uint32_t> ord(na);
-        for (uint32_t i = 0; i < na; ++i) ord[i] = i;
-        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ar[a] < ar[b]; });
+        need_device(X0);
+        // a multi-GPU handle holds one contiguous shard of reads per GPU: the shards are listed in GPU order
+        std::vector<drprg_index*> gpus = X0->gpus.empty() ? std::vector<drprg_index*>{X0} : X0->gpus;
+        uint64_t total = 0;
+        for (drprg_index* X : gpus) total += X->last_n_hits;
+        if (total > cap) return -(int64_t)total;
         uint64_t o = 0;
-        for (uint32_t a : ord) {
-            // reads that cannot keep anything are not sorted on the device; their flags are all 0, so sorting the keys alone is exact
-            if (!std::is_sorted(key.begin() + ab[a], key.begin() + ab[a] + ac[a])) std::sort(key.begin() + ab[a], key.begin() + ab[a] + ac[a]);
-            for (uint32_t j = ab[a]; j < ab[a] + ac[a]; ++j, ++o) {
-                const unsigned long long k = key[j];
-                read[o] = X->last_id_base + ar[a];
-                prg[o] = (uint32_t)(k >> 48);
-                fwd[o] = (uint8_t)(((k >> 47) & 1ull) ^ 1ull);
-                start[o] = (uint32_t)(k >> GKEY_KNODE_BITS) & ((1u << GKEY_START_BITS) - 1u);
-                knode[o] = (uint32_t)k & ((1u << GKEY_KNODE_BITS) - 1u);
-                kept[o] = kp[j];
+        for (drprg_index* X : gpus) {
+            CK(cudaSetDevice(X->device));
+            const uint64_t n = X->last_n_hits, na = X->last_n_active;
+            // the device keeps the hits grouped by read (slices in no particular order, sorted within a read that can keep
+            // hits): pandora's order (read, prg, strand, read_start, k-mer node) is restored here
+            std::vector<unsigned long long> key(n);
+            std::vector<uint8_t> kp(n);
+            std::vector<uint32_t> ar(na), ab(na), ac(na);
+            if (n) {
+                CK(cudaMemcpy(key.data(), X->gkey.p, n * 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(kp.data(), X->gkept.p, n, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ar.data(), X->act_read.p, na * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ab.data(), X->act_base.p, na * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ac.data(), X->act_count.p, na * 4, cudaMemcpyDeviceToHost));
             }
+            std::vector<uint32_t> ord(na);
+            for (uint32_t i = 0; i < na; ++i) ord[i] = i;
+            std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ar[a] < ar[b]; });
+            const uint64_t o0 = o;
+            for (uint32_t a : ord) {
+                // reads that cannot keep anything are not sorted on the device; their flags are all 0, so sorting the keys alone is exact
+                if (!std::is_sorted(key.begin() + ab[a], key.begin() + ab[a] + ac[a])) std::sort(key.begin() + ab[a], key.begin() + ab[a] + ac[a]);
+                for (uint32_t j = ab[a]; j < ab[a] + ac[a]; ++j, ++o) {
+                    const unsigned long long k = key[j];
+                    read[o] = X->last_id_base + ar[a];
+                    prg[o] = (uint32_t)(k >> 48);
+                    fwd[o] = (uint8_t)(((k >> 47) & 1ull) ^ 1ull);
+                    start[o] = (uint32_t)(k >> GKEY_KNODE_BITS) & ((1u << GKEY_START_BITS) - 1u);
+                    knode[o] = (uint32_t)k & ((1u << GKEY_KNODE_BITS) - 1u);
+                    kept[o] = kp[j];
+                }
+            }
+            if (o - o0 != n) throw std::runtime_error("grouped hits do not add up");
         }
-        if (o != n) throw std::runtime_error("grouped hits do not add up");
-        return (int64_t)n;
+        CK(cudaSetDevice(X0->device));
+        return (int64_t)total;
     } catch (const std::exception& e) {
         g_err = e.what();
         return INT64_MIN;

@@ -662,6 +662,49 @@ uint32_t cov_max_stretches(uint64_t hit_cap, int sm_count) {
     return (uint32_t)std::max<uint64_t>((uint64_t)sm_count, (4 * hit_cap + CV_STRETCH_MAX - 1) / CV_STRETCH_MAX) + 1;
 }
 
+// ---- cross-GPU signalling of a read-sharded run (flags live behind the root GPU's accumulator) ------------------
+__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t want) {  // spins until *flag >= want (system scope)
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v < want) __nanosleep(200);
+    } while (v < want);
+}
+__global__ void flag_publish_kernel(uint32_t* flag, uint32_t value) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// a shard is finished: its four scalars (bases / reads, lo24 | hi) join the root's, then the arrival counter goes up
+__global__ void shard_done_kernel(int32_t* root_tail, int4 scalars, uint32_t* arrivals) {
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(root_tail + 0), "r"(scalars.x) : "memory");
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(root_tail + 1), "r"(scalars.y) : "memory");
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(root_tail + 2), "r"(scalars.z) : "memory");
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(root_tail + 3), "r"(scalars.w) : "memory");
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(arrivals), "r"(1u) : "memory");
+}
+__global__ void add_scalars_kernel(int32_t* tail, int4 scalars) {
+    tail[0] += scalars.x;
+    tail[1] += scalars.y;
+    tail[2] += scalars.z;
+    tail[3] += scalars.w;
+}
+void launch_flag_wait(const uint32_t* flag, uint32_t want, cudaStream_t st) {
+    flag_wait_kernel<<<1, 1, 0, st>>>(flag, want);
+    ++g_launches;
+}
+void launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t st) {
+    flag_publish_kernel<<<1, 1, 0, st>>>(flag, value);
+    ++g_launches;
+}
+void launch_shard_done(int32_t* root_tail, const int32_t scalars[4], uint32_t* arrivals, cudaStream_t st) {
+    shard_done_kernel<<<1, 1, 0, st>>>(root_tail, make_int4(scalars[0], scalars[1], scalars[2], scalars[3]), arrivals);
+    ++g_launches;
+}
+void launch_add_scalars(int32_t* tail, const int32_t scalars[4], cudaStream_t st) {
+    add_scalars_kernel<<<1, 1, 0, st>>>(tail, make_int4(scalars[0], scalars[1], scalars[2], scalars[3]));
+    ++g_launches;
+}
+
 void launch_postprocess(const PostBuffers& P, PostCaps C, uint32_t read_id_base, uint64_t n_reads, uint32_t max_diff,
                         uint32_t min_thresh, const uint32_t* d_thresh_per_prg, const uint32_t* d_knode_base, uint32_t total_knodes, uint32_t n_loci,
                         int32_t* d_accum_dst, int remote_dst, int sm_count, cudaStream_t st, cudaEvent_t ev_grouped,

@@ -123,6 +123,11 @@ void launch_postprocess(const PostBuffers& P, PostCaps C, uint32_t read_id_base,
                         uint32_t min_thresh, const uint32_t* d_thresh_per_prg, const uint32_t* d_knode_base, uint32_t total_knodes, uint32_t n_loci,
                         int32_t* d_accum_dst, int remote_dst, int sm_count, cudaStream_t st, cudaEvent_t ev_grouped,
                         cudaEvent_t ev_clustered);
+// cross-GPU signalling of a read-sharded run: flags behind the root GPU's accumulator (system-scope acquire / release)
+void launch_flag_wait(const uint32_t* flag, uint32_t want, cudaStream_t st);      // spins until *flag >= want
+void launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t st);
+void launch_shard_done(int32_t* root_tail, const int32_t scalars[4], uint32_t* arrivals, cudaStream_t st);
+void launch_add_scalars(int32_t* tail, const int32_t scalars[4], cudaStream_t st);
 // S7: per-node log-probabilities then one warp per locus for the ML-path DP
 void launch_node_prob(const int32_t* d_cov, uint32_t total_knodes, const uint8_t* d_is_terminal, ModelParams P,
                       double* d_prob, cudaStream_t st);

@@ -54,7 +54,8 @@ def make_opts(threads=1, min_cluster_size=10, illumina=False, genome_size=441153
 # every symbol include/drprg_cuda.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "drprg_cuda_version", "drprg_cuda_last_error", "drprg_cuda_device_count", "drprg_cuda_index_load",
-    "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_map_genotype", "drprg_cuda_map_genotype_batch",
+    "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_index_load_multi", "drprg_cuda_index_n_gpus",
+    "drprg_cuda_shard_root", "drprg_cuda_shard_attach", "drprg_cuda_shard_done", "drprg_cuda_map_genotype", "drprg_cuda_map_genotype_batch",
     "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_batch_from_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
     "drprg_cuda_batch_wrap_device", "drprg_cuda_batch_free", "drprg_cuda_sample_begin", "drprg_cuda_map_batch",
     "drprg_cuda_accum_device_ptr", "drprg_cuda_accum_download", "drprg_cuda_accum_upload", "drprg_cuda_genotype",
@@ -150,10 +151,17 @@ class Batch:
 class Index:
     """PRG + k-mer graphs + minimizer table resident in HBM on one GPU."""
 
-    def __init__(self, prg_path=None, w=11, k=15, device=0, text=None):
+    def __init__(self, prg_path=None, w=11, k=15, device=0, text=None, n_gpus=None, devices=None):
+        """n_gpus (0 = all visible) or an explicit device list makes ONE handle shard every batch over several GPUs of the
+        box inside the library (drprg_cuda_index_load_multi)."""
         L = lib()
         h = C.c_void_p()
-        if text is not None:
+        if n_gpus is not None or devices is not None:
+            devs = None if devices is None else (C.c_int * len(devices))(*devices)
+            n = len(devices) if devices is not None else int(n_gpus)
+            rc = L.drprg_cuda_index_load_multi(str(prg_path).encode(), w, k, C.c_int(n), devs, C.byref(h))
+            device = devices[0] if devices else 0
+        elif text is not None:
             rc = L.drprg_cuda_index_load_text(text.encode(), w, k, device, C.byref(h))
         else:
             rc = L.drprg_cuda_index_load(str(prg_path).encode(), w, k, device, C.byref(h))
@@ -180,6 +188,23 @@ class Index:
 
     def __del__(self):
         self.close()
+
+    @property
+    def n_gpus(self):
+        return int(lib().drprg_cuda_index_n_gpus(self.h))
+
+    # ---- one process per GPU: the root rank's accumulator is the reduction target of the others ----
+    def shard_root(self, world_size):
+        """root rank: returns the 64-byte CUDA IPC handle of the accumulator for the other ranks"""
+        buf = C.create_string_buffer(64)
+        _check(lib().drprg_cuda_shard_root(self.h, C.c_int(world_size), buf), "drprg_cuda_shard_root")
+        return buf.raw
+
+    def shard_attach(self, world_size, handle):
+        _check(lib().drprg_cuda_shard_attach(self.h, C.c_int(world_size), C.c_char_p(bytes(handle))), "drprg_cuda_shard_attach")
+
+    def shard_done(self, stream=0):
+        _check(lib().drprg_cuda_shard_done(self.h, C.c_void_p(stream)), "drprg_cuda_shard_done")
 
     # ---- introspection (parity with the oracle) ----
     def knodes(self):

@@ -1,8 +1,16 @@
-"""Read-sharded multi-GPU driver (BASELINE config 3): one process per GPU, the index is
-replicated, each rank maps a contiguous shard of the reads, and the packed int32 accumulator
-[coverage | locus read counts | scalars] is summed in place with ONE allreduce (NCCL over NVLink via
-torch.distributed) before the genotype step, which only the root rank has to run (one VCF per sample; SURVEY §8e:
-"S7/S8 on rank 0").  Integer sums => bit-exact for any world size."""
+"""Read-sharded multi-GPU driver (BASELINE config 3), one process per GPU: the index is replicated, each
+rank maps a contiguous shard of the reads, and the packed int32 accumulator [coverage | locus read counts | scalars] is
+combined on the root rank, which runs the genotype step (one VCF per sample; SURVEY §8e: "S7/S8 on rank 0").
+Two ways to combine, both integer sums and therefore bit-exact for any world size:
+
+  fused (default)   the root exports its accumulator through CUDA IPC (`setup_fused_reduce`); every other rank's coverage
+                    merge kernel adds straight into it over NVLink (red.global.add on peer-mapped memory) and signals its
+                    arrival on the device; the root's genotype step waits for the arrivals on the device.  No collective
+                    call, no host barrier inside a sample.
+  allreduce         ONE in-place NCCL allreduce of the accumulator through torch.distributed (`allreduce_accum`): the
+                    plain-library form, kept as the cross-check (tools/sharded_parity.py compares the two).
+
+The same sharding inside ONE process is `lib.Index(prg, n_gpus=N)` (drprg_cuda_index_load_multi)."""
 from __future__ import annotations
 
 import numpy as np
@@ -48,6 +56,20 @@ def allreduce_accum(index, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def setup_fused_reduce(index, rank: int, world: int, group=None):
+    """Exchange the root's 64-byte CUDA IPC handle (rank 0 -> everyone) and attach it on the other ranks.  From then on
+    `index.map_batch` on a non-root rank adds into the root's accumulator; call `index.shard_done()` after the rank's last
+    batch of a sample; the root's `index.genotype()` waits for world - 1 arrivals on the device."""
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    box = [index.shard_root(world) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    if rank != 0:
+        index.shard_attach(world, box[0])
+    dist.barrier(group=group)  # nobody starts a sample before every rank is attached
 
 
 def host_threads_for_rank(rank: int, world: int, cores: int | None = None) -> int:

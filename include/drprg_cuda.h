@@ -64,6 +64,23 @@ int drprg_cuda_index_load(const char* prg_path, uint32_t w, uint32_t k, int devi
 int drprg_cuda_index_load_text(const char* prg_text, uint32_t w, uint32_t k, int device, drprg_index** out);
 void drprg_cuda_index_free(drprg_index*);
 
+/* ---- read sharding over the GPUs of one box (BASELINE config 3) ------------------------------------------
+ * (a) inside the library: ONE handle drives n_gpus devices (0 = all visible; devices = NULL means 0..n-1).  The index is
+ * replicated, every batch is cut into one contiguous shard of reads per GPU, one host thread per GPU issues the
+ * launches, and the coverage kernel of every non-root GPU adds straight into the root GPU's accumulator over NVLink
+ * (peer-mapped memory, red.global.add: integer sums, bit-exact for any GPU count) — the path's only exchange step needs no
+ * separate collective.  Every call that takes a drprg_index* works on such a handle (the drop-in call included), so the
+ * reference's single blocking call (Pandora::genotype_with, src/lib.rs:580-590) can use the whole box. */
+int drprg_cuda_index_load_multi(const char* prg_path, uint32_t w, uint32_t k, int n_gpus, const int* devices, drprg_index** out);
+int drprg_cuda_index_n_gpus(drprg_index*);
+/* (b) one PROCESS per GPU (torchrun / MPI style): the root rank exports its accumulator as a 64-byte CUDA IPC handle,
+ * the other ranks attach it and from then on add their coverage into it over NVLink exactly as in (a).  Per sample every
+ * rank calls sample_begin and map_batch on its shard; a non-root rank then calls shard_done (its scalars join the root's,
+ * the root's arrival counter goes up); the root's drprg_cuda_genotype waits on the device for world_size - 1 arrivals. */
+int drprg_cuda_shard_root(drprg_index*, int world_size, void* handle64_out);
+int drprg_cuda_shard_attach(drprg_index*, int world_size, const void* handle64);
+int drprg_cuda_shard_done(drprg_index*, void* stream);
+
 /* ---- the drop-in call: one sample, files in, pandora_genotyped.vcf out -------------------------- */
 int drprg_cuda_map_genotype(drprg_index*, const char* reads_path, const char* vcf_refs_fasta, const char* outdir,
                             const drprg_map_opts*, drprg_map_stats* out_stats /* may be NULL */);

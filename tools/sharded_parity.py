@@ -1,9 +1,16 @@
-"""Read-sharded run under torchrun (NCCL) against the same reads mapped by one process: accumulators and VCF must be
-identical for any world size.
+"""Read-sharded run with one process per GPU (torchrun) against the same reads mapped by one process: the fused reduce
+(peer-memory adds into the root's accumulator), the NCCL allreduce and the single-process run must give identical
+accumulators and VCF for any world size.
    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_parity.py [n_reads]"""
-import os, sys, json
+import json
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import numpy as np
+import torch
+import torch.distributed as dist
+
 from drprg_b200 import lib, sharded, workload
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -15,30 +22,61 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
 wl = workload.Config2()
 d, o = wl.reads(n, 0)                      # every rank generates the same reads and takes its slice
 lo, hi = sharded.shard_bounds(n, world, rank)
-ix = lib.Index(wl.prg_path, wl.w, wl.k, device=local)
 opts = lib.make_opts(illumina=True)
 sub_off = o[lo:hi + 1] - o[lo]
 words, _, lens = lib.pack_reads(d[int(o[lo]):int(o[hi])], sub_off, workload.STRIDE_WORDS)
+strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+
+
+def shard_batch(ix):
+    return ix.upload(words, None, lens, total_bases=int(sub_off[-1]), stride_words=workload.STRIDE_WORDS, read_id_base=lo)
+
+
+# ---- (1) NCCL allreduce of the accumulator
+ix = lib.Index(wl.prg_path, wl.w, wl.k, device=local)
 ix.sample_begin(opts, workload.READ_LEN)
-ix.map_batch(ix.upload(words, None, lens, total_bases=int(sub_off[-1]), stride_words=workload.STRIDE_WORDS, read_id_base=lo))
+ix.map_batch(shard_batch(ix))
 sharded.allreduce_accum(ix)
 torch.cuda.synchronize()
-acc = ix.accum_download()
-ok = None
+acc_nccl = ix.accum_download()
+vcf_nccl = None
 if rank == 0:
     ix.genotype(wl.refs_path)
-    vcf_sharded = [l for l in ix.vcf().splitlines() if not l.startswith("##fileDate")]
+    vcf_nccl = strip(ix.vcf())
+dist.barrier()
+# ---- (2) fused reduce: two samples in a row on fresh handles (the second one checks the epoch / arrival bookkeeping)
+fx = lib.Index(wl.prg_path, wl.w, wl.k, device=local)
+sharded.setup_fused_reduce(fx, rank, world)
+acc_fused, vcf_fused = [], []
+for sample in range(2):
+    fx.sample_begin(opts, workload.READ_LEN)
+    fx.map_batch(shard_batch(fx))
+    if rank == 0:
+        fx.genotype(wl.refs_path)          # waits on the device for the other ranks' arrivals
+        vcf_fused.append(strip(fx.vcf()))
+        acc_fused.append(fx.accum_download())
+    else:
+        fx.shard_done()
+ok = None
+if rank == 0:
     w2, _, l2 = lib.pack_reads(d, o, workload.STRIDE_WORDS)
-    ix.sample_begin(opts, workload.READ_LEN)
-    ix.map_batch(ix.upload(w2, None, l2, total_bases=int(o[-1]), stride_words=workload.STRIDE_WORDS))
-    whole = ix.accum_download()
-    ix.genotype(wl.refs_path)
-    vcf_whole = [l for l in ix.vcf().splitlines() if not l.startswith("##fileDate")]
-    # the four scalar words are lo24/hi partial sums: compare them decoded, everything else raw
-    acc_eq = bool((acc[:-4] == whole[:-4]).all()) and sharded.decode_scalars(acc[-4:]) == sharded.decode_scalars(whole[-4:])
-    ok = acc_eq and vcf_sharded == vcf_whole
-    print(json.dumps({"world": world, "reads": n, "accumulators_equal": acc_eq, "vcf_equal": vcf_sharded == vcf_whole,
-                      "vcf_lines": len(vcf_whole)}))
+    sx = lib.Index(wl.prg_path, wl.w, wl.k, device=local)
+    sx.sample_begin(opts, workload.READ_LEN)
+    sx.map_batch(sx.upload(w2, None, l2, total_bases=int(o[-1]), stride_words=workload.STRIDE_WORDS))
+    sx.genotype(wl.refs_path)
+    whole = sx.accum_download()
+    vcf_whole = strip(sx.vcf())
+
+    def same(acc):  # the four scalar words are lo24/hi partial sums: compare them decoded, everything else raw
+        return bool((acc[:-4] == whole[:-4]).all()) and sharded.decode_scalars(acc[-4:]) == sharded.decode_scalars(whole[-4:])
+
+    res = {"world": world, "reads": n, "nccl_accumulators_equal": same(acc_nccl), "nccl_vcf_equal": vcf_nccl == vcf_whole,
+           "fused_accumulators_equal": [same(a) for a in acc_fused], "fused_vcf_equal": [v == vcf_whole for v in vcf_fused],
+           "vcf_lines": len(vcf_whole)}
+    ok = res["nccl_accumulators_equal"] and res["nccl_vcf_equal"] and all(res["fused_accumulators_equal"]) and all(res["fused_vcf_equal"])
+    print(json.dumps(res))
+    if ok:
+        print("sharded parity ok")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok in (None, True) else 1)
