@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — mapped reads/s of the `pandora map` hot path (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl ours|reference] [--no-extras]
 
-A step = one pass of the whole hot path over one batch of synthetic reads (config 2):
-sketch -> index lookup -> sort -> cluster/filter -> k-mer coverage (S1-S5), [allreduce of the packed
-accumulator for N > 1], parameter estimation, ML-path and genotype kernels and VCF text (S6-S8).
-`value` times that with the packed reads already resident in HBM; `e2e` times the same call sequence
-from pinned HOST buffers (H2D inside the timed region) down to the VCF text on the host.
-`--impl reference` times the CPU oracle (restated pandora algorithm; the reference's pandora binary is
-not in the reference tree) on the box's host cores on the same workload.
+Workload = BASELINE config 3, the configuration the metric ("mapped reads/sec at 1/2/4/8 B200") is quoted on: the
+config-2 panel and genome with 30 M simulated 150 bp reads (~1000x panel depth), STRONG-scaled: the same 30 M reads are
+read-sharded over the N GPUs (rank r owns sub-shards [240 r/N, 240 (r+1)/N)), the index is replicated.  A step = one pass
+of the whole hot path over the sample: sketch -> index lookup -> grouping -> cluster/filter -> k-mer coverage (S1-S5) on
+every rank's shard, the coverage of the non-root ranks added straight into the root rank's accumulator over NVLink by the
+coverage kernel itself (no collective call; DRPRG_REDUCE=nccl switches to one NCCL allreduce for comparison), then
+parameter estimation, ML path, genotyping and the VCF text (S6-S8) on the root rank.
+`value` times that with the packed reads already resident in HBM; `e2e` times the same call sequence from pinned HOST
+buffers (H2D inside the timed region) down to the VCF text in host memory.  Extra keys (N = 1): `e2e_file` = the
+reference-facing plugin call drprg_cuda_map_genotype(reads_path, ...) on a 1 M-read FASTQ (plain and gzip), `config2`,
+`config4`, `config5` = the other BASELINE configurations.
+`--impl reference` times the CPU oracle (restated pandora algorithm; the reference's pandora binary is not in the
+reference tree) on the box's host cores on a bounded sample of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -24,13 +32,20 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-# dram__bytes_read.sum + dram__bytes_write.sum of screen_kernel + resolve_kernel for one 1 M-read launch, and the pipe
-# utilisation of screen_kernel, from profiles/r1_screen.md (ncu --set full of this workload; constants, not measured live)
-NCU_TRAFFIC_BYTES = 80.2e6
-NCU_ISSUE = {"alu_pipe_active_pct": 62.6, "issue_active_pct": 66.4, "warp_instr_per_read": 72.0, "dram_read_mb_screen": 44.3,
-             "source": "profiles/r1_screen.md"}
 METRIC = "mapped reads/sec (pandora-map hot path: sketch+lookup+cluster+coverage+ML path+genotype)"
 UNIT = "reads/s"
+CPU_SAMPLE_SUBSHARDS = 8  # 1 M reads: the bounded sample the CPU arms map
+
+
+def screen_profile():
+    """ncu-derived constants of the sketch+lookup kernels (per million reads), kept with the profile they come from"""
+    for name in ("r2_screen.json", "r1_screen.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            d["source"] = "profiles/" + name
+            return d
+    return None
 
 
 def measured_peak():
@@ -41,6 +56,13 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(wl, total_reads):
+    """identical in both arms (the driver compares the dicts)"""
+    from drprg_b200 import workload
+    return {"workload": wl.name, "reads_total": int(total_reads), "read_len": workload.READ_LEN,
+            "sharding": "reads split evenly over the GPUs (strong scaling), index replicated, genotype step on the root"}
 
 
 class ClockSampler:
@@ -90,41 +112,140 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_sample(wl, device):
+    """the bounded CPU sample: the first 1 M reads of the workload (sub-shards 0..7), ASCII on the host"""
+    parts = [wl.subshard_ascii(i, device)[0] for i in range(min(CPU_SAMPLE_SUBSHARDS, wl.n_subshards))]
+    data = np.concatenate(parts)
+    n = len(data) // 150
+    return data, np.arange(n + 1, dtype=np.uint64) * np.uint64(150), n
+
+
+def oracle_step(O, ox, data, off, oo, refs):
+    mr = O.MapRun(ox, data, off, oo)
+    return O.Genotype(ox, mr, oo, refs).vcf()
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (restated pandora map) with all host threads, same workload/metric."""
+    """CPU arm: the oracle (restated pandora map) with all host threads on a bounded sample of the same workload."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     from drprg_b200 import workload
+    try:
+        import torch
+        device = "cuda" if torch.cuda.is_available() else "cpu"  # read generation only: same sub-shards as the GPU arm
+    except Exception:
+        device = "cpu"
     cores = os.cpu_count() or 1
-    wl = workload.Config2()
-    data, off = wl.reads(args.reads, 0)
-    ix = O.Index(wl.prg_path, wl.w, wl.k)
+    wl = workload.Config3(total_reads=args.reads)
+    data, off, n = cpu_sample(wl, device)
+    ox = O.Index(wl.prg_path, wl.w, wl.k)
     opts = O.make_opts(threads=cores, illumina=True, genome_size=workload.GENOME_SIZE)
-
-    def step():
-        mr = O.MapRun(ix, data, off, opts)
-        O.Genotype(ix, mr, opts, wl.refs_path).vcf()
-
     for _ in range(args.warmup):
-        step()
+        oracle_step(O, ox, data, off, opts, wl.refs_path)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        oracle_step(O, ox, data, off, opts, wl.refs_path)
     dt = (time.perf_counter() - t0) / args.steps
-    v = args.reads / dt
+    v = n / dt
+    sample = (f"each step maps the first {n} reads of the workload (sub-shards 0-{CPU_SAMPLE_SUBSHARDS - 1}) and genotypes them: restated CPU "
+              f"oracle on {cores} threads, not the pandora binary (absent from the reference tree)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": wl.name, "reads_per_step": args.reads, "read_len": workload.READ_LEN},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.reads} reads per step (whole workload), restated CPU oracle, not the pandora binary"},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 (hash/cluster/coverage), f64 (likelihoods)", "data": f"synthetic (reads generated on {device})",
+        "config": workload_config(wl, args.reads),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def extras_single_gpu(lib, workload, sim, wl, ix, opts, torch, flush):
+    """the other BASELINE configurations and the file-level plugin call, measured on one GPU (bounded: a few seconds)"""
+    out = {}
+
+    def timed_steps(fn, steps=8, warmup=2):
+        for _ in range(warmup):
+            fn()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ms.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(ms))
+
+    # ---- config 2: 1 M reads per step, resident
+    codes = torch.cat([wl.subshard_codes(i) for i in range(8)])
+    n = codes.shape[0]
+    words, lens = wl.pack_codes(codes), torch.full((n,), workload.READ_LEN, dtype=torch.int32, device="cuda")
+    b = ix.wrap_device(words.data_ptr(), lens.data_ptr(), n, workload.STRIDE_WORDS, n * workload.READ_LEN, keep=(words, lens))
+
+    def step2():
+        ix.sample_begin(opts, workload.READ_LEN)
+        ix.map_batch(b)
+        ix.genotype(wl.refs_path)
+
+    ms = timed_steps(step2)
+    out["config2"] = {"workload": "config2: 1 M x 150 bp reads per step, resident in HBM", "ms_per_step": ms, "reads_per_s": n / (ms * 1e-3),
+                      "stage_ms": ix.last_timings()}
+    # ---- the plugin call on files: drprg_cuda_map_genotype(reads_path, vcf_refs, outdir) = Pandora::genotype_with
+    tmp = tempfile.mkdtemp(prefix="drprg_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    data = sim.BASES[codes.cpu().numpy()].reshape(-1)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(workload.READ_LEN)
+    fo = lib.make_opts(illumina=True, genome_size=workload.GENOME_SIZE, threads=os.cpu_count() or 1)
+    e2e_file = {}
+    for label, gz in (("plain", False), ("gzip", True)):
+        path = os.path.join(tmp, "reads.fq" + (".gz" if gz else ""))
+        sim.write_fastq_fast(path, data, off, gz=gz)
+        ms = timed_steps(lambda: ix.map_genotype(path, wl.refs_path, tmp, fo), steps=5 if not gz else 3, warmup=1)
+        e2e_file[label] = {"ms_per_sample": ms, "reads_per_s": n / (ms * 1e-3), "file_bytes": os.path.getsize(path),
+                           "samples_per_hour_per_gpu": 3.6e6 / ms}
+    out["e2e_file"] = {"call": "drprg_cuda_map_genotype(reads.fq[.gz], genes.fa, outdir): 1 M reads in, pandora_genotyped.vcf out "
+                               "(file read, parse, H2D, S1-S8, VCF write; page cache warm)", **e2e_file}
+    # ---- config 5: a batch of samples through drprg_cuda_map_genotype_batch (index resident)
+    import ctypes as C
+    k = 6
+    outs = []
+    for s in range(k):
+        od = os.path.join(tmp, f"out{s}")
+        os.makedirs(od, exist_ok=True)
+        outs.append(od.encode())
+    arr_r = (C.c_char_p * k)(*[os.path.join(tmp, "reads.fq").encode()] * k)
+    arr_o = (C.c_char_p * k)(*outs)
+    t0 = time.perf_counter()
+    rc = lib.lib().drprg_cuda_map_genotype_batch(ix.h, C.c_size_t(k), arr_r, wl.refs_path.encode(), arr_o, C.byref(fo), None)
+    dt = time.perf_counter() - t0
+    if rc == 0:
+        out["config5"] = {"workload": f"batch of {k} samples x 1 M reads (plain FASTQ files in, VCF files out) on one GPU; sample-sharding over GPUs is replicas only",
+                          "ms_per_sample": dt / k * 1e3, "samples_per_hour_per_gpu": 3600.0 * k / dt}
+    # ---- config 4: nanopore mode (no -I), ~10 kb reads at 5 % error
+    d4, o4 = sim.simulate_long_reads(wl.genome, 3000, mean_len=10_000, sigma=0.3, seed=workload.PANEL_SEED + 3, err=0.05)
+    w4, wo4, l4 = lib.pack_reads(d4, o4)
+    o4opts = lib.make_opts(illumina=False, genome_size=workload.GENOME_SIZE)
+    b4 = ix.upload(w4, wo4, l4, total_bases=int(o4[-1]))
+
+    def step4():
+        ix.sample_begin(o4opts, int(o4[1] - o4[0]))
+        ix.map_batch(b4)
+        ix.genotype(wl.refs_path)
+
+    ms = timed_steps(step4, steps=5, warmup=2)
+    out["config4"] = {"workload": "config4: 3 000 simulated nanopore reads (~10 kb, 5 % error, no -I) per step, resident in HBM "
+                                  "(the full 15 000-read shape is a -m gpu parity test)",
+                      "ms_per_step": ms, "reads_per_s": (len(o4) - 1) / (ms * 1e-3), "bases_per_s": float(o4[-1]) / (ms * 1e-3),
+                      "stage_ms": ix.last_timings()}
+    try:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    except Exception:
+        pass
+    return out
 
 
 def main():
@@ -132,9 +253,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=30_000_000, help="reads of the whole sample (all GPUs together)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -148,7 +270,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from drprg_b200 import lib, sharded, workload
+    from drprg_b200 import lib, sharded, sim, workload
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the map path has no CPU fallback")
@@ -156,27 +278,35 @@ def main():
     # sibling ranks do not need; must be set before the library creates its worker pool
     os.environ.setdefault("DRPRG_THREADS", str(sharded.host_threads_for_rank(rank, world)))
     torch.cuda.set_device(local_rank)
+    sharded.bind_to_gpu_numa_node(local_rank)  # pinned buffers and host threads next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    reduce_mode = os.environ.get("DRPRG_REDUCE", "fused")
 
-    wl = workload.Config2()
-    data, off = wl.reads(args.reads, rank)                      # this rank's shard (weak scaling)
-    n = len(off) - 1
-    total_bases = int(off[-1])
-    words, _, lens = lib.pack_reads(data, off, workload.STRIDE_WORDS)
+    wl = workload.Config3(total_reads=args.reads)
+    mine = wl.rank_subshards(rank, world)
+    n = len(mine) * wl.SUBSHARD
+    id_base = mine.start * wl.SUBSHARD
+    total_bases = n * workload.READ_LEN
+    # device-resident inputs (value) and pinned host inputs (e2e): this rank's contiguous part of the 30 M reads
+    d_words = torch.empty((n, workload.STRIDE_WORDS), dtype=torch.int32, device="cuda")
+    for j, i in enumerate(mine):
+        d_words[j * wl.SUBSHARD:(j + 1) * wl.SUBSHARD] = wl.pack_codes(wl.subshard_codes(i))
+    d_lens = torch.full((n,), workload.READ_LEN, dtype=torch.int32, device="cuda")
+    h_words = torch.empty((n, workload.STRIDE_WORDS), dtype=torch.int32).pin_memory()
+    h_words.copy_(d_words)
+    h_lens = torch.full((n,), workload.READ_LEN, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
     ix = lib.Index(wl.prg_path, wl.w, wl.k, device=local_rank)
     opts = lib.make_opts(illumina=True, genome_size=workload.GENOME_SIZE, min_cluster_size=10)
-
-    # device-resident inputs (value) and pinned host inputs (e2e)
-    d_words = torch.from_numpy(words.view(np.int32)).cuda()
-    d_lens = torch.from_numpy(lens.view(np.int32)).cuda()
-    h_words = torch.from_numpy(words.view(np.int32)).pin_memory()
-    h_lens = torch.from_numpy(lens.view(np.int32)).pin_memory()
+    if world > 1 and reduce_mode == "fused":
+        sharded.setup_fused_reduce(ix, rank, world)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     resident = ix.wrap_device(d_words.data_ptr(), d_lens.data_ptr(), n, workload.STRIDE_WORDS, total_bases,
-                              read_id_base=rank * n, keep=(d_words, d_lens))
+                              read_id_base=id_base, keep=(d_words, d_lens))
     stats = {}
 
     def hot_path(batch):
@@ -187,11 +317,16 @@ def main():
             stats.setdefault(k_, []).append(v_)
         stats.setdefault("hits", []).append(nh)
         if world > 1:
-            sharded.allreduce_accum(ix)  # the genotype step's first device->host copy is ordered after it on the same stream
-            if rank != 0:                # one VCF per sample: S6-S8 run on the root rank only
-                torch.cuda.current_stream().synchronize()
-                return None
-        ix.genotype(wl.refs_path)
+            if reduce_mode == "fused":
+                if rank != 0:          # this rank's coverage is already in the root's accumulator: report the arrival
+                    ix.shard_done()
+                    return None
+            else:
+                sharded.allreduce_accum(ix)
+                if rank != 0:
+                    torch.cuda.current_stream().synchronize()
+                    return None
+        ix.genotype(wl.refs_path)      # root: waits on the device for the other ranks' arrivals (fused mode)
         for k_, v_ in ix.last_genotype_timings().items():
             stats.setdefault("gt_" + k_, []).append(v_)
         return ix.vcf_view()  # the step's result: the VCF text in host memory (zero-copy view of the library's buffer)
@@ -200,7 +335,7 @@ def main():
         return hot_path(resident)
 
     def step_e2e():
-        b = ix.upload_ptrs(h_words.data_ptr(), h_lens.data_ptr(), n, workload.STRIDE_WORDS, total_bases, read_id_base=rank * n)
+        b = ix.upload_ptrs(h_words.data_ptr(), h_lens.data_ptr(), n, workload.STRIDE_WORDS, total_bases, read_id_base=id_base)
         try:
             return hot_path(b)
         finally:
@@ -209,6 +344,8 @@ def main():
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             flush.zero_()
+            if world > 1:
+                dist.barrier()
             fn()
         stats.clear()
         torch.cuda.synchronize()
@@ -217,6 +354,7 @@ def main():
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         l0 = lib.launch_count()
+        out = None
         for i in range(steps):
             flush.zero_()                      # L2 flush between timed iterations (outside the events)
             torch.cuda.synchronize()
@@ -238,63 +376,105 @@ def main():
         sampler.start()
     ms_step, launches, vcf_text, st = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, _, _, _ = timed(step_e2e, max(3, args.steps // 2), args.warmup)
 
-    total_reads = n * world
+    total_reads = wl.total_reads
     value = total_reads / (ms_step * 1e-3)
     e2e_value = total_reads / (ms_e2e * 1e-3)
-    # roofline of the dominant kernel (sketch+lookup): algorithmic bytes = packed bases + length word per read
-    # + 16 B per emitted hit, over the kernel's CUDA-event duration measured inside the library
+    # roofline of the dominant kernel pair (sketch+lookup) on this rank's shard: algorithmic bytes = packed bases +
+    # length word per read + 16 B per emitted hit, over the pair's CUDA-event duration measured inside the library
     k_ms = float(np.mean(st["sketch_lookup"]))
     hits = float(np.mean(st["hits"]))
     alg_bytes = n * (workload.STRIDE_WORDS * 4 + 4) + 16.0 * hits
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    prof = screen_profile()
+    issue_peak = ix.issue_peak() if rank == 0 else 0.0
     vcf_text = bytes(vcf_text) if vcf_text is not None else b""
     n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
-    kept_cluster_reads = int(ix.coverage()["locus_reads"].sum())  # reads (clusters) that support a panel locus, all ranks
-    h2d = int(h_words.numel() * 4 + h_lens.numel() * 4)
-    d2h = int(ix.n_accum * 4 + n_records * 64 + 8)
+    h2d = int(h_words.numel() * 4 + h_lens.numel() * 4) * world
+    d2h = int(len(vcf_text) + 4096)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 (hash/cluster/coverage), f64 (likelihoods)", "data": "synthetic",
-        "config": {"workload": wl.name, "reads_per_gpu_per_step": n, "read_len": workload.READ_LEN,
-                   "l2": "flushed with a 512 MiB memset between timed iterations", "sharding": f"reads x{world}, index replicated",
-                   "vcf_records": n_records, "reads_with_kept_cluster_per_step": kept_cluster_reads,
-                   "kept_cluster_reads_per_s": kept_cluster_reads / (ms_step * 1e-3)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 (hash/cluster/coverage), f64 (likelihoods)", "data": "synthetic (reads generated on cuda)",
+        "config": workload_config(wl, total_reads),
+        "run": {"reads_per_gpu_per_step": n, "l2": "inputs larger than L2 from 3 M reads per GPU; also flushed with a 512 MiB memset between timed iterations",
+                "reduce": ("none (one GPU)" if world == 1 else
+                           "fused: coverage kernel adds into the root accumulator over NVLink (CUDA IPC mapping), device-side arrival flags"
+                           if reduce_mode == "fused" else "NCCL allreduce of the accumulator (torch.distributed)"),
+                "vcf_records": n_records, "vcf_sha1": hashlib.sha1(b"\n".join(l for l in vcf_text.splitlines() if not l.startswith(b"##fileDate"))).hexdigest()},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                "what": "same steps from pinned host buffers: H2D of every rank's packed shard inside the timed region, VCF text read on the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "screen_kernel<15,10> + resolve_kernel<11,15> (S1+S2: k-mer screen of every read, then hash/probe/minimizer test of the flagged positions)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
-                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "issue_ceiling": NCU_ISSUE,
-                     "note": "the two kernels of the sketch+lookup stage carry all of the step's HBM traffic; kernel_ms is the CUDA-event time "
-                             "around the pair on the launch stream. screen_kernel streams each read once (DRAM read = the input, see "
-                             "profiles/) and is bound by the ALU pipe (shift/logic) and shared-memory bank conflicts of the Bloom probes "
-                             "(~72 warp-instructions per read), not by HBM; `traffic` is dram read+write of both kernels from the "
-                             "committed ncu capture (cold caches: resolve_kernel re-reads queue and words that are L2 hits in a real step). "
-                             "The longest single launch of the step is mlpath_level_kernel (30 warps, a latency chain per locus, "
-                             "stage_ms.gt_mlpath_kernel), which overlaps the genotype kernels and the VCF text. See DESIGN.md section 4."},
         "stage_ms": {k_: float(np.mean(v_)) for k_, v_ in st.items() if k_ != "hits"},
-        **({"stage_ms_per_step": {k_: [round(float(x), 4) for x in v_] for k_, v_ in st.items() if k_ in ("sketch_lookup", "gt_s8+vcf_text")}}
-           if os.environ.get("DRPRG_BENCH_VERBOSE") else {}),
     }
+    roof = {"bound": "hbm", "kernel": "screen_kernel<15,10> + resolve_kernel<11,15> (S1+S2: k-mer screen of every read, then hash/probe/minimizer test of the flagged positions)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "reads_per_launch": n}
+    if prof:
+        scale = n / 1e6
+        roof["traffic"] = prof.get("dram_bytes_per_million_reads", 0) * scale or None
+        roof["traffic_source"] = prof["source"]
+        wi = prof.get("warp_instr_per_read_screen", 0) + prof.get("warp_instr_per_read_resolve", 0)
+        if issue_peak > 0 and wi:
+            roof["issue"] = {"warp_instr_per_read": wi, "achieved_warp_instr_per_s": wi * n / (k_ms * 1e-3),
+                             "measured_int_issue_peak_warp_instr_per_s": issue_peak,
+                             "issue_frac": wi * n / (k_ms * 1e-3) / issue_peak,
+                             "note": "the pair is bound by instruction issue (32-bit multiply-add / shift / logic + one shared-memory probe per "
+                                     "k-mer position), not by HBM: issue_frac is its warp-instruction rate over the rate a pure INT32 "
+                                     "mad/shf/lop3 loop reaches on this GPU (measured in this run)"}
+    line["roofline"] = roof
+
+    if world > 1:
+        # sharded parity, outside the timed region: the root maps ALL 30 M reads alone (regenerated sub-shard by sub-shard)
+        # into one accumulator and must reproduce the sharded run's accumulator and VCF bit for bit
+        acc_sharded = ix.accum_download() if rank == 0 else None
+        dist.barrier()
+        if rank == 0:
+            sx = lib.Index(wl.prg_path, wl.w, wl.k, device=local_rank)
+            sx.sample_begin(opts, workload.READ_LEN)
+            group = 16  # 2 M reads per batch
+            for g0 in range(0, wl.n_subshards, group):
+                ids = range(g0, min(g0 + group, wl.n_subshards))
+                w = torch.cat([wl.pack_codes(wl.subshard_codes(i)) for i in ids])
+                l = torch.full((w.shape[0],), workload.READ_LEN, dtype=torch.int32, device="cuda")
+                sx.map_batch(sx.wrap_device(w.data_ptr(), l.data_ptr(), w.shape[0], workload.STRIDE_WORDS, w.shape[0] * workload.READ_LEN,
+                                            read_id_base=g0 * wl.SUBSHARD, keep=(w, l)))
+            sx.genotype(wl.refs_path)
+            whole = sx.accum_download()
+            vcf_whole = b"\n".join(l for l in bytes(sx.vcf_view()).splitlines() if not l.startswith(b"##fileDate"))
+            acc_ok = bool((acc_sharded[:-4] == whole[:-4]).all()) and sharded.decode_scalars(acc_sharded[-4:]) == sharded.decode_scalars(whole[-4:])
+            line["sharded_parity"] = bool(acc_ok and hashlib.sha1(vcf_whole).hexdigest() == line["run"]["vcf_sha1"])
+            line["sharded_parity_detail"] = {"accumulators_equal": acc_ok, "vcf_sha1_single_gpu": hashlib.sha1(vcf_whole).hexdigest()}
+            sx.close()
+        dist.barrier()
+    else:
+        line["sharded_parity"] = None
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            line["extras"] = extras_single_gpu(lib, workload, sim, wl, ix, opts, torch, flush)
+        except Exception as e:  # the headline must survive a failing side measurement
+            line["extras"] = {"error": repr(e)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py as O
         ox = O.Index(wl.prg_path, wl.w, wl.k)
         cores = os.cpu_count() or 1
         oo = O.make_opts(threads=cores, illumina=True, genome_size=workload.GENOME_SIZE)
+        data, off, ns = cpu_sample(wl, "cuda")
+        oracle_step(O, ox, data, off, oo, wl.refs_path)
         t0 = time.perf_counter()
-        mr = O.MapRun(ox, data, off, oo)
-        O.Genotype(ox, mr, oo, wl.refs_path).vcf()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"all {n} reads of the step once, restated CPU oracle on {cores} threads (not the pandora binary)"}
+        reps = 3
+        for _ in range(reps):
+            oracle_step(O, ox, data, off, oo, wl.refs_path)
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"the first {ns} reads of the workload (sub-shards 0-{CPU_SAMPLE_SUBSHARDS - 1}) mapped and genotyped {reps} times, "
+                                          f"restated CPU oracle on {cores} threads (not the pandora binary)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

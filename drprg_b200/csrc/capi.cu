@@ -702,7 +702,9 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
         PB.partials = X->partials.p; PB.n_partials = X->n_partials;
         if (X->reduce_dst && X->flag_ready) launch_flag_wait(X->flag_ready, X->epoch, st);  // root has zeroed its accumulator for this sample
         launch_postprocess(PB, PostCaps{X->hi.cap, queue_cap}, B->R.read_id_base, B->R.n_reads, X->opts.max_diff, X->min_thresh, X->d_thresh,
-                           X->d_knode_base, N, P, X->reduce_dst ? X->reduce_dst : X->d_accum, X->reduce_dst ? 1 : 0, X->sm_count, st,
+                           X->d_knode_base, N, P, X->reduce_dst ? X->reduce_dst : X->d_accum,
+                           (X->reduce_dst || X->accum_shared) ? 1 : 0,  // several GPUs add into one accumulator: every writer uses red
+                           X->sm_count, st,
                            X->ev[2], X->ev[3]);
         CK(cudaEventRecord(X->ev[4], st));
         CK(cudaGetLastError());
@@ -1967,4 +1969,14 @@ int drprg_cuda_format_g6(double v, char* out) {
     return (int)n;
 }
 uint64_t drprg_cuda_launch_count(void) { return launch_count(); }
+double drprg_cuda_issue_peak(drprg_index* X) {
+    try {
+        need_device(X);
+        CK(cudaSetDevice(X->device));
+        return measure_issue_peak(X->sm_count, 0);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 0.0;
+    }
+}
 }

@@ -548,9 +548,14 @@ constexpr uint32_t CV_STRETCH_MIN = 8192;      // a stretch is sized so that (ra
 constexpr uint32_t CV_STRETCH_MAX = 983040;    // bounds: a warp sees a sixteenth of it and its counters are 16 bit (61 440 < 65 536)
 constexpr uint32_t CV_UNROLL = 8;              // independent slot loads in flight per lane; 8 x 32 slots are compacted, then counted
 
-// slots per stretch for n slots when `waves` stretches fit the grid at once; a multiple of 512 (16 warps x 32 lanes)
-__host__ __device__ __forceinline__ unsigned long long cov_stretch_len(unsigned long long n, uint32_t waves) {
-    unsigned long long len = (n + waves - 1) / waves;
+// slots per stretch for n slots on a grid of `grid` CTAs and n_range key ranges: the (range, stretch) jobs fill the grid in
+// whole waves (one wave while a stretch stays below CV_STRETCH_MAX); a multiple of 512 (16 warps x 32 lanes)
+__host__ __device__ __forceinline__ unsigned long long cov_stretch_len(unsigned long long n, uint32_t grid, uint32_t n_range) {
+    const unsigned long long min_stretches = (n + CV_STRETCH_MAX - 1) / CV_STRETCH_MAX;
+    const unsigned long long waves = (min_stretches * n_range + grid - 1) / grid;          // at least this many waves
+    unsigned long long stretches = (waves < 1 ? 1 : waves) * grid / n_range;               // stretches that fill them
+    if (stretches < 1) stretches = 1;
+    unsigned long long len = (n + stretches - 1) / stretches;
     len = (len + 511ull) & ~511ull;
     return len < CV_STRETCH_MIN ? CV_STRETCH_MIN : (len > CV_STRETCH_MAX ? CV_STRETCH_MAX : len);
 }
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cov_count_kernel(const unsigned
     S.n2 = ctr[CTR_LKOVF];
     const unsigned long long n = S.n0 + S.n1 + S.n2;
     const uint32_t n_range = (n_keys + CV_RANGE - 1) / CV_RANGE;
-    const unsigned long long stretch_len = cov_stretch_len(n, max(1u, gridDim.x / n_range));
+    const unsigned long long stretch_len = cov_stretch_len(n, gridDim.x, n_range);
     const uint32_t n_stretch = (uint32_t)min((unsigned long long)max_stretches, (n + stretch_len - 1) / stretch_len);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned short* mine = s_cnt + (size_t)wid * CV_RANGE;
@@ -641,7 +646,7 @@ __global__ void cov_merge_kernel(unsigned long long* __restrict__ ctr, PostCaps 
                                  int32_t* __restrict__ dst, int remote) {
     if (batch_overflowed(ctr, C)) return;
     const unsigned long long n = ctr[CTR_HITS] + 2ull * ctr[CTR_ACTIVE] + ctr[CTR_LKOVF];
-    const unsigned long long stretch_len = cov_stretch_len(n, max(1u, count_grid / ((n_keys + CV_RANGE - 1) / CV_RANGE)));
+    const unsigned long long stretch_len = cov_stretch_len(n, count_grid, (n_keys + CV_RANGE - 1) / CV_RANGE);
     const uint32_t used = (uint32_t)min((unsigned long long)max_stretches, (n + stretch_len - 1) / stretch_len);
     unsigned long long kept = 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_keys; k += gridDim.x * blockDim.x) {
@@ -659,7 +664,8 @@ __global__ void cov_merge_kernel(unsigned long long* __restrict__ ctr, PostCaps 
 
 // stretches a hit capacity can produce: [hit_cap | 2 per active read <= 2 hit_cap | overflow <= hit_cap] slots
 uint32_t cov_max_stretches(uint64_t hit_cap, int sm_count) {
-    return (uint32_t)std::max<uint64_t>((uint64_t)sm_count, (4 * hit_cap + CV_STRETCH_MAX - 1) / CV_STRETCH_MAX) + 1;
+    // whole waves of the grid: at most (minimum stretches + one wave's worth) stretches
+    return (uint32_t)((4 * hit_cap + CV_STRETCH_MAX - 1) / CV_STRETCH_MAX + (uint64_t)sm_count) + 1;
 }
 
 // ---- cross-GPU signalling of a read-sharded run (flags live behind the root GPU's accumulator) ------------------

@@ -74,6 +74,9 @@ void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint
 // host mirror of the screen's filter addressing (used when the index is uploaded)
 void screen_filter_insert(uint32_t* filter, uint32_t n_words, uint32_t kmer, uint32_t k);
 constexpr uint32_t SCREEN_MAX_FILTER_WORDS = 54 * 1024;  // 216 KB of shared memory
+// warp-instructions per second the GPU issues for a pure 32-bit integer multiply-add / shift / logic mix (the screen
+// kernel's instruction classes): the issue-rate ceiling bench.py reports next to the HBM roofline
+double measure_issue_peak(int sm_count, cudaStream_t st);
 // S1 only (parity hook): emits key = read << 32 | start, val = hash << 1 | strand
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st);

@@ -956,6 +956,53 @@ void launch_sketch_lookup(const DevReads& R, const DevTable& T, uint32_t w, uint
     ++g_launches;
 }
 
+// ---- issue-rate yardstick for the roofline of the k-mer screen ------------------------------------------------------
+// The screen kernel is bound by instruction issue (multiply-add, shift and logic on 32-bit integers), not by HBM.  This
+// kernel issues the same instruction classes from eight independent dependency chains per thread with nothing else in
+// the loop, which is what the SM can issue at best for that mix; bench.py reports the screen's warp-instructions per
+// second as a fraction of it next to the HBM fraction.
+constexpr int ISSUE_OPS_PER_ITER = 32;  // 16 mad.lo + 8 shf + 8 lop3 per loop iteration
+__global__ void __launch_bounds__(1024, 1) issue_peak_kernel(uint32_t iters, uint32_t a, uint32_t b, uint32_t* __restrict__ out) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 8u + i + b;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
+            asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(b), "r"(a));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= x[i];
+    if (r == 0x12345678u) out[0] = r;  // never true in practice: keeps the chains alive
+}
+double measure_issue_peak(int sm_count, cudaStream_t st) {
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const uint32_t iters = 4096;
+    issue_peak_kernel<<<sm_count, 1024, 0, st>>>(64, 3u, 5u, d);  // warm-up
+    cudaEventRecord(e0, st);
+    issue_peak_kernel<<<sm_count, 1024, 0, st>>>(iters, 3u, 5u, d);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    g_launches += 2;
+    if (ms <= 0) return 0.0;
+    return (double)sm_count * 32.0 /* warps */ * (double)iters * ISSUE_OPS_PER_ITER / (ms * 1e-3);
+}
+
 void launch_sketch_only(const DevReads& R, uint32_t w, uint32_t k, unsigned long long* d_key, unsigned long long* d_val,
                         unsigned long long* d_count, uint64_t cap, int sm_count, uint32_t max_len, cudaStream_t st) {
     if (R.n_reads == 0) return;

@@ -63,7 +63,7 @@ SYMBOLS = [
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
-    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse",
+    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse", "drprg_cuda_issue_peak",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
         for f in ("drprg_cuda_pack_reads", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits", "drprg_cuda_gt_mlpath"):
             getattr(L, f).restype = C.c_int64
         L.drprg_cuda_launch_count.restype = C.c_uint64
+        L.drprg_cuda_issue_peak.restype = C.c_double
         for f in ("drprg_cuda_hash64", "drprg_cuda_hash64_inverse"):
             getattr(L, f).restype = C.c_uint64
             getattr(L, f).argtypes = [C.c_uint64, C.c_uint32]
@@ -369,6 +370,10 @@ class Index:
         d = dict(locus=locus, pos=pos, n_alleles=nal, gt=gt, gt_conf=conf, lik=lik, gaps=gaps, allele_knodes=kn)
         d.update(u)
         return d
+
+    def issue_peak(self):
+        """measured warp-instructions/s of a pure INT32 multiply-add / shift / logic loop on this GPU"""
+        return float(lib().drprg_cuda_issue_peak(self.h))
 
     def last_timings(self):
         o = np.zeros(4, np.float32)

@@ -82,6 +82,40 @@ def host_threads_for_rank(rank: int, world: int, cores: int | None = None) -> in
     return max(2, cores - 2 * (world - 1)) if rank == 0 else 2
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the host cores of the NUMA node the GPU hangs off (so that pinned buffers are first-touched
+    there and the upload threads run next to the GPU's PCIe root).  A no-op on single-node hosts; never fatal."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import subprocess
+        bus = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]  # sysfs uses a 4-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        if node >= 0 and len(nodes) > 1:
+            cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus"] = len(cpus)
+    except Exception:
+        pass
+    return info
+
+
 def allreduce_accum_host(accum: np.ndarray, group=None) -> np.ndarray:
     """Host-memory variant (gloo) used by the CPU tests of the sharding logic."""
     import torch

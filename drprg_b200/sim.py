@@ -295,6 +295,37 @@ def write_fastq(path, data, off, gz=False):
             f.write(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
 
 
+def write_fastq_fast(path, data, off, gz=False, seed=7):
+    """vectorised FASTQ writer for equal-length reads (benchmarks: a million records in a fraction of a second): fixed-width
+    headers, qualities drawn from the four binned Illumina symbols so that gzip sees realistic entropy"""
+    import zlib
+    n = len(off) - 1
+    L = int(off[1] - off[0]) if n else 0
+    if n == 0 or not (np.diff(off) == L).all():
+        return write_fastq(path, data, off, gz)
+    rng = np.random.default_rng(seed)
+    head = 11  # "@r" + 8 digits + newline
+    rec = head + L + 3 + L + 1
+    out = np.empty((n, rec), np.uint8)
+    out[:, 0], out[:, 1] = ord("@"), ord("r")
+    ids = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        out[:, 2 + d] = ord("0") + (ids // 10 ** (7 - d)) % 10
+    out[:, 10] = 10
+    out[:, head:head + L] = np.asarray(data, np.uint8).reshape(n, L)
+    out[:, head + L], out[:, head + L + 1], out[:, head + L + 2] = 10, ord("+"), 10
+    out[:, head + L + 3:head + 2 * L + 3] = np.frombuffer(b"F:,#", np.uint8)[rng.choice(4, size=(n, L), p=(0.85, 0.08, 0.05, 0.02))]
+    out[:, rec - 1] = 10
+    raw = out.tobytes()
+    with open(path, "wb") as f:
+        if gz:
+            co = zlib.compressobj(1, zlib.DEFLATED, 31)  # one gzip member, like `gzip -1`
+            f.write(co.compress(raw))
+            f.write(co.flush())
+        else:
+            f.write(raw)
+
+
 # --------------------------------------------------------------------------------------------
 def pack_reads(data, off, stride_words=0):
     """2-bit pack ASCII reads (A0 C1 G2 T3, base i of a read in bits [30-2*(i%16), 31-2*(i%16)] of

@@ -181,6 +181,9 @@ int drprg_cuda_last_genotype_timings(drprg_index*, double* out7);
 int drprg_cuda_format_g6(double v, char* out);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t drprg_cuda_launch_count(void);
+/* measured warp-instructions per second of a pure 32-bit integer multiply-add / shift / logic loop on this index's GPU: the
+ * issue-rate ceiling of the k-mer screen (which is bound by instruction issue, not by HBM); 0 on failure */
+double drprg_cuda_issue_peak(drprg_index*);
 
 #ifdef __cplusplus
 }
