@@ -281,7 +281,6 @@ def main():
     sharded.bind_to_gpu_numa_node(local_rank)  # pinned buffers and host threads next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     reduce_mode = os.environ.get("DRPRG_REDUCE", "fused")
 

@@ -374,7 +374,8 @@ def test_pandora_cuda_cli_drop_in(tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"DRPRG_MLPATH_UNITS": "1"}, {"DRPRG_MLPATH_UNITS": "0"}, {"DRPRG_MLPATH_GENERIC": "1", "DRPRG_MLPATH_UNITS": "0"},
-                                 {"DRPRG_MLPATH_LEVELS": "0"}, {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}, {"DRPRG_PACKED_SORT": "0"}])
+                                 {"DRPRG_MLPATH_LEVELS": "0"}, {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}, {"DRPRG_SCREEN_VARIANT": "0"},
+                                 {"DRPRG_SCREEN_VARIANT": "1"}])
 def test_alternative_kernel_variants_keep_parity(env):
     """the ML-path kernel has four implementations (level-parallel = default, run-parallel units, record-addressed chain,
     generic lifting), the
@@ -383,7 +384,7 @@ def test_alternative_kernel_variants_keep_parity(env):
     import subprocess, sys
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "toy_config1 or nanopore or low_min_cluster or short_read_kernel"], env=e, capture_output=True, text=True)
+                        "toy_config1 or nanopore or low_min_cluster or short_read_kernel or screened_lookup"], env=e, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
