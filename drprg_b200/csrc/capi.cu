@@ -1366,6 +1366,13 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
         return F;
     }
     static const bool host_only = getenv("DRPRG_HOST_INGEST") != nullptr && atoi(getenv("DRPRG_HOST_INGEST")) != 0;
+    // gzip: the whole stream is inflated on all host threads first (gzip_inflate.cpp; zlib's one-core gzread only for
+    // streams the parallel decoder declines), then the text takes the same device path as a plain file
+    Inflated local;
+    if (!pre && !host_only && file_is_gzip(reads_path)) {
+        inflate_file(reads_path, &local.p, &local.n);
+        pre = &local;
+    }
     IngestResult I;
     const int dev = X->device;
     if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); },

@@ -3,6 +3,7 @@
 // run under the argv of /root/reference/src/lib.rs:594-609; the VCF schema is the one
 // /root/reference/src/filter.rs:48-63 and src/lib.rs:935-1181 (VcfExt) consume.
 #include "genotype_host.hpp"
+#include "gzip_inflate.hpp"
 
 #include <zlib.h>
 
@@ -836,6 +837,34 @@ void slurp(const std::string& path, RawText& buf) {
         buf.n = fread(buf.p, 1, fsize, fp);
         fclose(fp);
         return;
+    }
+    {   // single-stream gzip: inflate on all host threads (gzip_inflate.cpp); anything it declines goes through zlib below
+        static const bool par = [] {
+            const char* e = getenv("DRPRG_PARALLEL_GZIP");
+            return !e || atoi(e) != 0;
+        }();
+        static const size_t min_size = [] {
+            const char* e = getenv("DRPRG_PARALLEL_GZIP_CHUNK");
+            return e && atol(e) > 0 ? (size_t)atol(e) * 2 : (size_t)(4u << 20);
+        }();
+        if (par && fsize >= min_size) {
+            uint8_t* z = (uint8_t*)calloc(fsize + 64, 1);  // the bit reader loads 8 bytes at a time: zero padding behind the image
+            if (z && fread(z, 1, fsize, fp) == fsize) {
+                const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+                char* text = nullptr;
+                size_t tn = 0;
+                const bool ok = parallel_gunzip(z, fsize, hw, &text, &tn);
+                free(z);
+                if (ok) {
+                    fclose(fp);
+                    buf.p = text;
+                    buf.n = tn;
+                    return;
+                }
+            } else {
+                free(z);
+            }
+        }
     }
     fclose(fp);
     gzFile f = gzopen(path.c_str(), "rb");

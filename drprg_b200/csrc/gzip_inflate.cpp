@@ -1,0 +1,552 @@
+// Parallel inflate of a SINGLE-STREAM gzip file (what `drprg predict -i reads.fastq.gz` usually gets:
+// /root/reference/src/predict.rs:166-170, docs/src/guide/predict.md:36).  zlib inflates one stream on one core
+// (~0.3 GB/s of text, 1 s per million 150 bp reads), 600x the GPU time of the sample; this file cuts the COMPRESSED
+// stream into chunks that are decoded side by side:
+//   1. block search   every chunk but the first starts at an unknown bit offset: candidate offsets are tried until a
+//                     dynamic-Huffman block header parses (complete code-length, literal/length and distance codes, an
+//                     end-of-block code) and the block decodes to the end of a plausible text block followed by another
+//                     valid header;
+//   2. decoding with an unknown window   a chunk does not know the 32 KB of text before it, so it decodes into 16-bit
+//                     symbols: 0..255 = a byte, 0x8000 | i = "byte i of the unknown window"; back-references copy
+//                     symbols, so the unknowns propagate exactly;
+//   3. resolution     chunk 0 has no unknowns; the last 32 KB of chunk t-1 (resolved) turn the symbols of chunk t into
+//                     bytes.  Only the 32 KB windows are chained sequentially, the bulk translation is parallel.
+// (The scheme is the two-pass decompression of Kerbiriou & Chikhi, "Parallel decompression of gzip-compressed files and
+// random access to DNA sequences", 2019 — restated here, no code taken.)
+// The CRC-32 and length of every member are verified (zlib's crc32 on the chunks, combined); any failure — a corrupt
+// file, or a stream this decoder does not handle — makes the caller fall back to zlib's sequential gzread.
+#include "gzip_inflate.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "genotype_host.hpp"  // parallel_for
+
+namespace drprg {
+namespace {
+
+constexpr uint32_t WIN = 32768;
+constexpr uint16_t UNKNOWN = 0x8000;
+
+// ---- bit reader over a byte range (LSB first, like deflate).  The caller guarantees 16 readable bytes behind p[n)
+// (zero padding), so a refill is one unaligned 64-bit load.
+struct Bits {
+    const uint8_t* p;
+    size_t n;        // bytes of real input
+    size_t pos = 0;  // next byte to load
+    uint64_t buf = 0;
+    int cnt = 0;     // valid bits in buf
+    bool over = false;
+    Bits(const uint8_t* p_, size_t n_, size_t bitpos) : p(p_), n(n_) {
+        pos = bitpos >> 3;
+        refill();
+        const int skip = (int)(bitpos & 7);
+        buf >>= skip;
+        cnt -= skip;
+    }
+    inline void refill() {  // afterwards cnt >= 56
+        if (pos > n + 8) {  // far past the end: decoding garbage (a wrong block-start guess or a truncated file)
+            over = true;
+            cnt |= 56;
+            return;
+        }
+        uint64_t w;
+        memcpy(&w, p + pos, 8);
+        buf |= w << cnt;
+        pos += (size_t)((63 - cnt) >> 3);
+        cnt |= 56;
+    }
+    inline uint32_t peek(int k) const { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
+    inline void drop(int k) {
+        buf >>= k;
+        cnt -= k;
+    }
+    inline uint32_t get(int k) {
+        if (cnt < k) refill();
+        const uint32_t v = peek(k);
+        drop(k);
+        return v;
+    }
+    size_t bit_position() const { return pos * 8 - (size_t)cnt; }  // next unread bit
+    bool exhausted() const { return bit_position() > n * 8; }
+};
+
+// ---- canonical Huffman decoding tables: one level of ROOT bits, longer (rare) codes by a canonical bit-by-bit walk ----
+struct Huff {
+    static constexpr int ROOT = 11;
+    // entry: bits 0..3 = code length (0 = needs the slow path), bits 4.. = symbol
+    uint16_t fast[1 << ROOT];
+    uint16_t count[16], symbol[320];
+    int max_len = 0;
+    bool build(const uint8_t* lens, int n) {  // false: over-subscribed or (incomplete with more than one code)
+        memset(count, 0, sizeof count);
+        for (int i = 0; i < n; ++i) ++count[lens[i]];
+        count[0] = 0;
+        int left = 1, codes = 0;
+        max_len = 0;
+        for (int l = 1; l < 16; ++l) {
+            left <<= 1;
+            left -= count[l];
+            if (left < 0) return false;
+            if (count[l]) max_len = l;
+            codes += count[l];
+        }
+        if (codes == 0) return false;
+        if (left > 0 && !(codes == 1 && count[1] == 1)) return false;  // incomplete: only a lone 1-bit code is allowed
+        uint16_t offs[16];
+        offs[1] = 0;
+        for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
+        for (int i = 0; i < n; ++i)
+            if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+        return true;
+    }
+    void fill_fast() {  // separate from build(): the block search builds thousands of tables it never decodes with
+        memset(fast, 0, sizeof fast);
+        int code = 0, idx = 0;
+        for (int l = 1; l <= std::min(ROOT, 15); ++l) {
+            for (int k = 0; k < count[l]; ++k, ++code, ++idx) {
+                // deflate codes are MSB-first in a stream that is read LSB-first: reverse the code
+                uint32_t rev = 0;
+                for (int b = 0; b < l; ++b) rev |= ((code >> b) & 1u) << (l - 1 - b);
+                for (uint32_t fill = rev; fill < (1u << ROOT); fill += 1u << l) fast[fill] = (uint16_t)((symbol[idx] << 4) | l);
+            }
+            code <<= 1;
+        }
+    }
+    // canonical decode bit by bit
+    inline int slow(Bits& b) const {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l <= max_len; ++l) {
+            code |= (int)b.get(1);
+            const int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c;
+            first += c;
+            first <<= 1;
+            code <<= 1;
+        }
+        return -1;
+    }
+    inline int decode(Bits& b) const {  // needs >= 15 bits in the buffer
+        const uint16_t e = fast[b.peek(ROOT)];
+        if (e & 15) {
+            b.drop(e & 15);
+            return e >> 4;
+        }
+        return slow(b);
+    }
+};
+
+const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct BlockCodes {
+    Huff lit, dist;
+    bool have_dist = false;
+};
+
+// parse a dynamic block header at the reader's position (after BFINAL/BTYPE); false = not a valid header
+bool read_dynamic_header(Bits& b, BlockCodes& C, bool fill = true) {
+    const uint32_t hlit = b.get(5) + 257, hdist = b.get(5) + 1, hclen = b.get(4) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    uint8_t cl[19] = {0};
+    for (uint32_t i = 0; i < hclen; ++i) cl[CL_ORDER[i]] = (uint8_t)b.get(3);
+    Huff clh;
+    if (!clh.build(cl, 19)) return false;
+    uint8_t lens[320];
+    uint32_t i = 0;
+    while (i < hlit + hdist) {
+        if (b.cnt < 32) b.refill();
+        const int sym = clh.slow(b);
+        if (sym < 0 || b.over) return false;
+        if (sym < 16) lens[i++] = (uint8_t)sym;
+        else {
+            uint32_t rep, val = 0;
+            if (sym == 16) {
+                if (i == 0) return false;
+                val = lens[i - 1];
+                rep = 3 + b.get(2);
+            } else if (sym == 17) rep = 3 + b.get(3);
+            else rep = 11 + b.get(7);
+            if (i + rep > hlit + hdist) return false;
+            while (rep--) lens[i++] = (uint8_t)val;
+        }
+    }
+    if (lens[256] == 0) return false;  // no end-of-block code
+    if (!C.lit.build(lens, (int)hlit)) return false;
+    // a distance alphabet with no code at all is legal when the block has only literals
+    bool any = false;
+    for (uint32_t k = 0; k < hdist; ++k) any = any || lens[hlit + k];
+    C.have_dist = any;
+    if (any && !C.dist.build(lens + hlit, (int)hdist)) return false;
+    if (fill) {
+        C.lit.fill_fast();
+        if (any) C.dist.fill_fast();
+    }
+    return true;
+}
+
+void fixed_codes(BlockCodes& C) {
+    uint8_t l[288];
+    for (int i = 0; i < 144; ++i) l[i] = 8;
+    for (int i = 144; i < 256; ++i) l[i] = 9;
+    for (int i = 256; i < 280; ++i) l[i] = 7;
+    for (int i = 280; i < 288; ++i) l[i] = 8;
+    C.lit.build(l, 288);
+    C.lit.fill_fast();
+    uint8_t d[30];
+    for (int i = 0; i < 30; ++i) d[i] = 5;
+    C.dist.build(d, 30);
+    C.dist.fill_fast();
+    C.have_dist = true;
+}
+
+// ---- a chunk's output: 16-bit symbols, the first WIN entries are the (unknown) window ----------------------------
+// (a plain growable array: std::vector would zero-fill every resize and check capacity on every literal)
+struct SymBuf {
+    uint16_t* p = nullptr;
+    size_t n = 0, cap = 0;  // n includes the window
+    SymBuf() = default;
+    SymBuf(const SymBuf&) = delete;
+    SymBuf& operator=(const SymBuf&) = delete;
+    SymBuf(SymBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    SymBuf& operator=(SymBuf&& o) noexcept {
+        if (this != &o) {
+            free(p);
+            p = o.p; n = o.n; cap = o.cap;
+            o.p = nullptr; o.n = o.cap = 0;
+        }
+        return *this;
+    }
+    ~SymBuf() { free(p); }
+    size_t size() const { return n - WIN; }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t c = std::max(want, cap + cap / 2 + 4096);
+        uint16_t* q = (uint16_t*)realloc(p, c * sizeof(uint16_t));
+        if (!q) throw std::bad_alloc();
+        p = q;
+        cap = c;
+    }
+    inline void room(size_t extra) {
+        if (n + extra > cap) reserve(n + extra);
+    }
+    void init_unknown() {
+        reserve(WIN + 65536);
+        for (uint32_t i = 0; i < WIN; ++i) p[i] = (uint16_t)(UNKNOWN | i);
+        n = WIN;
+    }
+    void init_empty() {
+        reserve(WIN + 65536);
+        memset(p, 0, WIN * sizeof(uint16_t));
+        n = WIN;
+    }
+    void release() {
+        free(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+};
+
+enum class Stop { EndOfMember, Limit, Error };
+
+// Decode blocks from the reader's position until the final block of the member ends or a block ends at/after bit
+// `limit_bit` (blocks are never cut).  text_only: a literal outside the plausible text range is an error (used while
+// validating a guessed block start).  Returns how it stopped; `end_bit` = position after the last decoded block.
+Stop decode_blocks(Bits& b, SymBuf& out, size_t limit_bit, bool text_only, size_t max_blocks, size_t& end_bit, size_t* n_blocks = nullptr) {
+    BlockCodes C;
+    size_t blocks = 0;
+    for (;;) {
+        if (b.over) return Stop::Error;
+        const uint32_t bfinal = b.get(1), btype = b.get(2);
+        if (btype == 3) return Stop::Error;
+        if (btype == 0) {
+            b.drop(b.cnt & 7);  // to the byte boundary
+            const uint32_t len = b.get(16), nlen = b.get(16);
+            if ((len ^ nlen) != 0xffffu) return Stop::Error;
+            out.room(len);
+            for (uint32_t i = 0; i < len; ++i) {
+                if (b.over) return Stop::Error;
+                out.p[out.n++] = (uint16_t)b.get(8);
+            }
+        } else {
+            if (btype == 1) fixed_codes(C);
+            else if (!read_dynamic_header(b, C)) return Stop::Error;
+            const uint16_t* lt = C.lit.fast;
+            const uint16_t* dt = C.dist.fast;
+            for (;;) {
+                out.room(520);
+                if (b.cnt < 48) {
+                    b.refill();
+                    if (b.over) return Stop::Error;
+                }
+                // up to two literals per refill (a literal/length code is at most 15 bits)
+                uint16_t e = lt[b.buf & ((1u << Huff::ROOT) - 1u)];
+                int sym;
+                if (e & 15) {
+                    b.drop(e & 15);
+                    sym = e >> 4;
+                    if (sym < 256 && !text_only) {
+                        out.p[out.n++] = (uint16_t)sym;
+                        e = lt[b.buf & ((1u << Huff::ROOT) - 1u)];
+                        if (!(e & 15)) continue;
+                        b.drop(e & 15);
+                        sym = e >> 4;
+                    }
+                } else {
+                    sym = C.lit.slow(b);
+                    if (sym < 0) return Stop::Error;
+                }
+                if (sym < 256) {
+                    if (text_only && (sym >= 0x80 || (sym < 0x20 && sym != '\n' && sym != '\r' && sym != '\t'))) return Stop::Error;
+                    out.p[out.n++] = (uint16_t)sym;
+                } else if (sym == 256) {
+                    break;
+                } else {
+                    const int li = sym - 257;
+                    if (li >= 29 || !C.have_dist) return Stop::Error;
+                    const uint32_t len = LEN_BASE[li] + b.peek(LEN_EXTRA[li]);
+                    b.drop(LEN_EXTRA[li]);
+                    if (b.cnt < 30) b.refill();
+                    const uint16_t de = dt[b.buf & ((1u << Huff::ROOT) - 1u)];
+                    int ds;
+                    if (de & 15) {
+                        b.drop(de & 15);
+                        ds = de >> 4;
+                    } else {
+                        ds = C.dist.slow(b);
+                    }
+                    if (ds < 0 || ds >= 30) return Stop::Error;
+                    const uint32_t dist = DIST_BASE[ds] + b.peek(DIST_EXTRA[ds]);
+                    b.drop(DIST_EXTRA[ds]);
+                    if (dist > out.n) return Stop::Error;
+                    uint16_t* d = out.p + out.n;
+                    const uint16_t* s = d - dist;
+                    if (dist >= 8) {  // copy in 16-byte steps (may run up to 7 symbols past the end: room() keeps slack)
+                        for (uint32_t i = 0; i < len; i += 8) memcpy(d + i, s + i, 16);
+                    } else {
+                        for (uint32_t i = 0; i < len; ++i) d[i] = s[i];
+                    }
+                    out.n += len;
+                }
+            }
+        }
+        ++blocks;
+        if (n_blocks) *n_blocks = blocks;
+        end_bit = b.bit_position();
+        if (b.exhausted()) return Stop::Error;
+        if (bfinal) return Stop::EndOfMember;
+        if (end_bit >= limit_bit || blocks >= max_blocks) return Stop::Limit;
+    }
+}
+
+// first bit offset >= from_bit (and < to_bit) at which a non-final dynamic block starts, decodes to plausible text and
+// is followed by another parseable block header; SIZE_MAX if none
+size_t find_block_start(const uint8_t* p, size_t n, size_t from_bit, size_t to_bit) {
+    for (size_t bit = from_bit; bit < to_bit; ++bit) {
+        // cheap reject first: BFINAL = 0, BTYPE = 2 and sane HLIT / HDIST without building anything
+        const size_t byte = bit >> 3;
+        if (byte + 4 >= n) return SIZE_MAX;
+        uint32_t w;
+        memcpy(&w, p + byte, 4);
+        w >>= bit & 7;
+        if ((w & 7u) != 4u) continue;               // bfinal 0, btype 10b (LSB first: 0, then 0,1)
+        if (((w >> 3) & 31u) > 29u) continue;       // hlit
+        if (((w >> 8) & 31u) > 29u) continue;       // hdist
+        Bits b(p, n, bit + 3);
+        BlockCodes C;
+        if (!read_dynamic_header(b, C, false)) continue;
+        // full check: the block (and the next one's header) must decode as text
+        Bits b2(p, n, bit);
+        SymBuf tmp;
+        tmp.init_unknown();
+        size_t end = 0;
+        const Stop s = decode_blocks(b2, tmp, SIZE_MAX, true, 2, end);
+        if (s == Stop::Error) continue;
+        if (tmp.size() < 1024 && s != Stop::EndOfMember) continue;  // implausibly small blocks: keep looking
+        return bit;
+    }
+    return SIZE_MAX;
+}
+
+// gzip member header at byte offset `at`; returns the offset of the deflate data or SIZE_MAX
+size_t skip_gzip_header(const uint8_t* p, size_t n, size_t at) {
+    if (at + 10 > n || p[at] != 0x1f || p[at + 1] != 0x8b || p[at + 2] != 8) return SIZE_MAX;
+    const uint8_t flg = p[at + 3];
+    size_t q = at + 10;
+    if (flg & 4) {
+        if (q + 2 > n) return SIZE_MAX;
+        q += 2 + (p[q] | (p[q + 1] << 8));
+    }
+    if (flg & 8) {
+        while (q < n && p[q]) ++q;
+        ++q;
+    }
+    if (flg & 16) {
+        while (q < n && p[q]) ++q;
+        ++q;
+    }
+    if (flg & 2) q += 2;
+    return q <= n ? q : SIZE_MAX;
+}
+
+struct Chunk {
+    size_t start_bit = 0;     // first block of the chunk
+    size_t end_bit = 0;       // after its last block
+    bool unknown_window = true;
+    SymBuf out;
+    Stop stop = Stop::Error;
+    bool ok = false;
+    size_t out_off = 0;       // byte offset in the final text
+    uint8_t last_window[WIN];  // resolved
+    uint32_t last_n = 0;
+};
+
+}  // namespace
+
+bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, size_t* out_n) {
+    *out = nullptr;
+    *out_n = 0;
+    static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    const size_t data0 = skip_gzip_header(gz, n, 0);
+    if (data0 == SIZE_MAX || n < data0 + 18) return false;
+    static const size_t chunk_min = [] {  // compressed bytes a chunk must have (tests lower it to cut small files)
+        const char* e = getenv("DRPRG_PARALLEL_GZIP_CHUNK");
+        return e && atol(e) > 0 ? (size_t)atol(e) : (size_t)(1u << 20);
+    }();
+    size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), (size_t)64, (n - data0) / chunk_min}));
+    if (T < 2) return false;  // small files: zlib is as fast
+    // ---- 1. chunk starts
+    std::vector<Chunk> ch(T);
+    ch[0].start_bit = data0 * 8;
+    ch[0].unknown_window = false;
+    std::vector<size_t> guess(T);
+    for (size_t t = 1; t < T; ++t) guess[t] = (data0 + (n - data0) * t / T) * 8;
+    parallel_for(T - 1, [&](size_t i) {
+        const size_t t = i + 1;
+        const size_t hi = t + 1 < T ? guess[t + 1] : (n - 8) * 8;
+        ch[t].start_bit = find_block_start(gz, n, guess[t], hi);
+    }, T);
+    const double t1 = now();
+    // chunks whose start was not found are merged into their predecessor
+    std::vector<Chunk> live;
+    live.reserve(T);
+    for (size_t t = 0; t < T; ++t)
+        if (t == 0 || ch[t].start_bit != SIZE_MAX) live.push_back(std::move(ch[t]));
+    T = live.size();
+    if (T < 2) return false;
+    // ---- 2. decode every chunk up to the start of the next one
+    parallel_for(T, [&](size_t t) {
+        Chunk& c = live[t];
+        if (c.unknown_window) c.out.init_unknown();
+        else c.out.init_empty();
+        c.out.reserve(WIN + (size_t)((n / T) * 4));
+        Bits b(gz, n, c.start_bit);
+        const size_t limit = t + 1 < T ? live[t + 1].start_bit : SIZE_MAX;
+        c.stop = decode_blocks(b, c.out, limit, false, SIZE_MAX, c.end_bit);
+        c.ok = (t + 1 < T) ? (c.stop == Stop::Limit && c.end_bit == limit) : (c.stop == Stop::EndOfMember);
+    }, T);
+    const double t2 = now();
+    for (size_t t = 0; t < T; ++t)
+        if (!live[t].ok) return false;  // a guessed start was wrong, a member ended early (multi-member file), or corrupt data
+    // trailer of the (single) member: CRC-32 and length
+    const size_t trailer = (live[T - 1].end_bit + 7) / 8;
+    if (trailer + 8 > n) return false;
+    uint32_t want_crc, want_len;
+    memcpy(&want_crc, gz + trailer, 4);
+    memcpy(&want_len, gz + trailer + 4, 4);
+    if (trailer + 8 != n) return false;  // further members or trailing bytes: the sequential reader handles those
+    // ---- 3. resolve: chain the 32 KB windows, then translate everything in parallel
+    size_t total = 0;
+    for (size_t t = 0; t < T; ++t) {
+        live[t].out_off = total;
+        total += live[t].out.size();
+    }
+    if ((uint32_t)total != want_len) return false;
+    for (size_t t = 0; t < T; ++t) {
+        Chunk& c = live[t];
+        const size_t sz = c.out.size();
+        const uint32_t keep = (uint32_t)std::min<size_t>(WIN, sz);
+        // window after this chunk = last WIN bytes of (previous window ++ this chunk's output)
+        uint8_t w[WIN];
+        uint32_t have = 0;
+        if (keep < WIN && t > 0) {
+            const uint32_t from_prev = std::min<uint32_t>(WIN - keep, live[t - 1].last_n);
+            memcpy(w, live[t - 1].last_window + (live[t - 1].last_n - from_prev), from_prev);
+            have = from_prev;
+        }
+        const uint16_t* s = c.out.p + WIN + (sz - keep);
+        for (uint32_t i = 0; i < keep; ++i) {
+            uint16_t x = s[i];
+            if (x & UNKNOWN) {
+                if (t == 0) return false;
+                const uint32_t off = x & 0x7fffu;  // index into the previous window, which holds its last last_n bytes
+                const Chunk& pc = live[t - 1];
+                if (off < WIN - pc.last_n) return false;  // before the start of the text
+                x = pc.last_window[off - (WIN - pc.last_n)];
+            }
+            w[have + i] = (uint8_t)x;
+        }
+        c.last_n = have + keep;
+        memcpy(c.last_window, w, c.last_n);
+    }
+    char* text = (char*)malloc(total + 1);
+    if (!text) return false;
+    std::vector<uint32_t> crcs(T, 0);
+    std::vector<char> bad(T, 0);
+    parallel_for(T, [&](size_t t) {
+        Chunk& c = live[t];
+        const size_t sz = c.out.size();
+        const uint16_t* s = c.out.p + WIN;
+        uint8_t* d = (uint8_t*)text + c.out_off;
+        const Chunk* pc = t ? &live[t - 1] : nullptr;
+        // one table turns every symbol into its byte: 0..255 map to themselves, 0x8000 | i to byte i of the window before
+        // this chunk (a reference before the start of the text maps to 0 and fails the CRC check below)
+        std::vector<uint8_t> lut(65536, 0);
+        for (uint32_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+        if (pc)
+            for (uint32_t off = WIN - pc->last_n; off < WIN; ++off) lut[UNKNOWN | off] = pc->last_window[off - (WIN - pc->last_n)];
+        const uint8_t* L = lut.data();
+        size_t i = 0;
+        for (; i + 8 <= sz; i += 8) {
+            d[i] = L[s[i]]; d[i + 1] = L[s[i + 1]]; d[i + 2] = L[s[i + 2]]; d[i + 3] = L[s[i + 3]];
+            d[i + 4] = L[s[i + 4]]; d[i + 5] = L[s[i + 5]]; d[i + 6] = L[s[i + 6]]; d[i + 7] = L[s[i + 7]];
+        }
+        for (; i < sz; ++i) d[i] = L[s[i]];
+        crcs[t] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), d, (uInt)std::min<size_t>(sz, 0x7fffffffu));
+        if (sz > 0x7fffffffu) bad[t] = 1;
+        c.out.release();
+    }, T);
+    uint32_t crc = 0;
+    bool ok = true;
+    for (size_t t = 0; t < T; ++t) {
+        ok = ok && !bad[t];
+        crc = t == 0 ? crcs[0] : (uint32_t)crc32_combine(crc, crcs[t], (z_off_t)(t + 1 < T ? live[t + 1].out_off - live[t].out_off : total - live[t].out_off));
+    }
+    if (!ok || crc != want_crc) {
+        free(text);
+        return false;
+    }
+    text[total] = 0;
+    *out = text;
+    *out_n = total;
+    if (timing)
+        fprintf(stderr, "[drprg-cuda] parallel gunzip: %zu chunks, %.1f MB -> %.1f MB, block search %.1f ms, decode %.1f ms, resolve + crc %.1f ms\n", T,
+                n / 1e6, total / 1e6, t1 - t0, t2 - t1, now() - t2);
+    return true;
+}
+
+}  // namespace drprg
