@@ -283,6 +283,8 @@ struct drprg_index {
     DBuf<uint32_t> d_gt_u32;
     DBuf<double> d_gt_f64;
     DBuf<int32_t> d_gt_i32;
+    DBuf<float> d_gt_f32;  // frs | strand-bias ratio (per record), depth proportions (per allele)
+    float minor_af = -1.0f;  // < 0: drprg's default (1.0, or 0.1 with --illumina)
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     cudaEvent_t ev_ml[2] = {nullptr, nullptr};
     cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr, st_acc = nullptr;
@@ -320,7 +322,7 @@ struct drprg_index {
         read_count.release(); read_base.release();
         partials.release();
         queue.release(); queue_kmer.release();
-        d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release();
+        d_gt_u32.release(); d_gt_f64.release(); d_gt_i32.release(); d_gt_f32.release();
         d_prob.release(); d_M.release(); d_len.release(); d_up.release(); d_path.release(); d_path_len.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
@@ -837,6 +839,7 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     MP.min_kmer_covg = X->fit.min_kmer_covg;
     MP.gt_err = X->opts.gt_error_rate;
     MP.gt_conf = X->opts.gt_conf;
+    MP.minor_af = X->minor_af >= 0.0f ? X->minor_af : (X->opts.illumina ? 0.1f : 1.0f);  // src/minor.rs:11-12,26-33
     X->d_prob.ensure(N); X->d_M.ensure(N); X->d_len.ensure(N);
     X->d_up.ensure((size_t)N * LV_MAX); X->d_path.ensure(N); X->d_path_len.ensure(P);
     launch_node_prob(X->d_accum, N, X->d_is_terminal, MP, X->d_prob.p, st);
@@ -929,11 +932,19 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         if (nr) {
             X->d_gt_u32.ensure((size_t)na * 6);
             X->d_gt_f64.ensure((size_t)na * 2 + nr);
-            X->d_gt_i32.ensure(nr);
+            X->d_gt_i32.ensure((size_t)nr * 3);
+            X->d_gt_f32.ensure((size_t)nr * 2 + na);
             uint32_t* u = X->d_gt_u32.p;
             double* f = X->d_gt_f64.p;
             DevGenotype DG{nr, na, X->d_rec_off, X->d_allele_off, X->d_allele_kn, u, u + na, u + 2 * (size_t)na, u + 3 * (size_t)na,
                            u + 4 * (size_t)na, u + 5 * (size_t)na, f, f + na, f + 2 * (size_t)na, X->d_gt_i32.p};
+            // the statistics drprg's filters derive from the record come out of the same kernel (they stay on the device
+            // until drprg_cuda_gt_filter_stats asks for them)
+            DG.covg_gt = X->d_gt_i32.p + nr;
+            DG.minor_gt = X->d_gt_i32.p + 2 * (size_t)nr;
+            DG.frs = X->d_gt_f32.p;
+            DG.sb_ratio = X->d_gt_f32.p + nr;
+            DG.pdp = X->d_gt_f32.p + 2 * (size_t)nr;
             launch_genotype(X->d_accum, DG, MP, s8);
             CK(cudaGetLastError());
             X->h_u32.resize((size_t)na * 6);
@@ -1915,7 +1926,8 @@ int drprg_cuda_gt_allele_knodes(drprg_index* X, uint32_t* out) {
 }
 int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec_off, const uint32_t* mean_fwd,
                              const uint32_t* mean_rev, const double* gaps, uint32_t exp_depth, double genotyping_error_rate,
-                             double min_gt_conf, double* lik, int32_t* gt, double* gt_conf) {
+                             double min_gt_conf, float minor_af, double* lik, int32_t* gt, double* gt_conf, int32_t* covg_gt,
+                             float* frs, float* sb_ratio, int32_t* minor_gt, float* pdp) {
     API_BEGIN
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1927,15 +1939,17 @@ int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec
     DBuf<uint32_t> d_u32;
     DBuf<double> d_f64;
     DBuf<int32_t> d_i32;
+    DBuf<float> d_f32;
     d_u32.ensure((size_t)n_records + 1 + 2 * (size_t)na);
     d_f64.ensure(2 * (size_t)na + n_records);
-    d_i32.ensure(n_records);
+    d_i32.ensure((size_t)n_records * 3);
+    d_f32.ensure((size_t)n_records * 2 + na);
     uint32_t *d_off = d_u32.p, *d_mf = d_off + n_records + 1, *d_mr = d_mf + na;
     double *d_gaps = d_f64.p, *d_lik = d_gaps + na, *d_conf = d_lik + na;
     struct Guard {
-        DBuf<uint32_t>& a; DBuf<double>& b; DBuf<int32_t>& c;
-        ~Guard() { a.release(); b.release(); c.release(); }
-    } guard{d_u32, d_f64, d_i32};
+        DBuf<uint32_t>& a; DBuf<double>& b; DBuf<int32_t>& c; DBuf<float>& d;
+        ~Guard() { a.release(); b.release(); c.release(); d.release(); }
+    } guard{d_u32, d_f64, d_i32, d_f32};
     CK(cudaMemcpy(d_off, rec_off, ((size_t)n_records + 1) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_mf, mean_fwd, (size_t)na * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_mr, mean_rev, (size_t)na * 4, cudaMemcpyHostToDevice));
@@ -1950,15 +1964,44 @@ int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec
     G.lik = d_lik;
     G.gt_conf = d_conf;
     G.gt = d_i32.p;
+    G.covg_gt = d_i32.p + n_records;
+    G.minor_gt = d_i32.p + 2 * (size_t)n_records;
+    G.frs = d_f32.p;
+    G.sb_ratio = d_f32.p + n_records;
+    G.pdp = d_f32.p + 2 * (size_t)n_records;
     ModelParams MP{};
     MP.exp_depth = exp_depth;
     MP.gt_err = genotyping_error_rate > 0 ? genotyping_error_rate : 0.01;
     MP.gt_conf = min_gt_conf;
+    MP.minor_af = minor_af;
     launch_genotype_rows(G, MP, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(lik, d_lik, (size_t)na * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(gt_conf, d_conf, (size_t)n_records * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(gt, d_i32.p, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    if (covg_gt) CK(cudaMemcpy(covg_gt, G.covg_gt, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    if (minor_gt) CK(cudaMemcpy(minor_gt, G.minor_gt, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    if (frs) CK(cudaMemcpy(frs, G.frs, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    if (sb_ratio) CK(cudaMemcpy(sb_ratio, G.sb_ratio, (size_t)n_records * 4, cudaMemcpyDeviceToHost));
+    if (pdp) CK(cudaMemcpy(pdp, G.pdp, (size_t)na * 4, cudaMemcpyDeviceToHost));
+    return 0;
+    API_END
+}
+int drprg_cuda_set_minor_af(drprg_index* X, float minor_af) {
+    X->minor_af = minor_af;
+    return 0;
+}
+int drprg_cuda_gt_filter_stats(drprg_index* X, int32_t* covg_gt, float* frs, float* sb_ratio, int32_t* minor_gt, float* pdp) {
+    API_BEGIN need_device(X);
+    if (!X->have_gt) throw std::runtime_error("no genotype results");
+    CK(cudaSetDevice(X->device));
+    const size_t nr = X->records.size(), na = X->GA.allele_off.empty() ? 0 : X->GA.allele_off.size() - 1;
+    if (!nr) return 0;
+    if (covg_gt) CK(cudaMemcpy(covg_gt, X->d_gt_i32.p + nr, nr * 4, cudaMemcpyDeviceToHost));
+    if (minor_gt) CK(cudaMemcpy(minor_gt, X->d_gt_i32.p + 2 * nr, nr * 4, cudaMemcpyDeviceToHost));
+    if (frs) CK(cudaMemcpy(frs, X->d_gt_f32.p, nr * 4, cudaMemcpyDeviceToHost));
+    if (sb_ratio) CK(cudaMemcpy(sb_ratio, X->d_gt_f32.p + nr, nr * 4, cudaMemcpyDeviceToHost));
+    if (pdp) CK(cudaMemcpy(pdp, X->d_gt_f32.p + 2 * nr, na * 4, cudaMemcpyDeviceToHost));
     return 0;
     API_END
 }

@@ -78,7 +78,73 @@ __global__ void genotype_kernel(DevGenotype G, ModelParams P) {
         if (a != best && G.lik[a] > second) second = G.lik[a];
     const double conf = (e - b > 1) ? fabs(G.lik[best] - second) : 0.0;
     G.gt_conf[r] = conf;
-    G.gt[r] = (conf >= P.gt_conf) ? (int32_t)(best - b) : -1;
+    const int32_t gt_pandora = (conf >= P.gt_conf) ? (int32_t)(best - b) : -1;
+    G.gt[r] = gt_pandora;
+    if (!G.covg_gt) return;
+    // ---- what drprg computes next from this record, fused here.  Everything below is f32 / i32
+    // like the Rust code; "None" is NaN.  drprg first nulls the call of a record without depth and GT_CONF 0
+    // (src/predict.rs:440-444), and its filters see that call.
+    const float NONE = __int_as_float(0x7fc00000);
+    const uint32_t na = e - b;
+    int32_t tot_f = 0, tot_r = 0;
+    for (uint32_t a = b; a < e; ++a) {
+        tot_f += (int32_t)G.mean_fwd[a];
+        tot_r += (int32_t)G.mean_rev[a];
+    }
+    const int32_t depth = tot_f + tot_r;
+    const int32_t gt = (depth == 0 && (float)conf == 0.0f) ? -1 : gt_pandora;
+    auto dp = [&](uint32_t i) { return (int32_t)G.mean_fwd[b + i] + (int32_t)G.mean_rev[b + i]; };
+    // Filterer::_covg_for_gt
+    G.covg_gt[r] = gt < 0 ? depth : dp((uint32_t)gt);
+    // VcfExt::fraction_read_support
+    float frs = NONE;
+    if (na < 2) frs = 1.0f;
+    else if (gt >= 0) {
+        const float called = (float)dp((uint32_t)gt);
+        int32_t other = 0;
+        if (gt > 0) other = dp(0);
+        else
+            for (uint32_t i = 0; i < na; ++i)
+                if ((int32_t)i != gt && dp(i) > other) other = dp(i);
+        frs = called / (called + (float)other);  // 0 / 0 = NaN = None
+    }
+    G.frs[r] = frs;
+    // Filterer::has_strand_bias: the ratio it compares with --min-strand-bias
+    float sb = NONE;
+    if (gt < 0) {
+        const float tf = (float)tot_f, tr = (float)tot_r, tt = tf + tr;
+        if (tt != 0.0f) sb = fminf(tf, tr) / tt;
+    } else {
+        const float f = (float)G.mean_fwd[b + gt], rv = (float)G.mean_rev[b + gt], sum = f + rv;
+        if (sum != 0.0f) sb = fminf(f, rv) / sum;
+    }
+    G.sb_ratio[r] = sb;
+    // VcfExt::depth_proportions (the PDP tag)
+    const float total_depth = (float)depth;
+    for (uint32_t i = 0; i < na; ++i) G.pdp[b + i] = depth ? (float)dp(i) / total_depth : NONE;
+    // MinorAllele::check_for_minor_alternate: the non-called allele with the largest depth proportion >= maf whose GAPS
+    // pass (stable ascending sort walked backwards: among equal proportions the higher allele index comes first)
+    int32_t minor = -1;
+    if (na >= 2 && depth != 0 && gt >= 0 && (float)G.gaps[b + gt] <= 0.39f) {
+        const float called_gaps = (float)G.gaps[b + gt];
+        int32_t pick = -1;
+        float pick_d = -1.0f;
+        for (uint32_t i = 0; i < na; ++i) {
+            if ((int32_t)i == gt) continue;
+            const float d = (float)dp(i) / total_depth, g = (float)G.gaps[b + i];
+            if (d >= P.minor_af && g <= 0.5f && g - called_gaps <= 0.2f && d >= pick_d) {
+                pick = (int32_t)i;
+                pick_d = d;
+            }
+        }
+        if (pick >= 0) {
+            const int32_t c = dp((uint32_t)pick);
+            const float f = (float)G.mean_fwd[b + pick], rv = (float)G.mean_rev[b + pick], sum = f + rv;
+            const bool bias = sum == 0.0f ? true : fminf(f, rv) / sum < 0.01f;
+            if (c >= 3 && !bias) minor = pick;
+        }
+    }
+    G.minor_gt[r] = minor;
 }
 
 void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st) {

@@ -5,6 +5,7 @@
 #include "genotype_host.hpp"
 #include "gzip_inflate.hpp"
 
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -848,8 +849,27 @@ void slurp(const std::string& path, RawText& buf) {
             return e && atol(e) > 0 ? (size_t)atol(e) * 2 : (size_t)(4u << 20);
         }();
         if (par && fsize >= min_size) {
-            uint8_t* z = (uint8_t*)calloc(fsize + 64, 1);  // the bit reader loads 8 bytes at a time: zero padding behind the image
-            if (z && fread(z, 1, fsize, fp) == fsize) {
+            uint8_t* z = (uint8_t*)malloc(fsize + 64);  // the bit reader loads 8 bytes at a time: zero padding behind the image
+            bool got_all = false;
+            if (z) {
+                memset(z + fsize, 0, 64);
+                // the compressed image is read by several threads at once (page-cache copies are memcpy-bound)
+                const int fd = fileno(fp);
+                const size_t RT = std::max<size_t>(1, std::min<size_t>(8, fsize / (8u << 20)));
+                std::vector<char> okv(RT, 0);
+                parallel_for(RT, [&](size_t t) {
+                    const size_t lo = fsize * t / RT, hi = fsize * (t + 1) / RT;
+                    size_t done = 0;
+                    while (lo + done < hi) {
+                        const ssize_t r = pread(fd, z + lo + done, hi - lo - done, (off_t)(lo + done));
+                        if (r <= 0) break;
+                        done += (size_t)r;
+                    }
+                    okv[t] = (lo + done == hi);
+                }, RT);
+                got_all = std::all_of(okv.begin(), okv.end(), [](char c) { return c != 0; });
+            }
+            if (z && got_all) {
                 const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
                 char* text = nullptr;
                 size_t tn = 0;

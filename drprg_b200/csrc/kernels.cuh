@@ -58,6 +58,7 @@ struct ModelParams {  // S6 output, computed on the host
     uint32_t window;       // max_num_kmers_to_average
     uint32_t min_kmer_covg;
     double gt_err, gt_conf;
+    float minor_af;        // drprg's --maf for the minor-allele statistic (src/minor.rs:19-33): 1.0, or 0.1 with --illumina
 };
 
 uint64_t launch_count();
@@ -161,6 +162,13 @@ struct DevGenotype {
     uint32_t *mean_fwd, *mean_rev, *med_fwd, *med_rev, *sum_fwd, *sum_rev;
     double *gaps, *lik, *gt_conf;
     int32_t* gt;
+    // optional (nullptr = skip): the per-record statistics drprg's Filterer / MinorAllele derive from the same vectors
+    // (src/filter.rs:212-301, src/minor.rs:70-127, VcfExt src/lib.rs:973-1058,1165-1180), in their f32 arithmetic
+    int32_t* covg_gt = nullptr;   // depth on the called allele (all alleles when the call is null)
+    float* frs = nullptr;         // fraction of read support; NaN = None
+    float* sb_ratio = nullptr;    // strand-bias ratio min(fwd, rev) / (fwd + rev); NaN = None
+    int32_t* minor_gt = nullptr;  // allele check_for_minor_alternate would switch the call to; -1 = none
+    float* pdp = nullptr;         // per allele: proportion of the position's depth; NaN when the depth is 0
 };
 void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st);
 // the likelihood / GT / GT_CONF kernel alone, on per-allele rows already in G.mean_fwd / G.mean_rev / G.gaps

@@ -63,7 +63,7 @@ SYMBOLS = [
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
-    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse", "drprg_cuda_issue_peak",
+    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_gt_filter_stats", "drprg_cuda_set_minor_af", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse", "drprg_cuda_issue_peak",
 ]
 
 
@@ -375,6 +375,20 @@ class Index:
         """measured warp-instructions/s of a pure INT32 multiply-add / shift / logic loop on this GPU"""
         return float(lib().drprg_cuda_issue_peak(self.h))
 
+    def filter_stats(self):
+        """per-record statistics of drprg's Filterer / MinorAllele, computed by the genotype kernel (see the header)"""
+        L = lib()
+        nr, na, nk = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        L.drprg_cuda_gt_counts(self.h, C.byref(nr), C.byref(na), C.byref(nk))
+        n, na = nr.value, na.value
+        cg = np.zeros(n, np.int32); frs = np.zeros(n, np.float32); sb = np.zeros(n, np.float32)
+        mg = np.zeros(n, np.int32); pdp = np.zeros(na, np.float32)
+        _check(L.drprg_cuda_gt_filter_stats(self.h, _p(cg), _p(frs), _p(sb), _p(mg), _p(pdp)), "drprg_cuda_gt_filter_stats")
+        return dict(covg_gt=cg, frs=frs, sb_ratio=sb, minor_gt=mg, pdp=pdp)
+
+    def set_minor_af(self, maf):
+        lib().drprg_cuda_set_minor_af(self.h, C.c_float(maf))
+
     def last_timings(self):
         o = np.zeros(4, np.float32)
         lib().drprg_cuda_last_timings(self.h, _p(o))
@@ -395,8 +409,9 @@ class Index:
         return st.asdict()
 
 
-def genotype_rows(rec_off, mean_fwd, mean_rev, gaps, exp_depth, err=0.01, min_gt_conf=0.0, device=0):
-    """the product's genotype_kernel on caller-supplied per-allele rows (parity hook for the reference's VCF fixtures)"""
+def genotype_rows(rec_off, mean_fwd, mean_rev, gaps, exp_depth, err=0.01, min_gt_conf=0.0, device=0, minor_af=1.0, stats=False):
+    """the product's genotype_kernel on caller-supplied per-allele rows (parity hook for the reference's VCF fixtures);
+    stats=True also returns the fused filter / minor-allele statistics"""
     rec_off = np.ascontiguousarray(rec_off, np.uint32)
     mf = np.ascontiguousarray(mean_fwd, np.uint32)
     mr = np.ascontiguousarray(mean_rev, np.uint32)
@@ -404,9 +419,14 @@ def genotype_rows(rec_off, mean_fwd, mean_rev, gaps, exp_depth, err=0.01, min_gt
     nr, na = len(rec_off) - 1, int(rec_off[-1])
     assert len(mf) == na and len(mr) == na and len(g) == na
     lik = np.zeros(na, np.float64); gt = np.zeros(nr, np.int32); conf = np.zeros(nr, np.float64)
+    cg = np.zeros(nr, np.int32); frs = np.zeros(nr, np.float32); sb = np.zeros(nr, np.float32)
+    mg = np.zeros(nr, np.int32); pdp = np.zeros(na, np.float32)
     rc = lib().drprg_cuda_genotype_rows(C.c_int(device), C.c_uint32(nr), _p(rec_off), _p(mf), _p(mr), _p(g), C.c_uint32(int(exp_depth)),
-                                        C.c_double(err), C.c_double(min_gt_conf), _p(lik), _p(gt), _p(conf))
+                                        C.c_double(err), C.c_double(min_gt_conf), C.c_float(minor_af), _p(lik), _p(gt), _p(conf),
+                                        _p(cg), _p(frs), _p(sb), _p(mg), _p(pdp))
     _check(rc, "drprg_cuda_genotype_rows")
+    if stats:
+        return lik, gt, conf, dict(covg_gt=cg, frs=frs, sb_ratio=sb, minor_gt=mg, pdp=pdp)
     return lik, gt, conf
 
 

@@ -166,10 +166,22 @@ int drprg_cuda_gt_allele_knodes(drprg_index*, uint32_t* out);
 /* S8's likelihood / GT / GT_CONF kernel on caller-supplied per-allele rows: rec_off[n_records+1] -> alleles, per allele the
  * MEAN_FWD_COVG, MEAN_REV_COVG and GAPS a pandora VCF record carries (e.g. /root/reference/tests/cases/predict/in.vcf), the
  * sample's integer expected depth E, -E error rate and --gt-conf.  Outputs lik[n_alleles], gt[n_records] (-1 = null call),
- * gt_conf[n_records].  This is the genotype_kernel of the product path, so the reference's VCF fixtures check it directly. */
+ * gt_conf[n_records] and — optional, NULL to skip — the filter statistics described at drprg_cuda_gt_filter_stats.  This
+ * is the genotype_kernel of the product path, so the reference's VCF fixtures check it directly. */
 int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec_off, const uint32_t* mean_fwd,
                              const uint32_t* mean_rev, const double* gaps, uint32_t exp_depth, double genotyping_error_rate,
-                             double min_gt_conf, double* lik, int32_t* gt, double* gt_conf);
+                             double min_gt_conf, float minor_af, double* lik, int32_t* gt, double* gt_conf, int32_t* covg_gt,
+                             float* frs, float* sb_ratio, int32_t* minor_gt, float* pdp);
+/* the per-record statistics drprg's Filterer (src/filter.rs:212-301) and MinorAllele (src/minor.rs:70-127)
+ * derive from a pandora record come out of the genotype kernel itself, in their f32 arithmetic and after drprg's nulling of
+ * calls without depth (src/predict.rs:440-444): covg_gt = Filterer::_covg_for_gt; frs = VcfExt::fraction_read_support
+ * (src/lib.rs:980-1011; NaN = None); sb_ratio = the ratio has_strand_bias compares with --min-strand-bias (NaN = None);
+ * minor_gt = the allele check_for_minor_alternate would switch the call to (-1 = none) for --maf minor_af; pdp[n_alleles] =
+ * VcfExt::depth_proportions, the PDP tag (src/lib.rs:1165-1174; NaN when the position has no depth).  Rust stays the
+ * source of truth for the thresholds; these are the inputs of its comparisons, saving the BCF round trip in batch mode. */
+int drprg_cuda_gt_filter_stats(drprg_index*, int32_t* covg_gt, float* frs, float* sb_ratio, int32_t* minor_gt, float* pdp);
+/* --maf for minor_gt (default: drprg's own, 1.0 or 0.1 with -I, src/minor.rs:11-12,26-33); takes effect at the next genotype */
+int drprg_cuda_set_minor_af(drprg_index*, float minor_af);
 /* kernel timing of the last map_batch in ms (CUDA events on its stream): [sketch_lookup, sort, cluster, coverage] */
 int drprg_cuda_last_timings(drprg_index*, float* out4);
 /* host wall time of the last drprg_cuda_genotype in ms: [accumulator download, parameter fit + log-prob histogram,

@@ -9,6 +9,7 @@ import os
 import numpy as np
 import pytest
 
+import rust_filters
 from drprg_b200 import lib
 from test_oracle_golden import FIXTURE_E, HAND_EDITED, vcf_rows
 
@@ -59,3 +60,16 @@ def test_genotype_rows_zero_depth_and_min_conf(golden):
     # --gt-conf above the confidence nulls the call
     lik, gt, conf = lib.genotype_rows([0, 2], [40, 0], [30, 1], [0.0, 1.0], 72, min_gt_conf=1e6)
     assert gt.tolist() == [-1] and conf[0] > 100
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURE_E))
+@pytest.mark.parametrize("maf", [0.1, 1.0])
+def test_fused_filter_statistics_on_reference_vcf_rows(golden, name, maf):
+    """the statistics drprg's Filterer / MinorAllele derive from a pandora record, computed by the genotype
+    kernel on the real pandora rows of the fixtures, against a numpy-f32 restatement of the Rust functions"""
+    keys, rec_off, mf, mr, gaps, want, gts, confs = fixture_rows(golden, name)
+    lik, gt, conf, stats = lib.genotype_rows(rec_off, mf, mr, gaps, FIXTURE_E[name], minor_af=maf, stats=True)
+    n = rust_filters.check_against(stats, rec_off, mf, mr, gaps, gt, conf, maf)
+    assert n == len(keys) and n >= 4
+    if name == "in.vcf":
+        assert np.isnan(stats["frs"]).sum() > 0 and (stats["minor_gt"] >= 0).sum() >= (1 if maf < 1 else 0)

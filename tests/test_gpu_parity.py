@@ -165,6 +165,10 @@ def assert_genotype_equal(gx, ox, mr, oo, refs):
     strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
     assert strip(gx.vcf()) == strip(og.vcf())
     assert bytes(gx.vcf_view()) == gx.vcf_bytes()  # the zero-copy view is the same text
+    # the filter / minor-allele statistics fused into the genotype kernel against the Rust restatement
+    import rust_filters
+    rust_filters.check_against(gx.filter_stats(), np.concatenate([[0], np.cumsum(gr["n_alleles"])]), gr["mean_fwd"], gr["mean_rev"],
+                               gr["gaps"], gr["gt"], gr["gt_conf"], 0.1 if oo.illumina else 1.0)
     return og
 
 
