@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libdrprg_cuda.so")
 SOURCES = ["sketch.cu", "cluster.cu", "mlpath.cu", "genotype.cu", "capi.cu", "multi.cu", "ingest.cu", "gzip_inflate.cpp",
-           "prg_graph.cpp", "genotype_host.cpp"]
+           "prg_graph.cpp", "genotype_host.cpp", "discover.cpp"]
 EXTRA = ["pandora_cuda_main.cpp"]
 HEADERS = ["kernels.cuh", "kernels_common.cuh", "prg_graph.hpp", "genotype_host.hpp", "ingest.hpp", "capi_internal.hpp",
            "gzip_inflate.hpp", "../../include/drprg_cuda.h"]

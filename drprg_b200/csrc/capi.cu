@@ -285,6 +285,10 @@ struct drprg_index {
     DBuf<int32_t> d_gt_i32;
     DBuf<float> d_gt_f32;  // frs | strand-bias ratio (per record), depth proportions (per allele)
     float minor_af = -1.0f;  // < 0: drprg's default (1.0, or 0.1 with --illumina)
+    // discover's front half from the map pass: kept hits of the sample, retained on request
+    bool retain_hits = false;
+    std::vector<RetainedHit> retained;
+    DiscoverResult discover;
     uint32_t max_locus_knodes = 0, max_locus_edges = 0;
     cudaEvent_t ev_ml[2] = {nullptr, nullptr};
     cudaStream_t st_ml = nullptr, st_gt = nullptr, st_copy = nullptr, st_acc = nullptr;
@@ -627,6 +631,7 @@ void sample_begin(drprg_index* X, const drprg_map_opts* o, uint32_t first_read_l
         launch_flag_publish(reinterpret_cast<uint32_t*>(X->d_accum + accum_flag_offset(X->n_accum)), X->epoch, 0);
     X->total_bases = X->n_reads = 0;
     X->own_bases = X->own_reads = 0;
+    X->retained.clear();
     X->scalars_in_buffer = false;
     X->hist_on_host = false;
     X->sample_open = true;
@@ -745,6 +750,25 @@ void map_batch(drprg_index* X, drprg_batch* B, cudaStream_t st, uint64_t* n_hits
     X->n_reads += B->R.n_reads;
     X->own_bases += B->total_bases;
     X->own_reads += B->R.n_reads;
+    if (X->retain_hits && nh) {  // the kept hits of this batch, grouped by read, pandora order within a read
+        const uint64_t na = X->last_n_active;
+        std::vector<unsigned long long> key(nh);
+        std::vector<uint8_t> kp(nh);
+        std::vector<uint32_t> ar(na), ab(na), ac(na);
+        CK(cudaMemcpy(key.data(), X->gkey.p, nh * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(kp.data(), X->gkept.p, nh, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ar.data(), X->act_read.p, na * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ab.data(), X->act_base.p, na * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ac.data(), X->act_count.p, na * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t a = 0; a < na; ++a)
+            for (uint32_t j = ab[a]; j < ab[a] + ac[a]; ++j) {
+                if (!kp[j]) continue;  // kept hits sit in slices the cluster kernels sorted
+                const unsigned long long k = key[j];
+                X->retained.push_back(RetainedHit{B->R.read_id_base + ar[a], (uint32_t)(k >> GKEY_KNODE_BITS) & ((1u << GKEY_START_BITS) - 1u),
+                                                  (uint32_t)k & ((1u << GKEY_KNODE_BITS) - 1u), (uint16_t)(k >> 48),
+                                                  (uint8_t)(((k >> 47) & 1ull) ^ 1ull)});
+            }
+    }
     if (n_hits) *n_hits = nh;
     if (n_kept) *n_kept = X->h_counters[CTR_KEPT];
 }
@@ -1986,6 +2010,65 @@ int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec
     if (pdp) CK(cudaMemcpy(pdp, G.pdp, (size_t)na * 4, cudaMemcpyDeviceToHost));
     return 0;
     API_END
+}
+/* ---- discover's mapping front half from the map pass ---- */
+int drprg_cuda_retain_hits(drprg_index* X, int on) {
+    for (drprg_index* g : (X->gpus.empty() ? std::vector<drprg_index*>{X} : X->gpus)) g->retain_hits = on != 0;
+    return 0;
+}
+int drprg_cuda_discover_candidates(drprg_index* X, const drprg_discover_opts* o, uint32_t* n_regions, uint64_t* n_region_reads) {
+    API_BEGIN need_device(X);
+    if (!X->have_gt) throw std::runtime_error("drprg_cuda_genotype has not run for this sample");
+    if (!X->retain_hits) throw std::runtime_error("drprg_cuda_retain_hits(idx, 1) must be set before the sample is mapped");
+    DiscoverOpts D;
+    if (o) {
+        if (o->covg_threshold) D.covg_threshold = o->covg_threshold;
+        if (o->min_len) D.min_len = o->min_len;
+        if (o->max_len) D.max_len = o->max_len;
+        if (o->padding != 0xffffffffu) D.padding = o->padding;
+        if (o->min_hits) D.min_hits = o->min_hits;
+    }
+    const std::vector<RetainedHit>* hits = &X->retained;
+    std::vector<RetainedHit> all;
+    if (X->gpus.size() > 1) {  // shards are contiguous read ranges: concatenation keeps the hits grouped by read
+        for (drprg_index* g : X->gpus) all.insert(all.end(), g->retained.begin(), g->retained.end());
+        hits = &all;
+    }
+    discover_candidates(X->H, X->present, X->mlpaths, X->h_acc.data(), *hits, D, X->discover);
+    if (n_regions) *n_regions = (uint32_t)X->discover.regions.size();
+    if (n_region_reads) *n_region_reads = X->discover.reads.size();
+    return 0;
+    API_END
+}
+int drprg_cuda_discover_regions(drprg_index* X, drprg_candidate_region* out) {
+    for (size_t i = 0; i < X->discover.regions.size(); ++i) {
+        const CandidateRegion& c = X->discover.regions[i];
+        out[i] = drprg_candidate_region{c.locus, c.start, c.end, c.pad_start, c.pad_end, c.n_reads, c.read_off};
+    }
+    return 0;
+}
+int drprg_cuda_discover_region_reads(drprg_index* X, uint32_t* read, uint32_t* start, uint32_t* end, uint8_t* fwd) {
+    for (size_t i = 0; i < X->discover.reads.size(); ++i) {
+        const ReadCoordinate& r = X->discover.reads[i];
+        read[i] = r.read;
+        start[i] = r.start;
+        end[i] = r.end;
+        fwd[i] = r.fwd;
+    }
+    return 0;
+}
+const char* drprg_cuda_discover_consensus(drprg_index* X, uint32_t locus, uint64_t* len) {
+    if (locus >= X->discover.consensus.size() || X->discover.consensus[locus].empty()) {
+        if (len) *len = 0;
+        return nullptr;
+    }
+    if (len) *len = X->discover.consensus[locus].size();
+    return X->discover.consensus[locus].c_str();
+}
+int drprg_cuda_discover_coverage(drprg_index* X, uint32_t locus, uint32_t* covg) {
+    if (locus >= X->discover.coverage.size()) return 1;
+    memcpy(covg, X->discover.coverage[locus].data(), X->discover.coverage[locus].size() * 4);
+    return 0;
 }
 int drprg_cuda_set_minor_af(drprg_index* X, float minor_af) {
     X->minor_af = minor_af;

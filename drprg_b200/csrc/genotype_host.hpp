@@ -76,6 +76,34 @@ std::vector<SiteRecord> merge_records(const Locus& L, const std::vector<uint32_t
 bool locus_coverage_outlier(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& kpath,
                             const std::vector<uint32_t>& lpath, const int32_t* cov, uint32_t global_covg);
 
+// ---- discover's mapping front half from the map pass (discover.cpp) ------------------------------
+struct RetainedHit {  // a kept hit of the sample, grouped by read, pandora order within a read
+    uint32_t read, start, knode;
+    uint16_t prg;
+    uint8_t fwd;
+};
+struct DiscoverOpts {  // pandora discover defaults (drprg overrides none of them)
+    uint32_t covg_threshold = 3, min_len = 1, max_len = 30, padding = 22, min_hits = 2;
+};
+struct ReadCoordinate {
+    uint32_t read, start, end;
+    uint8_t fwd;
+};
+struct CandidateRegion {
+    uint32_t locus = 0, start = 0, end = 0, pad_start = 0, pad_end = 0, n_reads = 0;
+    uint64_t read_off = 0;
+};
+struct DiscoverResult {
+    std::vector<std::string> consensus;           // per locus: ML sequence (empty when the locus is absent)
+    std::vector<std::vector<uint32_t>> coverage;  // per locus: per-base coverage along it
+    std::vector<CandidateRegion> regions;         // ordered by locus, then position
+    std::vector<ReadCoordinate> reads;            // per region, ordered by read id
+};
+std::vector<uint32_t> ml_path_base_coverage(const HostIndex& H, uint32_t locus, const std::vector<uint32_t>& kpath,
+                                            const std::vector<uint32_t>& lpath, const int32_t* cov);
+void discover_candidates(const HostIndex& H, const std::vector<char>& present, const std::vector<std::vector<uint32_t>>& mlpaths,
+                         const int32_t* cov, const std::vector<RetainedHit>& hits, const DiscoverOpts& o, DiscoverResult& R);
+
 struct GenotypeArrays {  // flattened over records / alleles, device results copied back
     std::vector<uint32_t> rec_off, allele_off, allele_kn;
     std::vector<uint32_t> mean_fwd, mean_rev, med_fwd, med_rev, sum_fwd, sum_rev;

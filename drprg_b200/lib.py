@@ -37,6 +37,15 @@ class MapStats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class DiscoverOpts(C.Structure):
+    _fields_ = [("covg_threshold", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32), ("padding", C.c_uint32), ("min_hits", C.c_uint32)]
+
+
+class CandidateRegion(C.Structure):
+    _fields_ = [("locus", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32), ("pad_start", C.c_uint32), ("pad_end", C.c_uint32),
+                ("n_reads", C.c_uint32), ("read_off", C.c_uint64)]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [
         ("w", C.c_uint32), ("k", C.c_uint32), ("n_loci", C.c_uint32), ("total_knodes", C.c_uint32),
@@ -63,7 +72,8 @@ SYMBOLS = [
     "drprg_cuda_index_knode_base", "drprg_cuda_index_knodes", "drprg_cuda_index_edges", "drprg_cuda_index_paths",
     "drprg_cuda_index_records", "drprg_cuda_index_min_path_length", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits",
     "drprg_cuda_gt_params", "drprg_cuda_gt_mlpath", "drprg_cuda_gt_counts", "drprg_cuda_gt_records",
-    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_gt_filter_stats", "drprg_cuda_set_minor_af", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse", "drprg_cuda_issue_peak",
+    "drprg_cuda_gt_alleles", "drprg_cuda_gt_allele_knodes", "drprg_cuda_genotype_rows", "drprg_cuda_gt_filter_stats", "drprg_cuda_set_minor_af", "drprg_cuda_retain_hits", "drprg_cuda_discover_candidates",
+    "drprg_cuda_discover_regions", "drprg_cuda_discover_region_reads", "drprg_cuda_discover_consensus", "drprg_cuda_discover_coverage", "drprg_cuda_last_timings", "drprg_cuda_last_genotype_timings", "drprg_cuda_format_g6", "drprg_cuda_launch_count", "drprg_cuda_hash64", "drprg_cuda_hash64_inverse", "drprg_cuda_issue_peak",
 ]
 
 
@@ -78,6 +88,7 @@ def lib():
         L.drprg_cuda_locus_name.restype = C.c_char_p
         L.drprg_cuda_vcf_text.restype = C.c_char_p
         L.drprg_cuda_vcf_view.restype = C.c_void_p
+        L.drprg_cuda_discover_consensus.restype = C.c_void_p
         for f in ("drprg_cuda_pack_reads", "drprg_cuda_sketch_batch", "drprg_cuda_last_hits", "drprg_cuda_gt_mlpath"):
             getattr(L, f).restype = C.c_int64
         L.drprg_cuda_launch_count.restype = C.c_uint64
@@ -385,6 +396,39 @@ class Index:
         mg = np.zeros(n, np.int32); pdp = np.zeros(na, np.float32)
         _check(L.drprg_cuda_gt_filter_stats(self.h, _p(cg), _p(frs), _p(sb), _p(mg), _p(pdp)), "drprg_cuda_gt_filter_stats")
         return dict(covg_gt=cg, frs=frs, sb_ratio=sb, minor_gt=mg, pdp=pdp)
+
+    # ---- discover's mapping front half from the map pass ----
+    def retain_hits(self, on=True):
+        lib().drprg_cuda_retain_hits(self.h, C.c_int(1 if on else 0))
+
+    def discover_candidates(self, covg_threshold=0, min_len=0, max_len=0, padding=0xFFFFFFFF, min_hits=0):
+        """after genotype(): {locus: (consensus, coverage)}, regions [(locus, start, end, pad_start, pad_end, reads)] with
+        reads = [(read, start, end, fwd)]"""
+        L = lib()
+        o = DiscoverOpts(covg_threshold, min_len, max_len, padding, min_hits)
+        nr, nrr = C.c_uint32(), C.c_uint64()
+        _check(L.drprg_cuda_discover_candidates(self.h, C.byref(o), C.byref(nr), C.byref(nrr)), "drprg_cuda_discover_candidates")
+        regs = (CandidateRegion * max(1, nr.value))()
+        L.drprg_cuda_discover_regions(self.h, regs)
+        n = nrr.value
+        rd = np.zeros(n, np.uint32); st = np.zeros(n, np.uint32); en = np.zeros(n, np.uint32); fw = np.zeros(n, np.uint8)
+        L.drprg_cuda_discover_region_reads(self.h, _p(rd), _p(st), _p(en), _p(fw))
+        loci = {}
+        for l in range(self.n_loci):
+            ln = C.c_uint64()
+            p = L.drprg_cuda_discover_consensus(self.h, C.c_uint32(l), C.byref(ln))
+            if not p:
+                continue
+            cov = np.zeros(ln.value, np.uint32)
+            L.drprg_cuda_discover_coverage(self.h, C.c_uint32(l), _p(cov))
+            loci[l] = (C.string_at(p, ln.value).decode(), cov)
+        regions = []
+        for i in range(nr.value):
+            r = regs[i]
+            a, b = r.read_off, r.read_off + r.n_reads
+            regions.append((r.locus, r.start, r.end, r.pad_start, r.pad_end,
+                            list(zip(rd[a:b].tolist(), st[a:b].tolist(), en[a:b].tolist(), fw[a:b].tolist()))))
+        return loci, regions
 
     def set_minor_af(self, maf):
         lib().drprg_cuda_set_minor_af(self.h, C.c_float(maf))

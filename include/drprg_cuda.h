@@ -132,6 +132,28 @@ const char* drprg_cuda_vcf_text(drprg_index*);
 /* the same text without a copy: pointer + length, valid until the next drprg_cuda_genotype on this handle */
 const char* drprg_cuda_vcf_view(drprg_index*, uint64_t* len);
 
+/* ---- one mapping pass for `pandora discover` and `pandora map` --------------------------------------
+ * drprg runs pandora twice per sample; the first half of `pandora discover` (src/predict.rs:247-256 -> src/lib.rs:513-578) is
+ * the same S1-S7 as the map step.  With hit retention switched on BEFORE the sample is mapped, drprg_cuda_discover_candidates
+ * (after drprg_cuda_genotype) returns what pandora's local assembler needs, from the pass that ran anyway: per present locus
+ * the maximum-likelihood sequence and its per-base coverage, the candidate regions (runs of coverage < covg_threshold with a
+ * length in [min_len, max_len], padded) and per region the reads with >= min_hits kept hits inside it (read id, span on the
+ * read, strand).  Fields left 0 take pandora discover's defaults (3, 1, 30, 2); padding 0xffffffff = default 22. */
+typedef struct {
+    uint32_t covg_threshold, min_len, max_len, padding, min_hits;
+} drprg_discover_opts;
+typedef struct {
+    uint32_t locus, start, end, pad_start, pad_end, n_reads; /* intervals on the locus's ML sequence, end exclusive */
+    uint64_t read_off;                                      /* first entry of the region in the read arrays */
+} drprg_candidate_region;
+int drprg_cuda_retain_hits(drprg_index*, int on);
+int drprg_cuda_discover_candidates(drprg_index*, const drprg_discover_opts* /* NULL = defaults */, uint32_t* n_regions,
+                                   uint64_t* n_region_reads);
+int drprg_cuda_discover_regions(drprg_index*, drprg_candidate_region* out /* n_regions */);
+int drprg_cuda_discover_region_reads(drprg_index*, uint32_t* read, uint32_t* start, uint32_t* end, uint8_t* fwd /* n_region_reads each */);
+const char* drprg_cuda_discover_consensus(drprg_index*, uint32_t locus, uint64_t* len); /* NULL: locus absent from the sample */
+int drprg_cuda_discover_coverage(drprg_index*, uint32_t locus, uint32_t* covg /* consensus length */);
+
 /* ---- introspection / parity hooks (same .so, used by tests and bench) --------------------------- */
 /* pandora's hash64 on a 2k-bit k-mer and its inverse (the k-mer screen is built from the inverse): host functions */
 uint64_t drprg_cuda_hash64(uint64_t kmer, uint32_t k);
