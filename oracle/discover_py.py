@@ -28,6 +28,9 @@ def _locus_tables(ox, locus):
     kpaths = []
     for r in range(n):
         g = base + r
+        if r == 0 or r == n - 1:  # the null start / end nodes of the k-mer graph carry no bases
+            kpaths.append([])
+            continue
         kpaths.append([(node_of(int(s), int(l)), int(s), int(l)) for s, l in zip(kn["iv_start"][io[g]:io[g + 1]], kn["iv_len"][io[g]:io[g + 1]])])
     return starts, lens, out, kpaths
 
