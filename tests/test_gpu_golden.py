@@ -72,4 +72,27 @@ def test_fused_filter_statistics_on_reference_vcf_rows(golden, name, maf):
     n = rust_filters.check_against(stats, rec_off, mf, mr, gaps, gt, conf, maf)
     assert n == len(keys) and n >= 4
     if name == "in.vcf":
-        assert np.isnan(stats["frs"]).sum() > 0 and (stats["minor_gt"] >= 0).sum() >= (1 if maf < 1 else 0)
+        assert np.isnan(stats["frs"]).sum() > 0  # null calls have no FRS
+
+
+def test_fused_minor_allele_statistic_constructed_rows():
+    """rows built to hit every branch of check_for_minor_alternate (src/minor.rs:70-127)"""
+    rows = [
+        ([40, 6], [38, 5], [0.0, 0.1]),        # alt holds 12 % of the depth, clean GAPS, both strands: minor allele 1
+        ([40, 6], [38, 0], [0.0, 0.1]),        # alt only on one strand: strand bias -> none
+        ([40, 1], [38, 1], [0.0, 0.1]),        # alt depth 2 < 3 -> none
+        ([40, 6], [38, 5], [0.0, 0.6]),        # alt GAPS above 0.5 -> none
+        ([40, 6], [38, 5], [0.4, 0.45]),       # called GAPS above 0.39 -> none
+        ([40, 6], [38, 5], [0.1, 0.35]),       # GAPS difference above 0.2 -> none
+        ([30, 5, 5], [30, 5, 5], [0.0, 0.0, 0.0]),  # two alts with equal proportions: the higher index wins
+        ([0, 0], [0, 0], [1.0, 1.0]),          # no depth: null call, nothing
+        ([5], [4], [0.0]),                     # single allele
+    ]
+    rec_off, mf, mr, gaps = [0], [], [], []
+    for f, r, g in rows:
+        mf += f; mr += r; gaps += g
+        rec_off.append(rec_off[-1] + len(f))
+    lik, gt, conf, stats = lib.genotype_rows(rec_off, mf, mr, gaps, 80, minor_af=0.1, stats=True)
+    rust_filters.check_against(stats, rec_off, mf, mr, gaps, gt, conf, 0.1)
+    assert stats["minor_gt"].tolist() == [1, -1, -1, -1, -1, -1, 2, -1, -1]
+    assert stats["covg_gt"].tolist()[:2] == [78, 78] and stats["frs"][8] == 1.0 and np.isnan(stats["frs"][7])
