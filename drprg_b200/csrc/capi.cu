@@ -2011,6 +2011,12 @@ int drprg_cuda_genotype_rows(int device, uint32_t n_records, const uint32_t* rec
     return 0;
     API_END
 }
+/* `pandora index` replacement: the files drprg's validate_index looks for, next to the PRG */
+int drprg_cuda_index_write(drprg_index* X, const char* prg_path) {
+    API_BEGIN write_pandora_index(X->H, prg_path);
+    return 0;
+    API_END
+}
 /* ---- discover's mapping front half from the map pass ---- */
 int drprg_cuda_retain_hits(drprg_index* X, int on) {
     for (drprg_index* g : (X->gpus.empty() ? std::vector<drprg_index*>{X} : X->gpus)) g->retain_hits = on != 0;

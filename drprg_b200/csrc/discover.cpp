@@ -162,4 +162,96 @@ void discover_candidates(const HostIndex& H, const std::vector<char>& present, c
     }
 }
 
+
+// ============================================================================================
+// `pandora index` replacement: drprg runs `pandora index -t T -w W -k K <prg>` when an index is
+// built (/root/reference/src/builder.rs:644-659 -> src/lib.rs:479-510) and again per sample when discover changed the PRG
+// (src/predict.rs:281-284), and later only checks that the files exist (validate_index, src/predict.rs:400-418:
+// `<prg>.k{K}.w{W}.idx` found by find_prg_index_in, src/lib.rs:1222-1231, and the `kmer_prgs/` directory,
+// src/builder.rs:257-269).  The loader of this library already computes what those files hold; this writes them in
+// pandora's text layout [P, from upstream Index::save / KmerGraph::save; no pandora binary here to read them back]:
+//   <prg>.k{K}.w{W}.idx            first line: number of distinct minimizer hashes; then one line per hash:
+//                                  hash \t n \t (prg_id, <path>, knode_id, strand) ...   with <path> = n{[s, e)[s, e)...}
+//   kmer_prgs/NN/<locus>.k{K}.w{W}.gfa   H line, then per k-mer node "S id path FC:i:0 RC:i:0" followed by its "L" edges
+// K-mer node ids are the ranks of this library's graphs (start node 0, terminus last): consistent between the two files.
+// ============================================================================================
+}  // namespace drprg
+
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <fstream>
+
+namespace drprg {
+
+static void append_path(std::string& s, const KPath& kp, uint32_t term_coord, bool is_start, bool is_end) {
+    if (kp.empty()) {  // null start [0, 0) / null end [L, L)
+        const uint32_t c = is_start ? 0u : term_coord;
+        (void)is_end;
+        s += "1{[" + std::to_string(c) + ", " + std::to_string(c) + ")}";
+        return;
+    }
+    s += std::to_string(kp.size()) + "{";
+    for (auto& sg : kp) s += "[" + std::to_string(sg.s) + ", " + std::to_string(sg.e) + ")";
+    s += "}";
+}
+
+void write_pandora_index(const HostIndex& H, const std::string& prg_path) {
+    const std::string suffix = ".k" + std::to_string(H.k) + ".w" + std::to_string(H.w);
+    // ---- the minimizer index
+    {
+        const std::string path = prg_path + suffix + ".idx";
+        std::ofstream f(path);
+        if (!f) throw std::runtime_error("cannot write " + path);
+        size_t distinct = 0;
+        for (size_t i = 0; i < H.records.size(); ++i)
+            if (i == 0 || H.records[i - 1].hash != H.records[i].hash) ++distinct;
+        std::string out = std::to_string(distinct) + "\n";
+        for (size_t i = 0; i < H.records.size();) {
+            size_t j = i;
+            while (j < H.records.size() && H.records[j].hash == H.records[i].hash) ++j;
+            out += std::to_string(H.records[i].hash) + "\t" + std::to_string(j - i);
+            for (size_t q = i; q < j; ++q) {
+                const Record& r = H.records[q];
+                const Locus& L = H.loci[r.prg];
+                out += "\t(" + std::to_string(r.prg) + ", ";
+                append_path(out, L.kpath[r.knode], L.end_coord(), false, false);
+                out += ", " + std::to_string(r.knode) + ", " + std::to_string((int)r.strand) + ")";
+            }
+            out += "\n";
+            if (out.size() > (1u << 20)) {
+                f << out;
+                out.clear();
+            }
+            i = j;
+        }
+        f << out;
+        if (!f) throw std::runtime_error("write error on " + path);
+    }
+    // ---- the k-mer graphs
+    const size_t slash = prg_path.find_last_of('/');
+    const std::string dir = (slash == std::string::npos ? std::string(".") : prg_path.substr(0, slash)) + "/kmer_prgs";
+    mkdir(dir.c_str(), 0755);
+    for (size_t l = 0; l < H.loci.size(); ++l) {
+        const Locus& L = H.loci[l];
+        char sub[16];
+        snprintf(sub, sizeof sub, "%02d", (int)(l / 4000) + 1);
+        const std::string d = dir + "/" + sub;
+        mkdir(d.c_str(), 0755);
+        const std::string path = d + "/" + L.name + suffix + ".gfa";
+        std::ofstream f(path);
+        if (!f) throw std::runtime_error("cannot write " + path);
+        std::string out = "H\tVN:Z:1.0\tbn:Z:--linear --singlearr\n";
+        const size_t n = L.kpath.size();
+        for (size_t r = 0; r < n; ++r) {
+            out += "S\t" + std::to_string(r) + "\t";
+            append_path(out, L.kpath[r], L.end_coord(), r == 0, r + 1 == n);
+            out += "\tFC:i:0\t\tRC:i:0\n";
+            for (uint32_t o : L.kout[r]) out += "L\t" + std::to_string(r) + "\t+\t" + std::to_string(o) + "\t+\t0M\n";
+        }
+        f << out;
+        if (!f) throw std::runtime_error("write error on " + path);
+    }
+}
+
 }  // namespace drprg

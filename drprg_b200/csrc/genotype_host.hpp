@@ -104,6 +104,10 @@ std::vector<uint32_t> ml_path_base_coverage(const HostIndex& H, uint32_t locus, 
 void discover_candidates(const HostIndex& H, const std::vector<char>& present, const std::vector<std::vector<uint32_t>>& mlpaths,
                          const int32_t* cov, const std::vector<RetainedHit>& hits, const DiscoverOpts& o, DiscoverResult& R);
 
+// pandora-compatible index files next to the PRG (`pandora index` replacement): <prg>.k{K}.w{W}.idx and
+// kmer_prgs/NN/<locus>.k{K}.w{W}.gfa
+void write_pandora_index(const HostIndex& H, const std::string& prg_path);
+
 struct GenotypeArrays {  // flattened over records / alleles, device results copied back
     std::vector<uint32_t> rec_off, allele_off, allele_kn;
     std::vector<uint32_t> mean_fwd, mean_rev, med_fwd, med_rev, sum_fwd, sum_rev;

@@ -63,7 +63,7 @@ def make_opts(threads=1, min_cluster_size=10, illumina=False, genome_size=441153
 # every symbol include/drprg_cuda.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "drprg_cuda_version", "drprg_cuda_last_error", "drprg_cuda_device_count", "drprg_cuda_index_load",
-    "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_index_load_multi", "drprg_cuda_index_n_gpus",
+    "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_index_load_multi", "drprg_cuda_index_n_gpus", "drprg_cuda_index_write",
     "drprg_cuda_shard_root", "drprg_cuda_shard_attach", "drprg_cuda_shard_done", "drprg_cuda_map_genotype", "drprg_cuda_map_genotype_batch",
     "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_batch_from_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
     "drprg_cuda_batch_wrap_device", "drprg_cuda_batch_free", "drprg_cuda_sample_begin", "drprg_cuda_map_batch",
@@ -200,6 +200,10 @@ class Index:
 
     def __del__(self):
         self.close()
+
+    def write_pandora_index(self, prg_path):
+        """the files `pandora index` would leave next to the PRG: <prg>.k{K}.w{W}.idx and kmer_prgs/NN/<locus>.k{K}.w{W}.gfa"""
+        _check(lib().drprg_cuda_index_write(self.h, str(prg_path).encode()), "drprg_cuda_index_write")
 
     @property
     def n_gpus(self):

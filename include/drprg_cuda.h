@@ -63,6 +63,11 @@ int drprg_cuda_device_count(void);
 int drprg_cuda_index_load(const char* prg_path, uint32_t w, uint32_t k, int device, drprg_index** out);
 int drprg_cuda_index_load_text(const char* prg_text, uint32_t w, uint32_t k, int device, drprg_index** out);
 void drprg_cuda_index_free(drprg_index*);
+/* `pandora index` replacement (Pandora::index_with, src/lib.rs:479-510, called at src/builder.rs:644-659
+ * and per sample at src/predict.rs:281-284): writes <prg_path>.k{K}.w{W}.idx and kmer_prgs/NN/<locus>.k{K}.w{W}.gfa next to
+ * the PRG in pandora's text layout — the files drprg's validate_index requires (src/predict.rs:400-418,
+ * find_prg_index_in src/lib.rs:1222-1231).  Works on a host-only handle (device = -1). */
+int drprg_cuda_index_write(drprg_index*, const char* prg_path);
 
 /* ---- read sharding over the GPUs of one box (BASELINE config 3) ------------------------------------------
  * (a) inside the library: ONE handle drives n_gpus devices (0 = all visible; devices = NULL means 0..n-1).  The index is
