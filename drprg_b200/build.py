@@ -11,10 +11,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libdrprg_cuda.so")
 SOURCES = ["sketch.cu", "cluster.cu", "mlpath.cu", "genotype.cu", "capi.cu", "multi.cu", "ingest.cu", "gzip_inflate.cpp",
-           "prg_graph.cpp", "genotype_host.cpp", "discover.cpp"]
+           "prg_graph.cpp", "genotype_host.cpp", "discover.cpp", "fastq_frame.cpp"]
 EXTRA = ["pandora_cuda_main.cpp"]
 HEADERS = ["kernels.cuh", "kernels_common.cuh", "prg_graph.hpp", "genotype_host.hpp", "ingest.hpp", "capi_internal.hpp",
-           "gzip_inflate.hpp", "../../include/drprg_cuda.h"]
+           "gzip_inflate.hpp", "fastq_frame.hpp", "../../include/drprg_cuda.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false"]
 HOST_FLAGS = "-fPIC,-O2,-Wall,-Wno-unused-function,-pthread"
 

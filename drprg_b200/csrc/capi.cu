@@ -2,6 +2,8 @@
 // (/root/reference/src/lib.rs:580-642) plus the staged interface used for multi-GPU read sharding,
 // benches and parity tests.  Owns all device memory of an index (plain cudaMalloc; no torch types).
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -22,6 +24,7 @@
 
 #include "../../include/drprg_cuda.h"
 #include "genotype_host.hpp"
+#include "fastq_frame.hpp"
 #include "ingest.hpp"
 #include "kernels.cuh"
 #include "prg_graph.hpp"
@@ -1639,6 +1642,46 @@ int drprg_cuda_read_fastx(const char* path, uint32_t threads, uint32_t** words, 
     API_END
 }
 void drprg_cuda_host_free(void* p) { free(p); }
+
+int drprg_cuda_frame_fastq(const char* path, uint32_t threads, uint8_t** ascii, uint32_t** lens, uint64_t* n_reads,
+                           uint64_t* total_bases, int* is_fastq) {
+    API_BEGIN* ascii = nullptr;
+    *lens = nullptr;
+    *n_reads = *total_bases = 0;
+    *is_fastq = 0;
+    TextSource src;
+    src.fd = open(path, O_RDONLY);
+    if (src.fd < 0) throw std::runtime_error(std::string("cannot open ") + path);
+    struct Closer {
+        int fd;
+        ~Closer() { close(fd); }
+    } closer{src.fd};
+    src.size = (size_t)lseek(src.fd, 0, SEEK_END);
+    char first = 0;
+    if (src.size < 8 || src.read(&first, 0, 1) != 1 || first != '@') return 0;
+    std::vector<char> buf(src.size / 2 + 64);
+    std::vector<FramedSlice> sl;
+    if (!fastq_frame_text(src, threads, buf.data(), sl)) return 0;
+    uint64_t n = 0, bases = 0;
+    for (const FramedSlice& z : sl) {
+        n += z.st.n_reads;
+        bases += z.st.total_bases;
+    }
+    *ascii = (uint8_t*)malloc(std::max<uint64_t>(1, bases));
+    *lens = (uint32_t*)malloc(std::max<uint64_t>(1, n) * 4);
+    uint64_t r = 0, at = 0;
+    for (const FramedSlice& z : sl)
+        for (size_t i = 0; i < z.lens.size(); ++i) {
+            memcpy(*ascii + at, buf.data() + z.starts[i], z.lens[i]);
+            at += z.lens[i];
+            (*lens)[r++] = z.lens[i];
+        }
+    *n_reads = n;
+    *total_bases = bases;
+    *is_fastq = 1;
+    return 0;
+    API_END
+}
 
 int drprg_cuda_batch_upload(drprg_index* X, const uint32_t* words, const uint64_t* word_off, uint32_t stride_words,
                             const uint32_t* lens, uint64_t n_reads, uint64_t total_bases, uint32_t read_id_base, void* stream,

@@ -33,7 +33,13 @@ namespace {
 class WorkerPool {
   public:
     static WorkerPool& get() {
-        static WorkerPool* p = new WorkerPool();  // leaked on purpose: workers may outlive static destructors
+        static WorkerPool* p = new WorkerPool(15u, true);  // leaked on purpose: workers may outlive static destructors
+        return *p;
+    }
+    // ingest / gzip inflate: coarse, long sections that want every core of the rank's share; its workers sleep between
+    // sections instead of spinning (the genotype step's short sections keep the small spinning pool above)
+    static WorkerPool& io() {
+        static WorkerPool* p = new WorkerPool(63u, false);
         return *p;
     }
     void run(size_t n, const std::function<void(size_t)>& fn, size_t max_threads) {
@@ -64,7 +70,7 @@ class WorkerPool {
     }
 
   private:
-    WorkerPool() {
+    WorkerPool(unsigned cap, bool spin) : spin_(spin) {
         // one process per GPU shares the host with its sibling ranks: the pool takes this rank's share of the cores
         // (DRPRG_THREADS overrides; LOCAL_WORLD_SIZE is what torchrun sets), otherwise 8 ranks x 16 spinning threads
         // would fight over the same cores
@@ -73,7 +79,7 @@ class WorkerPool {
         if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
         if (const char* e = getenv("DRPRG_THREADS")) budget = (unsigned)std::max(1, atoi(e));
         if (!budget) budget = std::max(1u, hw / ranks);
-        const unsigned n = std::min(15u, budget > 1 ? budget - 1 : 0);
+        const unsigned n = std::min(cap, budget > 1 ? budget - 1 : 0);
         for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
         for (auto& w : workers_) w.detach();
     }
@@ -95,7 +101,7 @@ class WorkerPool {
                 const char* e = getenv("DRPRG_SPIN");
                 return e ? atoi(e) : 4000;
             }();
-            for (int spin = 0; spin < spin_max && gen_hint_.load(std::memory_order_acquire) == seen; ++spin) {
+            for (int spin = 0; spin_ && spin < spin_max && gen_hint_.load(std::memory_order_acquire) == seen; ++spin) {
 #if defined(__x86_64__)
                 __builtin_ia32_pause();
 #endif
@@ -113,6 +119,7 @@ class WorkerPool {
             }
         }
     }
+    const bool spin_;
     std::vector<std::thread> workers_;
     std::mutex m_, run_mutex_;
     std::condition_variable cv_, done_cv_;
@@ -127,6 +134,9 @@ class WorkerPool {
 
 void parallel_for(size_t n, const std::function<void(size_t)>& fn, size_t max_threads) {
     WorkerPool::get().run(n, fn, max_threads);
+}
+void parallel_for_io(size_t n, const std::function<void(size_t)>& fn, size_t max_threads) {
+    WorkerPool::io().run(n, fn, max_threads);
 }
 
 static inline uint32_t sat16(int32_t c) { return c > 65535 ? 65535u : (uint32_t)(c < 0 ? 0 : c); }

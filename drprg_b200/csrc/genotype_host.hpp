@@ -18,6 +18,8 @@ namespace drprg {
 // Small persistent host thread pool (creating threads per call cost more than the work they did).
 // parallel_for(n, fn) runs fn(0..n-1) on the pool plus the calling thread and rethrows the first error.
 void parallel_for(size_t n, const std::function<void(size_t)>& fn, size_t max_threads = 8);
+// the same on the larger, non-spinning pool used by ingest and gzip inflate (up to 64 threads of the rank's core share)
+void parallel_for_io(size_t n, const std::function<void(size_t)>& fn, size_t max_threads = 64);
 
 struct SampleOpts {
     uint32_t min_cluster_size = 10;

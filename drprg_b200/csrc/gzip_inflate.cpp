@@ -17,6 +17,7 @@
 // file, or a stream this decoder does not handle — makes the caller fall back to zlib's sequential gzread.
 #include "gzip_inflate.hpp"
 
+#include <immintrin.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -82,8 +83,11 @@ struct Bits {
 // ---- canonical Huffman decoding tables: one level of ROOT bits, longer (rare) codes by a canonical bit-by-bit walk ----
 struct Huff {
     static constexpr int ROOT = 11;
-    // entry: bits 0..3 = code length (0 = needs the slow path), bits 4.. = symbol
-    uint16_t fast[1 << ROOT];
+    // entry: bits 0..3 = code length (0 = needs the slow path), 4..7 = number of extra bits, 8 = literal, 9 = end of block,
+    // 10 = invalid symbol, 16..31 = the literal / the length base / the distance base: one lookup gives everything the
+    // decoder needs (no second table for base and extra bits on the match path)
+    static constexpr uint32_t F_LIT = 1u << 8, F_EOB = 1u << 9, F_BAD = 1u << 10;
+    uint32_t fast[1 << ROOT];
     uint16_t count[16], symbol[320];
     int max_len = 0;
     bool build(const uint8_t* lens, int n) {  // false: over-subscribed or (incomplete with more than one code)
@@ -108,7 +112,9 @@ struct Huff {
             if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
         return true;
     }
-    void fill_fast() {  // separate from build(): the block search builds thousands of tables it never decodes with
+    static inline uint32_t litlen_entry(uint32_t sym);
+    static inline uint32_t dist_entry(uint32_t sym);
+    void fill_fast(bool is_dist) {  // separate from build(): the block search builds thousands of tables it never decodes with
         memset(fast, 0, sizeof fast);
         int code = 0, idx = 0;
         for (int l = 1; l <= std::min(ROOT, 15); ++l) {
@@ -116,7 +122,8 @@ struct Huff {
                 // deflate codes are MSB-first in a stream that is read LSB-first: reverse the code
                 uint32_t rev = 0;
                 for (int b = 0; b < l; ++b) rev |= ((code >> b) & 1u) << (l - 1 - b);
-                for (uint32_t fill = rev; fill < (1u << ROOT); fill += 1u << l) fast[fill] = (uint16_t)((symbol[idx] << 4) | l);
+                const uint32_t entry = (is_dist ? dist_entry(symbol[idx]) : litlen_entry(symbol[idx])) | (uint32_t)l;
+                for (uint32_t fill = rev; fill < (1u << ROOT); fill += 1u << l) fast[fill] = entry;
             }
             code <<= 1;
         }
@@ -135,14 +142,6 @@ struct Huff {
         }
         return -1;
     }
-    inline int decode(Bits& b) const {  // needs >= 15 bits in the buffer
-        const uint16_t e = fast[b.peek(ROOT)];
-        if (e & 15) {
-            b.drop(e & 15);
-            return e >> 4;
-        }
-        return slow(b);
-    }
 };
 
 const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -150,6 +149,17 @@ const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3
 const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+inline uint32_t Huff::litlen_entry(uint32_t sym) {
+    if (sym < 256) return (sym << 16) | F_LIT;
+    if (sym == 256) return F_EOB;
+    if (sym > 285) return F_BAD;
+    return ((uint32_t)LEN_BASE[sym - 257] << 16) | ((uint32_t)LEN_EXTRA[sym - 257] << 4);
+}
+inline uint32_t Huff::dist_entry(uint32_t sym) {
+    if (sym > 29) return F_BAD;
+    return ((uint32_t)DIST_BASE[sym] << 16) | ((uint32_t)DIST_EXTRA[sym] << 4);
+}
 
 struct BlockCodes {
     Huff lit, dist;
@@ -191,8 +201,8 @@ bool read_dynamic_header(Bits& b, BlockCodes& C, bool fill = true) {
     C.have_dist = any;
     if (any && !C.dist.build(lens + hlit, (int)hdist)) return false;
     if (fill) {
-        C.lit.fill_fast();
-        if (any) C.dist.fill_fast();
+        C.lit.fill_fast(false);
+        if (any) C.dist.fill_fast(true);
     }
     return true;
 }
@@ -204,11 +214,11 @@ void fixed_codes(BlockCodes& C) {
     for (int i = 256; i < 280; ++i) l[i] = 7;
     for (int i = 280; i < 288; ++i) l[i] = 8;
     C.lit.build(l, 288);
-    C.lit.fill_fast();
+    C.lit.fill_fast(false);
     uint8_t d[30];
     for (int i = 0; i < 30; ++i) d[i] = 5;
     C.dist.build(d, 30);
-    C.dist.fill_fast();
+    C.dist.fill_fast(true);
     C.have_dist = true;
 }
 
@@ -261,6 +271,88 @@ struct SymBuf {
 
 enum class Stop { EndOfMember, Limit, Error };
 
+// One Huffman-coded block, from after its header to its end-of-block code.  The input of this program is FASTQ text at
+// low compression levels: ~90 % of the output comes from short matches (deflate_fast accepts any 3-base match), so the
+// match path is the hot one: one table lookup for the length (base and extra-bit count packed in the entry), one for the
+// distance, and a copy that always moves 16 symbols before it looks at the length.  Bit budget: the buffer holds >= 48
+// bits at the top of the loop; two literals take <= 30, a length <= 20 and a distance <= 28 bits.
+template <bool TEXT_ONLY>
+Stop huffman_block(Bits& b, SymBuf& out, const BlockCodes& C) {
+    constexpr uint32_t MASK = (1u << Huff::ROOT) - 1u;
+    const uint32_t* lt = C.lit.fast;
+    const uint32_t* dt = C.dist.fast;
+    auto plausible = [](uint32_t sym) { return sym < 0x80 && (sym >= 0x20 || sym == '\n' || sym == '\r' || sym == '\t'); };
+    for (;;) {
+        out.room(520);
+        if (b.cnt < 48) {
+            b.refill();
+            if (b.over) return Stop::Error;
+        }
+        uint32_t e = lt[b.buf & MASK];
+        if (e & Huff::F_LIT) {
+            b.drop(e & 15);
+            if (TEXT_ONLY && !plausible(e >> 16)) return Stop::Error;
+            out.p[out.n++] = (uint16_t)(e >> 16);
+            e = lt[b.buf & MASK];
+            if (e & Huff::F_LIT) {
+                b.drop(e & 15);
+                if (TEXT_ONLY && !plausible(e >> 16)) return Stop::Error;
+                out.p[out.n++] = (uint16_t)(e >> 16);
+                continue;
+            }
+            if (b.cnt < 48) {  // the low bits stay where they are: e is still the entry of the next code
+                b.refill();
+                if (b.over) return Stop::Error;
+            }
+        }
+        if (!(e & 15)) {  // a code longer than ROOT bits
+            const int sym = C.lit.slow(b);
+            if (sym < 0) return Stop::Error;
+            e = Huff::litlen_entry((uint32_t)sym);
+            if (e & Huff::F_LIT) {
+                if (TEXT_ONLY && !plausible(e >> 16)) return Stop::Error;
+                out.p[out.n++] = (uint16_t)(e >> 16);
+                continue;
+            }
+            if (b.cnt < 48) b.refill();
+        } else {
+            b.drop(e & 15);
+        }
+        if (e & (Huff::F_EOB | Huff::F_BAD)) return (e & Huff::F_EOB) ? Stop::EndOfMember : Stop::Error;  // EndOfMember = "block ended" here
+        if (!C.have_dist) return Stop::Error;
+        const uint32_t lx = (e >> 4) & 15u;
+        const uint32_t len = (e >> 16) + b.peek((int)lx);
+        b.drop((int)lx);
+        uint32_t d = dt[b.buf & MASK];
+        if (!(d & 15)) {
+            const int ds = C.dist.slow(b);
+            if (ds < 0) return Stop::Error;
+            d = Huff::dist_entry((uint32_t)ds);
+            if (b.cnt < 16) b.refill();
+        } else {
+            b.drop(d & 15);
+        }
+        if (d & Huff::F_BAD) return Stop::Error;
+        const uint32_t dx = (d >> 4) & 15u;
+        const uint32_t dist = (d >> 16) + b.peek((int)dx);
+        b.drop((int)dx);
+        if (dist > out.n) return Stop::Error;
+        uint16_t* dst = out.p + out.n;
+        const uint16_t* src = dst - dist;
+        if (dist >= 8) {  // 16-byte steps (may run up to 15 symbols past the end: room() keeps the slack)
+            memcpy(dst, src, 16);
+            if (len > 8)
+                for (uint32_t i = 8; i < len; i += 8) memcpy(dst + i, src + i, 16);
+        } else if (dist == 1) {  // a run (quality strings): broadcast
+            const uint64_t v = 0x0001000100010001ull * src[0];
+            for (uint32_t i = 0; i < len; i += 4) memcpy(dst + i, &v, 8);
+        } else {
+            for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
+        }
+        out.n += len;
+    }
+}
+
 // Decode blocks from the reader's position until the final block of the member ends or a block ends at/after bit
 // `limit_bit` (blocks are never cut).  text_only: a literal outside the plausible text range is an error (used while
 // validating a guessed block start).  Returns how it stopped; `end_bit` = position after the last decoded block.
@@ -283,64 +375,8 @@ Stop decode_blocks(Bits& b, SymBuf& out, size_t limit_bit, bool text_only, size_
         } else {
             if (btype == 1) fixed_codes(C);
             else if (!read_dynamic_header(b, C)) return Stop::Error;
-            const uint16_t* lt = C.lit.fast;
-            const uint16_t* dt = C.dist.fast;
-            for (;;) {
-                out.room(520);
-                if (b.cnt < 48) {
-                    b.refill();
-                    if (b.over) return Stop::Error;
-                }
-                // up to two literals per refill (a literal/length code is at most 15 bits)
-                uint16_t e = lt[b.buf & ((1u << Huff::ROOT) - 1u)];
-                int sym;
-                if (e & 15) {
-                    b.drop(e & 15);
-                    sym = e >> 4;
-                    if (sym < 256 && !text_only) {
-                        out.p[out.n++] = (uint16_t)sym;
-                        e = lt[b.buf & ((1u << Huff::ROOT) - 1u)];
-                        if (!(e & 15)) continue;
-                        b.drop(e & 15);
-                        sym = e >> 4;
-                    }
-                } else {
-                    sym = C.lit.slow(b);
-                    if (sym < 0) return Stop::Error;
-                }
-                if (sym < 256) {
-                    if (text_only && (sym >= 0x80 || (sym < 0x20 && sym != '\n' && sym != '\r' && sym != '\t'))) return Stop::Error;
-                    out.p[out.n++] = (uint16_t)sym;
-                } else if (sym == 256) {
-                    break;
-                } else {
-                    const int li = sym - 257;
-                    if (li >= 29 || !C.have_dist) return Stop::Error;
-                    const uint32_t len = LEN_BASE[li] + b.peek(LEN_EXTRA[li]);
-                    b.drop(LEN_EXTRA[li]);
-                    if (b.cnt < 30) b.refill();
-                    const uint16_t de = dt[b.buf & ((1u << Huff::ROOT) - 1u)];
-                    int ds;
-                    if (de & 15) {
-                        b.drop(de & 15);
-                        ds = de >> 4;
-                    } else {
-                        ds = C.dist.slow(b);
-                    }
-                    if (ds < 0 || ds >= 30) return Stop::Error;
-                    const uint32_t dist = DIST_BASE[ds] + b.peek(DIST_EXTRA[ds]);
-                    b.drop(DIST_EXTRA[ds]);
-                    if (dist > out.n) return Stop::Error;
-                    uint16_t* d = out.p + out.n;
-                    const uint16_t* s = d - dist;
-                    if (dist >= 8) {  // copy in 16-byte steps (may run up to 7 symbols past the end: room() keeps slack)
-                        for (uint32_t i = 0; i < len; i += 8) memcpy(d + i, s + i, 16);
-                    } else {
-                        for (uint32_t i = 0; i < len; ++i) d[i] = s[i];
-                    }
-                    out.n += len;
-                }
-            }
+            const Stop r = text_only ? huffman_block<true>(b, out, C) : huffman_block<false>(b, out, C);
+            if (r == Stop::Error) return r;
         }
         ++blocks;
         if (n_blocks) *n_blocks = blocks;
@@ -401,6 +437,143 @@ size_t skip_gzip_header(const uint8_t* p, size_t n, size_t at) {
     return q <= n ? q : SIZE_MAX;
 }
 
+
+// ---- CRC-32 by carry-less multiplication (4 x 128-bit folding, then Barrett reduction; the folding constants are the
+// x^n mod P values of the reflected CRC-32 polynomial published in Intel's "Fast CRC Computation for Generic Polynomials
+// Using PCLMULQDQ").  zlib's table-driven crc32 runs at 1-3 GB/s per core, which made the checksum a visible part of
+// the inflate; the result is checked against zlib once per process and zlib is used if the CPU lacks PCLMUL/SSE4.1.
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul_raw(const uint8_t* buf, size_t len, uint32_t crc) {
+    // len >= 64 and a multiple of 16; crc is the raw (already inverted) register
+    alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+    alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+    alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};
+    alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+    x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+    x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+    x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+    x0 = _mm_load_si128((const __m128i*)k1k2);
+    buf += 64;
+    len -= 64;
+    while (len >= 64) {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+        x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+        x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+        y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+        y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+        y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+        x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+        x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        buf += 64;
+        len -= 64;
+    }
+    x0 = _mm_load_si128((const __m128i*)k3k4);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (len >= 16) {
+        x2 = _mm_loadu_si128((const __m128i*)buf);
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        buf += 16;
+        len -= 16;
+    }
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_and_si128(x1, x3);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_load_si128((const __m128i*)poly);
+    x2 = _mm_and_si128(x1, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+    x2 = _mm_and_si128(x2, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+
+uint32_t crc32_zlib(const uint8_t* d, size_t n) {
+    uLong c = crc32(0L, Z_NULL, 0);
+    while (n) {
+        const size_t step = std::min<size_t>(n, 1u << 30);
+        c = crc32(c, d, (uInt)step);
+        d += step;
+        n -= step;
+    }
+    return (uint32_t)c;
+}
+
+uint32_t crc32_fast_unchecked(const uint8_t* d, size_t n) {
+    if (n < 64) return crc32_zlib(d, n);
+    const size_t body = n & ~(size_t)15;
+    const uint32_t raw = crc32_clmul_raw(d, body, 0xffffffffu);
+    uLong c = (uLong)(raw ^ 0xffffffffu);
+    if (n > body) c = crc32(c, d + body, (uInt)(n - body));
+    return (uint32_t)c;
+}
+
+uint32_t crc32_fast(const uint8_t* d, size_t n) {
+    static const bool usable = [] {
+        if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1")) return false;
+        uint8_t t[4099];
+        uint32_t x = 12345;
+        for (auto& b : t) {
+            x = x * 1664525u + 1013904223u;
+            b = (uint8_t)(x >> 24);
+        }
+        for (size_t len : {64ul, 65ul, 80ul, 127ul, 128ul, 1000ul, 4096ul, 4099ul})
+            if (crc32_fast_unchecked(t, len) != crc32_zlib(t, len)) return false;
+        return true;
+    }();
+    return usable ? crc32_fast_unchecked(d, n) : crc32_zlib(d, n);
+}
+
+// symbols -> bytes: 32 symbols at a time when none of them refers to the unknown window (the common case after the first
+// few hundred KB of a chunk), through the lookup table otherwise
+__attribute__((target("avx2"))) void translate_avx2(const uint16_t* s, uint8_t* d, size_t n, const uint8_t* L) {
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i));
+        const __m256i b = _mm256_loadu_si256((const __m256i*)(s + i + 16));
+        if ((_mm256_movemask_epi8(_mm256_or_si256(a, b)) & 0xaaaaaaaa) == 0) {
+            const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8);
+            _mm256_storeu_si256((__m256i*)(d + i), p);
+        } else {
+            for (size_t j = i; j < i + 32; ++j) d[j] = L[s[j]];
+        }
+    }
+    for (; i < n; ++i) d[i] = L[s[i]];
+}
+void translate_scalar(const uint16_t* s, uint8_t* d, size_t n, const uint8_t* L) {
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        d[i] = L[s[i]]; d[i + 1] = L[s[i + 1]]; d[i + 2] = L[s[i + 2]]; d[i + 3] = L[s[i + 3]];
+        d[i + 4] = L[s[i + 4]]; d[i + 5] = L[s[i + 5]]; d[i + 6] = L[s[i + 6]]; d[i + 7] = L[s[i + 7]];
+    }
+    for (; i < n; ++i) d[i] = L[s[i]];
+}
+
 struct Chunk {
     size_t start_bit = 0;     // first block of the chunk
     size_t end_bit = 0;       // after its last block
@@ -427,7 +600,9 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         const char* e = getenv("DRPRG_PARALLEL_GZIP_CHUNK");
         return e && atol(e) > 0 ? (size_t)atol(e) : (size_t)(1u << 20);
     }();
-    size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)std::max(1u, threads), (size_t)64, (n - data0) / chunk_min}));
+    // more chunks than threads: the chunks decode at different speeds and are handed out dynamically
+    const size_t n_threads = std::max(1u, threads);
+    size_t T = std::max<size_t>(1, std::min<size_t>({n_threads * 4, (size_t)512, (n - data0) / chunk_min}));
     if (T < 2) return false;  // small files: zlib is as fast
     // ---- 1. chunk starts
     std::vector<Chunk> ch(T);
@@ -435,11 +610,11 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     ch[0].unknown_window = false;
     std::vector<size_t> guess(T);
     for (size_t t = 1; t < T; ++t) guess[t] = (data0 + (n - data0) * t / T) * 8;
-    parallel_for(T - 1, [&](size_t i) {
+    parallel_for_io(T - 1, [&](size_t i) {
         const size_t t = i + 1;
         const size_t hi = t + 1 < T ? guess[t + 1] : (n - 8) * 8;
         ch[t].start_bit = find_block_start(gz, n, guess[t], hi);
-    }, T);
+    }, n_threads);
     const double t1 = now();
     // chunks whose start was not found are merged into their predecessor
     std::vector<Chunk> live;
@@ -449,7 +624,7 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     T = live.size();
     if (T < 2) return false;
     // ---- 2. decode every chunk up to the start of the next one
-    parallel_for(T, [&](size_t t) {
+    parallel_for_io(T, [&](size_t t) {
         Chunk& c = live[t];
         if (c.unknown_window) c.out.init_unknown();
         else c.out.init_empty();
@@ -458,7 +633,7 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         const size_t limit = t + 1 < T ? live[t + 1].start_bit : SIZE_MAX;
         c.stop = decode_blocks(b, c.out, limit, false, SIZE_MAX, c.end_bit);
         c.ok = (t + 1 < T) ? (c.stop == Stop::Limit && c.end_bit == limit) : (c.stop == Stop::EndOfMember);
-    }, T);
+    }, n_threads);
     const double t2 = now();
     for (size_t t = 0; t < T; ++t)
         if (!live[t].ok) return false;  // a guessed start was wrong, a member ended early (multi-member file), or corrupt data
@@ -503,11 +678,12 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         c.last_n = have + keep;
         memcpy(c.last_window, w, c.last_n);
     }
+    const double t3 = now();
     char* text = (char*)malloc(total + 1);
     if (!text) return false;
     std::vector<uint32_t> crcs(T, 0);
-    std::vector<char> bad(T, 0);
-    parallel_for(T, [&](size_t t) {
+    std::vector<double> tt(T, 0), tc(T, 0), tf(T, 0);
+    parallel_for_io(T, [&](size_t t) {
         Chunk& c = live[t];
         const size_t sz = c.out.size();
         const uint16_t* s = c.out.p + WIN;
@@ -519,21 +695,23 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         for (uint32_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
         if (pc)
             for (uint32_t off = WIN - pc->last_n; off < WIN; ++off) lut[UNKNOWN | off] = pc->last_window[off - (WIN - pc->last_n)];
-        const uint8_t* L = lut.data();
-        size_t i = 0;
-        for (; i + 8 <= sz; i += 8) {
-            d[i] = L[s[i]]; d[i + 1] = L[s[i + 1]]; d[i + 2] = L[s[i + 2]]; d[i + 3] = L[s[i + 3]];
-            d[i + 4] = L[s[i + 4]]; d[i + 5] = L[s[i + 5]]; d[i + 6] = L[s[i + 6]]; d[i + 7] = L[s[i + 7]];
-        }
-        for (; i < sz; ++i) d[i] = L[s[i]];
-        crcs[t] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), d, (uInt)std::min<size_t>(sz, 0x7fffffffu));
-        if (sz > 0x7fffffffu) bad[t] = 1;
+        static const bool avx2 = __builtin_cpu_supports("avx2");
+        const double a0 = timing ? now() : 0;
+        if (avx2) translate_avx2(s, d, sz, lut.data());
+        else translate_scalar(s, d, sz, lut.data());
+        const double a1 = timing ? now() : 0;
+        crcs[t] = crc32_fast(d, sz);
+        const double a2 = timing ? now() : 0;
         c.out.release();
-    }, T);
+        if (timing) {
+            tt[t] = a1 - a0;
+            tc[t] = a2 - a1;
+            tf[t] = now() - a2;
+        }
+    }, n_threads);
     uint32_t crc = 0;
     bool ok = true;
     for (size_t t = 0; t < T; ++t) {
-        ok = ok && !bad[t];
         crc = t == 0 ? crcs[0] : (uint32_t)crc32_combine(crc, crcs[t], (z_off_t)(t + 1 < T ? live[t + 1].out_off - live[t].out_off : total - live[t].out_off));
     }
     if (!ok || crc != want_crc) {
@@ -543,9 +721,17 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     text[total] = 0;
     *out = text;
     *out_n = total;
-    if (timing)
-        fprintf(stderr, "[drprg-cuda] parallel gunzip: %zu chunks, %.1f MB -> %.1f MB, block search %.1f ms, decode %.1f ms, resolve + crc %.1f ms\n", T,
-                n / 1e6, total / 1e6, t1 - t0, t2 - t1, now() - t2);
+    if (timing) {
+        double st = 0, sc = 0, sf = 0;
+        for (size_t t = 0; t < T; ++t) {
+            st += tt[t];
+            sc += tc[t];
+            sf += tf[t];
+        }
+        fprintf(stderr, "[drprg-cuda] parallel gunzip: %zu chunks, %.1f MB -> %.1f MB, block search %.1f ms, decode %.1f ms, window chain %.1f ms, "
+                        "translate + crc %.1f ms (thread-ms: translate %.0f, crc %.0f, free %.0f)\n", T,
+                n / 1e6, total / 1e6, t1 - t0, t2 - t1, t3 - t2, now() - t3, st, sc, sf);
+    }
     return true;
 }
 

@@ -14,6 +14,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@
 #include <string>
 #include <vector>
 
+#include "fastq_frame.hpp"
 #include "genotype_host.hpp"
 #include "ingest.hpp"
 #include "kernels.cuh"
@@ -58,6 +60,28 @@ struct Staging {  // process-wide pinned double buffer + grow-only device text /
     size_t rec_cap = 0;
     unsigned long long* d_scalars = nullptr;  // [0] n newlines, [1] bad framing, [2] max len, [3] total bases, [4] dropped
     unsigned long long* h_scalars = nullptr;
+    char* pinned_seq = nullptr;  // host-framed path: the sequence lines of the whole file
+    size_t seq_cap = 0;
+    uint32_t* h_rec = nullptr;   // host-framed path: sequence start | length per read (2 x hrec_cap)
+    size_t hrec_cap = 0;
+    void ensure_seq(size_t bytes) {
+        if (bytes <= seq_cap) return;
+        if (pinned_seq) cudaFreeHost(pinned_seq);
+        pinned_seq = nullptr;
+        seq_cap = 0;
+        const size_t want = bytes + bytes / 8 + (1u << 20);
+        ICK(cudaMallocHost(&pinned_seq, want));
+        seq_cap = want;
+    }
+    void ensure_hrec(size_t reads) {
+        if (reads <= hrec_cap) return;
+        if (h_rec) cudaFreeHost(h_rec);
+        h_rec = nullptr;
+        hrec_cap = 0;
+        const size_t want = reads + reads / 8 + 1024;
+        ICK(cudaMallocHost(&h_rec, want * 2 * sizeof(uint32_t)));
+        hrec_cap = want;
+    }
     void ensure_host() {
         for (int i = 0; i < 2; ++i)
             if (!pinned[i]) {
@@ -252,7 +276,163 @@ struct ByteSource {
     }
 };
 
+// records (sequence start, raw length in g_stage.d_rec) -> 2-bit words, lengths (0 = dropped), dropped-read count
+void pack_records(const char* text, uint64_t n, uint32_t max_len, uint64_t total_bases, uint32_t first_len, IngestResult& out,
+                  cudaStream_t st, const std::function<void*(size_t)>& alloc) {
+    uint32_t *d_start = g_stage.d_rec, *d_rawlen = g_stage.d_rec + g_stage.rec_cap, *d_bad = g_stage.d_rec + 2 * g_stage.rec_cap;
+    auto dev_alloc = [&](size_t bytes) -> void* {
+        if (alloc) return alloc(bytes);
+        void* p = nullptr;
+        ICK(cudaMalloc(&p, bytes));
+        return p;
+    };
+    auto need_temp = [&](size_t bytes) {
+        if (bytes <= g_stage.temp_cap) return;
+        ICK(cudaStreamSynchronize(st));
+        if (g_stage.d_temp) cudaFree(g_stage.d_temp);
+        g_stage.d_temp = nullptr;
+        g_stage.temp_cap = bytes + bytes / 4 + 1024;
+        ICK(cudaMalloc(&g_stage.d_temp, g_stage.temp_cap));
+    };
+    try {
+        const unsigned rb = (unsigned)((n + 255) / 256);
+        ICK(cudaMemsetAsync(d_bad, 0, n * 4, st));
+        ICK(cudaMemsetAsync(g_stage.d_scalars + 4, 0, sizeof(unsigned long long), st));
+        out.max_len = max_len;
+        out.total_bases = total_bases;
+        out.first_read_len = first_len;
+        out.n_reads = n;
+        out.b_lens = std::max<uint64_t>(1, n) * 4;
+        out.d_lens = (uint32_t*)dev_alloc(out.b_lens);
+        if (out.max_len <= SHORT_READ_MAX) {
+            uint32_t stride = std::max(1u, (out.max_len + 15) / 16);
+            stride += stride & 1u;  // even: every read starts 8-byte aligned (wide loads in the screen kernel)
+            out.stride_words = stride;
+            out.b_words = (n * (uint64_t)stride + 2) * 4;
+            out.d_words = (uint32_t*)dev_alloc(out.b_words);
+            const uint64_t items = n * (uint64_t)stride;
+            pack_stride_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n, stride, out.d_words, d_bad);
+        } else {
+            out.b_off = (n + 1) * 8;
+            out.d_word_off = (uint64_t*)dev_alloc(out.b_off);
+            unsigned long long* d_nw = nullptr;
+            ICK(cudaMalloc(&d_nw, (n + 1) * 8));
+            ICK(cudaMemsetAsync(d_nw + n, 0, 8, st));
+            nwords_kernel<<<rb, 256, 0, st>>>(d_rawlen, n, d_nw);
+            size_t t2 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
+            need_temp(t2);
+            cub::DeviceScan::ExclusiveSum(g_stage.d_temp, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
+            unsigned long long total_words = 0;
+            ICK(cudaMemcpyAsync(&total_words, out.d_word_off + n, 8, cudaMemcpyDeviceToHost, st));
+            ICK(cudaStreamSynchronize(st));
+            cudaFree(d_nw);
+            out.b_words = (total_words + 2) * 4;
+            out.d_words = (uint32_t*)dev_alloc(out.b_words);
+            pack_ragged_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n,
+                                                                                (const unsigned long long*)out.d_word_off, out.d_words, d_bad);
+        }
+        finish_lens_kernel<<<rb, 256, 0, st>>>(d_rawlen, d_bad, n, out.d_lens, g_stage.d_scalars);
+        ICK(cudaGetLastError());
+        ICK(cudaMemcpyAsync(g_stage.h_scalars, g_stage.d_scalars, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ICK(cudaStreamSynchronize(st));
+        out.n_dropped = g_stage.h_scalars[4];
+    } catch (...) {
+        for (void* p : {(void*)out.d_words, (void*)out.d_word_off, (void*)out.d_lens})
+            if (p) cudaFree(p);
+        out = IngestResult();
+        throw;
+    }
+}
+
+void ensure_records(uint64_t n) {  // grow-only scratch: cudaMalloc / cudaFree per sample cost more than the kernels
+    if (n <= g_stage.rec_cap) return;
+    if (g_stage.d_rec) cudaFree(g_stage.d_rec);
+    g_stage.d_rec = nullptr;
+    g_stage.rec_cap = 0;
+    const size_t want = n + n / 8 + 1024;
+    ICK(cudaMalloc(&g_stage.d_rec, want * 3 * sizeof(uint32_t)));
+    g_stage.rec_cap = want;
+}
+
 }  // namespace
+
+// ---- host-framed path: only the sequence lines cross PCIe ------------------------------------------------------------
+// The text (a plain file read in pieces by the pool threads, or a gzip file already inflated into host memory) is cut into
+// slices at record starts; every slice is framed by one thread (fastq_frame.cpp) straight into its own part of a pinned
+// buffer — the sequence lines of the slice [lo, hi) go to offset lo / 2, which cannot collide with the next slice because
+// a record's sequence is less than half of its bytes — and the thread that framed a slice also queues its H2D copy, so
+// the copies overlap the framing of the other slices.  Then (start, length) of every read is uploaded and the same pack
+// kernels as in the device-parsed path run.  false = not strict 4-line FASTQ (nothing is left behind; the caller goes on
+// with the device parser / host parser).
+static bool ingest_fastq_framed(const TextSource& src, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
+                                const std::function<void*(size_t)>& alloc) {
+    static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+    const double t0 = now_ms_i();
+    if (src.size < 8 || src.size / 2 + 64 >= 0xfff00000ull) return false;  // 32-bit sequence offsets
+    ICK(cudaSetDevice(device));
+    g_stage.ensure_host();
+    g_stage.ensure_seq(src.size / 2 + 64);
+    g_stage.ensure_device(device, src.size / 2 + 64);
+    char* const pinned = g_stage.pinned_seq;
+    char* const d_text = g_stage.d_text;
+    std::vector<FramedSlice> sl;
+    std::atomic<bool> cuda_failed{false};
+    const bool is_fastq = fastq_frame_text(src, threads, pinned, sl, [&](size_t at, size_t bytes) {
+        if (cudaSetDevice(device) != cudaSuccess ||
+            cudaMemcpyAsync(d_text + at, pinned + at, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            cuda_failed = true;
+            return false;
+        }
+        return true;
+    });
+    if (!is_fastq || cuda_failed) {
+        cudaStreamSynchronize(st);  // the queued copies read the pinned buffer
+        cudaGetLastError();
+        if (cuda_failed) throw std::runtime_error("reads file: upload error");
+        return false;
+    }
+    const size_t S = sl.size();
+    const double t1 = now_ms_i();
+    // ---- totals, then (start, length) of every read to the device
+    FrameStats T;
+    std::vector<size_t> first(S + 1, 0);
+    bool have_first = false;
+    for (size_t s = 0; s < S; ++s) {
+        const FrameStats& z = sl[s].st;
+        first[s + 1] = first[s] + z.n_reads;
+        if (z.n_reads && !have_first) {
+            T.first_len = z.first_len;
+            have_first = true;
+        }
+        T.max_len = std::max(T.max_len, z.max_len);
+        T.total_bases += z.total_bases;
+    }
+    const uint64_t n = first[S];
+    if (n == 0) {
+        cudaStreamSynchronize(st);
+        return false;
+    }
+    if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
+    g_stage.ensure_hrec(n);
+    ensure_records(n);
+    uint32_t* h_start = g_stage.h_rec;
+    uint32_t* h_len = g_stage.h_rec + g_stage.hrec_cap;
+    parallel_for(S, [&](size_t s) {
+        const size_t k = sl[s].lens.size();
+        if (!k) return;
+        memcpy(h_start + first[s], sl[s].starts.data(), k * 4);
+        memcpy(h_len + first[s], sl[s].lens.data(), k * 4);
+    }, std::max<size_t>(1, std::min<size_t>(threads, 8)));
+    ICK(cudaMemcpyAsync(g_stage.d_rec, h_start, n * 4, cudaMemcpyHostToDevice, st));
+    ICK(cudaMemcpyAsync(g_stage.d_rec + g_stage.rec_cap, h_len, n * 4, cudaMemcpyHostToDevice, st));
+    const double t2 = now_ms_i();
+    pack_records(d_text, n, T.max_len, T.total_bases, T.first_len, out, st, alloc);
+    if (timing)
+        fprintf(stderr, "[drprg-cuda] ingest (host-framed): %.1f MB text in %zu slices, frame + queue H2D %.2f ms, record table %.2f ms, "
+                        "upload tail + pack %.2f ms\n", src.size / 1e6, S, t1 - t0, t2 - t1, now_ms_i() - t2);
+    return true;
+}
 
 bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
                          const std::function<void*(size_t)>& alloc, const char* mem, size_t mem_size) {
@@ -280,11 +460,20 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
     } else if (got < 1 || magic[0] != '@') {
         return false;  // FASTA, leading blank lines, empty file: host parser
     }
-    if (!is_gz && src.fsize >= 0xfff00000ull) return false;  // 32-bit text offsets
-
     std::lock_guard<std::mutex> lock(g_stage.m);
     static const bool timing = getenv("DRPRG_TIMING") != nullptr;
+    // DRPRG_INGEST=device keeps the device-side parser below (the second implementation; tests compare the two)
+    static const bool framed_on = !(getenv("DRPRG_INGEST") && std::string(getenv("DRPRG_INGEST")) == "device");
+    if (framed_on && !is_gz) {
+        TextSource ts;
+        ts.fd = src.fd;
+        ts.mem = mem;
+        ts.size = src.fsize;
+        if (ingest_fastq_framed(ts, device, threads, out, st, alloc)) return true;
+        out = IngestResult();
+    }
     const double ti0 = now_ms_i();
+    if (!is_gz && src.fsize >= 0xfff00000ull) return false;  // 32-bit text offsets
     ICK(cudaSetDevice(device));
     g_stage.ensure_host();
     g_stage.ensure_device(device, is_gz ? std::max<size_t>(src.fsize * 4, 1u << 20) : src.fsize + 1);
@@ -357,79 +546,18 @@ bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, 
     const uint64_t n = n_lines / 4;
     if (n > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
     // ---- records
-    if (n > g_stage.rec_cap) {  // grow-only scratch: cudaMalloc / cudaFree per sample cost more than the kernels
-        if (g_stage.d_rec) cudaFree(g_stage.d_rec);
-        g_stage.d_rec = nullptr;
-        g_stage.rec_cap = n + n / 8 + 1024;
-        ICK(cudaMalloc(&g_stage.d_rec, g_stage.rec_cap * 3 * sizeof(uint32_t)));
-    }
-    uint32_t *d_start = g_stage.d_rec, *d_rawlen = g_stage.d_rec + g_stage.rec_cap, *d_bad = g_stage.d_rec + 2 * g_stage.rec_cap;
-    auto cleanup = [&]() {};
-    auto dev_alloc = [&](size_t bytes) -> void* {
-        if (alloc) return alloc(bytes);
-        void* p = nullptr;
-        ICK(cudaMalloc(&p, bytes));
-        return p;
-    };
-    try {
-        ICK(cudaMemsetAsync(d_bad, 0, n * 4, st));
+    ensure_records(n);
+    uint32_t *d_start = g_stage.d_rec, *d_rawlen = g_stage.d_rec + g_stage.rec_cap;
+    {
         const unsigned rb = (unsigned)((n + 255) / 256);
         fastq_records_kernel<<<rb, 256, 0, st>>>(text, g_stage.d_nl, n, d_start, d_rawlen, g_stage.d_scalars);
         ICK(cudaMemcpyAsync(g_stage.h_scalars, g_stage.d_scalars, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         uint32_t first_len = 0;
         ICK(cudaMemcpyAsync(&first_len, d_rawlen, 4, cudaMemcpyDeviceToHost, st));
         ICK(cudaStreamSynchronize(st));
-        if (g_stage.h_scalars[1]) {  // '@' / '+' framing broken somewhere: not strict 4-line FASTQ
-            cleanup();
-            return false;
-        }
-        out.max_len = (uint32_t)g_stage.h_scalars[2];
-        out.total_bases = g_stage.h_scalars[3];
-        out.first_read_len = first_len;
-        out.n_reads = n;
-        out.b_lens = std::max<uint64_t>(1, n) * 4;
-        out.d_lens = (uint32_t*)dev_alloc(out.b_lens);
-        if (out.max_len <= SHORT_READ_MAX) {
-            uint32_t stride = std::max(1u, (out.max_len + 15) / 16);
-            stride += stride & 1u;  // even: every read starts 8-byte aligned (wide loads in the screen kernel)
-            out.stride_words = stride;
-            out.b_words = (n * (uint64_t)stride + 2) * 4;
-            out.d_words = (uint32_t*)dev_alloc(out.b_words);
-            const uint64_t items = n * (uint64_t)stride;
-            pack_stride_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n, stride, out.d_words, d_bad);
-        } else {
-            out.b_off = (n + 1) * 8;
-            out.d_word_off = (uint64_t*)dev_alloc(out.b_off);
-            unsigned long long* d_nw = nullptr;
-            ICK(cudaMalloc(&d_nw, (n + 1) * 8));
-            ICK(cudaMemsetAsync(d_nw + n, 0, 8, st));
-            nwords_kernel<<<rb, 256, 0, st>>>(d_rawlen, n, d_nw);
-            size_t t2 = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
-            need_temp(t2);
-            cub::DeviceScan::ExclusiveSum(g_stage.d_temp, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
-            unsigned long long total_words = 0;
-            ICK(cudaMemcpyAsync(&total_words, out.d_word_off + n, 8, cudaMemcpyDeviceToHost, st));
-            ICK(cudaStreamSynchronize(st));
-            cudaFree(d_nw);
-            out.b_words = (total_words + 2) * 4;
-            out.d_words = (uint32_t*)dev_alloc(out.b_words);
-            pack_ragged_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n,
-                                                                                (const unsigned long long*)out.d_word_off, out.d_words, d_bad);
-        }
-        finish_lens_kernel<<<rb, 256, 0, st>>>(d_rawlen, d_bad, n, out.d_lens, g_stage.d_scalars);
-        ICK(cudaGetLastError());
-        ICK(cudaMemcpyAsync(g_stage.h_scalars, g_stage.d_scalars, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        ICK(cudaStreamSynchronize(st));
-        out.n_dropped = g_stage.h_scalars[4];
-    } catch (...) {
-        cleanup();
-        for (void* p : {(void*)out.d_words, (void*)out.d_word_off, (void*)out.d_lens})
-            if (p) cudaFree(p);
-        out = IngestResult();
-        throw;
+        if (g_stage.h_scalars[1]) return false;  // '@' / '+' framing broken somewhere: not strict 4-line FASTQ
+        pack_records(text, n, (uint32_t)g_stage.h_scalars[2], g_stage.h_scalars[3], first_len, out, st, alloc);
     }
-    cleanup();
     if (timing)
         fprintf(stderr, "[drprg-cuda] ingest: %.1f MB text, read+H2D %.2f ms, newline scan %.2f ms, records+pack %.2f ms\n", total / 1e6,
                 ti1 - ti0, ti2 - ti1, now_ms_i() - ti2);

@@ -144,6 +144,24 @@ def read_fastx(path, threads=8):
     return w, o, l, n.value, tb.value, fl.value
 
 
+def frame_fastq(path, threads=8):
+    """host half of the file ingest (no GPU): (ascii uint8[total_bases], lens uint32[n]) or None when the framer declines"""
+    L = lib()
+    ascii_, lens = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint32)()
+    n, tb, ok = C.c_uint64(), C.c_uint64(), C.c_int()
+    _check(L.drprg_cuda_frame_fastq(str(path).encode(), C.c_uint32(threads), C.byref(ascii_), C.byref(lens), C.byref(n),
+                                    C.byref(tb), C.byref(ok)), "drprg_cuda_frame_fastq")
+    try:
+        if not ok.value:
+            return None
+        a = np.ctypeslib.as_array(ascii_, (max(1, tb.value),)).copy()[:tb.value]
+        l = np.ctypeslib.as_array(lens, (max(1, n.value),)).copy()[:n.value]
+    finally:
+        for p in (ascii_, lens):
+            L.drprg_cuda_host_free(p)
+    return a, l
+
+
 class Batch:
     def __init__(self, index, handle, n_reads, keep=()):
         self.index, self.h, self.n_reads, self._keep = index, handle, n_reads, keep

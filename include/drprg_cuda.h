@@ -104,6 +104,12 @@ int64_t drprg_cuda_pack_reads(const uint8_t* ascii, const uint64_t* off, uint64_
 int drprg_cuda_read_fastx(const char* path, uint32_t threads, uint32_t** words, uint64_t** word_off, uint32_t** lens,
                           uint64_t* n_reads, uint64_t* total_bases, uint32_t* first_read_len);
 void drprg_cuda_host_free(void*);
+/* host half of the file ingest (test hook, no GPU): frames a plain strict 4-line FASTQ on the IO threads exactly as
+ * drprg_cuda_map_genotype does before the upload; *ascii = the sequence lines back to back in read order, *lens = their
+ * lengths.  Returns 0 and *is_fastq = 0 for input the framer declines (FASTA, wrapped records, blank lines: the
+ * general parser takes those).  Replaces the reads-file reader behind /root/reference/src/predict.rs:166-170. */
+int drprg_cuda_frame_fastq(const char* path, uint32_t threads, uint8_t** ascii, uint32_t** lens, uint64_t* n_reads,
+                           uint64_t* total_bases, int* is_fastq);
 
 /* H2D copy of a packed batch (pinned staging inside).  read_id_base = global id of the batch's first read. */
 int drprg_cuda_batch_upload(drprg_index*, const uint32_t* words, const uint64_t* word_off /* NULL if stride */,

@@ -508,6 +508,18 @@ def test_device_fastq_ingest_long_reads_and_fallbacks(tmp_path):
     assert not info["parsed_on_device"] and info["n_reads"] == 10
 
 
+@pytest.mark.parametrize("env", [{"DRPRG_INGEST": "device"}, {"DRPRG_FRAME_SLICE": "2048"}])
+def test_file_ingest_variants_keep_parity(env):
+    """the reads file reaches the GPU in two ways: framed on the host (default: only the sequence lines cross PCIe; here
+    also with 2 KB slices so that every test file is cut at many record boundaries) or as raw text parsed by the device
+    kernels (DRPRG_INGEST=device, the second implementation).  Both must build the host parser's batch."""
+    import subprocess, sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "device_fastq_ingest or drop_in_call or cli_drop_in"], env=e, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def _panel_path_reads(seed, n, lens_choices):
     """reads cut from the toy panel's reference sequences (so their minimizers are indexed), random strand, a few
     substitutions, assorted lengths; plus homopolymer / repeat / non-ACGT / random decoys"""

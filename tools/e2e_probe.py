@@ -1,22 +1,23 @@
-"""Drop-in call from a FASTQ file (drprg_cuda_map_genotype): wall time with the device FASTQ parser vs the host parser.
+"""Drop-in call from a FASTQ file (drprg_cuda_map_genotype): wall time with the host-framed ingest (default), the device
+FASTQ parser (DRPRG_INGEST=device) and the host parser (DRPRG_HOST_INGEST=1).
    python tools/e2e_probe.py [n_reads]"""
 import sys, os, subprocess, json, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "run":
     from drprg_b200 import lib, workload, sim
     fq, gz, prg, refs = sys.argv[2:6]
-    ix = lib.Index(prg, 11, 15); opts = lib.make_opts(illumina=True, threads=16)
+    ix = lib.Index(prg, 11, 15); opts = lib.make_opts(illumina=True, threads=os.cpu_count() or 1)
     out = tempfile.mkdtemp()
     res = {}
     for name, path in (("plain", fq), ("gzip", gz)):
         ts = []
-        for i in range(4):
+        for i in range(6):
             t0 = time.perf_counter(); st = ix.map_genotype(path, refs, out, opts); ts.append((time.perf_counter() - t0) * 1e3)
         res[name] = dict(wall_ms_min=round(min(ts[1:]), 2), ingest_ms=round(st["ms_ingest"], 2), map_ms=round(st["ms_map"], 2),
                          genotype_ms=round(st["ms_genotype"], 2), n_reads=st["n_reads"], records=st["n_records"])
     import hashlib
     res["vcf_sha1"] = hashlib.sha1(b"".join(l for l in open(os.path.join(out, "pandora_genotyped.vcf"), "rb") if not l.startswith(b"##fileDate"))).hexdigest()[:12]
-    print(json.dumps({"host_ingest": os.environ.get("DRPRG_HOST_INGEST", "0"), **res}))
+    print(json.dumps({"host_ingest": os.environ.get("DRPRG_HOST_INGEST", "0"), "ingest": os.environ.get("DRPRG_INGEST", "framed"), **res}))
 else:
     from drprg_b200 import workload, sim
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
@@ -34,5 +35,5 @@ else:
     rec[:, 12 + L:12 + 2 * L] = ord("I"); rec[:, 12 + 2 * L] = 10
     rec.tofile(fq)
     subprocess.run(f"gzip -1 -c {fq} > {gz}", shell=True, check=True)
-    for h in ("0", "1"):
-        subprocess.run([sys.executable, __file__, "run", fq, gz, wl.prg_path, wl.refs_path], env=dict(os.environ, DRPRG_HOST_INGEST=h))
+    for extra in ({}, {"DRPRG_INGEST": "device"}, {"DRPRG_HOST_INGEST": "1"}):
+        subprocess.run([sys.executable, __file__, "run", fq, gz, wl.prg_path, wl.refs_path], env=dict(os.environ, **extra))
