@@ -7,6 +7,7 @@
 
 #include <immintrin.h>
 
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -17,42 +18,6 @@
 
 namespace drprg {
 namespace {
-
-// offsets of the '\n' bytes of p[0..n) into nl (room for cap), stops early when nl is full; returns the count and sets
-// `scanned` to the number of bytes looked at
-__attribute__((target("avx2"))) size_t newlines_avx2(const char* p, size_t n, uint32_t* nl, size_t cap, size_t& scanned) {
-    size_t k = 0, i = 0;
-    const __m256i needle = _mm256_set1_epi8('\n');
-    for (; i + 32 <= n && k + 32 <= cap; i += 32) {
-        const __m256i v = _mm256_loadu_si256((const __m256i*)(p + i));
-        uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, needle));
-        while (m) {
-            nl[k++] = (uint32_t)i + (uint32_t)__builtin_ctz(m);
-            m &= m - 1;
-        }
-    }
-    if (i + 32 > n)
-        for (; i < n && k < cap; ++i)
-            if (p[i] == '\n') nl[k++] = (uint32_t)i;
-    scanned = i;
-    return k;
-}
-size_t newlines_scalar(const char* p, size_t n, uint32_t* nl, size_t cap, size_t& scanned) {
-    size_t k = 0;
-    const char* q = p;
-    const char* e = p + n;
-    while (q < e && k < cap) {
-        const char* h = (const char*)memchr(q, '\n', (size_t)(e - q));
-        if (!h) {
-            q = e;
-            break;
-        }
-        nl[k++] = (uint32_t)(h - p);
-        q = h + 1;
-    }
-    scanned = (size_t)(q - p);
-    return k;
-}
 
 }  // namespace
 
@@ -79,7 +44,7 @@ size_t fastq_next_record(const char* t, size_t n, size_t p) {
 inline bool FastqFramer::line(const char* ls, const char* le) {
     switch (phase_) {
         case 0:
-            if (le - ls < 2 || *ls != '@') return false;  // blank line, empty header or broken framing
+            if (le == ls || *ls != '@') return false;  // blank line or broken framing
             break;
         case 1: {
             size_t len = (size_t)(le - ls);
@@ -93,6 +58,7 @@ inline bool FastqFramer::line(const char* ls, const char* le) {
         }
         case 2:
             if (le == ls || *ls != '+') return false;
+            plus_plain_ = (le - ls == 1);
             break;
         default: {
             size_t len = (size_t)(le - ls);
@@ -105,6 +71,7 @@ inline bool FastqFramer::line(const char* ls, const char* le) {
             S_.min_len = std::min<uint32_t>(S_.min_len, (uint32_t)seq_len_);
             S_.total_bases += seq_len_;
             S_.seq_bytes = fill_;
+            plain_prev_ = plus_plain_;
             break;
         }
     }
@@ -112,23 +79,54 @@ inline bool FastqFramer::line(const char* ls, const char* le) {
     return true;
 }
 
-bool FastqFramer::feed(const char* p, size_t n, size_t& used) {
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    constexpr size_t NL = 4096;
-    uint32_t nl[NL];
-    size_t line_start = 0, at = 0;
-    while (at < n) {
-        const size_t stretch = std::min<size_t>(n - at, 1u << 30);
-        size_t scanned = 0;
-        const size_t k = avx2 ? newlines_avx2(p + at, stretch, nl, NL, scanned) : newlines_scalar(p + at, stretch, nl, NL, scanned);
-        for (size_t i = 0; i < k; ++i) {
-            const size_t le = at + nl[i];
-            if (!line(p + line_start, p + le)) return false;
-            line_start = le + 1;
-        }
-        at += scanned;
+// number of '\n' in p[0..n); reads up to 31 bytes past p + n (the callers leave that much readable text behind the span)
+__attribute__((target("avx2,popcnt"))) static inline uint32_t count_newlines_avx2(const char* p, size_t n) {
+    const __m256i needle = _mm256_set1_epi8('\n');
+    uint32_t c = 0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32)
+        c += (uint32_t)__builtin_popcount((uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), needle)));
+    if (i < n) {
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), needle));
+        c += (uint32_t)__builtin_popcount(m & (uint32_t)((1ull << (n - i)) - 1ull));
     }
-    used = line_start;
+    return c;
+}
+
+bool FastqFramer::feed(const char* p, size_t n, size_t& used) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+    size_t at = 0;  // always a line start
+    for (;;) {
+        // A record whose sequence is as long as the previous one's (every Illumina file): after the header line the
+        // other three line ends are where they were last time; one vector pass confirms that the span holds exactly those
+        // three newlines, so the record is framed without looking for its lines one by one.
+        if (avx2 && phase_ == 0 && plain_prev_ && at < n) {
+            const char* r = p + at;
+            const char* he = (const char*)memchr(r, '\n', n - at);
+            if (!he) break;
+            const size_t L = seq_len_, h = (size_t)(he - r);  // r[h] = end of the header line
+            const size_t n2 = h + 1 + L, n3 = n2 + 2, n4 = n3 + 1 + L;
+            if (at + n4 + 33 <= n && h >= 1 && r[0] == '@' && r[n2] == '\n' && r[n2 + 1] == '+' && r[n3] == '\n' && r[n4] == '\n' &&
+                r[h - 1] != '\r' && (L == 0 || (r[n2 - 1] != '\r' && r[n4 - 1] != '\r')) && count_newlines_avx2(r + h + 1, n4 - h) == 3 &&
+                fill_ + L <= cap_ && base_ + fill_ + L <= 0xfffffff0ull) {
+                memcpy(out_ + fill_, r + h + 1, L);
+                starts_.push_back(base_ + (uint32_t)fill_);
+                lens_.push_back((uint32_t)L);
+                fill_ += L;
+                ++S_.n_reads;
+                S_.total_bases += L;
+                S_.seq_bytes = fill_;
+                at += n4 + 1;
+                continue;
+            }
+        }
+        if (at >= n) break;
+        const char* le = (const char*)memchr(p + at, '\n', n - at);
+        if (!le) break;
+        if (!line(p + at, le)) return false;
+        at = (size_t)(le - p) + 1;
+    }
+    used = at;
     return true;
 }
 
@@ -202,24 +200,43 @@ bool fastq_frame_text(const TextSource& src, uint32_t threads, char* seq_buf, st
             size_t used = 0;
             ok = F.feed(src.mem + lo, hi - lo, used) && F.finish(src.mem + lo + used, hi - lo - used, hi == src.size);
         } else {
-            constexpr size_t CH = 512u << 10;  // stays in the core's L2: the file bytes reach DRAM once (page cache -> here)
-            if (buf.size() < 2 * CH) buf.resize(2 * CH);
-            size_t at = lo, carry = 0;
-            while (ok && at < hi) {
-                const size_t want = std::min(CH, hi - at);
-                if (buf.size() < carry + want) buf.resize(std::max(buf.size() * 2, carry + want));
-                if (src.read(buf.data() + carry, at, want) != want) {
-                    Z.state = -2;
-                    failed = true;
-                    return;
-                }
-                at += want;
-                size_t used = 0;
-                ok = F.feed(buf.data(), carry + want, used);
-                carry = carry + want - used;
-                if (ok && carry) memmove(buf.data(), buf.data() + used, carry);
+            // default: pread into an L2-resident bounce buffer.  DRPRG_FRAME_MMAP=1 maps the slice instead (populated in one
+            // call, framed in place): it saves the copy but 16+ threads mapping and unmapping contend on the address-space
+            // lock, and the framing is bound by per-core memory bandwidth either way (measured: no gain)
+            static const bool use_mmap = getenv("DRPRG_FRAME_MMAP") && atoi(getenv("DRPRG_FRAME_MMAP")) != 0;
+            static const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+            void* map = MAP_FAILED;
+            size_t map_lo = 0, map_len = 0;
+            if (use_mmap) {
+                map_lo = lo / page * page;
+                map_len = hi - map_lo;
+                map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, src.fd, (off_t)map_lo);
             }
-            ok = ok && F.finish(buf.data(), carry, hi == src.size);
+            if (map != MAP_FAILED) {
+                const char* t = (const char*)map + (lo - map_lo);
+                size_t used = 0;
+                ok = F.feed(t, hi - lo, used) && F.finish(t + used, hi - lo - used, hi == src.size);
+                munmap(map, map_len);
+            } else {
+                constexpr size_t CH = 512u << 10;  // stays in the core's L2
+                if (buf.size() < 2 * CH) buf.resize(2 * CH);
+                size_t at = lo, carry = 0;
+                while (ok && at < hi) {
+                    const size_t want = std::min(CH, hi - at);
+                    if (buf.size() < carry + want) buf.resize(std::max(buf.size() * 2, carry + want));
+                    if (src.read(buf.data() + carry, at, want) != want) {
+                        Z.state = -2;
+                        failed = true;
+                        return;
+                    }
+                    at += want;
+                    size_t used = 0;
+                    ok = F.feed(buf.data(), carry + want, used);
+                    carry = carry + want - used;
+                    if (ok && carry) memmove(buf.data(), buf.data() + used, carry);
+                }
+                ok = ok && F.finish(buf.data(), carry, hi == src.size);
+            }
         }
         if (!ok) {
             Z.state = -1;

@@ -41,6 +41,7 @@ class FastqFramer {
     std::vector<uint32_t>&starts_, &lens_;
     uint32_t phase_ = 0;  // 0 header, 1 sequence, 2 plus, 3 quality
     size_t seq_len_ = 0;
+    bool plus_plain_ = false, plain_prev_ = false;  // the last '+' line was a lone '+'; the last record may serve as a template
     FrameStats S_;
 };
 
