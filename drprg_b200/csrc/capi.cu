@@ -1054,13 +1054,20 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         if (locus_reads[l] <= 0 || !wait_for_locus(l) || plen[l] == 0xffffffffu || plen[l] == 0) return;
         const Locus& L = H.loci[l];
         LocusOut& O = lout[l];
+        static const bool vt = getenv("DRPRG_TIMING_VERIFY") != nullptr;
+        const double v0 = vt ? now_ms() : 0;
         O.kp.assign(path + H.knode_base[l], path + H.knode_base[l] + plen[l]);
         std::vector<uint32_t> lp = local_path_of(L, O.kp);
+        const double v1 = vt ? now_ms() : 0;
         if (locus_coverage_outlier(H, l, O.kp, lp, cov, X->fit.covg)) return;
+        const double v2 = vt ? now_ms() : 0;
         O.present = true;
         auto& S = X->sites[l];
         std::vector<SiteRecord> extra;
         find_ml_path_records(H, l, S.ref_path, lp, S.known, extra);
+        if (vt && l == X->loci_by_size[0])
+            fprintf(stderr, "[drprg-cuda] verify of the largest locus (%u k-mer nodes on the path): local path %.1f us, outlier %.1f us, records %.1f us; published at %.3f ms after tw1\n",
+                    plen[l], (v1 - v0) * 1e3, (v2 - v1) * 1e3, (now_ms() - v2) * 1e3, v0 - tw1);
         if (!extra.empty()) {  // the ML path spells alleles the site table lacks: merge them in for this sample only
             std::vector<SiteRecord> all = S.biallelic;
             for (auto& r : extra) all.push_back(std::move(r));
@@ -1389,6 +1396,28 @@ struct Inflated {  // a gzip reads file inflated ahead of time (batch mode)
     ~Inflated() { free(p); }
 };
 
+// the packed reads an ingest left on the device, as a batch of this index
+drprg_batch* batch_from_ingest(drprg_index* X, const IngestResult& I, uint32_t read_id_base) {
+    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
+    B->owned = true;
+    B->device = X->device;
+    B->d_words = I.d_words;
+    B->d_lens = I.d_lens;
+    B->d_off = I.d_word_off;
+    B->b_words = I.b_words;
+    B->b_lens = I.b_lens;
+    B->b_off = I.b_off;
+    B->R = DevReads{I.d_words, I.d_word_off, I.stride_words, I.d_lens, I.n_reads, read_id_base};
+    B->total_bases = I.total_bases;
+    B->max_len = I.stride_words ? I.stride_words * 16u : I.max_len;
+    if (I.max_len > SHORT_READ_MAX) {  // the segment table is built from the lengths on the host
+        std::vector<uint32_t> lens(I.n_reads);
+        CK(cudaMemcpy(lens.data(), I.d_lens, I.n_reads * 4, cudaMemcpyDeviceToHost));
+        build_segments(X, B.get(), lens.data(), I.n_reads, I.total_bases, 0);
+    }
+    return B.release();
+}
+
 FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threads, const Inflated* pre = nullptr) {
     need_device(X);
     CK(cudaSetDevice(X->device));
@@ -1415,23 +1444,7 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
     const int dev = X->device;
     if (!host_only && ingest_fastq_device(reads_path, X->device, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); },
                                           pre ? pre->p : nullptr, pre ? pre->n : 0)) {
-        std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(new drprg_batch(), free_batch);
-        B->owned = true;
-        B->device = X->device;
-        B->d_words = I.d_words;
-        B->d_lens = I.d_lens;
-        B->d_off = I.d_word_off;
-        B->b_words = I.b_words;
-        B->b_lens = I.b_lens;
-        B->b_off = I.b_off;
-        B->R = DevReads{I.d_words, I.d_word_off, I.stride_words, I.d_lens, I.n_reads, 0};
-        B->total_bases = I.total_bases;
-        B->max_len = I.stride_words ? I.stride_words * 16u : I.max_len;
-        if (I.max_len > SHORT_READ_MAX) {  // the segment table is built from the lengths on the host
-            std::vector<uint32_t> lens(I.n_reads);
-            CK(cudaMemcpy(lens.data(), I.d_lens, I.n_reads * 4, cudaMemcpyDeviceToHost));
-            build_segments(X, B.get(), lens.data(), I.n_reads, I.total_bases, 0);
-        }
+        std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(batch_from_ingest(X, I, 0), free_batch);
         F.B = B.release();
         F.n_dropped = I.n_dropped;
         F.first_read_len = I.first_read_len;
@@ -1449,6 +1462,90 @@ FileBatch batch_from_file(drprg_index* X, const char* reads_path, uint32_t threa
     return F;
 }
 
+// A reads file of any size, mapped wave by wave: plain strict FASTQ (or a gzip file inflated into host memory) is cut at
+// record starts into waves of ~1 GiB of text; every wave is framed on the host, uploaded (sequence lines only), packed and
+// mapped into the sample's accumulators before the next one is read, so a 30 M-read file (9.4 GB of text, BASELINE
+// config 3) needs 0.5 GiB of pinned and 1 GiB of device memory instead of the whole text, and files beyond the 8 GB limit
+// of one ingest still take the fast path.  false = the general path (batch_from_file) must handle the file; a sample
+// that was begun here is begun again there.
+struct WaveTotals {
+    uint64_t n = 0, dropped = 0, bases = 0, hits = 0, kept = 0;
+    uint32_t first_len = 0;
+    size_t waves = 0;
+    double ms_ingest = 0, ms_map = 0;
+};
+bool map_file_in_waves(drprg_index* X, const char* reads_path, const drprg_map_opts* o, const Inflated* pre, WaveTotals& W) {
+    static const bool off = [] {
+        const char* h = getenv("DRPRG_HOST_INGEST");
+        const char* d = getenv("DRPRG_INGEST");
+        return (h && atoi(h) != 0) || (d && std::string(d) == "device");
+    }();
+    if (off || is_multi(X)) return false;
+    static const size_t wave_bytes = [] {
+        const char* e = getenv("DRPRG_WAVE_BYTES");
+        return e && atol(e) > 0 ? (size_t)atol(e) : (size_t)(1u << 30);
+    }();
+    TextSource F;
+    struct Closer {
+        int fd = -1;
+        ~Closer() {
+            if (fd >= 0) close(fd);
+        }
+    } closer;
+    Inflated local;
+    if (!pre && file_is_gzip(reads_path)) {  // gzip: inflated on all host threads first (gzip_inflate.cpp)
+        inflate_file(reads_path, &local.p, &local.n);
+        pre = &local;
+    }
+    if (pre) {
+        F.mem = pre->p;
+        F.size = pre->n;
+    } else {
+        closer.fd = open(reads_path, O_RDONLY);
+        if (closer.fd < 0) throw std::runtime_error(std::string("cannot open ") + reads_path);
+        F.fd = closer.fd;
+        F.size = (size_t)lseek(closer.fd, 0, SEEK_END);
+    }
+    char first = 0;
+    if (F.size < 8 || F.read(&first, 0, 1) != 1 || first != '@') return false;
+    const uint32_t threads = o ? std::max(1u, o->threads) : 1u;
+    const int dev = X->device;
+    std::vector<char> scratch;
+    size_t lo = 0;
+    while (lo < F.size) {
+        size_t hi = F.size - lo <= wave_bytes + wave_bytes / 4 ? F.size : F.boundary(lo + wave_bytes, scratch);
+        if (hi == SIZE_MAX) throw std::runtime_error(std::string("read error in ") + reads_path);
+        if (hi <= lo) hi = F.size;
+        TextSource S;
+        S.fd = F.fd;
+        S.mem = F.mem ? F.mem + lo : nullptr;
+        S.size = hi - lo;
+        S.origin = lo;
+        IngestResult I;
+        const double tw0 = now_ms();
+        if (!ingest_fastq_text(S, dev, threads, I, 0, [dev](size_t bytes) { return g_pool.get(bytes, dev); })) return false;
+        if (W.n + I.n_reads > 0xfffffff0ull) throw std::runtime_error("more than 2^32 reads in one sample");
+        std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(batch_from_ingest(X, I, (uint32_t)W.n), free_batch);
+        if (W.waves == 0) {
+            W.first_len = I.first_read_len;
+            sample_begin(X, o, I.first_read_len);
+        }
+        uint64_t nh = 0, nk = 0;
+        const double tw1 = now_ms();
+        map_batch(X, B.get(), 0, &nh, &nk);
+        W.ms_ingest += tw1 - tw0;
+        W.ms_map += now_ms() - tw1;
+        W.n += I.n_reads;
+        W.dropped += I.n_dropped;
+        W.bases += I.total_bases;
+        W.hits += nh;
+        W.kept += nk;
+        ++W.waves;
+        lo = hi;
+    }
+    return W.waves > 0;
+}
+
 int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, const char* outdir, const drprg_map_opts* o,
                drprg_map_stats* stats, const Inflated* pre = nullptr) {
     need_device(X);
@@ -1457,16 +1554,34 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     // any GPU work is done
     std::ofstream log(std::string(outdir) + "/pandora.log");
     if (!log) throw std::runtime_error(std::string("cannot write ") + outdir + "/pandora.log");
-    FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1, pre);
-    std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(F.B, free_batch);
     struct {
         uint64_t n_dropped, total_bases;
-    } pr{F.n_dropped, B->total_bases};
-    const double t1 = now_ms();
-    sample_begin_any(X, o, F.first_read_len);
-    uint64_t nh = 0, nk = 0;
-    const uint64_t n = B->R.n_reads;
-    map_batch_any(X, B.get(), 0, &nh, &nk);
+    } pr{0, 0};
+    uint64_t nh = 0, nk = 0, n = 0;
+    bool on_device = true;
+    size_t waves = 0;
+    double t1 = t0, wave_ingest_ms = -1, wave_map_ms = 0;
+    WaveTotals W;
+    if (map_file_in_waves(X, reads_path, o, pre, W)) {
+        pr.n_dropped = W.dropped;
+        pr.total_bases = W.bases;
+        nh = W.hits;
+        nk = W.kept;
+        n = W.n;
+        waves = W.waves;
+        wave_ingest_ms = W.ms_ingest;  // ingest and map alternate wave by wave
+        wave_map_ms = W.ms_map;
+    } else {
+        FileBatch F = batch_from_file(X, reads_path, o ? o->threads : 1, pre);
+        std::unique_ptr<drprg_batch, void (*)(drprg_batch*)> B(F.B, free_batch);
+        pr.n_dropped = F.n_dropped;
+        pr.total_bases = B->total_bases;
+        on_device = F.on_device;
+        t1 = now_ms();
+        sample_begin_any(X, o, F.first_read_len);
+        n = B->R.n_reads;
+        map_batch_any(X, B.get(), 0, &nh, &nk);
+    }
     const double t2 = now_ms();
     genotype(X, vcf_refs, "sample");
     std::ofstream vcf(std::string(outdir) + "/pandora_genotyped.vcf");
@@ -1482,14 +1597,14 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     s.n_loci_present = (uint32_t)X->contigs.size();
     s.n_records = (uint32_t)X->records.size();
     s.exp_depth_covg = X->fit.E;
-    s.ms_ingest = t1 - t0;
-    s.ms_map = t2 - t1;
+    s.ms_ingest = wave_ingest_ms >= 0 ? wave_ingest_ms : t1 - t0;
+    s.ms_map = wave_ingest_ms >= 0 ? wave_map_ms : t2 - t1;
     s.ms_genotype = t3 - t2;
     s.ms_total = t3 - t0;
     if (stats) *stats = s;
     log << "drprg-cuda map: reads=" << n << " dropped=" << pr.n_dropped << " bases=" << pr.total_bases << " hits=" << nh
         << " kept=" << nk << " loci=" << s.n_loci_present << " records=" << s.n_records << " E=" << s.exp_depth_covg
-        << " ingest=" << (F.on_device ? "device" : "host") << "\nkernel ms: sketch_lookup=" << X->timings[0] << " sort=" << X->timings[1] << " cluster=" << X->timings[2]
+        << " ingest=" << (waves ? "host-framed, " + std::to_string(waves) + " wave(s)" : on_device ? "device" : "host") << "\nkernel ms: sketch_lookup=" << X->timings[0] << " sort=" << X->timings[1] << " cluster=" << X->timings[2]
         << " coverage=" << X->timings[3] << "\nwall ms: ingest=" << s.ms_ingest << " map=" << s.ms_map
         << " genotype=" << s.ms_genotype << " total=" << s.ms_total << "\n";
     return 0;

@@ -146,7 +146,7 @@ size_t TextSource::read(char* buf, size_t at, size_t n) const {
     }
     size_t done = 0;
     while (done < n) {
-        const ssize_t r = pread(fd, buf + done, n - done, (off_t)(at + done));
+        const ssize_t r = pread(fd, buf + done, n - done, (off_t)(origin + at + done));
         if (r <= 0) break;
         done += (size_t)r;
     }
@@ -208,12 +208,12 @@ bool fastq_frame_text(const TextSource& src, uint32_t threads, char* seq_buf, st
             void* map = MAP_FAILED;
             size_t map_lo = 0, map_len = 0;
             if (use_mmap) {
-                map_lo = lo / page * page;
-                map_len = hi - map_lo;
+                map_lo = (src.origin + lo) / page * page;
+                map_len = src.origin + hi - map_lo;
                 map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, src.fd, (off_t)map_lo);
             }
             if (map != MAP_FAILED) {
-                const char* t = (const char*)map + (lo - map_lo);
+                const char* t = (const char*)map + (src.origin + lo - map_lo);
                 size_t used = 0;
                 ok = F.feed(t, hi - lo, used) && F.finish(t + used, hi - lo - used, hi == src.size);
                 munmap(map, map_len);

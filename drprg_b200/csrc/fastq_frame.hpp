@@ -51,6 +51,7 @@ struct TextSource {
     int fd = -1;
     const char* mem = nullptr;
     size_t size = 0;
+    size_t origin = 0;  // file offset of this source's byte 0 (a wave of a larger file); `mem` already points at byte 0
     size_t read(char* buf, size_t at, size_t n) const;                 // bytes [at, at + n) -> buf; returns the count read
     size_t boundary(size_t b, std::vector<char>& scratch) const;       // first record start at or after byte b (size = none); SIZE_MAX: read error
 };

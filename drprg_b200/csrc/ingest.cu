@@ -434,6 +434,15 @@ static bool ingest_fastq_framed(const TextSource& src, int device, uint32_t thre
     return true;
 }
 
+bool ingest_fastq_text(const TextSource& src, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
+                       const std::function<void*(size_t)>& alloc) {
+    out = IngestResult();
+    std::lock_guard<std::mutex> lock(g_stage.m);
+    if (ingest_fastq_framed(src, device, threads, out, st, alloc)) return true;
+    out = IngestResult();
+    return false;
+}
+
 bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
                          const std::function<void*(size_t)>& alloc, const char* mem, size_t mem_size) {
     out = IngestResult();

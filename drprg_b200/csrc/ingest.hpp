@@ -23,4 +23,11 @@ struct IngestResult {  // device buffers from cudaMalloc, owned by the caller
 bool ingest_fastq_device(const std::string& path, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
                          const std::function<void*(size_t)>& alloc = nullptr, const char* mem = nullptr, size_t mem_size = 0);
 
+struct TextSource;
+// Host-framed ingest of one piece of FASTQ text (a whole file, or a wave of a large one that starts and ends at record
+// starts): only the sequence lines are uploaded (fastq_frame.cpp), then packed on the device.  false = not strict 4-line
+// FASTQ.  The text must be smaller than 8 GB (32-bit offsets into the sequence buffer).
+bool ingest_fastq_text(const TextSource& src, int device, uint32_t threads, IngestResult& out, cudaStream_t st,
+                       const std::function<void*(size_t)>& alloc = nullptr);
+
 }  // namespace drprg

@@ -508,11 +508,14 @@ def test_device_fastq_ingest_long_reads_and_fallbacks(tmp_path):
     assert not info["parsed_on_device"] and info["n_reads"] == 10
 
 
-@pytest.mark.parametrize("env", [{"DRPRG_INGEST": "device"}, {"DRPRG_FRAME_SLICE": "2048"}])
+@pytest.mark.parametrize("env", [{"DRPRG_INGEST": "device"}, {"DRPRG_FRAME_SLICE": "2048"}, {"DRPRG_WAVE_BYTES": "30000", "DRPRG_FRAME_SLICE": "4096"},
+                                 {"DRPRG_FRAME_MMAP": "1", "DRPRG_FRAME_SLICE": "8192"}])
 def test_file_ingest_variants_keep_parity(env):
     """the reads file reaches the GPU in two ways: framed on the host (default: only the sequence lines cross PCIe; here
     also with 2 KB slices so that every test file is cut at many record boundaries) or as raw text parsed by the device
-    kernels (DRPRG_INGEST=device, the second implementation).  Both must build the host parser's batch."""
+    kernels (DRPRG_INGEST=device, the second implementation).  Both must build the host parser's batch.  The drop-in call
+    maps a file wave by wave (DRPRG_WAVE_BYTES, default 1 GiB of text per wave): with 30 KB waves every test file takes
+    several and the VCF must not change."""
     import subprocess, sys
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
