@@ -90,6 +90,28 @@ class Config3(Config2):
         w = (pad.view(n, STRIDE_WORDS, 16) << shifts).sum(-1)
         return ((w + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)  # uint32 bit pattern as int32
 
+    def write_fastq(self, path, n_subshards=None, device="cuda"):
+        """the first n_subshards sub-shards as one plain 4-line FASTQ (fixed-width ids, constant qualities; 315 bytes per
+        read): the file form of the workload for the drop-in call.  Returns the number of reads written."""
+        n_sub = self.n_subshards if n_subshards is None else min(n_subshards, self.n_subshards)
+        L = READ_LEN
+        with open(path, "wb") as f:
+            for i in range(n_sub):
+                codes = self.subshard_codes(i, device).cpu().numpy()
+                n = codes.shape[0]
+                rec = np.empty((n, 11 + L + 3 + L + 1), np.uint8)
+                ids = np.arange(i * n, (i + 1) * n, dtype=np.int64)
+                rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+                for d in range(8):
+                    rec[:, 2 + d] = ord("0") + (ids // 10 ** (7 - d)) % 10
+                rec[:, 10] = 10
+                rec[:, 11:11 + L] = sim.BASES[codes]
+                rec[:, 11 + L], rec[:, 12 + L], rec[:, 13 + L] = 10, ord("+"), 10
+                rec[:, 14 + L:14 + 2 * L] = ord("F")
+                rec[:, 14 + 2 * L] = 10
+                f.write(rec.tobytes())
+        return n_sub * self.SUBSHARD
+
     def subshard_ascii(self, i, device="cuda"):
         """(data, off) like sim.simulate_reads, on the host (CPU baselines, oracle checks)"""
         codes = self.subshard_codes(i, device).cpu().numpy()

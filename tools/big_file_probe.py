@@ -15,21 +15,7 @@ tmp = tempfile.mkdtemp(prefix="drprg_big_", dir=root)
 fq = os.path.join(tmp, "reads.fq")
 L = workload.READ_LEN
 t0 = time.perf_counter()
-with open(fq, "wb") as f:
-    for i in range(wl.n_subshards):
-        codes = wl.subshard_codes(i).cpu().numpy()
-        n = codes.shape[0]
-        rec = np.empty((n, 11 + L + 3 + L + 1), np.uint8)
-        ids = np.arange(i * n, (i + 1) * n, dtype=np.int64)
-        rec[:, 0], rec[:, 1] = ord("@"), ord("r")
-        for d in range(8):
-            rec[:, 2 + d] = ord("0") + (ids // 10 ** (7 - d)) % 10
-        rec[:, 10] = 10
-        rec[:, 11:11 + L] = sim.BASES[codes]
-        rec[:, 11 + L], rec[:, 12 + L], rec[:, 13 + L] = 10, ord("+"), 10
-        rec[:, 14 + L:14 + 2 * L] = ord("F")
-        rec[:, 14 + 2 * L] = 10
-        f.write(rec.tobytes())
+wl.write_fastq(fq)
 t_write = time.perf_counter() - t0
 ix = lib.Index(wl.prg_path, wl.w, wl.k, device=0)
 fo = lib.make_opts(illumina=True, genome_size=workload.GENOME_SIZE, threads=os.cpu_count() or 1)
