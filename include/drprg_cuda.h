@@ -75,7 +75,9 @@ int drprg_cuda_index_write(drprg_index*, const char* prg_path);
  * launches, and the coverage kernel of every non-root GPU adds straight into the root GPU's accumulator over NVLink
  * (peer-mapped memory, red.global.add: integer sums, bit-exact for any GPU count) — the path's only exchange step needs no
  * separate collective.  Every call that takes a drprg_index* works on such a handle (the drop-in call included), so the
- * reference's single blocking call (Pandora::genotype_with, src/lib.rs:580-590) can use the whole box. */
+ * reference's single blocking call (Pandora::genotype_with, src/lib.rs:580-590) can use the whole box.  Sharding pays for
+ * batches that are already packed (drprg_cuda_batch_upload); a reads FILE is bound by the host's framing rate and is
+ * mapped wave by wave on the root GPU. */
 int drprg_cuda_index_load_multi(const char* prg_path, uint32_t w, uint32_t k, int n_gpus, const int* devices, drprg_index** out);
 int drprg_cuda_index_n_gpus(drprg_index*);
 /* (b) one PROCESS per GPU (torchrun / MPI style): the root rank exports its accumulator as a 64-byte CUDA IPC handle,
