@@ -378,14 +378,20 @@ static bool ingest_fastq_framed(const TextSource& src, int device, uint32_t thre
     char* const d_text = g_stage.d_text;
     std::vector<FramedSlice> sl;
     std::atomic<bool> cuda_failed{false};
-    const bool is_fastq = fastq_frame_text(src, threads, pinned, sl, [&](size_t at, size_t bytes) {
-        if (cudaSetDevice(device) != cudaSuccess ||
-            cudaMemcpyAsync(d_text + at, pinned + at, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-            cuda_failed = true;
-            return false;
-        }
-        return true;
-    });
+    bool is_fastq = false;
+    try {
+        is_fastq = fastq_frame_text(src, threads, pinned, sl, [&](size_t at, size_t bytes) {
+            if (cudaSetDevice(device) != cudaSuccess ||
+                cudaMemcpyAsync(d_text + at, pinned + at, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+                cuda_failed = true;
+                return false;
+            }
+            return true;
+        });
+    } catch (...) {
+        cudaStreamSynchronize(st);  // copies of the slices framed so far still read the pinned buffer
+        throw;
+    }
     if (!is_fastq || cuda_failed) {
         cudaStreamSynchronize(st);  // the queued copies read the pinned buffer
         cudaGetLastError();

@@ -65,7 +65,7 @@ SYMBOLS = [
     "drprg_cuda_version", "drprg_cuda_last_error", "drprg_cuda_device_count", "drprg_cuda_index_load",
     "drprg_cuda_index_load_text", "drprg_cuda_index_free", "drprg_cuda_index_load_multi", "drprg_cuda_index_n_gpus", "drprg_cuda_index_write",
     "drprg_cuda_shard_root", "drprg_cuda_shard_attach", "drprg_cuda_shard_done", "drprg_cuda_map_genotype", "drprg_cuda_map_genotype_batch",
-    "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_batch_from_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
+    "drprg_cuda_pack_reads", "drprg_cuda_read_fastx", "drprg_cuda_frame_fastq", "drprg_cuda_batch_from_fastx", "drprg_cuda_host_free", "drprg_cuda_batch_upload",
     "drprg_cuda_batch_wrap_device", "drprg_cuda_batch_free", "drprg_cuda_sample_begin", "drprg_cuda_map_batch",
     "drprg_cuda_accum_device_ptr", "drprg_cuda_accum_download", "drprg_cuda_accum_upload", "drprg_cuda_genotype",
     "drprg_cuda_write_vcf", "drprg_cuda_vcf_text", "drprg_cuda_vcf_view", "drprg_cuda_index_info", "drprg_cuda_locus_name",

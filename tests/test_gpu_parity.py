@@ -519,7 +519,7 @@ def test_file_ingest_variants_keep_parity(env):
     import subprocess, sys
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "device_fastq_ingest or drop_in_call or cli_drop_in"], env=e, capture_output=True, text=True)
+                        "device_fastq_ingest or drop_in_call or cli_drop_in or batch_of_samples"], env=e, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
