@@ -1,5 +1,5 @@
 """profiles/r2_screen.json + .md from an `ncu --set full` capture of screen_kernel / resolve_kernel on a 1 M-read batch:
-   ncu -i rep --page raw --csv > raw.csv ; python tools/make_screen_profile.py raw.csv n_reads out_prefix"""
+   ncu -i rep --page raw --csv > raw.csv ; python tools/make_screen_profile.py raw.csv n_reads out_prefix [how]"""
 import csv
 import json
 import sys
@@ -46,7 +46,7 @@ d = {
     "warp_instr_per_read_resolve": per["resolve"]["warp_instr"] / n_reads,
     "dram_bytes_per_million_reads": (per["screen"]["dram_read_bytes"] + per["screen"]["dram_write_bytes"] + per["resolve"]["dram_read_bytes"] + per["resolve"]["dram_write_bytes"]) * scale,
     "kernels": per,
-    "how": "ncu --set full --clock-control none on one launch of each kernel (cold caches, serialised); see profiles/README.md",
+    "how": sys.argv[4] if len(sys.argv) > 4 else "ncu --set full --clock-control none on one launch of each kernel (cold caches, serialised); see profiles/README.md",
 }
 json.dump(d, open(out + ".json", "w"), indent=1)
 with open(out + ".md", "w") as f:
