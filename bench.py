@@ -62,7 +62,8 @@ def workload_config(wl, total_reads):
     """identical in both arms (the driver compares the dicts)"""
     from drprg_b200 import workload
     return {"workload": wl.name, "reads_total": int(total_reads), "read_len": workload.READ_LEN,
-            "sharding": "reads split evenly over the GPUs (strong scaling), index replicated, genotype step on the root"}
+            "sharding": "contiguous shards of the reads, one per GPU (strong scaling; even for `value`, sized by each rank's measured upload "
+                        "bandwidth for `e2e`), index replicated, genotype step on the root"}
 
 
 class ClockSampler:
@@ -316,9 +317,23 @@ def main():
     for j, i in enumerate(mine):
         d_words[j * wl.SUBSHARD:(j + 1) * wl.SUBSHARD] = wl.pack_codes(wl.subshard_codes(i))
     d_lens = torch.full((n,), workload.READ_LEN, dtype=torch.int32, device="cuda")
-    h_words = torch.empty((n, workload.STRIDE_WORDS), dtype=torch.int32).pin_memory()
-    h_words.copy_(d_words)
-    h_lens = torch.full((n,), workload.READ_LEN, dtype=torch.int32).pin_memory()
+    # The host-buffer (e2e) loop shards by measured upload bandwidth: on the 8-GPU boxes of this pool the eight concurrent
+    # H2D streams do not get equal shares of the host's memory / PCIe paths (tools/h2d_concurrency.py: 21.7 GB/s each for
+    # GPUs 0-3, 33.3 GB/s each for GPUs 4-7, 51.6 GB/s alone), and a step ends when the slowest upload does.  Every rank
+    # still maps a contiguous range of the same 240 sub-shards; the sum over ranks is the same 30 M reads.
+    mine_e2e, h2d_gbps = mine, None
+    if world > 1 and os.environ.get("DRPRG_E2E_SHARDS", "bandwidth") == "bandwidth":
+        h2d_gbps = sharded.concurrent_h2d_gbps(torch, dist)
+        mine_e2e = sharded.proportional_subshards(wl.n_subshards, h2d_gbps, rank)
+    n_e = len(mine_e2e) * wl.SUBSHARD
+    id_base_e = mine_e2e.start * wl.SUBSHARD
+    h_words = torch.empty((n_e, workload.STRIDE_WORDS), dtype=torch.int32).pin_memory()
+    if mine_e2e == mine:
+        h_words.copy_(d_words)
+    else:
+        for j, i in enumerate(mine_e2e):
+            h_words[j * wl.SUBSHARD:(j + 1) * wl.SUBSHARD].copy_(wl.pack_codes(wl.subshard_codes(i)))
+    h_lens = torch.full((n_e,), workload.READ_LEN, dtype=torch.int32).pin_memory()
     torch.cuda.synchronize()
 
     ix = lib.Index(wl.prg_path, wl.w, wl.k, device=local_rank)
@@ -356,7 +371,7 @@ def main():
         return hot_path(resident)
 
     def step_e2e():
-        b = ix.upload_ptrs(h_words.data_ptr(), h_lens.data_ptr(), n, workload.STRIDE_WORDS, total_bases, read_id_base=id_base)
+        b = ix.upload_ptrs(h_words.data_ptr(), h_lens.data_ptr(), n_e, workload.STRIDE_WORDS, n_e * workload.READ_LEN, read_id_base=id_base_e)
         try:
             return hot_path(b)
         finally:
@@ -413,7 +428,7 @@ def main():
     issue_peak = ix.issue_peak() if rank == 0 else 0.0
     vcf_text = bytes(vcf_text) if vcf_text is not None else b""
     n_records = sum(1 for l in vcf_text.splitlines() if not l.startswith(b"#"))
-    h2d = int(h_words.numel() * 4 + h_lens.numel() * 4) * world
+    h2d = int(total_reads * (workload.STRIDE_WORDS * 4 + 4))  # all ranks together: words + lengths of the 30 M reads
     d2h = int(len(vcf_text) + 4096)
 
     line = {
@@ -427,7 +442,9 @@ def main():
                            if reduce_mode == "fused" else "NCCL allreduce of the accumulator (torch.distributed)"),
                 "vcf_records": n_records, "vcf_sha1": hashlib.sha1(b"\n".join(l for l in vcf_text.splitlines() if not l.startswith(b"##fileDate"))).hexdigest()},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                "what": "same steps from pinned host buffers: H2D of every rank's packed shard inside the timed region, VCF text read on the host"},
+                "what": "same steps from pinned host buffers: H2D of every rank's packed shard inside the timed region, VCF text read on the host",
+                "reads_per_rank": "even" if mine_e2e == mine or h2d_gbps is None else
+                                  "proportional to each rank's measured concurrent H2D bandwidth: " + ", ".join(f"{g:.0f}" for g in h2d_gbps) + " GB/s"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "stage_ms": {k_: float(np.mean(v_)) for k_, v_ in st.items() if k_ != "hits"},

@@ -124,3 +124,46 @@ def allreduce_accum_host(accum: np.ndarray, group=None) -> np.ndarray:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.numpy()
+
+
+def concurrent_h2d_gbps(torch, dist, mb: int = 64, reps: int = 6):
+    """every rank uploads a pinned buffer to its GPU at the same time: the GB/s each one gets (list over ranks, identical
+    on all ranks).  Used to size the host-buffer shards: a sharded step ends when the slowest upload does."""
+    import time
+    world = dist.get_world_size()
+    h = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    h.fill_(1)
+    d = torch.empty(mb << 20, dtype=torch.uint8, device="cuda")
+    best = 0.0
+    for rnd in range(3):  # the first round warms up; the better of the next two counts
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        gbps = reps * mb / 1024.0 / (time.perf_counter() - t0)
+        if rnd:
+            best = max(best, gbps)
+    t = torch.zeros(world, dtype=torch.float64, device="cuda")
+    t[dist.get_rank()] = best
+    dist.all_reduce(t)
+    return [float(x) for x in t.cpu()]
+
+
+def proportional_subshards(n_subshards: int, weights, rank: int) -> range:
+    """contiguous ranges of sub-shards, sizes proportional to `weights` (largest-remainder apportionment, at least one
+    per rank); returns this rank's range"""
+    w = [max(1e-9, float(x)) for x in weights]
+    tot = sum(w)
+    quota = [n_subshards * x / tot for x in w]
+    cnt = [max(1, int(q)) for q in quota]
+    while sum(cnt) > n_subshards:  # the minimum of one pushed the sum over: take from the largest
+        cnt[cnt.index(max(cnt))] -= 1
+    rem = sorted(range(len(w)), key=lambda i: quota[i] - int(quota[i]), reverse=True)
+    i = 0
+    while sum(cnt) < n_subshards:
+        cnt[rem[i % len(rem)]] += 1
+        i += 1
+    start = sum(cnt[:rank])
+    return range(start, start + cnt[rank])

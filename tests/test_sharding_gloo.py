@@ -70,3 +70,15 @@ def test_sample_shard_covers_every_sample_once():
         parts = [sharded.sample_shard(items, g, r) for r in range(g)]
         assert sorted(sum(parts, [])) == sorted(items)
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_proportional_subshards_partition():
+    """bench.py's host-buffer shards (sized by measured upload bandwidth): contiguous, complete, at least one sub-shard per rank"""
+    from drprg_b200 import sharded
+    for n, w in ((240, [21.7] * 4 + [33.3] * 4), (240, [1, 1]), (240, [50.0]), (8, [50] + [1] * 7), (17, [3, 2, 2, 9, 1])):
+        rs = [sharded.proportional_subshards(n, w, r) for r in range(len(w))]
+        assert rs[0].start == 0 and rs[-1].stop == n
+        assert all(a.stop == b.start for a, b in zip(rs, rs[1:]))
+        assert all(len(r) >= 1 for r in rs)
+    rs = [len(sharded.proportional_subshards(240, [21.7] * 4 + [33.3] * 4, r)) for r in range(8)]
+    assert rs == [24] * 4 + [36] * 4
