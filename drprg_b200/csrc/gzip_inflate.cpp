@@ -13,8 +13,13 @@
 //                     bytes.  Only the 32 KB windows are chained sequentially, the bulk translation is parallel.
 // (The scheme is the two-pass decompression of Kerbiriou & Chikhi, "Parallel decompression of gzip-compressed files and
 // random access to DNA sequences", 2019 — restated here, no code taken.)
-// The CRC-32 and length of every member are verified (zlib's crc32 on the chunks, combined); any failure — a corrupt
-// file, or a stream this decoder does not handle — makes the caller fall back to zlib's sequential gzread.
+// Concatenated members (`cat a.gz b.gz`, lanes of one sample) and bgzip / BGZF files (one member per <= 64 KB) are handled
+// by the same passes: a gzip member header close behind a nominal chunk boundary is the preferred chunk start (nothing
+// before it can be referenced: no unknown window), and a chunk decodes through any member ends on its way, recording each
+// member's trailer.
+// The CRC-32 and length of EVERY member are verified (PCLMUL CRC-32 on the pieces between member ends, combined across
+// chunk boundaries); any failure — a corrupt file, or a stream this decoder does not handle — makes the caller fall back
+// to zlib's sequential gzread.
 #include "gzip_inflate.hpp"
 
 #include <immintrin.h>
@@ -574,10 +579,16 @@ void translate_scalar(const uint16_t* s, uint8_t* d, size_t n, const uint8_t* L)
     for (; i < n; ++i) d[i] = L[s[i]];
 }
 
+struct MemberEnd {
+    size_t out_pos;        // symbols of the chunk's output that belong to members ending at or before this one
+    uint32_t crc, len;     // the member's trailer
+};
 struct Chunk {
-    size_t start_bit = 0;     // first block of the chunk
-    size_t end_bit = 0;       // after its last block
+    size_t start_bit = 0;     // first block of the chunk, or (member_start) the first byte of a gzip member header, in bits
+    size_t end_bit = 0;       // after its last block / member
     bool unknown_window = true;
+    bool member_start = false;         // the chunk begins with a member header: nothing before it can be referenced
+    std::vector<MemberEnd> members;    // members that end inside this chunk
     SymBuf out;
     Stop stop = Stop::Error;
     bool ok = false;
@@ -585,6 +596,74 @@ struct Chunk {
     uint8_t last_window[WIN];  // resolved
     uint32_t last_n = 0;
 };
+
+// first gzip member header at a byte offset in [from_byte, to_byte) whose deflate data starts with blocks that decode as
+// text (concatenated .gz files, bgzip / BGZF blocks); SIZE_MAX if none.  A member start is the best chunk start there is:
+// back-references cannot cross it, so the chunk needs no unknown window.
+size_t find_member_start(const uint8_t* p, size_t n, size_t from_byte, size_t to_byte) {
+    size_t at = from_byte;
+    while (at + 18 < n && at < to_byte) {
+        const uint8_t* h = (const uint8_t*)memchr(p + at, 0x1f, std::min(to_byte, n - 18) - at);
+        if (!h) return SIZE_MAX;
+        at = (size_t)(h - p);
+        if (p[at + 1] == 0x8b && p[at + 2] == 8 && (p[at + 3] & 0xe0) == 0) {
+            const size_t q = skip_gzip_header(p, n, at);
+            if (q != SIZE_MAX && q + 8 <= n) {
+                Bits b(p, n, q * 8);
+                SymBuf tmp;
+                tmp.init_empty();
+                size_t end = 0;
+                if (decode_blocks(b, tmp, SIZE_MAX, true, 2, end) != Stop::Error) return at;
+            }
+        }
+        ++at;
+    }
+    return SIZE_MAX;
+}
+
+// Decodes a chunk: from its start (a block start inside a member, or a member header) through any number of member
+// boundaries up to `limit_bit` — the start of the next chunk (same two kinds) — or, for the last chunk, to the end of the
+// file.  Every member that ends inside the chunk is recorded with its trailer.  false: corrupt data, a wrong start guess,
+// or the chunk did not end exactly where the next one starts.
+bool decode_chunk(const uint8_t* gz, size_t n, Chunk& c, size_t limit_bit, bool last) {
+    size_t pos_bit = c.start_bit;
+    bool at_header = c.member_start;
+    for (;;) {
+        if (at_header) {
+            const size_t byte = pos_bit >> 3;
+            if (!last && pos_bit == limit_bit) {
+                c.end_bit = pos_bit;
+                return true;
+            }
+            if (byte == n) {  // end of the file
+                c.end_bit = pos_bit;
+                return last;
+            }
+            if (!last && pos_bit > limit_bit) return false;
+            const size_t q = skip_gzip_header(gz, n, byte);
+            if (q == SIZE_MAX || q + 8 > n) return false;
+            pos_bit = q * 8;
+        }
+        Bits b(gz, n, pos_bit);
+        size_t end = pos_bit;
+        const Stop r = decode_blocks(b, c.out, last ? SIZE_MAX : limit_bit, false, SIZE_MAX, end);
+        if (r == Stop::Error) return false;
+        if (r == Stop::Limit) {  // stopped after a block at or beyond the next chunk's first block
+            c.end_bit = end;
+            return !last && end == limit_bit;
+        }
+        // end of a member: trailer, then the next header (or the end of the file)
+        const size_t trailer = (end + 7) / 8;
+        if (trailer + 8 > n) return false;
+        MemberEnd m;
+        m.out_pos = c.out.size();
+        memcpy(&m.crc, gz + trailer, 4);
+        memcpy(&m.len, gz + trailer + 4, 4);
+        c.members.push_back(m);
+        pos_bit = (trailer + 8) * 8;
+        at_header = true;
+    }
+}
 
 }  // namespace
 
@@ -613,7 +692,21 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     parallel_for_io(T - 1, [&](size_t i) {
         const size_t t = i + 1;
         const size_t hi = t + 1 < T ? guess[t + 1] : (n - 8) * 8;
-        ch[t].start_bit = find_block_start(gz, n, guess[t], hi);
+        // a member header close behind the nominal boundary (bgzip: every <= 64 KB; `cat a.gz b.gz`: wherever the files
+        // meet) is taken as it is; otherwise the first dynamic block start, unless a member starts before it
+        const size_t near = std::min(hi >> 3, (guess[t] >> 3) + (256u << 10));
+        size_t m = find_member_start(gz, n, guess[t] >> 3, near);
+        if (m == SIZE_MAX) {
+            const size_t blk = find_block_start(gz, n, guess[t], hi);
+            m = find_member_start(gz, n, near, blk == SIZE_MAX ? (hi >> 3) : (blk >> 3));
+            if (m == SIZE_MAX) {
+                ch[t].start_bit = blk;
+                return;
+            }
+        }
+        ch[t].start_bit = m * 8;
+        ch[t].member_start = true;
+        ch[t].unknown_window = false;
     }, n_threads);
     const double t1 = now();
     // chunks whose start was not found are merged into their predecessor
@@ -629,28 +722,19 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         if (c.unknown_window) c.out.init_unknown();
         else c.out.init_empty();
         c.out.reserve(WIN + (size_t)((n / T) * 4));
-        Bits b(gz, n, c.start_bit);
-        const size_t limit = t + 1 < T ? live[t + 1].start_bit : SIZE_MAX;
-        c.stop = decode_blocks(b, c.out, limit, false, SIZE_MAX, c.end_bit);
-        c.ok = (t + 1 < T) ? (c.stop == Stop::Limit && c.end_bit == limit) : (c.stop == Stop::EndOfMember);
+        c.ok = decode_chunk(gz, n, c, t + 1 < T ? live[t + 1].start_bit : SIZE_MAX, t + 1 == T);
     }, n_threads);
     const double t2 = now();
     for (size_t t = 0; t < T; ++t)
         if (!live[t].ok) return false;  // a guessed start was wrong, a member ended early (multi-member file), or corrupt data
-    // trailer of the (single) member: CRC-32 and length
-    const size_t trailer = (live[T - 1].end_bit + 7) / 8;
-    if (trailer + 8 > n) return false;
-    uint32_t want_crc, want_len;
-    memcpy(&want_crc, gz + trailer, 4);
-    memcpy(&want_len, gz + trailer + 4, 4);
-    if (trailer + 8 != n) return false;  // further members or trailing bytes: the sequential reader handles those
+    // the last chunk must have run to the end of the file, through the last member's trailer
+    if ((live[T - 1].end_bit >> 3) != n || live[T - 1].members.empty()) return false;
     // ---- 3. resolve: chain the 32 KB windows, then translate everything in parallel
     size_t total = 0;
     for (size_t t = 0; t < T; ++t) {
         live[t].out_off = total;
         total += live[t].out.size();
     }
-    if ((uint32_t)total != want_len) return false;
     for (size_t t = 0; t < T; ++t) {
         Chunk& c = live[t];
         const size_t sz = c.out.size();
@@ -681,7 +765,7 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     const double t3 = now();
     char* text = (char*)malloc(total + 1);
     if (!text) return false;
-    std::vector<uint32_t> crcs(T, 0);
+    std::vector<std::vector<uint32_t>> crcs(T);  // per chunk: CRC-32 of every piece between member ends
     std::vector<double> tt(T, 0), tc(T, 0), tf(T, 0);
     parallel_for_io(T, [&](size_t t) {
         Chunk& c = live[t];
@@ -700,7 +784,14 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         if (avx2) translate_avx2(s, d, sz, lut.data());
         else translate_scalar(s, d, sz, lut.data());
         const double a1 = timing ? now() : 0;
-        crcs[t] = crc32_fast(d, sz);
+        {   // the chunk's output is cut at the member ends inside it; the pieces are combined per member afterwards
+            size_t from = 0;
+            for (size_t i = 0; i <= c.members.size(); ++i) {
+                const size_t to = i < c.members.size() ? c.members[i].out_pos : sz;
+                crcs[t].push_back(to > from ? crc32_fast(d + from, to - from) : 0u);
+                from = to;
+            }
+        }
         const double a2 = timing ? now() : 0;
         c.out.release();
         if (timing) {
@@ -709,12 +800,34 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
             tf[t] = now() - a2;
         }
     }, n_threads);
-    uint32_t crc = 0;
+    // every member's CRC-32 and length (mod 2^32), pieces combined across chunk boundaries
     bool ok = true;
-    for (size_t t = 0; t < T; ++t) {
-        crc = t == 0 ? crcs[0] : (uint32_t)crc32_combine(crc, crcs[t], (z_off_t)(t + 1 < T ? live[t + 1].out_off - live[t].out_off : total - live[t].out_off));
+    {
+        uint32_t run_crc = 0;
+        size_t run_len = 0, n_members = 0;
+        for (size_t t = 0; t < T && ok; ++t) {
+            const Chunk& c = live[t];
+            const size_t sz = total - c.out_off - (t + 1 < T ? total - live[t + 1].out_off : 0);
+            size_t from = 0;
+            for (size_t i = 0; i <= c.members.size() && ok; ++i) {
+                const size_t to = i < c.members.size() ? c.members[i].out_pos : sz;
+                const size_t len = to - from;
+                if (len) {
+                    run_crc = run_len ? (uint32_t)crc32_combine(run_crc, crcs[t][i], (z_off_t)len) : crcs[t][i];
+                    run_len += len;
+                }
+                if (i < c.members.size()) {
+                    ok = run_crc == c.members[i].crc && (uint32_t)run_len == c.members[i].len;
+                    run_crc = 0;
+                    run_len = 0;
+                    ++n_members;
+                }
+                from = to;
+            }
+        }
+        ok = ok && run_len == 0 && n_members > 0;
     }
-    if (!ok || crc != want_crc) {
+    if (!ok) {
         free(text);
         return false;
     }

@@ -40,8 +40,8 @@ def test_single_stream_levels(tmp_path, level):
     check(gz, d, o, threads=3)
 
 
-def test_multi_member_and_header_fields_fall_back(tmp_path):
-    """concatenated members (bgzip / cat a.gz b.gz) and optional header fields: declined or handled, result identical"""
+def test_multi_member_and_header_fields(tmp_path):
+    """concatenated members (cat a.gz b.gz) and optional header fields (file name): result identical to zlib's"""
     d, o = fastq_text(40_000, 150, 3)
     raw = tmp_path / "r.fq"
     sim.write_fastq_fast(str(raw), d, o)
@@ -82,6 +82,37 @@ def test_corrupt_stream_is_an_error_not_garbage(tmp_path):
     blob = bytearray(co.compress(raw.read_bytes()) + co.flush())
     blob[len(blob) // 2] ^= 0x5A
     bad = tmp_path / "bad.fq.gz"
+    bad.write_bytes(bytes(blob))
+    with pytest.raises(lib.DrprgCudaError):
+        lib.read_fastx(bad, threads=8)
+
+
+def test_bgzf_blocks_and_many_members(tmp_path):
+    """bgzip-style input (every <= 64 KB of text its own gzip member, plus the empty EOF member) and `cat a.gz b.gz c.gz`
+    of members of different sizes and levels: chunks start at member headers, members end inside chunks, every member's
+    CRC-32 and length is verified"""
+    d, o = fastq_text(70_000, 150, 9)
+    raw = tmp_path / "r.fq"
+    sim.write_fastq_fast(str(raw), d, o)
+    text = raw.read_bytes()
+    bg = tmp_path / "r.fq.bgz.gz"
+    with open(bg, "wb") as f:
+        for i in range(0, len(text), 65280):
+            f.write(gzip.compress(text[i:i + 65280], 6, mtime=0))
+        f.write(gzip.compress(b"", 6, mtime=0))
+    check(bg, d, o)
+    check(bg, d, o, threads=3)
+    cuts = [0, len(text) // 7, len(text) // 7 + 100, len(text) // 2, len(text)]
+    cat = tmp_path / "cat.fq.gz"
+    with open(cat, "wb") as f:
+        for i, (a, b) in enumerate(zip(cuts, cuts[1:])):
+            f.write(gzip.compress(text[a:b], (1, 9, 6, 1)[i], mtime=i))
+    check(cat, d, o)
+    # one member's CRC damaged: never garbage
+    blob = bytearray(cat.read_bytes())
+    first_len = len(gzip.compress(text[cuts[0]:cuts[1]], 1, mtime=0))
+    blob[first_len - 8] ^= 0x01  # CRC field of the first member
+    bad = tmp_path / "badcrc.fq.gz"
     bad.write_bytes(bytes(blob))
     with pytest.raises(lib.DrprgCudaError):
         lib.read_fastx(bad, threads=8)
