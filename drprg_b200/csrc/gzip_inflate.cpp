@@ -679,9 +679,17 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         const char* e = getenv("DRPRG_PARALLEL_GZIP_CHUNK");
         return e && atol(e) > 0 ? (size_t)atol(e) : (size_t)(1u << 20);
     }();
-    // more chunks than threads: the chunks decode at different speeds and are handed out dynamically
+    // more chunks than threads (they decode at different speeds and are handed out dynamically), and never more than
+    // 8 MB of compressed bytes per chunk: a large file becomes many chunks that are decoded GROUP BY GROUP, so the 16-bit
+    // symbol buffers (2 bytes per byte of text) only ever exist for one group
     const size_t n_threads = std::max(1u, threads);
-    size_t T = std::max<size_t>(1, std::min<size_t>({n_threads * 4, (size_t)512, (n - data0) / chunk_min}));
+    static const size_t group_env = [] {  // tests set a small group so that small files take several
+        const char* e = getenv("DRPRG_PARALLEL_GZIP_GROUP");
+        return e && atol(e) > 0 ? (size_t)atol(e) : (size_t)0;
+    }();
+    const size_t group = group_env ? group_env : n_threads * 4;
+    const size_t chunk_bytes = std::min<size_t>(std::max<size_t>(chunk_min, (n - data0) / (n_threads * 4)), std::max<size_t>(chunk_min, 8u << 20));
+    size_t T = std::max<size_t>(1, std::min<size_t>((n - data0) / chunk_bytes, (size_t)1 << 16));
     if (T < 2) return false;  // small files: zlib is as fast
     // ---- 1. chunk starts
     std::vector<Chunk> ch(T);
@@ -716,90 +724,113 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         if (t == 0 || ch[t].start_bit != SIZE_MAX) live.push_back(std::move(ch[t]));
     T = live.size();
     if (T < 2) return false;
-    // ---- 2. decode every chunk up to the start of the next one
-    parallel_for_io(T, [&](size_t t) {
-        Chunk& c = live[t];
-        if (c.unknown_window) c.out.init_unknown();
-        else c.out.init_empty();
-        c.out.reserve(WIN + (size_t)((n / T) * 4));
-        c.ok = decode_chunk(gz, n, c, t + 1 < T ? live[t + 1].start_bit : SIZE_MAX, t + 1 == T);
-    }, n_threads);
-    const double t2 = now();
-    for (size_t t = 0; t < T; ++t)
-        if (!live[t].ok) return false;  // a guessed start was wrong, a member ended early (multi-member file), or corrupt data
+    // ---- 2 + 3, group by group: decode every chunk up to the start of the next one; chain the 32 KB windows; translate
+    char* text = nullptr;
+    size_t total = 0;
+    struct TextGuard {  // freed unless the function succeeds
+        char*& p;
+        bool keep = false;
+        ~TextGuard() {
+            if (!keep) {
+                free(p);
+                p = nullptr;
+            }
+        }
+    } guard{text};
+    std::vector<std::vector<uint32_t>> crcs(T);  // per chunk: CRC-32 of every piece between member ends
+    std::vector<size_t> out_size(T, 0);
+    std::vector<double> tt(T, 0), tc(T, 0), tf(T, 0);
+    double ms_decode = 0, ms_chain = 0, ms_translate = 0;
+    for (size_t g0 = 0; g0 < T; g0 += group) {
+        const size_t g1 = std::min(T, g0 + group);
+        const double ta = now();
+        parallel_for_io(g1 - g0, [&](size_t i) {
+            const size_t t = g0 + i;
+            Chunk& c = live[t];
+            if (c.unknown_window) c.out.init_unknown();
+            else c.out.init_empty();
+            c.out.reserve(WIN + (size_t)((n / T) * 4));
+            c.ok = decode_chunk(gz, n, c, t + 1 < T ? live[t + 1].start_bit : SIZE_MAX, t + 1 == T);
+        }, n_threads);
+        const double tb = now();
+        for (size_t t = g0; t < g1; ++t)
+            if (!live[t].ok) return false;  // a guessed start was wrong, or corrupt data
+        for (size_t t = g0; t < g1; ++t) {
+            Chunk& c = live[t];
+            c.out_off = total;
+            out_size[t] = c.out.size();
+            total += out_size[t];
+            const size_t sz = out_size[t];
+            const uint32_t keep = (uint32_t)std::min<size_t>(WIN, sz);
+            // window after this chunk = last WIN bytes of (previous window ++ this chunk's output)
+            uint8_t w[WIN];
+            uint32_t have = 0;
+            if (keep < WIN && t > 0) {
+                const uint32_t from_prev = std::min<uint32_t>(WIN - keep, live[t - 1].last_n);
+                memcpy(w, live[t - 1].last_window + (live[t - 1].last_n - from_prev), from_prev);
+                have = from_prev;
+            }
+            const uint16_t* s = c.out.p + WIN + (sz - keep);
+            for (uint32_t i = 0; i < keep; ++i) {
+                uint16_t x = s[i];
+                if (x & UNKNOWN) {
+                    if (t == 0) return false;
+                    const uint32_t off = x & 0x7fffu;  // index into the previous window, which holds its last last_n bytes
+                    const Chunk& pc = live[t - 1];
+                    if (off < WIN - pc.last_n) return false;  // before the start of the text
+                    x = pc.last_window[off - (WIN - pc.last_n)];
+                }
+                w[have + i] = (uint8_t)x;
+            }
+            c.last_n = have + keep;
+            memcpy(c.last_window, w, c.last_n);
+        }
+        const double tc0 = now();
+        {   // the text grows by this group's output (realloc moves large blocks by remapping, not by copying)
+            char* q = (char*)realloc(text, total + 1);
+            if (!q) return false;
+            text = q;
+        }
+        parallel_for_io(g1 - g0, [&](size_t i) {
+            const size_t t = g0 + i;
+            Chunk& c = live[t];
+            const size_t sz = out_size[t];
+            const uint16_t* s = c.out.p + WIN;
+            uint8_t* d = (uint8_t*)text + c.out_off;
+            const Chunk* pc = t ? &live[t - 1] : nullptr;
+            // one table turns every symbol into its byte: 0..255 map to themselves, 0x8000 | i to byte i of the window
+            // before this chunk (a reference before the start of the text maps to 0 and fails the CRC check below)
+            std::vector<uint8_t> lut(65536, 0);
+            for (uint32_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+            if (pc)
+                for (uint32_t off = WIN - pc->last_n; off < WIN; ++off) lut[UNKNOWN | off] = pc->last_window[off - (WIN - pc->last_n)];
+            static const bool avx2 = __builtin_cpu_supports("avx2");
+            const double a0 = timing ? now() : 0;
+            if (avx2) translate_avx2(s, d, sz, lut.data());
+            else translate_scalar(s, d, sz, lut.data());
+            const double a1 = timing ? now() : 0;
+            {   // the chunk's output is cut at the member ends inside it; the pieces are combined per member afterwards
+                size_t from = 0;
+                for (size_t k = 0; k <= c.members.size(); ++k) {
+                    const size_t to = k < c.members.size() ? c.members[k].out_pos : sz;
+                    crcs[t].push_back(to > from ? crc32_fast(d + from, to - from) : 0u);
+                    from = to;
+                }
+            }
+            const double a2 = timing ? now() : 0;
+            c.out.release();
+            if (timing) {
+                tt[t] = a1 - a0;
+                tc[t] = a2 - a1;
+                tf[t] = now() - a2;
+            }
+        }, n_threads);
+        ms_decode += tb - ta;
+        ms_chain += tc0 - tb;
+        ms_translate += now() - tc0;
+    }
     // the last chunk must have run to the end of the file, through the last member's trailer
     if ((live[T - 1].end_bit >> 3) != n || live[T - 1].members.empty()) return false;
-    // ---- 3. resolve: chain the 32 KB windows, then translate everything in parallel
-    size_t total = 0;
-    for (size_t t = 0; t < T; ++t) {
-        live[t].out_off = total;
-        total += live[t].out.size();
-    }
-    for (size_t t = 0; t < T; ++t) {
-        Chunk& c = live[t];
-        const size_t sz = c.out.size();
-        const uint32_t keep = (uint32_t)std::min<size_t>(WIN, sz);
-        // window after this chunk = last WIN bytes of (previous window ++ this chunk's output)
-        uint8_t w[WIN];
-        uint32_t have = 0;
-        if (keep < WIN && t > 0) {
-            const uint32_t from_prev = std::min<uint32_t>(WIN - keep, live[t - 1].last_n);
-            memcpy(w, live[t - 1].last_window + (live[t - 1].last_n - from_prev), from_prev);
-            have = from_prev;
-        }
-        const uint16_t* s = c.out.p + WIN + (sz - keep);
-        for (uint32_t i = 0; i < keep; ++i) {
-            uint16_t x = s[i];
-            if (x & UNKNOWN) {
-                if (t == 0) return false;
-                const uint32_t off = x & 0x7fffu;  // index into the previous window, which holds its last last_n bytes
-                const Chunk& pc = live[t - 1];
-                if (off < WIN - pc.last_n) return false;  // before the start of the text
-                x = pc.last_window[off - (WIN - pc.last_n)];
-            }
-            w[have + i] = (uint8_t)x;
-        }
-        c.last_n = have + keep;
-        memcpy(c.last_window, w, c.last_n);
-    }
-    const double t3 = now();
-    char* text = (char*)malloc(total + 1);
-    if (!text) return false;
-    std::vector<std::vector<uint32_t>> crcs(T);  // per chunk: CRC-32 of every piece between member ends
-    std::vector<double> tt(T, 0), tc(T, 0), tf(T, 0);
-    parallel_for_io(T, [&](size_t t) {
-        Chunk& c = live[t];
-        const size_t sz = c.out.size();
-        const uint16_t* s = c.out.p + WIN;
-        uint8_t* d = (uint8_t*)text + c.out_off;
-        const Chunk* pc = t ? &live[t - 1] : nullptr;
-        // one table turns every symbol into its byte: 0..255 map to themselves, 0x8000 | i to byte i of the window before
-        // this chunk (a reference before the start of the text maps to 0 and fails the CRC check below)
-        std::vector<uint8_t> lut(65536, 0);
-        for (uint32_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
-        if (pc)
-            for (uint32_t off = WIN - pc->last_n; off < WIN; ++off) lut[UNKNOWN | off] = pc->last_window[off - (WIN - pc->last_n)];
-        static const bool avx2 = __builtin_cpu_supports("avx2");
-        const double a0 = timing ? now() : 0;
-        if (avx2) translate_avx2(s, d, sz, lut.data());
-        else translate_scalar(s, d, sz, lut.data());
-        const double a1 = timing ? now() : 0;
-        {   // the chunk's output is cut at the member ends inside it; the pieces are combined per member afterwards
-            size_t from = 0;
-            for (size_t i = 0; i <= c.members.size(); ++i) {
-                const size_t to = i < c.members.size() ? c.members[i].out_pos : sz;
-                crcs[t].push_back(to > from ? crc32_fast(d + from, to - from) : 0u);
-                from = to;
-            }
-        }
-        const double a2 = timing ? now() : 0;
-        c.out.release();
-        if (timing) {
-            tt[t] = a1 - a0;
-            tc[t] = a2 - a1;
-            tf[t] = now() - a2;
-        }
-    }, n_threads);
     // every member's CRC-32 and length (mod 2^32), pieces combined across chunk boundaries
     bool ok = true;
     {
@@ -807,7 +838,7 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         size_t run_len = 0, n_members = 0;
         for (size_t t = 0; t < T && ok; ++t) {
             const Chunk& c = live[t];
-            const size_t sz = total - c.out_off - (t + 1 < T ? total - live[t + 1].out_off : 0);
+            const size_t sz = out_size[t];
             size_t from = 0;
             for (size_t i = 0; i <= c.members.size() && ok; ++i) {
                 const size_t to = i < c.members.size() ? c.members[i].out_pos : sz;
@@ -827,11 +858,9 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
         }
         ok = ok && run_len == 0 && n_members > 0;
     }
-    if (!ok) {
-        free(text);
-        return false;
-    }
+    if (!ok) return false;
     text[total] = 0;
+    guard.keep = true;
     *out = text;
     *out_n = total;
     if (timing) {
@@ -841,9 +870,9 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
             sc += tc[t];
             sf += tf[t];
         }
-        fprintf(stderr, "[drprg-cuda] parallel gunzip: %zu chunks, %.1f MB -> %.1f MB, block search %.1f ms, decode %.1f ms, window chain %.1f ms, "
-                        "translate + crc %.1f ms (thread-ms: translate %.0f, crc %.0f, free %.0f)\n", T,
-                n / 1e6, total / 1e6, t1 - t0, t2 - t1, t3 - t2, now() - t3, st, sc, sf);
+        fprintf(stderr, "[drprg-cuda] parallel gunzip: %zu chunks in groups of %zu, %.1f MB -> %.1f MB, block search %.1f ms, decode %.1f ms, "
+                        "window chain %.1f ms, translate + crc %.1f ms (thread-ms: translate %.0f, crc %.0f, free %.0f)\n", T, group,
+                n / 1e6, total / 1e6, t1 - t0, ms_decode, ms_chain, ms_translate, st, sc, sf);
     }
     return true;
 }

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 os.environ.setdefault("DRPRG_PARALLEL_GZIP_CHUNK", "65536")  # read once by the library: cut even small files into chunks
+os.environ.setdefault("DRPRG_PARALLEL_GZIP_GROUP", "5")      # ... and decode them in groups of five (large files: 4 x threads)
 
 from drprg_b200 import lib, sim
 
