@@ -655,8 +655,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint8_t* __restrict__ needs_mean, MlUnitsDev L, const uint32_t* __restrict__ level_singles, ModelParams P,
     uint32_t* __restrict__ path, uint32_t* __restrict__ path_len, uint32_t max_nodes, uint32_t max_edges,
     volatile uint32_t* done,     // done != nullptr: path / path_len are host-mapped and done[l] tells the host that locus l is there
-    const double* d_thresh,      // != nullptr: the probability threshold is read from device memory (computed by prob_thresh_kernel)
-    uint32_t dbg) {              // timing experiments only (DRPRG_ML_DBG): bit 0 skips the lifting pointers, bit 1 the division, bit 2 the choice loop's compare chain
+    const double* d_thresh) {    // != nullptr: the probability threshold is read from device memory (computed by prob_thresh_kernel)
     extern __shared__ double s_dyn[];
     const uint32_t l = blockIdx.x;
     if (l >= n_loci) return;
@@ -709,14 +708,12 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     uint32_t s0, ns;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(s0), "=r"(ns) : "r"(lvs));
     for (uint32_t u = 0; u < n_levels; ++u) {
-        if (dbg & 128u) break;
         uint32_t s1, ns1;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(s1), "=r"(ns1) : "r"(lvs + 8u * (u + 1)));
         const uint32_t lo = single_warp ? s0 : s0 + ns, hi = single_warp ? s0 + ns : s1;
         s0 = s1;
         ns = ns1;
         for (uint32_t idx = lo + sub; idx < hi; idx += 64) {
-            if ((dbg & 8u) || ((dbg & 4u) && !single_warp) || ((dbg & 16u) && single_warp)) break;
             const uint32_t a = lds32(lvn + 4u * idx);
             double Mj = 0.0;
             uint32_t lenj = 0, prevj = term;
@@ -732,7 +729,6 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                 lds_len_t(v, lv, tv);
                 const double Mv = lds64(v + L_M);
                 if (v == term || lv > 0u) {
-                    if (dbg & 1u) { sts32(a + L_UP, v); Tj = tv; } else
                     Tj = level_link(a, v, steps2);  // independent of the sums below: overlaps them
                     prevj = v;
                     lenj = 1 + lv;
@@ -766,7 +762,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                     max_mean = is_term ? thresh : mean_v;
                     if (!is_term) max_len = lv;
                 }
-                if (lenj) { if (dbg & 1u) { sts32(a + L_UP, prevj); Tj = prevj; } else Tj = level_link(a, prevj, steps2); }
+                if (lenj) Tj = level_link(a, prevj, steps2);
             }
             if (!lenj) {  // dead end (or no acceptable successor): points at the terminus like pandora's default
 #pragma unroll
@@ -774,7 +770,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
             }
             sts_pair32(a + L_LEN, lenj, Tj);
             if (e0w & 1u) {  // 0/0 = NaN for a dead end: never chosen, like pandora
-                const double mean_j = (dbg & 2u) ? Mj : div_small(Mj, lenj);
+                const double mean_j = div_small(Mj, lenj);
                 asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + L_M), "d"(Mj), "d"(mean_j));
             } else {
                 sts64(a + L_M, Mj);
@@ -784,7 +780,7 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     }
     if (tid == 0) {
         uint32_t cnt = 0, p = lds32(recs + L_UP);
-        while (p != term && cnt < n && !(dbg & 64u)) {
+        while (p != term && cnt < n) {
             path[base + cnt++] = (p - recs) / REC;
             p = lds32(p + L_UP);
         }
@@ -817,26 +813,10 @@ bool launch_mlpath(uint32_t n_loci, const uint32_t* d_knode_base, const uint32_t
             MlUnitsDev L{d_locus_level_off, d_level_start, d_level_nodes};
             upload_rcp_table();
             const bool streamed = h_path && h_path_len && h_done;  // results straight into host-mapped memory, locus by locus
-            static const uint32_t ml_dbg = getenv("DRPRG_ML_DBG") ? (uint32_t)atoi(getenv("DRPRG_ML_DBG")) : 0u;
-            cudaEvent_t dbg_e0 = nullptr, dbg_e1 = nullptr;
-            if (ml_dbg) {
-                cudaEventCreate(&dbg_e0);
-                cudaEventCreate(&dbg_e1);
-                cudaEventRecord(dbg_e0, st);
-            }
             mlpath_level_kernel<<<n_loci, ML_LEVEL_THREADS, lvl_smem, st>>>(
                 n_loci, d_knode_base, d_edge_off, d_edges, d_prob, d_locus_reads, d_needs_mean, L, d_level_singles, P,
                 streamed ? h_path : d_path, streamed ? h_path_len : d_path_len, max_locus_knodes, max_locus_edges,
-                streamed ? h_done : nullptr, d_thresh, ml_dbg);
-            if (ml_dbg) {  // timing experiment: the kernel's own duration, whatever the host makes of its (wrong) paths
-                cudaEventRecord(dbg_e1, st);
-                cudaEventSynchronize(dbg_e1);
-                float ms = 0;
-                cudaEventElapsedTime(&ms, dbg_e0, dbg_e1);
-                fprintf(stderr, "[drprg-cuda] DRPRG_ML_DBG=%u: mlpath_level_kernel %.4f ms\n", ml_dbg, ms);
-                cudaEventDestroy(dbg_e0);
-                cudaEventDestroy(dbg_e1);
-            }
+                streamed ? h_done : nullptr, d_thresh);
             ++g_launches;
             return streamed;
         }
