@@ -1,7 +1,9 @@
 // `pandora`-argv-compatible front end of libdrprg_cuda: lets an unmodified drprg use the GPU path through its
 // own -p/--pandora option (/root/reference/src/predict.rs:137-144).  `map` (the argv built at
-// /root/reference/src/lib.rs:594-617 + src/predict.rs:288-294) runs on the GPU; every other sub-command
-// (`index`, `discover`: src/lib.rs:479-578) is handed to the real pandora named by $DRPRG_REAL_PANDORA.
+// /root/reference/src/lib.rs:594-617 + src/predict.rs:288-294) runs on the GPU; `index` (argv of src/lib.rs:479-510,
+// `-t N -w W -k K <prg>` at src/predict.rs:283 and src/builder.rs:644-657) is served by the library's own index builder,
+// which writes <prg>.kK.wW.idx and kmer_prgs/ in pandora's layout (no GPU needed); every other sub-command (`discover`:
+// src/lib.rs:513-578) is handed to the real pandora named by $DRPRG_REAL_PANDORA.
 #include <unistd.h>
 
 #include <cstdio>
@@ -16,13 +18,41 @@
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: pandora_cuda map [pandora map options] <prg> <reads>\n");
+        fprintf(stderr, "usage: pandora_cuda map [pandora map options] <prg> <reads> | pandora_cuda index [-t N] [-w W] [-k K] <prg>\n");
         return 2;
+    }
+    if (strcmp(argv[1], "index") == 0) {
+        uint32_t w = 14, k = 15;  // pandora's defaults; drprg always passes -w and -k
+        std::string prg;
+        for (int i = 2; i < argc; ++i) {
+            std::string a = argv[i];
+            auto val = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
+            if (a == "-w") w = (uint32_t)atoi(val());
+            else if (a == "-k") k = (uint32_t)atoi(val());
+            else if (a == "-t" || a == "--threads") val();
+            else if (a == "-v" || a == "-vv") continue;
+            else if (!a.empty() && a[0] == '-') {
+                fprintf(stderr, "pandora_cuda index: unsupported option %s\n", a.c_str());
+                return 2;
+            } else prg = a;
+        }
+        if (prg.empty()) {
+            fprintf(stderr, "usage: pandora_cuda index [-t N] [-w W] [-k K] <prg>\n");
+            return 2;
+        }
+        drprg_index* idx = nullptr;
+        if (drprg_cuda_index_load(prg.c_str(), w, k, -1 /* host-only handle */, &idx) != 0 || drprg_cuda_index_write(idx, prg.c_str()) != 0) {
+            fprintf(stderr, "pandora_cuda index: %s\n", drprg_cuda_last_error());
+            if (idx) drprg_cuda_index_free(idx);
+            return 1;
+        }
+        drprg_cuda_index_free(idx);
+        return 0;
     }
     if (strcmp(argv[1], "map") != 0) {
         const char* real = getenv("DRPRG_REAL_PANDORA");
         if (!real) {
-            fprintf(stderr, "pandora_cuda: only `map` runs on the GPU; set DRPRG_REAL_PANDORA for `%s`\n", argv[1]);
+            fprintf(stderr, "pandora_cuda: `map` and `index` are served here; set DRPRG_REAL_PANDORA for `%s`\n", argv[1]);
             return 2;
         }
         argv[0] = const_cast<char*>(real);

@@ -72,3 +72,24 @@ def test_written_index_files_round_trip(tmp_path, which, w):
         edges = sorted((int(r.split("\t")[1]), int(r.split("\t")[3])) for r in rows if r.startswith("L\t"))
         want_e = sorted((r_, int(t) - int(base[l])) for r_ in range(n) for t in okn["edges"][eo[int(base[l]) + r_]:eo[int(base[l]) + r_ + 1]])
         assert edges == want_e
+
+
+def test_pandora_cuda_index_subcommand(tmp_path):
+    """`pandora_cuda index -t N -w W -k K <prg>` — the argv drprg builds at src/predict.rs:283 (and src/builder.rs:644-657
+    through Pandora::index_with, src/lib.rs:479-510) — writes the same files as the library call, without a GPU"""
+    import filecmp
+    import subprocess
+    a, b = tmp_path / "a", tmp_path / "b"
+    for d in (a, b):
+        d.mkdir()
+        shutil.copy(TOY_PRG, d / "dr.prg")
+    exe = os.path.join(os.path.dirname(lib.SO_PATH), "pandora_cuda")
+    r = subprocess.run([exe, "index", "-t", "2", "-w", "11", "-k", "15", str(a / "dr.prg")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gx = lib.Index(b / "dr.prg", 11, 15, device=-1)
+    gx.write_pandora_index(b / "dr.prg")
+    assert filecmp.cmp(a / "dr.prg.k15.w11.idx", b / "dr.prg.k15.w11.idx", shallow=False)
+    for name in ("gid", "pncA"):
+        assert filecmp.cmp(a / "kmer_prgs" / "01" / f"{name}.k15.w11.gfa", b / "kmer_prgs" / "01" / f"{name}.k15.w11.gfa", shallow=False)
+    bad = subprocess.run([exe, "index", "-w", "11", "-k", "15", str(tmp_path / "missing.prg")], capture_output=True, text=True)
+    assert bad.returncode != 0 and "cannot open" in bad.stderr
