@@ -676,19 +676,59 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     const uint32_t edg = recs + (max_nodes + 1) * REC;
     const uint32_t lvn = edg + (max_edges + 1) * 4u;  // record addresses in level order
     const uint32_t lvs = (lvn + max_nodes * 4u + 7u) & ~7u;  // per level: first index into lvn, number of single-successor nodes (8-byte aligned pairs)
-    for (uint32_t i = tid; i <= n; i += ML_LEVEL_THREADS) {
-        const uint32_t a = recs + i * REC;
-        if (i < n) sts64(a + L_PR, prob[base + i]);
-        sts32(a + L_EOFF, (edg + (edge_off[base + i] - e_base) * 4u) | (i < n ? (uint32_t)needs_mean[base + i] : 0u));
+    // The locus moves into shared memory in batches of four independent global loads per thread and array: one load per
+    // iteration made the setup a chain of L2 round trips (25 us for the largest locus, measured)
+    constexpr uint32_t UNR = 4, STEP = UNR * ML_LEVEL_THREADS;
+    for (uint32_t i0 = tid; i0 <= n; i0 += STEP) {
+        double pr[UNR];
+        uint32_t eo[UNR], nm[UNR];
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) {
+            const uint32_t i = i0 + u * ML_LEVEL_THREADS;
+            pr[u] = i < n ? prob[base + i] : 0.0;
+            eo[u] = i <= n ? edge_off[base + i] : 0u;
+            nm[u] = i < n ? (uint32_t)needs_mean[base + i] : 0u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) {
+            const uint32_t i = i0 + u * ML_LEVEL_THREADS;
+            const uint32_t a = recs + i * REC;
+            if (i < n) sts64(a + L_PR, pr[u]);
+            if (i <= n) sts32(a + L_EOFF, (edg + (eo[u] - e_base) * 4u) | nm[u]);
+        }
     }
-    for (uint32_t i = tid; i < n_edges; i += ML_LEVEL_THREADS) sts32(edg + i * 4u, recs + edges[e_base + i] * REC);
+    for (uint32_t i0 = tid; i0 < n_edges; i0 += STEP) {
+        uint32_t e[UNR];
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) e[u] = i0 + u * ML_LEVEL_THREADS < n_edges ? edges[e_base + i0 + u * ML_LEVEL_THREADS] : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u)
+            if (i0 + u * ML_LEVEL_THREADS < n_edges) sts32(edg + (i0 + u * ML_LEVEL_THREADS) * 4u, recs + e[u] * REC);
+    }
     const uint32_t u0 = L.locus_unit_off[l], n_levels = L.locus_unit_off[l + 1] - u0;
     const uint32_t s00 = L.unit_start[u0];
-    for (uint32_t i = tid; i <= n_levels; i += ML_LEVEL_THREADS) {
-        sts32(lvs + 8u * i, L.unit_start[u0 + i] - s00);
-        sts32(lvs + 8u * i + 4u, i < n_levels ? level_singles[u0 + i] : 0u);
+    for (uint32_t i0 = tid; i0 <= n_levels; i0 += STEP) {
+        uint32_t us[UNR], ls[UNR];
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) {
+            const uint32_t i = i0 + u * ML_LEVEL_THREADS;
+            us[u] = i <= n_levels ? L.unit_start[u0 + i] : 0u;
+            ls[u] = i < n_levels ? level_singles[u0 + i] : 0u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) {
+            const uint32_t i = i0 + u * ML_LEVEL_THREADS;
+            if (i <= n_levels) sts_pair32(lvs + 8u * i, us[u] - s00, ls[u]);
+        }
     }
-    for (uint32_t i = tid; i + 1 < n; i += ML_LEVEL_THREADS) sts32(lvn + 4u * i, recs + L.unit_nodes[s00 + i] * REC);
+    for (uint32_t i0 = tid; i0 + 1 < n; i0 += STEP) {
+        uint32_t un[UNR];
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u) un[u] = i0 + u * ML_LEVEL_THREADS + 1 < n ? L.unit_nodes[s00 + i0 + u * ML_LEVEL_THREADS] : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < UNR; ++u)
+            if (i0 + u * ML_LEVEL_THREADS + 1 < n) sts32(lvn + 4u * (i0 + u * ML_LEVEL_THREADS), recs + un[u] * REC);
+    }
     const double tol = 0.000001;
     const double thresh = d_thresh ? *d_thresh : P.thresh;
     const uint32_t term = recs + (n - 1) * REC;
@@ -778,13 +818,32 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        uint32_t cnt = 0, p = lds32(recs + L_UP);
-        while (p != term && cnt < n) {
-            path[base + cnt++] = (p - recs) / REC;
-            p = lds32(p + L_UP);
+    // The chosen path, element i = the node i + 1 steps below the source: every thread walks to its own elements through
+    // the lifting pointers (64-step hops, then the low bits) instead of one thread following 700 successor pointers one
+    // after the other (18 us on the largest locus, measured).  The terminus points at itself on every level, so a walk
+    // that overshoots stays there; the path ends at the first element that is the terminus.
+    __shared__ uint32_t s_cnt;
+    if (tid == 0) s_cnt = n;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += ML_LEVEL_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint32_t x = term;
+        if (i < n) {
+            x = recs;
+            const uint32_t steps = i + 1;
+            for (uint32_t q = steps >> 6; q; --q) x = lds32(x + L_UP + 4u * 6u);
+#pragma unroll
+            for (int b = 5; b >= 0; --b)
+                if ((steps >> b) & 1u) x = lds32(x + L_UP + 4u * b);
+            if (x != term) path[base + i] = (x - recs) / REC;
+            else atomicMin(&s_cnt, i);
         }
-        path_len[l] = cnt;
+        if (__syncthreads_or(x == term)) break;
+    }
+    if (done) __threadfence_system();  // this thread's part of the path, before the flag below
+    __syncthreads();
+    if (tid == 0) {
+        path_len[l] = s_cnt;
         if (done) {  // the loci finish at different times (170 .. 860 levels): the host verifies each one as it lands
             __threadfence_system();
             done[l] = 1u;
