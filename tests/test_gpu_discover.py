@@ -64,3 +64,29 @@ def test_panel_sample_low_depth():
     loci, regions = run(prg, refs, d, o, len(g))
     assert len(loci) >= 3
     run(prg, refs, d, o, len(g), covg_threshold=5, min_len=3, max_len=40)
+
+
+def test_one_pass_through_the_pandora_mirror(tmp_path):
+    """the reference-shaped calls: Pandora.genotype_with(..., retain_hits=True) on a reads FILE (mapped wave by wave), then
+    Pandora.discover_candidates() — the same regions and reads as the staged calls on the same reads in memory"""
+    from drprg_b200.pandora import Pandora
+    p, prg, refs = small_panel()
+    d, o, g, pl = panel_sample(p, 12_000, seed=61)
+    fq = tmp_path / "reads.fq"
+    sim.write_fastq(str(fq), d, o)
+    pan = Pandora.from_path()
+    pan.genotype_with(prg, refs, fq, tmp_path, ["-t", "4", "-w", "11", "-k", "15", "-c", "10", "-I"], retain_hits=True)
+    loci_f, regions_f = pan.discover_candidates()
+    # staged reference run (drprg's -g is fixed at the Mtb genome size in genotype_with)
+    gx = lib.Index(prg, 11, 15, device=0)
+    go = lib.make_opts(illumina=True, genome_size=4411532)
+    words, woff, lens = lib.pack_reads(d, o, 10)
+    gx.retain_hits(True)
+    gx.sample_begin(go, 150)
+    gx.map_batch(gx.upload(words, woff, lens, total_bases=int(o[-1]), stride_words=10))
+    gx.genotype(refs)
+    loci_s, regions_s = gx.discover_candidates()
+    assert sorted(loci_f) == sorted(loci_s) and len(regions_f) == len(regions_s) and len(regions_s) > 0
+    for l in loci_s:
+        assert loci_f[l][0] == loci_s[l][0] and (loci_f[l][1] == loci_s[l][1]).all()
+    assert regions_f == regions_s

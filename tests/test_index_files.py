@@ -93,3 +93,17 @@ def test_pandora_cuda_index_subcommand(tmp_path):
         assert filecmp.cmp(a / "kmer_prgs" / "01" / f"{name}.k15.w11.gfa", b / "kmer_prgs" / "01" / f"{name}.k15.w11.gfa", shallow=False)
     bad = subprocess.run([exe, "index", "-w", "11", "-k", "15", str(tmp_path / "missing.prg")], capture_output=True, text=True)
     assert bad.returncode != 0 and "cannot open" in bad.stderr
+
+
+def test_pandora_mirror_index_with(tmp_path):
+    """drprg_b200.pandora.Pandora.index_with mirrors Pandora::index_with (src/lib.rs:479-510) with the argv of src/predict.rs:283"""
+    from drprg_b200.pandora import DependencyError, Pandora
+    prg = tmp_path / "dr.prg"
+    shutil.copy(TOY_PRG, prg)
+    pan = Pandora(device=-1)
+    pan.index_with(prg, ["-t", "2", "-w", "14", "-k", "15"])
+    assert (tmp_path / "dr.prg.k15.w14.idx").exists() and (tmp_path / "kmer_prgs" / "01" / "gid.k15.w14.gfa").exists()
+    with pytest.raises(DependencyError):
+        pan.index_with(tmp_path / "missing.prg", ["-w", "14", "-k", "15"])
+    with pytest.raises(DependencyError):
+        pan.index_with(prg, ["--bogus"])
