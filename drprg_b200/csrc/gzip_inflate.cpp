@@ -690,6 +690,8 @@ bool parallel_gunzip(const uint8_t* gz, size_t n, uint32_t threads, char** out, 
     const size_t group = group_env ? group_env : n_threads * 4;
     const size_t chunk_bytes = std::min<size_t>(std::max<size_t>(chunk_min, (n - data0) / (n_threads * 4)), std::max<size_t>(chunk_min, 8u << 20));
     size_t T = std::max<size_t>(1, std::min<size_t>((n - data0) / chunk_bytes, (size_t)1 << 16));
+    // whole groups: a last group of a few chunks would leave most threads idle for a full chunk's decode time
+    if (T > group && (n - data0) / ((T + group - 1) / group * group) >= chunk_min) T = (T + group - 1) / group * group;
     if (T < 2) return false;  // small files: zlib is as fast
     // ---- 1. chunk starts
     std::vector<Chunk> ch(T);
