@@ -201,8 +201,9 @@ bool fastq_frame_text(const TextSource& src, uint32_t threads, char* seq_buf, st
             ok = F.feed(src.mem + lo, hi - lo, used) && F.finish(src.mem + lo + used, hi - lo - used, hi == src.size);
         } else {
             // default: pread into an L2-resident bounce buffer.  DRPRG_FRAME_MMAP=1 maps the slice instead (populated in one
-            // call, framed in place): it saves the copy but 16+ threads mapping and unmapping contend on the address-space
-            // lock, and the framing is bound by per-core memory bandwidth either way (measured: no gain)
+            // call, framed in place): it saves the copy, but mapping, populating and unmapping page-cache (tmpfs) pages
+            // from 16 threads costs far more — 10 M reads from a 3.15 GB file: 64 ms with pread, 134-191 ms mapped (1, 4
+            // and 16 MB slices; tools/frame_mmap_ab.sh)
             static const bool use_mmap = getenv("DRPRG_FRAME_MMAP") && atoi(getenv("DRPRG_FRAME_MMAP")) != 0;
             static const size_t page = (size_t)sysconf(_SC_PAGESIZE);
             void* map = MAP_FAILED;
