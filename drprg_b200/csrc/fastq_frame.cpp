@@ -41,6 +41,58 @@ size_t fastq_next_record(const char* t, size_t n, size_t p) {
     return n;
 }
 
+__attribute__((target("avx2"))) static void stream_lines_avx2(char* dst, const char* src, size_t n_lines) {
+    for (size_t i = 0; i < n_lines; ++i) {
+        const __m256i a = _mm256_load_si256((const __m256i*)(src + 64 * i));
+        const __m256i b = _mm256_load_si256((const __m256i*)(src + 64 * i + 32));
+        _mm256_stream_si256((__m256i*)(dst + 64 * i), a);
+        _mm256_stream_si256((__m256i*)(dst + 64 * i + 32), b);
+    }
+}
+
+// stage_ mirrors the destination's position inside a 64-byte line: byte k of the pending output sits at
+// stage_[phase_off_ + k], so whole destination lines are whole (aligned) staging lines
+void FastqFramer::flush(bool all) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    char* dst = out_ + flushed_;
+    const char* src = stage_ + phase_off_;
+    size_t n = staged_;
+    if (!n) return;
+    size_t done = 0;
+    if (avx2 && n >= 128) {
+        const size_t head = phase_off_ ? 64 - phase_off_ : 0;  // up to the first line boundary: ordinary stores
+        if (head) memcpy(dst, src, head);
+        const size_t lines = (n - head) / 64;
+        stream_lines_avx2(dst + head, src + head, lines);
+        done = head + lines * 64;
+    }
+    if (all) {
+        memcpy(dst + done, src + done, n - done);
+        done = n;
+        _mm_sfence();  // the streamed lines are globally visible before the slice's H2D copy is queued
+    }
+    // keep the unflushed tail at its line phase
+    const size_t left = n - done;
+    flushed_ += done;
+    const size_t new_phase = (size_t)((uintptr_t)(out_ + flushed_) & 63u);
+    if (left) memmove(stage_ + new_phase, src + done, left);
+    phase_off_ = new_phase;
+    staged_ = left;
+}
+
+inline void FastqFramer::put(const char* p, size_t len) {
+    if (flushed_ == 0 && staged_ == 0) phase_off_ = (size_t)((uintptr_t)out_ & 63u);
+    while (len) {
+        const size_t room = STAGE - staged_;
+        const size_t take = len < room ? len : room;
+        memcpy(stage_ + phase_off_ + staged_, p, take);
+        staged_ += take;
+        p += take;
+        len -= take;
+        if (staged_ == STAGE) flush(false);
+    }
+}
+
 inline bool FastqFramer::line(const char* ls, const char* le) {
     switch (phase_) {
         case 0:
@@ -50,7 +102,7 @@ inline bool FastqFramer::line(const char* ls, const char* le) {
             size_t len = (size_t)(le - ls);
             if (len && le[-1] == '\r') --len;
             if (fill_ + len > cap_ || base_ + fill_ + len > 0xfffffff0ull) return false;
-            memcpy(out_ + fill_, ls, len);
+            put(ls, len);
             starts_.push_back(base_ + (uint32_t)fill_);
             fill_ += len;
             seq_len_ = len;
@@ -109,7 +161,7 @@ bool FastqFramer::feed(const char* p, size_t n, size_t& used) {
             if (at + n4 + 33 <= n && h >= 1 && r[0] == '@' && r[n2] == '\n' && r[n2 + 1] == '+' && r[n3] == '\n' && r[n4] == '\n' &&
                 r[h - 1] != '\r' && (L == 0 || (r[n2 - 1] != '\r' && r[n4 - 1] != '\r')) && count_newlines_avx2(r + h + 1, n4 - h) == 3 &&
                 fill_ + L <= cap_ && base_ + fill_ + L <= 0xfffffff0ull) {
-                memcpy(out_ + fill_, r + h + 1, L);
+                put(r + h + 1, L);
                 starts_.push_back(base_ + (uint32_t)fill_);
                 lens_.push_back((uint32_t)L);
                 fill_ += L;
@@ -135,6 +187,7 @@ bool FastqFramer::finish(const char* p, size_t n, bool end_of_file) {
         if (!end_of_file) return false;
         if (!line(p, p + n)) return false;
     }
+    flush(true);
     return phase_ == 0;  // the slice must end on a record boundary
 }
 

@@ -35,6 +35,16 @@ class FastqFramer {
 
   private:
     bool line(const char* ls, const char* le);
+    // The sequence bytes go through a small cache-resident staging buffer and leave it as whole 64-byte lines written
+    // with non-temporal stores: an ordinary memcpy into the (pinned, never re-read by the CPU) output would first READ
+    // every destination line into the cache — a quarter of the framing thread's memory traffic.
+    void put(const char* p, size_t len);
+    void flush(bool all);
+    static constexpr size_t STAGE = 8192;
+    alignas(64) char stage_[STAGE + 64];
+    size_t staged_ = 0;    // bytes in stage_ (from stage_ + phase_off_)
+    size_t flushed_ = 0;   // bytes of the output already written
+    size_t phase_off_ = 0; // (out_ + flushed_) & 63 at the last flush: stage_ keeps the destination's line phase
     char* out_;
     size_t cap_, fill_ = 0;
     uint32_t base_;
