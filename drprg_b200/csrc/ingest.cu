@@ -277,8 +277,10 @@ struct ByteSource {
 };
 
 // records (sequence start, raw length in g_stage.d_rec) -> 2-bit words, lengths (0 = dropped), dropped-read count
+// h_lens (optional): the raw lengths on the host — the ragged layout's word offsets are then a host prefix sum uploaded
+// with the other tables (the device-parsed path has the lengths on the device only and scans them there)
 void pack_records(const char* text, uint64_t n, uint32_t max_len, uint64_t total_bases, uint32_t first_len, IngestResult& out,
-                  cudaStream_t st, const std::function<void*(size_t)>& alloc) {
+                  cudaStream_t st, const std::function<void*(size_t)>& alloc, const uint32_t* h_lens = nullptr) {
     uint32_t *d_start = g_stage.d_rec, *d_rawlen = g_stage.d_rec + g_stage.rec_cap, *d_bad = g_stage.d_rec + 2 * g_stage.rec_cap;
     auto dev_alloc = [&](size_t bytes) -> void* {
         if (alloc) return alloc(bytes);
@@ -315,18 +317,29 @@ void pack_records(const char* text, uint64_t n, uint32_t max_len, uint64_t total
         } else {
             out.b_off = (n + 1) * 8;
             out.d_word_off = (uint64_t*)dev_alloc(out.b_off);
-            unsigned long long* d_nw = nullptr;
-            ICK(cudaMalloc(&d_nw, (n + 1) * 8));
-            ICK(cudaMemsetAsync(d_nw + n, 0, 8, st));
-            nwords_kernel<<<rb, 256, 0, st>>>(d_rawlen, n, d_nw);
-            size_t t2 = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
-            need_temp(t2);
-            cub::DeviceScan::ExclusiveSum(g_stage.d_temp, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
             unsigned long long total_words = 0;
-            ICK(cudaMemcpyAsync(&total_words, out.d_word_off + n, 8, cudaMemcpyDeviceToHost, st));
-            ICK(cudaStreamSynchronize(st));
-            cudaFree(d_nw);
+            if (h_lens) {
+                std::vector<uint64_t> off(n + 1);
+                for (uint64_t r = 0; r < n; ++r) {
+                    off[r] = total_words;
+                    total_words += (h_lens[r] + 15u) >> 4;
+                }
+                off[n] = total_words;
+                ICK(cudaMemcpyAsync(out.d_word_off, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+                ICK(cudaStreamSynchronize(st));  // `off` dies with this scope
+            } else {
+                unsigned long long* d_nw = nullptr;
+                ICK(cudaMalloc(&d_nw, (n + 1) * 8));
+                ICK(cudaMemsetAsync(d_nw + n, 0, 8, st));
+                nwords_kernel<<<rb, 256, 0, st>>>(d_rawlen, n, d_nw);
+                size_t t2 = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
+                need_temp(t2);
+                cub::DeviceScan::ExclusiveSum(g_stage.d_temp, t2, d_nw, (unsigned long long*)out.d_word_off, (int64_t)(n + 1), st);
+                ICK(cudaMemcpyAsync(&total_words, out.d_word_off + n, 8, cudaMemcpyDeviceToHost, st));
+                ICK(cudaStreamSynchronize(st));
+                cudaFree(d_nw);
+            }
             out.b_words = (total_words + 2) * 4;
             out.d_words = (uint32_t*)dev_alloc(out.b_words);
             pack_ragged_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(text, d_start, d_rawlen, n,
@@ -433,7 +446,7 @@ static bool ingest_fastq_framed(const TextSource& src, int device, uint32_t thre
     ICK(cudaMemcpyAsync(g_stage.d_rec, h_start, n * 4, cudaMemcpyHostToDevice, st));
     ICK(cudaMemcpyAsync(g_stage.d_rec + g_stage.rec_cap, h_len, n * 4, cudaMemcpyHostToDevice, st));
     const double t2 = now_ms_i();
-    pack_records(d_text, n, T.max_len, T.total_bases, T.first_len, out, st, alloc);
+    pack_records(d_text, n, T.max_len, T.total_bases, T.first_len, out, st, alloc, h_len);
     if (timing)
         fprintf(stderr, "[drprg-cuda] ingest (host-framed): %.1f MB text in %zu slices, frame + queue H2D %.2f ms, record table %.2f ms, "
                         "upload tail + pack %.2f ms\n", src.size / 1e6, S, t1 - t0, t2 - t1, now_ms_i() - t2);
