@@ -1,13 +1,15 @@
-// Device-side ingest of 4-line FASTQ (plain or gzip), SURVEY.md §8f rank 2: the reads file that `drprg predict`
-// hands to the map step (/root/reference/src/predict.rs:166-170, 288-294) is brought to the GPU as RAW TEXT and is
-// parsed and 2-bit packed there.  The host only moves bytes: pool threads pread() slices of the file (or one thread
-// inflates the gzip stream) into two pinned staging buffers whose H2D copies overlap the next slice's read.
-//   newline_positions   cub::DeviceSelect over the text -> offsets of every '\n'
-//   fastq_records       one thread per record: checks the '@' / '+' framing, sequence start and length ('\r' stripped)
+// Ingest of 4-line FASTQ (plain, or gzip inflated into host memory), SURVEY.md §8f rank 2: the reads file that `drprg
+// predict` hands to the map step (/root/reference/src/predict.rs:166-170, 288-294) becomes a 2-bit packed batch in HBM.
+// Default path (ingest_fastq_text / ingest_fastq_framed): the record structure is found on the HOST (fastq_frame.cpp),
+// only the sequence lines and a (start, length) table cross PCIe, and the device packs:
 //   pack_stride/ragged  ASCII -> 2-bit words (first base in the top bits), non-ACGT reads flagged
 //   finish_lens         lens[r] = 0 for a flagged read (pandora drops it), dropped-read count
-// Anything that is not strict 4-line FASTQ (FASTA, wrapped records, blank lines, >= 4 GiB of text) is left to the host
-// parser (load_reads_packed), which produces the same packed layout.
+// Second implementation (ingest_fastq_device with DRPRG_INGEST=device; the round-1 path, kept for A/B and parity): the
+// RAW TEXT goes to the GPU through two pinned staging buffers and is parsed there:
+//   newline_positions   cub::DeviceSelect over the text -> offsets of every '\n'
+//   fastq_records       one thread per record: checks the '@' / '+' framing, sequence start and length ('\r' stripped)
+// Anything that is not strict 4-line FASTQ (FASTA, wrapped records, blank lines) is left to the general host parser
+// (load_reads_packed), which produces the same packed layout.
 #include <cuda_runtime.h>
 #include <fcntl.h>
 #include <unistd.h>

@@ -1,4 +1,4 @@
-// Device-side FASTQ ingest: raw text to the GPU, parsed and 2-bit packed there.
+// FASTQ ingest: framed on the host, sequence lines to the GPU, 2-bit packed there (ingest.cu).
 #pragma once
 #include <cuda_runtime.h>
 
