@@ -306,7 +306,18 @@ struct drprg_index {
     PinnedBuf<int32_t> h_gt, h_acc;
     double gt_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::string> contigs;
-    std::string vcf;
+    // pandora_genotyped.vcf: header written by the host, record lines written by the device kernels straight into this
+    // host-mapped pinned buffer (genotype.cu: vcf_*_kernel); vcf_len bytes are valid, NUL-terminated
+    PinnedBuf<char> h_vcf;
+    size_t vcf_len = 0;
+    std::string vcf_header, vcf_fallback;
+    char* d_vcf_prefix = nullptr;
+    uint32_t *d_vcf_prefix_off = nullptr, *d_vcf_slot_off = nullptr, *d_vcf_ctl = nullptr;  // ctl: [0] text bytes, [1] flags
+    DBuf<char> d_vcf_slots;
+    DBuf<uint32_t> d_vcf_line_len, d_vcf_out_off;
+    PinnedBuf<uint32_t> h_vcf_ctl;
+    size_t vcf_prefix_bytes = 0, vcf_slot_bytes = 0;
+    bool ga_stale = false;  // the per-allele / per-record arrays are in the pinned download buffers, not yet in GA
     bool have_gt = false;
     bool ml_in_flight = false;  // the ML-path kernel of an unfinished drprg_cuda_genotype may still be writing h_path / h_done
     DBuf<double> d_prob, d_M;
@@ -334,6 +345,9 @@ struct drprg_index {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         h_path.release(); h_plen.release(); h_u32.release(); h_done.release(); h_f64.release(); h_gt.release(); h_acc.release();
+        h_vcf.release(); h_vcf_ctl.release(); d_vcf_slots.release(); d_vcf_line_len.release(); d_vcf_out_off.release();
+        for (void* p : {(void*)d_vcf_prefix, (void*)d_vcf_prefix_off, (void*)d_vcf_slot_off, (void*)d_vcf_ctl})
+            if (p) cudaFree(p);
         for (auto& e : ev_ml)
             if (e) cudaEventDestroy(e);
         if (st_copy) cudaStreamDestroy(st_copy);
@@ -789,6 +803,29 @@ void flush_scalars(drprg_index* X) {
     X->scalars_in_buffer = true;
 }
 
+// The genotype arrays of the last sample as host vectors (getters, the host text formatter): the step itself leaves them
+// in the pinned download buffers, the copies into GA are made on first use.
+void ensure_ga(drprg_index* X) {
+    if (!X->ga_stale) return;
+    GenotypeArrays& G = X->GA;
+    const size_t nr = X->records.size(), na = G.allele_off.empty() ? 0 : G.allele_off.size() - 1;
+    std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
+    for (auto* v : cols) v->resize(na);
+    G.gaps.resize(na);
+    G.lik.resize(na);
+    G.gt_conf.resize(nr);
+    G.gt.resize(nr);
+    if (nr) {
+        std::copy(X->h_gt.begin(), X->h_gt.end(), G.gt.begin());
+        for (int c = 0; c < 6; ++c)
+            std::copy(X->h_u32.begin() + (size_t)c * na, X->h_u32.begin() + (size_t)(c + 1) * na, cols[c]->begin());
+        std::copy(X->h_f64.begin(), X->h_f64.begin() + na, G.gaps.begin());
+        std::copy(X->h_f64.begin() + na, X->h_f64.begin() + 2 * (size_t)na, G.lik.begin());
+        std::copy(X->h_f64.begin() + 2 * (size_t)na, X->h_f64.end(), G.gt_conf.begin());
+    }
+    X->ga_stale = false;
+}
+
 void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
     if (!X->sample_open) throw std::runtime_error("drprg_cuda_sample_begin was not called");
     need_device(X);
@@ -947,15 +984,33 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             X->d_rec_off = to_device(G.rec_off);
             X->d_allele_off = to_device(G.allele_off);
             X->d_allele_kn = to_device(G.allele_kn);
+            {   // the static columns of every record line and the slots of the sample columns (VCF text on the device)
+                std::vector<char> prefix;
+                std::vector<uint32_t> poff(1, 0), soff(1, 0);
+                for (size_t i = 0; i < X->records.size(); ++i) {
+                    const std::string& t = vcf_record_prefix(H, *X->records[i]);
+                    prefix.insert(prefix.end(), t.begin(), t.end());
+                    poff.push_back((uint32_t)prefix.size());
+                    soff.push_back(soff.back() + (uint32_t)vcf_sample_column_bound(G.rec_off[i + 1] - G.rec_off[i]));
+                }
+                for (void* p : {(void*)X->d_vcf_prefix, (void*)X->d_vcf_prefix_off, (void*)X->d_vcf_slot_off})
+                    if (p) cudaFree(p);
+                X->d_vcf_prefix = to_device(prefix);
+                X->d_vcf_prefix_off = to_device(poff);
+                X->d_vcf_slot_off = to_device(soff);
+                X->vcf_prefix_bytes = prefix.size();
+                X->vcf_slot_bytes = soff.back();
+                if (!X->d_vcf_ctl) CK(cudaMalloc(&X->d_vcf_ctl, 2 * sizeof(uint32_t)));
+            }
             X->csr_records = X->sample_records.empty() ? X->records : std::vector<const SiteRecord*>();
         }
         const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
-        std::vector<uint32_t>* cols[6] = {&G.mean_fwd, &G.mean_rev, &G.med_fwd, &G.med_rev, &G.sum_fwd, &G.sum_rev};
-        for (auto* v : cols) v->resize(na);
-        G.gaps.resize(na);
-        G.lik.resize(na);
-        G.gt_conf.resize(nr);
-        G.gt.resize(nr);
+        format_vcf_header(X->contigs, sample_name, X->vcf_header);
+        const size_t hl = X->vcf_header.size();
+        X->h_vcf.resize(hl + X->vcf_prefix_bytes + X->vcf_slot_bytes + 1);
+        memcpy(X->h_vcf.data(), X->vcf_header.data(), hl);
+        X->h_vcf_ctl.resize(2);
+        X->h_vcf_ctl.data()[0] = X->h_vcf_ctl.data()[1] = 0;
         if (nr) {
             X->d_gt_u32.ensure((size_t)na * 6);
             X->d_gt_f64.ensure((size_t)na * 2 + nr);
@@ -973,7 +1028,18 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             DG.sb_ratio = X->d_gt_f32.p + nr;
             DG.pdp = X->d_gt_f32.p + 2 * (size_t)nr;
             launch_genotype(X->d_accum, DG, MP, s8);
+            // the record lines: formatted by the device into the host-mapped text buffer, right behind the header
+            X->d_vcf_slots.ensure(X->vcf_slot_bytes + 1);
+            X->d_vcf_line_len.ensure(nr);
+            X->d_vcf_out_off.ensure((size_t)nr + 1);
+            CK(cudaMemsetAsync(X->d_vcf_ctl, 0, 2 * sizeof(uint32_t), s8));
+            DevVcfText VT{X->d_vcf_prefix, X->d_vcf_prefix_off, X->d_vcf_slot_off, X->d_vcf_slots.p, X->d_vcf_line_len.p,
+                          X->d_vcf_out_off.p, X->h_vcf.data() + hl, X->d_vcf_ctl, X->d_vcf_ctl + 1};
+            static const bool host_text = getenv("DRPRG_VCF_TEXT") && std::string(getenv("DRPRG_VCF_TEXT")) == "host";
+            if (!host_text) launch_vcf_text(DG, VT, s8);
             CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(X->h_vcf_ctl.data(), X->d_vcf_ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s8));
+            // the arrays themselves (getters, drprg_cuda_gt_*): downloaded into pinned buffers, unpacked on first use
             X->h_u32.resize((size_t)na * 6);
             X->h_f64.resize((size_t)na * 2 + nr);
             CK(cudaMemcpyAsync(X->h_u32.data(), u, X->h_u32.size() * 4, cudaMemcpyDeviceToHost, s8));
@@ -981,17 +1047,26 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             X->h_gt.resize(nr);
             CK(cudaMemcpyAsync(X->h_gt.data(), X->d_gt_i32.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, s8));
             CK(cudaStreamSynchronize(s8));
-            std::copy(X->h_gt.begin(), X->h_gt.end(), G.gt.begin());
-            for (int c = 0; c < 6; ++c)
-                std::copy(X->h_u32.begin() + (size_t)c * na, X->h_u32.begin() + (size_t)(c + 1) * na, cols[c]->begin());
-            std::copy(X->h_f64.begin(), X->h_f64.begin() + na, G.gaps.begin());
-            std::copy(X->h_f64.begin() + na, X->h_f64.begin() + 2 * (size_t)na, G.lik.begin());
-            std::copy(X->h_f64.begin() + 2 * (size_t)na, X->h_f64.end(), G.gt_conf.begin());
+            X->ga_stale = true;
+            if (host_text) X->h_vcf_ctl.data()[1] = 1u;
+        } else {
+            X->ga_stale = true;
         }
         const double tf0 = now_ms();
-        format_vcf(H, X->records, G, X->contigs, sample_name, X->vcf);
+        if (X->h_vcf_ctl.data()[1]) {
+            // a value the device formatter refuses (exponent notation, a rounding tie, -0, inf / nan) — or DRPRG_VCF_TEXT=host:
+            // the host formatter writes the whole text
+            ensure_ga(X);
+            format_vcf(H, X->records, G, X->contigs, sample_name, X->vcf_fallback);
+            X->h_vcf.resize(X->vcf_fallback.size() + 1);
+            memcpy(X->h_vcf.data(), X->vcf_fallback.data(), X->vcf_fallback.size());
+            X->vcf_len = X->vcf_fallback.size();
+        } else {
+            X->vcf_len = hl + X->h_vcf_ctl.data()[0];
+        }
+        X->h_vcf.data()[X->vcf_len] = 0;
         static const bool timing = getenv("DRPRG_TIMING") != nullptr;
-        if (timing) fprintf(stderr, "[drprg-cuda] s8 kernels+copies %.3f ms, vcf text %.3f ms\n", tf0 - ts0, now_ms() - tf0);
+        if (timing) fprintf(stderr, "[drprg-cuda] s8 + vcf text kernels + downloads %.3f ms, host text (fallback only) %.3f ms\n", tf0 - ts0, now_ms() - tf0);
     };
     // ---- speculative pass: every locus with reads present, cached merged site tables
     {
@@ -1589,7 +1664,7 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     genotype(X, vcf_refs, "sample");
     std::ofstream vcf(std::string(outdir) + "/pandora_genotyped.vcf");
     if (!vcf) throw std::runtime_error(std::string("cannot write ") + outdir + "/pandora_genotyped.vcf");
-    vcf << X->vcf;
+    vcf.write(X->h_vcf.data(), (std::streamsize)X->vcf_len);
     const double t3 = now_ms();
     drprg_map_stats s{};
     s.n_reads = n;
@@ -1885,14 +1960,14 @@ int drprg_cuda_write_vcf(drprg_index* X, const char* path) {
     API_BEGIN if (!X->have_gt) throw std::runtime_error("no genotype results");
     std::ofstream f(path);
     if (!f) throw std::runtime_error(std::string("cannot write ") + path);
-    f << X->vcf;
+    f.write(X->h_vcf.data(), (std::streamsize)X->vcf_len);
     return 0;
     API_END
 }
-const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->vcf.c_str() : ""; }
+const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->h_vcf.data() : ""; }
 const char* drprg_cuda_vcf_view(drprg_index* X, uint64_t* len) {
-    if (len) *len = X->have_gt ? X->vcf.size() : 0;
-    return X->have_gt ? X->vcf.data() : "";
+    if (len) *len = X->have_gt ? X->vcf_len : 0;
+    return X->have_gt ? X->h_vcf.data() : "";
 }
 
 uint64_t drprg_cuda_hash64(uint64_t kmer, uint32_t k) { return hash64_host(kmer, k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1)); }
@@ -2077,6 +2152,7 @@ int drprg_cuda_gt_counts(drprg_index* X, uint32_t* n_records, uint32_t* n_allele
     return 0;
 }
 int drprg_cuda_gt_records(drprg_index* X, uint32_t* locus, uint32_t* pos, uint32_t* n_alleles, int32_t* gt, double* gt_conf) {
+    ensure_ga(X);
     for (size_t i = 0; i < X->records.size(); ++i) {
         locus[i] = X->records[i]->locus;
         pos[i] = X->records[i]->pos;
@@ -2088,6 +2164,7 @@ int drprg_cuda_gt_records(drprg_index* X, uint32_t* locus, uint32_t* pos, uint32
 }
 int drprg_cuda_gt_alleles(drprg_index* X, double* lik, double* gaps, uint32_t* mean_fwd, uint32_t* mean_rev, uint32_t* med_fwd,
                           uint32_t* med_rev, uint32_t* sum_fwd, uint32_t* sum_rev, uint32_t* n_knodes) {
+    ensure_ga(X);
     const GenotypeArrays& G = X->GA;
     const size_t na = G.lik.size();
     memcpy(lik, G.lik.data(), na * 8);

@@ -147,6 +147,179 @@ __global__ void genotype_kernel(DevGenotype G, ModelParams P) {
     G.minor_gt[r] = minor;
 }
 
+// ============================================================================================
+// VCF text on the device: the per-record lines of pandora_genotyped.vcf
+// ============================================================================================
+// The CHROM..FORMAT columns of a record never change for a site table, so they sit in device memory as a byte array;
+// only the sample column (GT : six integer vectors : GAPS : LIKELIHOOD : GT_CONF) is formatted per sample.  "%g" with
+// six significant digits is the host formatter's fast path (genotype_host.cpp::format_g6, pinned against printf by
+// tests/test_host_cpu.py) restated with explicit round-to-nearest operations: scale to a six-digit integer, refuse
+// anything within 1e-6 of a rounding tie and everything that needs exponent notation.  A refused value raises a flag
+// and the host formats that sample's text itself, so the text is byte-identical either way.
+__device__ __forceinline__ char* dev_put_uint(char* o, uint32_t v) {
+    char tmp[10];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10u);
+        v /= 10u;
+    } while (v);
+    while (n) *o++ = tmp[--n];
+    return o;
+}
+
+__device__ char* dev_format_g6(double v, char* o, uint32_t& refused) {
+    if (v == 0.0) {
+        if (signbit(v)) refused = 1u;  // "-0": left to the host
+        *o++ = '0';
+        return o;
+    }
+    const double a = fabs(v);
+    if (!(a >= 1e-4 && a < 999999.0)) {  // exponent notation, inf, nan
+        refused = 1u;
+        return o;
+    }
+    const double P10[11] = {1e-4, 1e-3, 1e-2, 1e-1, 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6};
+    const double SC[10] = {1e9, 1e8, 1e7, 1e6, 1e5, 1e4, 1e3, 1e2, 1e1, 1e0};  // 10^(5 - e10)
+    int e10 = -4;
+    while (a >= P10[e10 + 5]) ++e10;  // a in [10^e10, 10^(e10+1))
+    const double x = __dmul_rn(a, SC[e10 + 4]);
+    const double fl = floor(x);
+    const double frac = __dsub_rn(x, fl);
+    if (fabs(__dsub_rn(frac, 0.5)) < 1e-6) {
+        refused = 1u;
+        return o;
+    }
+    uint32_t n = (uint32_t)fl + (frac > 0.5 ? 1u : 0u);
+    if (n >= 1000000u) {
+        n = 100000u;
+        ++e10;
+        if (e10 > 5) {
+            refused = 1u;
+            return o;
+        }
+    }
+    char d[6];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        d[i] = (char)('0' + n % 10u);
+        n /= 10u;
+    }
+    int last = 5;
+    while (last > 0 && d[last] == '0') --last;  // significant digits d[0..last]
+    if (v < 0) *o++ = '-';
+    if (e10 >= 0) {
+        for (int i = 0; i <= e10; ++i) *o++ = d[i];  // integer part (zeros included)
+        if (last > e10) {
+            *o++ = '.';
+            for (int i = e10 + 1; i <= last; ++i) *o++ = d[i];
+        }
+    } else {
+        *o++ = '0';
+        *o++ = '.';
+        for (int i = 0; i < -e10 - 1; ++i) *o++ = '0';
+        for (int i = 0; i <= last; ++i) *o++ = d[i];
+    }
+    return o;
+}
+
+// one thread per record: the sample column into the record's slot (slot_off: static upper bounds), its length
+__global__ void vcf_sample_column_kernel(DevGenotype G, DevVcfText V) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.n_records) return;
+    const uint32_t b = G.rec_off[r], e = G.rec_off[r + 1];
+    char* const o0 = V.slots + V.slot_off[r];
+    char* o = o0;
+    uint32_t refused = 0;
+    const int32_t gt = G.gt[r];
+    if (gt < 0) *o++ = '.';
+    else o = dev_put_uint(o, (uint32_t)gt);
+    const uint32_t* cols[6] = {G.mean_fwd, G.mean_rev, G.med_fwd, G.med_rev, G.sum_fwd, G.sum_rev};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        *o++ = ':';
+        for (uint32_t a = b; a < e; ++a) {
+            if (a > b) *o++ = ',';
+            o = dev_put_uint(o, cols[c][a]);
+        }
+    }
+    *o++ = ':';
+    for (uint32_t a = b; a < e; ++a) {
+        if (a > b) *o++ = ',';
+        o = dev_format_g6(G.gaps[a], o, refused);
+    }
+    *o++ = ':';
+    for (uint32_t a = b; a < e; ++a) {
+        if (a > b) *o++ = ',';
+        o = dev_format_g6(G.lik[a], o, refused);
+    }
+    *o++ = ':';
+    o = dev_format_g6(G.gt_conf[r], o, refused);
+    *o++ = '\n';
+    V.line_len[r] = (V.prefix_off[r + 1] - V.prefix_off[r]) + (uint32_t)(o - o0);
+    if (refused) atomicOr(V.flags, 1u);
+}
+
+// one CTA: exclusive scan of the line lengths -> where every line starts in the text; total length
+__global__ void vcf_line_offsets_kernel(uint32_t n, const uint32_t* __restrict__ line_len, uint32_t* __restrict__ out_off,
+                                        uint32_t* __restrict__ total /* host-mapped */) {
+    __shared__ uint32_t s_part[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const uint32_t i = i0 + tid;
+        const uint32_t v = i < n ? line_len[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t p = lane < (blockDim.x >> 5) ? s_part[lane] : 0u, pi = p;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, pi, d);
+                if (lane >= (uint32_t)d) pi += t;
+            }
+            s_part[lane] = pi - p;  // exclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < n) out_off[i] = carry + s_part[warp] + incl - v;
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_carry = carry + s_part[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out_off[n] = s_carry;
+        *total = s_carry;
+    }
+}
+
+// one warp per record: static columns + sample column -> the text (host-mapped pinned memory: no separate download)
+__global__ void vcf_gather_kernel(uint32_t n, DevVcfText V, const uint32_t* __restrict__ out_off) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (r >= n) return;
+    char* dst = V.text + out_off[r];
+    const uint32_t p0 = V.prefix_off[r], pl = V.prefix_off[r + 1] - p0;
+    for (uint32_t i = lane; i < pl; i += 32) dst[i] = V.prefix[p0 + i];
+    const char* src = V.slots + V.slot_off[r];
+    const uint32_t dl = V.line_len[r] - pl;
+    for (uint32_t i = lane; i < dl; i += 32) dst[pl + i] = src[i];
+}
+
+void launch_vcf_text(const DevGenotype& G, const DevVcfText& V, cudaStream_t st) {
+    if (!G.n_records) return;
+    vcf_sample_column_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, V);
+    vcf_line_offsets_kernel<<<1, 1024, 0, st>>>(G.n_records, V.line_len, V.out_off, V.total);
+    vcf_gather_kernel<<<(G.n_records * 32 + 255) / 256, 256, 0, st>>>(G.n_records, V, V.out_off);
+    g_launches += 3;
+}
+
 void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st) {
     if (!G.n_records) return;
     allele_stats_kernel<<<(G.n_alleles + 127) / 128, 128, 0, st>>>(d_cov, G, P.min_kmer_covg);

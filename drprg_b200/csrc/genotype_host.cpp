@@ -623,10 +623,8 @@ size_t format_g6(double v, char* out) {
     return (size_t)(o - out);
 }
 
-void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
-                const std::vector<std::string>& contigs, const std::string& sample, std::string& s) {
+void format_vcf_header(const std::vector<std::string>& contigs, const std::string& sample, std::string& s) {
     s.clear();  // keeps its capacity: a fresh ~1 MB string would be mmap'ed and page-faulted in on every sample
-    s.reserve(4096 + recs.size() * 256);
     char date[32];
     time_t t = time(nullptr);
     strftime(date, sizeof date, "%d/%m/%y", localtime(&t));
@@ -651,6 +649,24 @@ void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, 
          "##FORMAT=<ID=GT_CONF,Number=1,Type=Float,Description=\"Genotype confidence\">\n";
     for (auto& c : contigs) s += "##contig=<ID=" + c + ">\n";
     s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + sample + "\n";
+}
+
+// CHROM .. FORMAT columns of a record (they never change for a site: formatted once and cached)
+const std::string& vcf_record_prefix(const HostIndex& H, const SiteRecord& r) {
+    if (r.text_prefix.empty()) {
+        std::string& t = r.text_prefix;
+        t = H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
+        for (size_t a = 0; a < r.alts.size(); ++a) t += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
+        t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
+             "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
+    }
+    return r.text_prefix;
+}
+
+void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
+                const std::vector<std::string>& contigs, const std::string& sample, std::string& s) {
+    format_vcf_header(contigs, sample, s);
+    s.reserve(4096 + recs.size() * 256);
     // Records are independent lines.  Each worker formats a contiguous range with raw pointer writes into its own
     // buffer (an upper bound on the line length is known: prefix + 12 bytes per integer + 26 per float), then the
     // ranges are copied into place in parallel.
@@ -683,13 +699,7 @@ void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, 
         for (size_t i = lo; i < hi; ++i) {
             const SiteRecord& r = *recs[i];
             const uint32_t b = G.rec_off[i], e = G.rec_off[i + 1];
-            if (r.text_prefix.empty()) {  // CHROM .. FORMAT columns never change for a site: format once
-                std::string& t = r.text_prefix;
-                t = H.loci[r.locus].name + "\t" + std::to_string(r.pos + 1) + "\t.\t" + (r.ref.empty() ? "." : r.ref) + "\t";
-                for (size_t a = 0; a < r.alts.size(); ++a) t += (a ? "," : "") + (r.alts[a].empty() ? std::string(".") : r.alts[a]);
-                t += "\t.\t.\tVC=" + r.vc + ";GRAPHTYPE=" + r.graphtype +
-                     "\tGT:MEAN_FWD_COVG:MEAN_REV_COVG:MED_FWD_COVG:MED_REV_COVG:SUM_FWD_COVG:SUM_REV_COVG:GAPS:LIKELIHOOD:GT_CONF\t";
-            }
+            vcf_record_prefix(H, r);
             memcpy(o, r.text_prefix.data(), r.text_prefix.size());
             o += r.text_prefix.size();
             if (G.gt[i] < 0) *o++ = '.';

@@ -119,6 +119,10 @@ struct GenotypeArrays {  // flattened over records / alleles, device results cop
 void format_vcf(const HostIndex& H, const std::vector<const SiteRecord*>& recs, const GenotypeArrays& G,
                 const std::vector<std::string>& contigs, const std::string& sample, std::string& out);
 
+void format_vcf_header(const std::vector<std::string>& contigs, const std::string& sample, std::string& out);
+const std::string& vcf_record_prefix(const HostIndex& H, const SiteRecord& r);  // CHROM .. FORMAT columns, cached
+// upper bound of a record's sample column (GT : 6 integer vectors : GAPS : LIKELIHOOD : GT_CONF, newline) with na alleles
+inline size_t vcf_sample_column_bound(size_t na) { return 16 + na * (6 * 12 + 2 * 28) + 40; }
 size_t format_g6(double v, char* out);  // printf("%g") text of v, out has room for 40 chars
 std::map<std::string, std::string> load_fasta(const std::string& path);
 

@@ -171,6 +171,19 @@ struct DevGenotype {
     float* pdp = nullptr;         // per allele: proportion of the position's depth; NaN when the depth is 0
 };
 void launch_genotype(const int32_t* d_cov, const DevGenotype& G, ModelParams P, cudaStream_t st);
+// the VCF record lines formatted on the device (genotype.cu): static CHROM..FORMAT columns + the sample column
+struct DevVcfText {
+    const char* prefix;          // the records' static columns, back to back
+    const uint32_t* prefix_off;  // n_records + 1
+    const uint32_t* slot_off;    // n_records + 1: upper bounds of the sample columns
+    char* slots;                 // scratch for the sample columns
+    uint32_t* line_len;          // n_records
+    uint32_t* out_off;           // n_records + 1
+    char* text;                  // the lines, back to back (device address of host-mapped pinned memory)
+    uint32_t* total;             // bytes of text written (host-mapped)
+    uint32_t* flags;             // bit 0: a value was refused by the device formatter (host-mapped)
+};
+void launch_vcf_text(const DevGenotype& G, const DevVcfText& V, cudaStream_t st);
 // the likelihood / GT / GT_CONF kernel alone, on per-allele rows already in G.mean_fwd / G.mean_rev / G.gaps
 void launch_genotype_rows(const DevGenotype& G, ModelParams P, cudaStream_t st);
 

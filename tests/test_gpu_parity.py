@@ -379,12 +379,13 @@ def test_pandora_cuda_cli_drop_in(tmp_path):
 
 @pytest.mark.parametrize("env", [{"DRPRG_MLPATH_UNITS": "1"}, {"DRPRG_MLPATH_UNITS": "0"}, {"DRPRG_MLPATH_GENERIC": "1", "DRPRG_MLPATH_UNITS": "0"},
                                  {"DRPRG_MLPATH_LEVELS": "0"}, {"DRPRG_SKETCH_VARIANT": "0"}, {"DRPRG_SCREEN": "0"}, {"DRPRG_SCREEN_VARIANT": "0"},
-                                 {"DRPRG_SCREEN_VARIANT": "1"}])
+                                 {"DRPRG_SCREEN_VARIANT": "1"}, {"DRPRG_VCF_TEXT": "host"}])
 def test_alternative_kernel_variants_keep_parity(env):
     """the ML-path kernel has four implementations (level-parallel = default, run-parallel units, record-addressed chain,
     generic lifting), the
-    sketch kernel a switchable variant and the k-mer screen in front of it can be turned off (every read sketched); each
-    must give the oracle's results.  The switches are read once per process."""
+    sketch kernel a switchable variant and the k-mer screen in front of it can be turned off (every read sketched); the
+    VCF record lines are formatted on the device (default) or by the host formatter (DRPRG_VCF_TEXT=host); each must give
+    the oracle's results.  The switches are read once per process."""
     import subprocess, sys
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
