@@ -309,7 +309,7 @@ struct drprg_index {
     // pandora_genotyped.vcf: header written by the host, record lines written by the device kernels straight into this
     // host-mapped pinned buffer (genotype.cu: vcf_*_kernel); vcf_len bytes are valid, NUL-terminated
     PinnedBuf<char> h_vcf;
-    size_t vcf_len = 0;
+    size_t vcf_len = 0, vcf_begin = 0;  // the text is h_vcf[vcf_begin, vcf_begin + vcf_len)
     std::string vcf_header, vcf_fallback;
     char* d_vcf_prefix = nullptr;
     uint32_t *d_vcf_prefix_off = nullptr, *d_vcf_slot_off = nullptr, *d_vcf_ctl = nullptr;  // ctl: [0] text bytes, [1] flags
@@ -1006,9 +1006,12 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
         }
         const uint32_t nr = (uint32_t)X->records.size(), na = (uint32_t)G.allele_off.size() - 1;
         format_vcf_header(X->contigs, sample_name, X->vcf_header);
-        const size_t hl = X->vcf_header.size();
-        X->h_vcf.resize(hl + X->vcf_prefix_bytes + X->vcf_slot_bytes + 1);
-        memcpy(X->h_vcf.data(), X->vcf_header.data(), hl);
+        // the header is padded in front so that the record lines start 16-byte aligned (the device writes them with
+        // 128-bit stores); the text handed out begins at vcf_begin
+        const size_t hl_raw = X->vcf_header.size(), pad = (16 - hl_raw % 16) % 16, hl = hl_raw + pad;
+        X->h_vcf.resize(hl + X->vcf_prefix_bytes + X->vcf_slot_bytes + 32);
+        X->vcf_begin = pad;
+        memcpy(X->h_vcf.data() + pad, X->vcf_header.data(), hl_raw);
         X->h_vcf_ctl.resize(2);
         X->h_vcf_ctl.data()[0] = X->h_vcf_ctl.data()[1] = 0;
         if (nr) {
@@ -1034,7 +1037,8 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             X->d_vcf_out_off.ensure((size_t)nr + 1);
             CK(cudaMemsetAsync(X->d_vcf_ctl, 0, 2 * sizeof(uint32_t), s8));
             DevVcfText VT{X->d_vcf_prefix, X->d_vcf_prefix_off, X->d_vcf_slot_off, X->d_vcf_slots.p, X->d_vcf_line_len.p,
-                          X->d_vcf_out_off.p, X->h_vcf.data() + hl, X->d_vcf_ctl, X->d_vcf_ctl + 1};
+                          X->d_vcf_out_off.p, X->h_vcf.data() + hl, (uint32_t)(X->vcf_prefix_bytes + X->vcf_slot_bytes), X->d_vcf_ctl,
+                          X->d_vcf_ctl + 1};
             static const bool host_text = getenv("DRPRG_VCF_TEXT") && std::string(getenv("DRPRG_VCF_TEXT")) == "host";
             if (!host_text) launch_vcf_text(DG, VT, s8);
             CK(cudaGetLastError());
@@ -1060,11 +1064,12 @@ void genotype(drprg_index* X, const char* vcf_refs, const char* sample) {
             format_vcf(H, X->records, G, X->contigs, sample_name, X->vcf_fallback);
             X->h_vcf.resize(X->vcf_fallback.size() + 1);
             memcpy(X->h_vcf.data(), X->vcf_fallback.data(), X->vcf_fallback.size());
+            X->vcf_begin = 0;
             X->vcf_len = X->vcf_fallback.size();
         } else {
-            X->vcf_len = hl + X->h_vcf_ctl.data()[0];
+            X->vcf_len = hl_raw + X->h_vcf_ctl.data()[0];
         }
-        X->h_vcf.data()[X->vcf_len] = 0;
+        X->h_vcf.data()[X->vcf_begin + X->vcf_len] = 0;
         static const bool timing = getenv("DRPRG_TIMING") != nullptr;
         if (timing) fprintf(stderr, "[drprg-cuda] s8 + vcf text kernels + downloads %.3f ms, host text (fallback only) %.3f ms\n", tf0 - ts0, now_ms() - tf0);
     };
@@ -1664,7 +1669,7 @@ int run_sample(drprg_index* X, const char* reads_path, const char* vcf_refs, con
     genotype(X, vcf_refs, "sample");
     std::ofstream vcf(std::string(outdir) + "/pandora_genotyped.vcf");
     if (!vcf) throw std::runtime_error(std::string("cannot write ") + outdir + "/pandora_genotyped.vcf");
-    vcf.write(X->h_vcf.data(), (std::streamsize)X->vcf_len);
+    vcf.write(X->h_vcf.data() + X->vcf_begin, (std::streamsize)X->vcf_len);
     const double t3 = now_ms();
     drprg_map_stats s{};
     s.n_reads = n;
@@ -1960,14 +1965,14 @@ int drprg_cuda_write_vcf(drprg_index* X, const char* path) {
     API_BEGIN if (!X->have_gt) throw std::runtime_error("no genotype results");
     std::ofstream f(path);
     if (!f) throw std::runtime_error(std::string("cannot write ") + path);
-    f.write(X->h_vcf.data(), (std::streamsize)X->vcf_len);
+    f.write(X->h_vcf.data() + X->vcf_begin, (std::streamsize)X->vcf_len);
     return 0;
     API_END
 }
-const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->h_vcf.data() : ""; }
+const char* drprg_cuda_vcf_text(drprg_index* X) { return X->have_gt ? X->h_vcf.data() + X->vcf_begin : ""; }
 const char* drprg_cuda_vcf_view(drprg_index* X, uint64_t* len) {
     if (len) *len = X->have_gt ? X->vcf_len : 0;
-    return X->have_gt ? X->h_vcf.data() : "";
+    return X->have_gt ? X->h_vcf.data() + X->vcf_begin : "";
 }
 
 uint64_t drprg_cuda_hash64(uint64_t kmer, uint32_t k) { return hash64_host(kmer, k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1)); }

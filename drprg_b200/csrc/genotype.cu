@@ -300,23 +300,53 @@ __global__ void vcf_line_offsets_kernel(uint32_t n, const uint32_t* __restrict__
     }
 }
 
-// one warp per record: static columns + sample column -> the text (host-mapped pinned memory: no separate download)
+// The text goes to host-mapped pinned memory, i.e. over PCIe: every thread assembles 16 consecutive bytes of the OUTPUT
+// (finding the record its first byte belongs to by binary search over the line offsets) and stores them with one 128-bit
+// write, so a warp emits 512 contiguous bytes — byte stores per record would cross the bus as 32-byte packets.
 __global__ void vcf_gather_kernel(uint32_t n, DevVcfText V, const uint32_t* __restrict__ out_off) {
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (r >= n) return;
-    char* dst = V.text + out_off[r];
-    const uint32_t p0 = V.prefix_off[r], pl = V.prefix_off[r + 1] - p0;
-    for (uint32_t i = lane; i < pl; i += 32) dst[i] = V.prefix[p0 + i];
-    const char* src = V.slots + V.slot_off[r];
-    const uint32_t dl = V.line_len[r] - pl;
-    for (uint32_t i = lane; i < dl; i += 32) dst[pl + i] = src[i];
+    const uint32_t total = out_off[n];
+    const uint32_t o0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+    if (o0 >= total) return;
+    uint32_t lo = 0, hi = n;  // the record r with out_off[r] <= o0 < out_off[r + 1] (empty lines cannot occur)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (out_off[mid] <= o0) lo = mid;
+        else hi = mid;
+    }
+    uint32_t r = lo;
+    uint32_t line0 = out_off[r], line1 = out_off[r + 1];
+    uint32_t p0 = V.prefix_off[r], pl = V.prefix_off[r + 1] - p0;
+    const char* slot = V.slots + V.slot_off[r];
+    union {
+        uint4 v;
+        char c[16];
+    } w;
+    w.v = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t o = o0 + k;
+        if (o >= total) break;
+        while (o >= line1) {  // next record
+            ++r;
+            line0 = line1;
+            line1 = out_off[r + 1];
+            p0 = V.prefix_off[r];
+            pl = V.prefix_off[r + 1] - p0;
+            slot = V.slots + V.slot_off[r];
+        }
+        const uint32_t i = o - line0;
+        w.c[k] = i < pl ? V.prefix[p0 + i] : slot[i - pl];
+    }
+    *reinterpret_cast<uint4*>(V.text + o0) = w.v;  // text is 16-byte aligned; the buffer has room past `total`
 }
 
 void launch_vcf_text(const DevGenotype& G, const DevVcfText& V, cudaStream_t st) {
     if (!G.n_records) return;
     vcf_sample_column_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, V);
     vcf_line_offsets_kernel<<<1, 1024, 0, st>>>(G.n_records, V.line_len, V.out_off, V.total);
-    vcf_gather_kernel<<<(G.n_records * 32 + 255) / 256, 256, 0, st>>>(G.n_records, V, V.out_off);
+    // one thread per 16 bytes of text; the grid is sized for the upper bound of the text (threads past the end return)
+    const uint32_t max_chunks = (V.text_bound + 15u) / 16u;
+    vcf_gather_kernel<<<(max_chunks + 255) / 256, 256, 0, st>>>(G.n_records, V, V.out_off);
     g_launches += 3;
 }
 

@@ -179,7 +179,8 @@ struct DevVcfText {
     char* slots;                 // scratch for the sample columns
     uint32_t* line_len;          // n_records
     uint32_t* out_off;           // n_records + 1
-    char* text;                  // the lines, back to back (device address of host-mapped pinned memory)
+    char* text;                  // the lines, back to back (host-mapped pinned memory, 16-byte aligned, text_bound + 16 bytes)
+    uint32_t text_bound;         // upper bound of the text's length
     uint32_t* total;             // bytes of text written (host-mapped)
     uint32_t* flags;             // bit 0: a value was refused by the device formatter (host-mapped)
 };
