@@ -649,6 +649,7 @@ __device__ __forceinline__ uint32_t level_link(uint32_t a, uint32_t v, uint32_t 
 }
 
 constexpr int ML_LEVEL_THREADS = 128;
+constexpr uint32_t ML_FAN = 4;  // successors whose records are fetched side by side (nodes with more take the serial loop)
 __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
     uint32_t n_loci, const uint32_t* __restrict__ knode_base, const uint32_t* __restrict__ edge_off,
     const uint32_t* __restrict__ edges, const double* __restrict__ prob, const int32_t* __restrict__ locus_reads,
@@ -782,6 +783,44 @@ __global__ void __launch_bounds__(ML_LEVEL_THREADS) mlpath_level_kernel(
                 const uint32_t e1 = lds32(a + REC + L_EOFF) & ~3u;
                 double max_mean = -(double)FLT_MAX;
                 uint32_t max_len = 0;
+                const uint32_t deg = (e1 - e0) >> 2;
+                if (deg <= ML_FAN) {
+                    // Up to ML_FAN successors (almost every node): everything the ordered comparison needs is fetched
+                    // for ALL successors first — successor, its (length, window tail), (sum, mean) and the score that would
+                    // leave the window — so the shared-memory latencies of the edges overlap instead of adding up
+                    // (one edge after the other cost ~135-165 cycles each, measured); the comparison itself is pandora's
+                    // sequential rule on registers, the arithmetic and its order are unchanged.
+                    uint32_t vv[ML_FAN], lvv[ML_FAN], tvv[ML_FAN];
+                    double Mvv[ML_FAN], meanv[ML_FAN], pT[ML_FAN];
+#pragma unroll
+                    for (uint32_t k = 0; k < ML_FAN; ++k) vv[k] = k < deg ? lds32(e0 + 4u * k) : term;
+#pragma unroll
+                    for (uint32_t k = 0; k < ML_FAN; ++k) {
+                        lds_len_t(vv[k], lvv[k], tvv[k]);
+                        lds_sum_mean(vv[k], Mvv[k], meanv[k]);
+                    }
+#pragma unroll
+                    for (uint32_t k = 0; k < ML_FAN; ++k) pT[k] = lds64(tvv[k] + L_PR);
+#pragma unroll
+                    for (uint32_t k = 0; k < ML_FAN; ++k) {
+                        if (k < deg) {
+                            const bool is_term = (vv[k] == term);
+                            const bool take = is_term ? (thresh > max_mean + tol)
+                                                      : ((meanv[k] > max_mean + tol) || (max_mean - meanv[k] <= tol && lvv[k] > max_len));
+                            if (take) {
+                                Mj = pj + Mvv[k];
+                                lenj = 1 + lvv[k];
+                                prevj = vv[k];
+                                if (lenj > P.window) {
+                                    Mj -= pT[k];
+                                    lenj -= 1;
+                                }
+                                max_mean = is_term ? thresh : meanv[k];
+                                if (!is_term) max_len = lvv[k];
+                            }
+                        }
+                    }
+                } else
                 for (uint32_t e = e0; e < e1; e += 4u) {
                     const uint32_t v = lds32(e);
                     const bool is_term = (v == term);
