@@ -2350,6 +2350,25 @@ int drprg_cuda_format_g6(double v, char* out) {
     out[n] = 0;
     return (int)n;
 }
+int drprg_cuda_format_g6_device(int device, const double* v, uint32_t n, char* out, uint8_t* len, uint8_t* refused) {
+    API_BEGIN CK(cudaSetDevice(device));
+    DBuf<double> dv;
+    DBuf<char> dout;
+    DBuf<uint8_t> dl, dr;
+    dv.ensure(n);
+    dout.ensure(48ull * n);
+    dl.ensure(n);
+    dr.ensure(n);
+    CK(cudaMemcpy(dv.p, v, (size_t)n * 8, cudaMemcpyHostToDevice));
+    launch_format_g6_batch(dv.p, n, dout.p, dl.p, dr.p, 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, 48ull * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(len, dl.p, n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(refused, dr.p, n, cudaMemcpyDeviceToHost));
+    dv.release(); dout.release(); dl.release(); dr.release();
+    return 0;
+    API_END
+}
 uint64_t drprg_cuda_launch_count(void) { return launch_count(); }
 double drprg_cuda_issue_peak(drprg_index* X) {
     try {

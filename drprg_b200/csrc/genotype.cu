@@ -340,6 +340,23 @@ __global__ void vcf_gather_kernel(uint32_t n, DevVcfText V, const uint32_t* __re
     *reinterpret_cast<uint4*>(V.text + o0) = w.v;  // text is 16-byte aligned; the buffer has room past `total`
 }
 
+// test hook: the device "%g" on arbitrary values (48 bytes per value, its length, and whether the device refused it)
+__global__ void format_g6_batch_kernel(const double* __restrict__ v, uint32_t n, char* __restrict__ out, uint8_t* __restrict__ len,
+                                       uint8_t* __restrict__ refused) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r = 0;
+    char* o0 = out + 48ull * i;
+    char* o = dev_format_g6(v[i], o0, r);
+    len[i] = (uint8_t)(o - o0);
+    refused[i] = (uint8_t)r;
+}
+void launch_format_g6_batch(const double* d_v, uint32_t n, char* d_out, uint8_t* d_len, uint8_t* d_refused, cudaStream_t st) {
+    if (!n) return;
+    format_g6_batch_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_v, n, d_out, d_len, d_refused);
+    ++g_launches;
+}
+
 void launch_vcf_text(const DevGenotype& G, const DevVcfText& V, cudaStream_t st) {
     if (!G.n_records) return;
     vcf_sample_column_kernel<<<(G.n_records + 127) / 128, 128, 0, st>>>(G, V);

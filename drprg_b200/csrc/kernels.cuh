@@ -185,6 +185,7 @@ struct DevVcfText {
     uint32_t* flags;             // bit 0: a value was refused by the device formatter (host-mapped)
 };
 void launch_vcf_text(const DevGenotype& G, const DevVcfText& V, cudaStream_t st);
+void launch_format_g6_batch(const double* d_v, uint32_t n, char* d_out, uint8_t* d_len, uint8_t* d_refused, cudaStream_t st);
 // the likelihood / GT / GT_CONF kernel alone, on per-allele rows already in G.mean_fwd / G.mean_rev / G.gaps
 void launch_genotype_rows(const DevGenotype& G, ModelParams P, cudaStream_t st);
 

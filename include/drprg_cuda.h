@@ -226,6 +226,10 @@ int drprg_cuda_last_timings(drprg_index*, float* out4);
 int drprg_cuda_last_genotype_timings(drprg_index*, double* out7);
 /* the VCF writer's float formatting (printf "%g"); out needs 48 bytes.  Exposed so tests can pin it against printf. */
 int drprg_cuda_format_g6(double v, char* out);
+/* the same formatting as the DEVICE does it for the VCF record lines (genotype.cu): out = 48 bytes per value, len[i] its
+ * length, refused[i] = 1 where the device formatter declines (exponent notation, rounding ties, -0, inf, nan: the host
+ * formatter then writes the sample's text).  Test hook. */
+int drprg_cuda_format_g6_device(int device, const double* v, uint32_t n, char* out, uint8_t* len, uint8_t* refused);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t drprg_cuda_launch_count(void);
 /* measured warp-instructions per second of a pure 32-bit integer multiply-add / shift / logic loop on this index's GPU: the

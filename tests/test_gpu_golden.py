@@ -96,3 +96,39 @@ def test_fused_minor_allele_statistic_constructed_rows():
     rust_filters.check_against(stats, rec_off, mf, mr, gaps, gt, conf, 0.1)
     assert stats["minor_gt"].tolist() == [1, -1, -1, -1, -1, -1, 2, -1, -1]
     assert stats["covg_gt"].tolist()[:2] == [78, 78] and stats["frs"][8] == 1.0 and np.isnan(stats["frs"][7])
+
+
+def test_device_float_formatting_matches_printf_g():
+    """the VCF record lines are formatted by a kernel: its "%g" must be byte-identical to printf wherever it answers, and it
+    must decline (host fallback) exactly the cases it cannot print that way: exponent notation, rounding ties, -0, inf, nan"""
+    import ctypes as C
+    L = lib.lib()
+    rng = np.random.default_rng(0)
+    vals = [0.0, 1.0, -1.0, 0.5, 0.25, 0.125, 0.2, 1 / 3, 2 / 3, 0.666667, 1e-4, 9.99999e-5, 123456.5, 999999.4, 999999.5,
+            999999.6, 1e6, -144.0, -0.0001, 100000.0, 99999.95, 0.000123456789, 5e-324, 1e300, float("inf"), float("nan"), -0.0,
+            0.1 + 0.2, 1234565.0, 12.34565, 0.3333335, 2.5e-5, 1.0000005, 1.00000049999, 322.1215, -716.9895]
+    vals += list(-np.exp(rng.uniform(-12, 14, 60000)))               # likelihood-like magnitudes
+    vals += list(rng.uniform(0, 1000, 30000)) + list(rng.integers(0, 40, 5000) / rng.integers(1, 40, 5000))
+    vals += [round(float(x), 5) + 5e-7 for x in rng.uniform(0, 100, 5000)]   # near decimal ties
+    v = np.ascontiguousarray(np.array(vals, np.float64))
+    n = len(v)
+    out = np.zeros(48 * n, np.uint8)
+    ln = np.zeros(n, np.uint8)
+    ref = np.zeros(n, np.uint8)
+    rc = L.drprg_cuda_format_g6_device(C.c_int(0), v.ctypes.data_as(C.c_void_p), C.c_uint32(n), out.ctypes.data_as(C.c_void_p),
+                                       ln.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+    assert rc == 0, L.drprg_cuda_last_error()
+    answered = 0
+    for i in range(n):
+        want = "%g" % float(v[i])
+        if ref[i]:
+            # declined: only what the fast path cannot print (exponent form, non-finite, -0, or within 1e-6 of a tie)
+            a = abs(float(v[i]))
+            near_tie = np.isfinite(a) and a > 0 and 1e-4 <= a < 999999.0 and \
+                abs((a * 10 ** (5 - int(np.floor(np.log10(a))))) % 1 - 0.5) < 1e-4
+            assert "e" in want or not np.isfinite(a) or want == "-0" or near_tie or a >= 999999.0, (v[i], want)
+        else:
+            got = bytes(out[48 * i:48 * i + int(ln[i])]).decode()
+            assert got == want, (float(v[i]), got, want)
+            answered += 1
+    assert answered > 0.9 * n
